@@ -1,0 +1,76 @@
+/* TEST INFRASTRUCTURE — CPU restatement of the reference's photon-mapping path.
+ *
+ * This is the checker for the CUDA path, not part of the product: only tests/,
+ * __graft_entry__.smoke() and bench.py's cpu_baseline leg may load it.
+ *
+ * Parity status: PINNED.  The reference ships no tests or golden vectors for this path
+ * (SURVEY.md §4), so the pin is the reference itself run here: with rng = ORC_RNG_LIBC and
+ * accel = ORC_ACCEL_BSP this restatement reproduces performPhotonMappingNative
+ * (photonmap.c:408) BIT FOR BIT for the same srand() seed (tests/test_oracle_vs_reference.py
+ * compares the raw atlases of oracle/_ref/libfmgi_ref.so and of this file), and the committed
+ * fixtures under tests/golden/ were produced by the compiled reference
+ * (oracle/make_golden.py).
+ */
+#ifndef FMGI_PHOTON_ORACLE_H
+#define FMGI_PHOTON_ORACLE_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* Layout-identical to the reference's Rectangle (rectangle.h:19-26): four float4 + one int4,
+ * 80 bytes, 16-byte aligned.  lm = {atlas base index, tiles across width, tiles across height, 0}. */
+typedef struct __attribute__((aligned(16))) orc_rect {
+    float pos[4], width[4], height[4], n[4];
+    int32_t lm[4];
+} orc_rect;
+
+enum { ORC_RNG_LIBC = 0, ORC_RNG_PHILOX = 1 };
+enum { ORC_ACCEL_BSP = 0, ORC_ACCEL_LINEAR = 1 };
+
+typedef struct orc_stats {
+    uint64_t photons, rays, deposits, mirror_bounces, rect_tests;
+} orc_stats;
+
+/* rectangle.c:67-95 */
+float orc_intersects(const orc_rect *rect, const float src[3], const float dir[3], float closest);
+/* rectangle.c:205-230 */
+int orc_tile_id(const orc_rect *rect, const float p[3]);
+/* photonmap.c:414-418: (uint64)(int spa * float area) */
+uint64_t orc_photon_budget(const orc_rect *emitter, int samples_per_area);
+
+/* Philox4x32-10 (Salmon et al., SC'11; Random123 v1.14 constants). */
+void orc_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]);
+
+/* Whole bake, same emitter order and budgets as performPhotonMappingNative (photonmap.c:408-434).
+ * texels: numTexels x float4, accumulated in place.
+ * rng = ORC_RNG_LIBC   : libc rand() in the reference's draw order; caller seeds with srand().
+ * rng = ORC_RNG_PHILOX : the CUDA path's stream (key = {seed, emitter}, counter =
+ *                        {photon lo, photon hi, event, 0}; event 0 = emission (dx, dy, xi1, xi2),
+ *                        event b>=1 = bounce b (roulette, xi1, xi2)); xi = (word >> 8) * 2^-24.
+ * photon_first/photon_count select a sub-range of every emitter's photons in PHILOX mode
+ * (count 0 = all), mirroring the multi-GPU sharding; ignored in LIBC mode. */
+void orc_bake(const orc_rect *walls, int num_walls,
+              const orc_rect *windows, int num_windows,
+              const orc_rect *lights, int num_lights,
+              float *texels, int samples_per_area, int max_depth,
+              int accel, int rng, uint32_t seed,
+              int shard, int num_shards, orc_stats *stats);
+
+/* Per-photon path record in PHILOX mode: for photons [first, first+count) of emitter
+ * `emitter_index`, texel_out[(i*max_depth)+b] = atlas index deposited at bounce b, or -1. */
+void orc_trace_paths(const orc_rect *walls, int num_walls,
+                     const orc_rect *emitter, int is_window, int emitter_index,
+                     int max_depth, uint32_t seed, uint64_t first, int count, int32_t *texel_out);
+
+/* Batch closest hit (linear scan or BSP): hit index into walls (-1 = miss) and distance. */
+void orc_closest_hit(const orc_rect *walls, int num_walls, int accel,
+                     const float *origins, const float *dirs, int num_rays,
+                     int32_t *hit_index, float *hit_dist);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
