@@ -1,0 +1,617 @@
+// C ABI of libfmgi_cuda.so (include/fmgi.h): the reference's performGlobalIlluminationCl entry
+// point (global_illumination_cl.h:10), the options/counters extension and the parity probes.
+// Replaces the OpenCL host code of global_illumination_cl.c:148-321.
+#include <cuda_runtime.h>
+
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <memory>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "trace_soup.cuh"
+
+using namespace fmgi;
+
+namespace {
+
+thread_local std::string g_last_error;
+
+int fail(int code, const std::string &msg)
+{
+    g_last_error = msg;
+    return code;
+}
+
+#define FMGI_CUDA(expr)                                                                             \
+    do {                                                                                            \
+        cudaError_t err__ = (expr);                                                                 \
+        if (err__ != cudaSuccess)                                                                   \
+            return fail(FMGI_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(err__));      \
+    } while (0)
+
+double now_ms()
+{
+    using namespace std::chrono;
+    return duration<double, std::milli>(steady_clock::now().time_since_epoch()).count();
+}
+
+struct DeviceGuard {
+    int prev = -1;
+    explicit DeviceGuard(int dev) { cudaGetDevice(&prev); cudaSetDevice(dev); }
+    ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
+fmgi_options resolve(const fmgi_options *in)
+{
+    fmgi_options o;
+    fmgi_default_options(&o);
+    if (in) {
+        size_t n = in->struct_size ? in->struct_size : sizeof(fmgi_options);
+        if (n > sizeof(fmgi_options)) n = sizeof(fmgi_options);
+        memcpy(&o, in, n);
+        o.struct_size = sizeof(fmgi_options);
+    }
+    if (o.max_depth <= 0) o.max_depth = 8;
+    if (o.num_shards <= 0) { o.num_shards = 1; o.shard = 0; }
+    if (o.num_gpus <= 0) o.num_gpus = 1;
+    return o;
+}
+
+template <typename T>
+cudaError_t upload(T **dst, const std::vector<T> &src)
+{
+    *dst = nullptr;
+    size_t bytes = src.size() * sizeof(T);
+    cudaError_t e = cudaMalloc((void **)dst, bytes ? bytes : sizeof(T));
+    if (e != cudaSuccess) return e;
+    if (bytes) e = cudaMemcpy(*dst, src.data(), bytes, cudaMemcpyHostToDevice);
+    return e;
+}
+
+}  // namespace
+
+struct fmgi_scene {
+    int device = 0;
+    HostScene host;
+    // device tables
+    AxisRect *d_axis = nullptr;
+    GeneralRect *d_general = nullptr;
+    ShadeRect *d_shade = nullptr;
+    EmitterRec *d_emitters = nullptr;
+    unsigned long long *d_jobs = nullptr;       // job_begin[E+1] then photon_first[E]
+    unsigned long long *d_counters = nullptr;   // 4 counters + work counter
+    unsigned long long *h_jobs = nullptr;       // pinned staging
+    unsigned long long *h_counters = nullptr;   // pinned
+    cudaEvent_t ev_start = nullptr, ev_stop = nullptr;
+    cudaStream_t last_stream = nullptr;
+    bool traced = false;
+    int num_sms = 0, clock_khz = 0, blocks_per_sm = 0;
+    size_t smem_bytes = 0;
+    int tier = FMGI_TIER_SOUP;
+    uint64_t launches = 0;
+    uint64_t tests_per_ray = 0;
+};
+
+namespace {
+
+TraceParams base_params(const fmgi_scene *s)
+{
+    TraceParams p;
+    memset(&p, 0, sizeof p);
+    p.axis = reinterpret_cast<const float4 *>(s->d_axis);
+    p.general = reinterpret_cast<const float4 *>(s->d_general);
+    for (int g = 0; g <= kNumAxisGroups; g++) p.group_begin[g] = s->host.group_begin[g];
+    p.num_general = (int)s->host.general.size();
+    p.shade = reinterpret_cast<const float4 *>(s->d_shade);
+    p.emitters = reinterpret_cast<const float4 *>(s->d_emitters);
+    p.num_emitters = (int)s->host.emitters.size();
+    p.job_begin = s->d_jobs;
+    p.photon_first = s->d_jobs + (p.num_emitters + 1);
+    p.work_counter = s->d_counters + 4;
+    p.counters = s->d_counters;
+    return p;
+}
+
+// Fills the pinned job tables for (spa, shard): emitter e's N photons (photonmap.c:414-418) are
+// split into num_shards contiguous index ranges.  Returns the shard's photon total.
+unsigned long long fill_jobs(const fmgi_scene *s, int spa, const fmgi_options &o, unsigned long long *jobs)
+{
+    const int E = (int)s->host.emitters.size();
+    unsigned long long total = 0;
+    for (int e = 0; e < E; e++) {
+        const unsigned long long n = photon_budget(s->host.emitter_area[e], spa);
+        const unsigned long long first = (unsigned long long)((unsigned __int128)n * o.shard / o.num_shards);
+        const unsigned long long last = (unsigned long long)((unsigned __int128)n * (o.shard + 1) / o.num_shards);
+        jobs[e] = total;
+        jobs[E + 1 + e] = first;
+        total += last - first;
+    }
+    jobs[E] = total;
+    return total;
+}
+
+template <bool kProbe>
+cudaError_t launch_trace(fmgi_scene *s, const TraceParams &p, int deposit, int blocks, cudaStream_t st)
+{
+    auto go = [&](auto kernel) {
+        cudaError_t e = cudaSuccess;
+        if (s->smem_bytes > 48 * 1024)
+            e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->smem_bytes);
+        if (e != cudaSuccess) return e;
+        kernel<<<blocks, kTraceThreads, s->smem_bytes, st>>>(p);
+        s->launches++;
+        return cudaGetLastError();
+    };
+    if (kProbe) return go(k_trace_soup<FMGI_DEPOSIT_VEC4, true>);
+    switch (deposit) {
+        case FMGI_DEPOSIT_SCALAR: return go(k_trace_soup<FMGI_DEPOSIT_SCALAR, false>);
+        case FMGI_DEPOSIT_WARP_AGG: return go(k_trace_soup<FMGI_DEPOSIT_WARP_AGG, false>);
+        default: return go(k_trace_soup<FMGI_DEPOSIT_VEC4, false>);
+    }
+}
+
+}  // namespace
+
+extern "C" {
+
+void fmgi_default_options(fmgi_options *opt)
+{
+    if (!opt) return;
+    memset(opt, 0, sizeof *opt);
+    opt->struct_size = sizeof *opt;
+    opt->max_depth = 8;          // photonmap.c:173
+    opt->seed = 1;
+    opt->num_gpus = 1;
+    opt->num_shards = 1;
+    opt->tier = FMGI_TIER_AUTO;
+    opt->deposit = FMGI_DEPOSIT_VEC4;
+}
+
+const char *fmgi_last_error(void) { return g_last_error.c_str(); }
+const char *fmgi_version(void) { return "fmgi-b200 0.1 (sm_100a)"; }
+
+int fmgi_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+int fmgi_scene_create(fmgi_scene **out, const fmgi_rect *walls, int num_walls, const fmgi_rect *windows,
+                      int num_windows, const fmgi_rect *lights, int num_lights, int num_texels,
+                      const fmgi_options *opt)
+{
+    if (!out) return fail(FMGI_ERR_ARG, "out is NULL");
+    *out = nullptr;
+    if ((num_walls && !walls) || (num_windows && !windows) || (num_lights && !lights))
+        return fail(FMGI_ERR_ARG, "NULL rectangle table with non-zero count");
+    const fmgi_options o = resolve(opt);
+    int ndev = 0;
+    FMGI_CUDA(cudaGetDeviceCount(&ndev));
+    if (o.device < 0 || o.device >= ndev) return fail(FMGI_ERR_ARG, "device ordinal out of range");
+
+    std::unique_ptr<fmgi_scene> s(new fmgi_scene);
+    s->device = o.device;
+    const char *why = prepare_scene(s->host, walls, num_walls, windows, num_windows, lights, num_lights, num_texels);
+    if (why[0]) return fail(FMGI_ERR_ARG, why);
+
+    DeviceGuard guard(o.device);
+    cudaDeviceProp prop;
+    FMGI_CUDA(cudaGetDeviceProperties(&prop, o.device));
+    s->num_sms = prop.multiProcessorCount;
+    FMGI_CUDA(cudaDeviceGetAttribute(&s->clock_khz, cudaDevAttrClockRate, o.device));
+
+    s->smem_bytes = s->host.axis.size() * sizeof(AxisRect) + s->host.general.size() * sizeof(GeneralRect);
+    s->tier = FMGI_TIER_SOUP;
+    if (s->smem_bytes > (size_t)prop.sharedMemPerBlockOptin)
+        return fail(FMGI_ERR_UNSUPPORTED, "rectangle soup does not fit in shared memory (grid tier required)");
+    s->tests_per_ray = s->host.axis.size() + s->host.general.size();
+
+    FMGI_CUDA(upload(&s->d_axis, s->host.axis));
+    FMGI_CUDA(upload(&s->d_general, s->host.general));
+    FMGI_CUDA(upload(&s->d_shade, s->host.shade));
+    FMGI_CUDA(upload(&s->d_emitters, s->host.emitters));
+    const size_t E = s->host.emitters.size();
+    FMGI_CUDA(cudaMalloc((void **)&s->d_jobs, (2 * E + 2) * sizeof(unsigned long long)));
+    FMGI_CUDA(cudaMalloc((void **)&s->d_counters, 8 * sizeof(unsigned long long)));
+    FMGI_CUDA(cudaMallocHost((void **)&s->h_jobs, (2 * E + 2) * sizeof(unsigned long long)));
+    FMGI_CUDA(cudaMallocHost((void **)&s->h_counters, 8 * sizeof(unsigned long long)));
+    memset(s->h_counters, 0, 8 * sizeof(unsigned long long));
+    FMGI_CUDA(cudaEventCreate(&s->ev_start));
+    FMGI_CUDA(cudaEventCreate(&s->ev_stop));
+
+    if (s->smem_bytes > 48 * 1024)
+        FMGI_CUDA(cudaFuncSetAttribute(k_trace_soup<FMGI_DEPOSIT_VEC4, false>,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->smem_bytes));
+    FMGI_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&s->blocks_per_sm, k_trace_soup<FMGI_DEPOSIT_VEC4, false>,
+                                                            kTraceThreads, s->smem_bytes));
+    if (s->blocks_per_sm < 1) return fail(FMGI_ERR_CUDA, "trace kernel does not fit on an SM");
+    *out = s.release();
+    return FMGI_OK;
+}
+
+void fmgi_scene_destroy(fmgi_scene *s)
+{
+    if (!s) return;
+    DeviceGuard guard(s->device);
+    cudaFree(s->d_axis); cudaFree(s->d_general); cudaFree(s->d_shade); cudaFree(s->d_emitters);
+    cudaFree(s->d_jobs); cudaFree(s->d_counters);
+    cudaFreeHost(s->h_jobs); cudaFreeHost(s->h_counters);
+    if (s->ev_start) cudaEventDestroy(s->ev_start);
+    if (s->ev_stop) cudaEventDestroy(s->ev_stop);
+    delete s;
+}
+
+uint64_t fmgi_scene_photon_count(const fmgi_scene *s, int spa, const fmgi_options *opt)
+{
+    if (!s) return 0;
+    const fmgi_options o = resolve(opt);
+    std::vector<unsigned long long> jobs(2 * s->host.emitters.size() + 2);
+    return fill_jobs(s, spa, o, jobs.data());
+}
+
+int fmgi_scene_trace(fmgi_scene *s, void *atlas_dev, int spa, const fmgi_options *opt, void *cuda_stream)
+{
+    if (!s || !atlas_dev) return fail(FMGI_ERR_ARG, "scene or atlas is NULL");
+    const fmgi_options o = resolve(opt);
+    if (o.shard < 0 || o.shard >= o.num_shards) return fail(FMGI_ERR_ARG, "shard out of range");
+    DeviceGuard guard(s->device);
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    const int E = (int)s->host.emitters.size();
+
+    if (s->traced) FMGI_CUDA(cudaEventSynchronize(s->ev_stop));   // pinned staging is reused
+    const unsigned long long total = fill_jobs(s, spa, o, s->h_jobs);
+    FMGI_CUDA(cudaMemcpyAsync(s->d_jobs, s->h_jobs, (2 * E + 2) * sizeof(unsigned long long),
+                              cudaMemcpyHostToDevice, st));
+    FMGI_CUDA(cudaMemsetAsync(s->d_counters, 0, 8 * sizeof(unsigned long long), st));
+
+    TraceParams p = base_params(s);
+    p.total_jobs = total;
+    p.atlas = reinterpret_cast<float4 *>(atlas_dev);
+    p.max_depth = o.max_depth;
+    p.seed = o.seed;
+
+    FMGI_CUDA(cudaEventRecord(s->ev_start, st));
+    if (total > 0) {
+        // persistent grid: one wave of resident CTAs, never more warps than chunks of work
+        unsigned long long want = (total + kChunkPhotons - 1) / kChunkPhotons;
+        want = (want * 32 + kTraceThreads - 1) / kTraceThreads;
+        const unsigned long long wave = (unsigned long long)s->num_sms * s->blocks_per_sm;
+        const int blocks = (int)(want < wave ? (want ? want : 1) : wave);
+        FMGI_CUDA(launch_trace<false>(s, p, o.deposit, blocks, st));
+    }
+    FMGI_CUDA(cudaEventRecord(s->ev_stop, st));
+    FMGI_CUDA(cudaMemcpyAsync(s->h_counters, s->d_counters, 8 * sizeof(unsigned long long),
+                              cudaMemcpyDeviceToHost, st));
+    s->last_stream = st;
+    s->traced = true;
+    return FMGI_OK;
+}
+
+int fmgi_scene_sync(fmgi_scene *s, fmgi_stats *stats)
+{
+    if (!s) return fail(FMGI_ERR_ARG, "scene is NULL");
+    DeviceGuard guard(s->device);
+    FMGI_CUDA(cudaStreamSynchronize(s->last_stream));
+    if (stats) {
+        memset(stats, 0, sizeof *stats);
+        stats->photons = s->h_counters[0];
+        stats->rays = s->h_counters[1];
+        stats->deposits = s->h_counters[2];
+        stats->mirror_bounces = s->h_counters[3];
+        stats->rect_tests = s->h_counters[1] * s->tests_per_ray;
+        stats->kernel_launches = s->launches;
+        if (s->traced) {
+            float ms = 0;
+            FMGI_CUDA(cudaEventElapsedTime(&ms, s->ev_start, s->ev_stop));
+            stats->trace_ms = ms;
+        }
+        stats->num_gpus = 1;
+        stats->tier = s->tier;
+        stats->num_sms = s->num_sms;
+        stats->sm_clock_khz = s->clock_khz;
+    }
+    return FMGI_OK;
+}
+
+// ---- host-buffer bake ---------------------------------------------------------------------------------
+
+int fmgi_bake(struct Geometry *geo_, int spa, const fmgi_options *opt, fmgi_stats *stats)
+{
+    fmgi_geometry *geo = reinterpret_cast<fmgi_geometry *>(geo_);
+    if (!geo) return fail(FMGI_ERR_ARG, "geo is NULL");
+    if (geo->numTexels < 0 || (geo->numTexels && !geo->texels)) return fail(FMGI_ERR_ARG, "bad texel atlas");
+    const double t_begin = now_ms();
+    fmgi_options o = resolve(opt);
+    int ndev = 0;
+    FMGI_CUDA(cudaGetDeviceCount(&ndev));
+    if (ndev < 1) return fail(FMGI_ERR_CUDA, "no CUDA device");
+    const int G = o.num_gpus > ndev ? ndev : o.num_gpus;
+    const size_t atlas_bytes = (size_t)geo->numTexels * sizeof(float4);
+
+    struct PerGpu {
+        fmgi_scene *scene = nullptr;
+        float4 *atlas = nullptr;
+        cudaStream_t stream = nullptr;
+        fmgi_stats st;
+        int rc = FMGI_OK;
+        std::string err;
+        double h2d_ms = 0;
+    };
+    std::vector<PerGpu> gpus(G);
+
+    auto worker = [&](int g) {
+        PerGpu &me = gpus[g];
+        auto bail = [&](int rc) { me.rc = rc; me.err = g_last_error; };
+        fmgi_options og = o;
+        og.device = o.device + g < ndev ? o.device + g : g;
+        // the caller's shard is subdivided over this call's GPUs
+        og.num_shards = o.num_shards * G;
+        og.shard = o.shard * G + g;
+        if (cudaSetDevice(og.device) != cudaSuccess) return bail(fail(FMGI_ERR_CUDA, "cudaSetDevice failed"));
+        int rc = fmgi_scene_create(&me.scene, geo->walls, geo->numWalls, geo->windows, geo->numWindows, geo->lights,
+                                   geo->numLights, geo->numTexels, &og);
+        if (rc) return bail(rc);
+        cudaSetDevice(og.device);
+        if (cudaStreamCreateWithFlags(&me.stream, cudaStreamNonBlocking) != cudaSuccess ||
+            cudaMalloc((void **)&me.atlas, atlas_bytes ? atlas_bytes : 16) != cudaSuccess)
+            return bail(fail(FMGI_ERR_CUDA, "atlas allocation failed"));
+        const double t0 = now_ms();
+        cudaError_t e;
+        // GPU 0 starts from the caller's atlas (CL_MEM_COPY_HOST_PTR, global_illumination_cl.c:295)
+        if (g == 0) e = cudaMemcpyAsync(me.atlas, geo->texels, atlas_bytes, cudaMemcpyHostToDevice, me.stream);
+        else e = cudaMemsetAsync(me.atlas, 0, atlas_bytes, me.stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(me.stream);
+        if (e != cudaSuccess) return bail(fail(FMGI_ERR_CUDA, std::string("atlas upload: ") + cudaGetErrorString(e)));
+        me.h2d_ms = now_ms() - t0;
+        rc = fmgi_scene_trace(me.scene, me.atlas, spa, &og, me.stream);
+        if (rc) return bail(rc);
+        rc = fmgi_scene_sync(me.scene, &me.st);
+        if (rc) return bail(rc);
+    };
+
+    if (G == 1) worker(0);
+    else {
+        std::vector<std::thread> th;
+        for (int g = 0; g < G; g++) th.emplace_back(worker, g);
+        for (auto &t : th) t.join();
+    }
+
+    int rc = FMGI_OK;
+    for (int g = 0; g < G; g++)
+        if (gpus[g].rc) { rc = gpus[g].rc; g_last_error = gpus[g].err; }
+
+    double reduce_ms = 0, d2h_ms = 0;
+    const int dev0 = gpus[0].scene ? gpus[0].scene->device : 0;
+    if (rc == FMGI_OK) {
+        cudaSetDevice(dev0);
+        cudaError_t e = cudaSuccess;
+        if (G > 1) {
+            // fold the peers' atlases into GPU 0's, reading them over NVLink peer mappings
+            const double t0 = now_ms();
+            std::vector<const float4 *> peers;
+            std::vector<float4 *> staged;
+            for (int g = 1; g < G && e == cudaSuccess; g++) {
+                int can = 0;
+                cudaDeviceCanAccessPeer(&can, dev0, gpus[g].scene->device);
+                if (can) {
+                    cudaError_t pe = cudaDeviceEnablePeerAccess(gpus[g].scene->device, 0);
+                    if (pe != cudaSuccess && pe != cudaErrorPeerAccessAlreadyEnabled) can = 0;
+                    cudaGetLastError();
+                }
+                if (can) peers.push_back(gpus[g].atlas);
+                else {
+                    float4 *tmp = nullptr;
+                    e = cudaMalloc((void **)&tmp, atlas_bytes ? atlas_bytes : 16);
+                    if (e == cudaSuccess)
+                        e = cudaMemcpyPeer(tmp, dev0, gpus[g].atlas, gpus[g].scene->device, atlas_bytes);
+                    staged.push_back(tmp);
+                    peers.push_back(tmp);
+                }
+            }
+            const float4 **d_peers = nullptr;
+            if (e == cudaSuccess) e = cudaMalloc((void **)&d_peers, peers.size() * sizeof(float4 *));
+            if (e == cudaSuccess)
+                e = cudaMemcpy(d_peers, peers.data(), peers.size() * sizeof(float4 *), cudaMemcpyHostToDevice);
+            if (e == cudaSuccess && geo->numTexels > 0) {
+                const int blocks = gpus[0].scene->num_sms * 8;
+                k_fold_peers<<<blocks, 256, 0, gpus[0].stream>>>(gpus[0].atlas, d_peers, (int)peers.size(),
+                                                               (size_t)geo->numTexels);
+                gpus[0].scene->launches++;
+                e = cudaGetLastError();
+                if (e == cudaSuccess) e = cudaStreamSynchronize(gpus[0].stream);
+            }
+            cudaFree(d_peers);
+            for (float4 *t : staged) cudaFree(t);
+            reduce_ms = now_ms() - t0;
+        }
+        if (e == cudaSuccess) {
+            const double t0 = now_ms();
+            e = cudaMemcpyAsync(geo->texels, gpus[0].atlas, atlas_bytes, cudaMemcpyDeviceToHost, gpus[0].stream);
+            if (e == cudaSuccess) e = cudaStreamSynchronize(gpus[0].stream);
+            d2h_ms = now_ms() - t0;
+        }
+        if (e != cudaSuccess) rc = fail(FMGI_ERR_CUDA, std::string("atlas fold/read-back: ") + cudaGetErrorString(e));
+    }
+
+    if (stats) {
+        memset(stats, 0, sizeof *stats);
+        for (int g = 0; g < G; g++) {
+            const fmgi_stats &s = gpus[g].st;
+            stats->photons += s.photons; stats->rays += s.rays; stats->deposits += s.deposits;
+            stats->mirror_bounces += s.mirror_bounces; stats->rect_tests += s.rect_tests;
+            if (gpus[g].scene) stats->kernel_launches += gpus[g].scene->launches;
+            if (s.trace_ms > stats->trace_ms) stats->trace_ms = s.trace_ms;
+            if (gpus[g].h2d_ms > stats->h2d_ms) stats->h2d_ms = gpus[g].h2d_ms;
+        }
+        stats->reduce_ms = reduce_ms;
+        stats->d2h_ms = d2h_ms;
+        stats->num_gpus = G;
+        stats->tier = gpus[0].st.tier;
+        stats->num_sms = gpus[0].st.num_sms;
+        stats->sm_clock_khz = gpus[0].st.sm_clock_khz;
+    }
+    for (int g = 0; g < G; g++) {
+        if (gpus[g].scene) cudaSetDevice(gpus[g].scene->device);
+        if (gpus[g].atlas) cudaFree(gpus[g].atlas);
+        if (gpus[g].stream) cudaStreamDestroy(gpus[g].stream);
+        fmgi_scene_destroy(gpus[g].scene);
+    }
+    if (stats) stats->total_ms = now_ms() - t_begin;
+    return rc;
+}
+
+// ---- the reference boundary (global_illumination_cl.h:10) -------------------------------------------------
+
+void performGlobalIlluminationCl(struct Geometry *geo, int numSamplesPerArea)
+{
+    fmgi_options o;
+    fmgi_default_options(&o);
+    if (const char *v = getenv("FMGI_MAX_DEPTH")) o.max_depth = atoi(v);
+    if (const char *v = getenv("FMGI_SEED")) o.seed = (uint32_t)strtoul(v, nullptr, 0);
+    if (const char *v = getenv("FMGI_GPUS")) o.num_gpus = atoi(v);
+    if (const char *v = getenv("FMGI_DEPOSIT")) o.deposit = atoi(v);
+    fmgi_stats st;
+    const int rc = fmgi_bake(geo, numSamplesPerArea, &o, &st);
+    if (rc != FMGI_OK) {
+        printf("[Err] photon mapping on the GPU failed: %s\n", fmgi_last_error());
+        exit(1);
+    }
+    printf("[INF] photon-mapped %llu photons / %llu bounces on %d GPU(s): trace %.1f ms (%.3g bounces/s), total %.1f ms\n",
+           (unsigned long long)st.photons, (unsigned long long)st.deposits, st.num_gpus, st.trace_ms,
+           st.trace_ms > 0 ? st.deposits / (st.trace_ms * 1e-3) : 0.0, st.total_ms);
+    if (const char *v = getenv("FMGI_STATS"))
+        if (atoi(v))
+            printf("[INF] rays %llu, mirror bounces %llu, rectangle tests %llu, h2d %.2f ms, d2h %.2f ms, fold %.2f ms, "
+                   "launches %llu\n",
+                   (unsigned long long)st.rays, (unsigned long long)st.mirror_bounces,
+                   (unsigned long long)st.rect_tests, st.h2d_ms, st.d2h_ms, st.reduce_ms,
+                   (unsigned long long)st.kernel_launches);
+}
+
+// ---- parity probes ---------------------------------------------------------------------------------------------
+
+int fmgi_probe_closest_hit(fmgi_scene *s, const float *origins, const float *dirs, int n, int32_t *hit_index,
+                           float *hit_dist)
+{
+    if (!s || !origins || !dirs || !hit_index || !hit_dist || n < 0) return fail(FMGI_ERR_ARG, "bad argument");
+    if (n == 0) return FMGI_OK;
+    DeviceGuard guard(s->device);
+    float *d_o = nullptr, *d_d = nullptr, *d_t = nullptr;
+    int32_t *d_i = nullptr;
+    const size_t vb = (size_t)n * 3 * sizeof(float);
+    FMGI_CUDA(cudaMalloc((void **)&d_o, vb));
+    FMGI_CUDA(cudaMalloc((void **)&d_d, vb));
+    FMGI_CUDA(cudaMalloc((void **)&d_t, (size_t)n * sizeof(float)));
+    FMGI_CUDA(cudaMalloc((void **)&d_i, (size_t)n * sizeof(int32_t)));
+    FMGI_CUDA(cudaMemcpy(d_o, origins, vb, cudaMemcpyHostToDevice));
+    FMGI_CUDA(cudaMemcpy(d_d, dirs, vb, cudaMemcpyHostToDevice));
+    if (s->smem_bytes > 48 * 1024)
+        FMGI_CUDA(cudaFuncSetAttribute(k_probe_closest_hit, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)s->smem_bytes));
+    const TraceParams p = base_params(s);
+    int blocks = (n + 255) / 256;
+    if (blocks > s->num_sms * 4) blocks = s->num_sms * 4;
+    k_probe_closest_hit<<<blocks, 256, s->smem_bytes>>>(p, d_o, d_d, n, d_i, d_t);
+    s->launches++;
+    FMGI_CUDA(cudaGetLastError());
+    FMGI_CUDA(cudaMemcpy(hit_index, d_i, (size_t)n * sizeof(int32_t), cudaMemcpyDeviceToHost));
+    FMGI_CUDA(cudaMemcpy(hit_dist, d_t, (size_t)n * sizeof(float), cudaMemcpyDeviceToHost));
+    cudaFree(d_o); cudaFree(d_d); cudaFree(d_t); cudaFree(d_i);
+    return FMGI_OK;
+}
+
+int fmgi_probe_tile_ids(fmgi_scene *s, const int32_t *rect_index, const float *points, int n, int32_t *tile_ids)
+{
+    if (!s || !rect_index || !points || !tile_ids || n < 0) return fail(FMGI_ERR_ARG, "bad argument");
+    if (n == 0) return FMGI_OK;
+    for (int i = 0; i < n; i++)
+        if (rect_index[i] < 0 || rect_index[i] >= s->host.num_walls) return fail(FMGI_ERR_ARG, "rect index out of range");
+    DeviceGuard guard(s->device);
+    float *d_p = nullptr;
+    int32_t *d_r = nullptr, *d_t = nullptr;
+    FMGI_CUDA(cudaMalloc((void **)&d_p, (size_t)n * 3 * sizeof(float)));
+    FMGI_CUDA(cudaMalloc((void **)&d_r, (size_t)n * sizeof(int32_t)));
+    FMGI_CUDA(cudaMalloc((void **)&d_t, (size_t)n * sizeof(int32_t)));
+    FMGI_CUDA(cudaMemcpy(d_p, points, (size_t)n * 3 * sizeof(float), cudaMemcpyHostToDevice));
+    FMGI_CUDA(cudaMemcpy(d_r, rect_index, (size_t)n * sizeof(int32_t), cudaMemcpyHostToDevice));
+    int blocks = (n + 255) / 256;
+    if (blocks > s->num_sms * 8) blocks = s->num_sms * 8;
+    k_probe_tile_ids<<<blocks, 256>>>(reinterpret_cast<const float4 *>(s->d_shade), d_r, d_p, n, d_t);
+    s->launches++;
+    FMGI_CUDA(cudaGetLastError());
+    FMGI_CUDA(cudaMemcpy(tile_ids, d_t, (size_t)n * sizeof(int32_t), cudaMemcpyDeviceToHost));
+    cudaFree(d_p); cudaFree(d_r); cudaFree(d_t);
+    return FMGI_OK;
+}
+
+int fmgi_probe_philox(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4])
+{
+    if (!ctr || !key || !out) return fail(FMGI_ERR_ARG, "bad argument");
+    uint32_t *d = nullptr;
+    FMGI_CUDA(cudaMalloc((void **)&d, 4 * sizeof(uint32_t)));
+    k_probe_philox<<<1, 1>>>(ctr[0], ctr[1], ctr[2], ctr[3], key[0], key[1], d);
+    FMGI_CUDA(cudaGetLastError());
+    FMGI_CUDA(cudaMemcpy(out, d, 4 * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+    cudaFree(d);
+    return FMGI_OK;
+}
+
+int fmgi_probe_sample_dirs(const float normal[3], int sky, uint32_t seed, int n, float *dirs_out)
+{
+    if (!normal || !dirs_out || n < 0) return fail(FMGI_ERR_ARG, "bad argument");
+    if (n == 0) return FMGI_OK;
+    float u[3], v[3];
+    sampler_basis(normal, u, v);
+    float *d = nullptr;
+    FMGI_CUDA(cudaMalloc((void **)&d, (size_t)n * 3 * sizeof(float)));
+    k_probe_sample_dirs<<<(n + 255) / 256, 256>>>(make_float4(normal[0], normal[1], normal[2], 0),
+                                                  make_float4(u[0], u[1], u[2], 0), make_float4(v[0], v[1], v[2], 0),
+                                                  sky, seed, n, d);
+    FMGI_CUDA(cudaGetLastError());
+    FMGI_CUDA(cudaMemcpy(dirs_out, d, (size_t)n * 3 * sizeof(float), cudaMemcpyDeviceToHost));
+    cudaFree(d);
+    return FMGI_OK;
+}
+
+int fmgi_probe_paths(fmgi_scene *s, int emitter_index, int max_depth, uint32_t seed, uint64_t first, int count,
+                     int32_t *texel_out)
+{
+    if (!s || !texel_out || count < 0 || max_depth < 1) return fail(FMGI_ERR_ARG, "bad argument");
+    const int E = (int)s->host.emitters.size();
+    if (emitter_index < 0 || emitter_index >= E) return fail(FMGI_ERR_ARG, "emitter index out of range");
+    if (count == 0) return FMGI_OK;
+    DeviceGuard guard(s->device);
+    if (s->traced) FMGI_CUDA(cudaEventSynchronize(s->ev_stop));
+    // one-emitter job table: every other emitter has an empty range
+    unsigned long long total = 0;
+    for (int e = 0; e < E; e++) {
+        s->h_jobs[e] = total;
+        s->h_jobs[E + 1 + e] = e == emitter_index ? first : 0;
+        if (e == emitter_index) total += (unsigned long long)count;
+    }
+    s->h_jobs[E] = total;
+    FMGI_CUDA(cudaMemcpy(s->d_jobs, s->h_jobs, (2 * E + 2) * sizeof(unsigned long long), cudaMemcpyHostToDevice));
+    FMGI_CUDA(cudaMemset(s->d_counters, 0, 8 * sizeof(unsigned long long)));
+    int32_t *d_path = nullptr;
+    const size_t pb = (size_t)count * max_depth * sizeof(int32_t);
+    FMGI_CUDA(cudaMalloc((void **)&d_path, pb));
+    FMGI_CUDA(cudaMemset(d_path, 0xff, pb));
+    TraceParams p = base_params(s);
+    p.total_jobs = total;
+    p.max_depth = max_depth;
+    p.seed = seed;
+    p.path_out = d_path;
+    int blocks = (count + kTraceThreads - 1) / kTraceThreads;
+    if (blocks > s->num_sms) blocks = s->num_sms;
+    FMGI_CUDA(launch_trace<true>(s, p, 0, blocks, nullptr));
+    FMGI_CUDA(cudaMemcpy(texel_out, d_path, pb, cudaMemcpyDeviceToHost));
+    cudaFree(d_path);
+    return FMGI_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,149 @@
+// Host-side scene precompute: Rectangle soup -> traversal and shading tables.
+//
+// Compiled with -ffp-contract=off: the per-rectangle constants that feed the texel index
+// (width/|width|, |width| ...) must be the very floats the reference recomputes on every call of
+// getTileIdAt (rectangle.c:205-230) and the sampler basis must be the one
+// getCosineDistributedRandomRay builds (vector3_cl.c:139-144), so each expression below keeps
+// the reference's operation order: length() = sqrtf(x*x + y*y + z*z) (vector3_cl.c:93),
+// div_vec3() = multiply by 1.0f/len (vector3_cl.c:53-58), normalized() likewise (:95-100).
+#include <cmath>
+#include <cstring>
+
+#include "scene_tables.h"
+
+namespace fmgi {
+
+namespace {
+
+struct V3 { float x, y, z; };
+inline V3 ld(const float *p) { return {p[0], p[1], p[2]}; }
+inline float length(V3 a) { return sqrtf(a.x * a.x + a.y * a.y + a.z * a.z); }
+inline V3 scale(V3 a, float s) { return {a.x * s, a.y * s, a.z * s}; }
+inline float dot(V3 a, V3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+inline V3 cross(V3 a, V3 b) { return {a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x}; }
+inline V3 normalized(V3 a) { float fac = 1.0f / length(a); return scale(a, fac); }
+inline void st(float *d, V3 a) { d[0] = a.x; d[1] = a.y; d[2] = a.z; }
+
+// vector3_cl.c:139-144 (identical in getDiffuseSkyRandomRay :118-123)
+void sampler_basis(V3 n, V3 &u, V3 &v)
+{
+    u = {0, 0, 1};
+    if (fabs(dot(u, n)) >= 0.999999f)
+        u = {0, 1, 0};
+    v = normalized(cross(u, n));
+    u = normalized(cross(v, n));
+}
+
+int single_axis(V3 a)
+{
+    int nz = (a.x != 0) + (a.y != 0) + (a.z != 0);
+    if (nz != 1) return -1;
+    return a.x != 0 ? 0 : (a.y != 0 ? 1 : 2);
+}
+
+inline float comp(V3 a, int k) { return k == 0 ? a.x : (k == 1 ? a.y : a.z); }
+
+bool finite3(V3 a) { return std::isfinite(a.x) && std::isfinite(a.y) && std::isfinite(a.z); }
+
+}  // namespace
+
+void sampler_basis(const float n[3], float u[3], float v[3])
+{
+    V3 uu, vv;
+    sampler_basis(ld(n), uu, vv);
+    st(u, uu); st(v, vv);
+}
+
+uint64_t photon_budget(float area, int samples_per_area)
+{
+    float n = samples_per_area * area;      // int * float -> float, photonmap.c:418
+    if (!(n > 0)) return 0;
+    return (uint64_t)n;
+}
+
+const char *prepare_scene(HostScene &out, const fmgi_rect *walls, int num_walls,
+                          const fmgi_rect *windows, int num_windows,
+                          const fmgi_rect *lights, int num_lights, int num_texels)
+{
+    out = HostScene();
+    out.num_walls = num_walls; out.num_windows = num_windows; out.num_lights = num_lights;
+    out.num_texels = num_texels;
+    if (num_walls < 0 || num_windows < 0 || num_lights < 0 || num_texels < 0)
+        return "negative count";
+
+    std::vector<AxisRect> groups[kNumAxisGroups];
+    out.shade.resize(num_walls);
+
+    for (int r = 0; r < num_walls; r++) {
+        const fmgi_rect &w = walls[r];
+        V3 pos = ld(w.pos), wd = ld(w.width), ht = ld(w.height), n = ld(w.n);
+        if (!finite3(pos) || !finite3(wd) || !finite3(ht) || !finite3(n))
+            return "non-finite wall rectangle";
+        int base = w.lightmap[0], tw = w.lightmap[1], th = w.lightmap[2];
+        if (tw < 1 || th < 1 || base < 0 || (int64_t)base + (int64_t)tw * th > (int64_t)num_texels)
+            return "wall lightmap tile range lies outside the atlas";
+
+        float wlen = length(wd), hlen = length(ht);
+        ShadeRect &s = out.shade[r];
+        memset(&s, 0, sizeof s);
+        V3 u, v;
+        sampler_basis(n, u, v);
+        if (tw > 32767 || th > 32767)
+            return "more than 32767 lightmap tiles along one edge of a wall";
+        st(s.pos, pos); s.base = base;
+        st(s.wn, scale(wd, 1.0f / wlen)); s.wlen = wlen;
+        st(s.hn, scale(ht, 1.0f / hlen)); s.hlen = hlen;
+        st(s.n, n); s.tiles = tw | (th << 16);
+        st(s.u, u);
+        st(s.v, v);
+
+        if (!(wlen > 0) || !(hlen > 0) || !(length(n) > 0))
+            continue;                       // degenerate: zero area, can never be hit
+
+        int ai = single_axis(wd), aj = single_axis(ht), ak = single_axis(n);
+        if (ai >= 0 && aj >= 0 && ak >= 0 && ai != aj && ak != ai && ak != aj) {
+            // in-plane axes in ascending order, whichever of width/height they belong to
+            int i = ai < aj ? ai : aj, j = ai < aj ? aj : ai;
+            V3 far = {pos.x + wd.x + ht.x, pos.y + wd.y + ht.y, pos.z + wd.z + ht.z};
+            AxisRect a;
+            a.c = comp(pos, ak);
+            a.lo_i = fminf(comp(pos, i), comp(far, i)); a.hi_i = fmaxf(comp(pos, i), comp(far, i));
+            a.lo_j = fminf(comp(pos, j), comp(far, j)); a.hi_j = fmaxf(comp(pos, j), comp(far, j));
+            a.id = r; a.pad0 = a.pad1 = 0;
+            groups[2 * ak + (comp(n, ak) > 0 ? 0 : 1)].push_back(a);
+        } else {
+            GeneralRect g;
+            g.nx = n.x; g.ny = n.y; g.nz = n.z; g.nd = dot(n, pos);
+            V3 wn = scale(wd, 1.0f / wlen), hn = scale(ht, 1.0f / hlen);
+            g.wx = wn.x; g.wy = wn.y; g.wz = wn.z; g.wlen = wlen;
+            g.hx = hn.x; g.hy = hn.y; g.hz = hn.z; g.hlen = hlen;
+            g.px = pos.x; g.py = pos.y; g.pz = pos.z; g.id = r;
+            out.general.push_back(g);
+        }
+    }
+    for (int g = 0; g < kNumAxisGroups; g++) {
+        out.group_begin[g] = (int)out.axis.size();
+        out.axis.insert(out.axis.end(), groups[g].begin(), groups[g].end());
+    }
+    out.group_begin[kNumAxisGroups] = (int)out.axis.size();
+
+    // emitters: windows first, then lights (photonmap.c:412-431)
+    for (int e = 0; e < num_windows + num_lights; e++) {
+        const fmgi_rect &w = e < num_windows ? windows[e] : lights[e - num_windows];
+        V3 n = ld(w.n);
+        if (!finite3(ld(w.pos)) || !finite3(ld(w.width)) || !finite3(ld(w.height)) || !finite3(n))
+            return "non-finite emitter rectangle";
+        EmitterRec er;
+        memset(&er, 0, sizeof er);
+        V3 u, v;
+        sampler_basis(n, u, v);
+        st(er.pos, ld(w.pos)); er.is_window = e < num_windows;
+        st(er.width, ld(w.width)); st(er.height, ld(w.height));
+        st(er.n, n); st(er.u, u); st(er.v, v);
+        out.emitters.push_back(er);
+        out.emitter_area.push_back(length(ld(w.width)) * length(ld(w.height)));   // photonmap.c:417
+    }
+    return "";
+}
+
+}  // namespace fmgi

@@ -1,0 +1,98 @@
+// Device-side scene tables derived from the reference's Rectangle soup (rectangle.h:19-26).
+// Built once per scene on the host (scene_prep.cpp), uploaded, then staged into shared memory by
+// the trace kernel (soup tier) or walked from L2 (grid tier).
+#pragma once
+#include <stdint.h>
+#include <vector>
+
+#include "../../include/fmgi.h"
+
+namespace fmgi {
+
+// ---- closest-hit tables -------------------------------------------------------------------
+
+// One collider whose width/height/normal are axis parallel (everything parseLayout.c emits).
+// Stored in the group of its normal axis k and normal sign; (i, j) are the two in-plane axes
+// in ascending order.  32 bytes = two 16-byte shared-memory broadcasts per test.
+struct AxisRect {
+    float c;            // plane coordinate pos[k]
+    float lo_i, hi_i;   // extent along in-plane axis i (edges inclusive, rectangle.c:93)
+    float lo_j;
+    float hi_j;
+    int32_t id;         // index into the caller's wall table
+    int32_t pad0, pad1;
+};
+
+// Arbitrarily oriented collider: the full plane + two projections of rectangle.c:67-95.
+struct GeneralRect {
+    float nx, ny, nz, nd;       // unit normal, n . pos
+    float wx, wy, wz, wlen;     // width / |width|, |width|
+    float hx, hy, hz, hlen;     // height / |height|, |height|
+    float px, py, pz;           // pos
+    int32_t id;
+};
+
+// Group g = 2*k + (normal sign > 0 ? 0 : 1).  A ray can only hit group g if d[k] has the
+// opposite sign of the normal (back-face culling, rectangle.c:70-72).
+enum { kNumAxisGroups = 6 };
+
+// ---- shading tables (read once per hit / per emission) ---------------------------------------
+
+// Everything the bounce needs about the wall that was hit, as six float4 (96 B).  q0..q2 feed the
+// texel index, q3..q5 the sampler frame; EmitterRec shares the q3..q5 layout so that emission
+// and re-emission run through the same code.
+struct ShadeRect {
+    float pos[3]; int32_t base;      // q0: pos, atlas base index lightmapSetup[0]
+    float wn[3];  float wlen;        // q1: width * (1/|width|) as div_vec3 computes it, |width|
+    float hn[3];  float hlen;        // q2: height * (1/|height|), |height|
+    float n[3];   int32_t tiles;     // q3: unit normal as stored by the reference; tiles_w | tiles_h << 16
+    float u[3];   int32_t pad0;      // q4: sampler basis U (vector3_cl.c:139-144)
+    float v[3];   int32_t pad1;      // q5: sampler basis V
+};
+static_assert(sizeof(ShadeRect) == 96, "ShadeRect is six float4");
+
+struct EmitterRec {
+    float pos[3];    int32_t is_window;   // q0  photonmap.c:169-171,179-181
+    float width[3];  float pad0;          // q1
+    float height[3]; float pad1;          // q2
+    float n[3];      float pad2;          // q3
+    float u[3];      float pad3;          // q4
+    float v[3];      float pad4;          // q5
+};
+static_assert(sizeof(EmitterRec) == 96, "EmitterRec is six float4");
+
+// ---- uniform grid over the floor plan (grid tier) --------------------------------------------
+
+struct GridDesc {
+    float x0, y0;           // world position of cell (0,0)'s corner
+    float cell, inv_cell;   // cell edge, 1/edge
+    int32_t nx, ny;
+    float zmin, zmax;       // vertical extent of all colliders
+};
+
+struct HostScene {
+    int num_walls = 0, num_windows = 0, num_lights = 0, num_texels = 0;
+    std::vector<AxisRect> axis;           // grouped: group_begin[g] .. group_begin[g+1]
+    int group_begin[kNumAxisGroups + 1] = {0};
+    std::vector<GeneralRect> general;
+    std::vector<ShadeRect> shade;         // per wall
+    std::vector<EmitterRec> emitters;     // windows then lights
+    std::vector<float> emitter_area;      // |w|*|h| in float (photonmap.c:417)
+    // grid tier
+    GridDesc grid = {};
+    std::vector<int32_t> cell_begin;      // nx*ny + 1 offsets into cell_items
+    std::vector<int32_t> cell_items;      // per cell: indices into `axis` (>= 0) or ~index into `general`
+};
+
+// photonmap.c:414-418: N = (uint64)(int spa * float area)
+uint64_t photon_budget(float area, int samples_per_area);
+
+// Returns an empty string on success, else the reason the scene was rejected.
+const char *prepare_scene(HostScene &out, const fmgi_rect *walls, int num_walls,
+                          const fmgi_rect *windows, int num_windows,
+                          const fmgi_rect *lights, int num_lights, int num_texels);
+
+// vector3_cl.c:139-144: the basis both hemisphere samplers build around a normal.
+void sampler_basis(const float n[3], float u[3], float v[3]);
+
+}  // namespace fmgi

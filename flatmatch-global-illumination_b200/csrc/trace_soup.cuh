@@ -1,0 +1,238 @@
+// Soup tier: persistent photon-tracing kernel with the whole rectangle soup in shared memory,
+// plus the probe kernels that expose its device functions to the parity tests.
+#pragma once
+#include "trace_kernels.cuh"
+
+namespace fmgi {
+
+__device__ __forceinline__ float4 ldg4(const float4 *p) { return __ldg(p); }
+
+// Binary search: largest e with job_begin[e] <= job (job < total_jobs).
+__device__ __forceinline__ int find_emitter(const unsigned long long *__restrict__ job_begin, int num_emitters,
+                                            unsigned long long job)
+{
+    int lo = 0, hi = num_emitters - 1;
+    while (lo < hi) {
+        const int mid = (lo + hi + 1) >> 1;
+        if (__ldg(job_begin + mid) <= job) lo = mid; else hi = mid - 1;
+    }
+    return lo;
+}
+
+template <int kDeposit, bool kProbe>
+__global__ void __launch_bounds__(kTraceThreads, 3) k_trace_soup(const TraceParams p)
+{
+    extern __shared__ float4 smem[];
+    const int n_axis4 = 2 * p.group_begin[kNumAxisGroups];
+    const int n_gen4 = 4 * p.num_general;
+    for (int i = threadIdx.x; i < n_axis4; i += blockDim.x) smem[i] = p.axis[i];
+    for (int i = threadIdx.x; i < n_gen4; i += blockDim.x) smem[n_axis4 + i] = p.general[i];
+    __syncthreads();
+
+    SoupTables soup;
+    soup.axis = smem;
+    soup.general = smem + n_axis4;
+#pragma unroll
+    for (int g = 0; g <= kNumAxisGroups; g++) soup.group_begin[g] = p.group_begin[g];
+    soup.num_general = p.num_general;
+
+    const int lane = threadIdx.x & 31;
+    const unsigned lt_mask = (1u << lane) - 1u;
+
+    // photon state
+    bool alive = false, is_new = false, mirror = false;
+    float px = 0, py = 0, pz = 0, dx = 0, dy = 0, dz = 1;
+    float cr = 0, cg = 0, cb = 0, roulette = 0;
+    int depth = 0, emitter = 0, hit_id = 0;
+    unsigned long long photon = 0;
+    // warp-uniform work range
+    unsigned long long w_next = 0, w_end = 0;
+    int w_emitter = 0;
+    bool exhausted = false;
+    unsigned n_photons = 0, n_rays = 0, n_deposits = 0, n_mirror = 0;
+
+    for (;;) {
+        // ---- A. refill dead lanes from the warp's chunk of the photon index space ---------------
+        is_new = false;
+        if (!exhausted) {
+            unsigned dead = __ballot_sync(kFullMask, !alive);
+            while (dead) {
+                if (w_next == w_end) {
+                    unsigned long long base = 0;
+                    if (lane == 0) base = atomicAdd(p.work_counter, (unsigned long long)kChunkPhotons);
+                    base = __shfl_sync(kFullMask, base, 0);
+                    if (base >= p.total_jobs) { exhausted = true; break; }
+                    w_next = base;
+                    w_end = min(base + (unsigned long long)kChunkPhotons, p.total_jobs);
+                    w_emitter = find_emitter(p.job_begin, p.num_emitters, w_next);
+                }
+                const unsigned long long avail = w_end - w_next;
+                const int rank = __popc(dead & lt_mask);
+                if (!alive && (unsigned long long)rank < avail) {
+                    const unsigned long long job = w_next + (unsigned long long)rank;
+                    int e = w_emitter;
+                    while (job >= __ldg(p.job_begin + e + 1)) e++;     // chunk straddles emitters: rare
+                    emitter = e;
+                    photon = __ldg(p.photon_first + e) + (job - __ldg(p.job_begin + e));
+                    alive = true; is_new = true; depth = 0;
+                    n_photons++;
+                }
+                const unsigned long long want = (unsigned long long)__popc(dead);
+                w_next += want < avail ? want : avail;
+                dead = __ballot_sync(kFullMask, !alive);
+            }
+        }
+        if (__ballot_sync(kFullMask, alive) == 0u) break;
+
+        bool dep = false;
+        int idx = 0;
+        if (alive) {
+            // ---- P. one Philox block per event: emission (event 0) or the bounce just done --------
+            const Philox4 w = philox4x32_10((uint32_t)photon, (uint32_t)(photon >> 32), (uint32_t)depth, 0u,
+                                            p.seed, (uint32_t)emitter);
+            // ---- S. new direction -------------------------------------------------------------------
+            const float4 *frame = is_new ? p.emitters + 6 * emitter : p.shade + 6 * hit_id;
+            const float4 fn = ldg4(frame + 3);
+            if (is_new) {
+                // photonmap.c:169-185
+                const float4 e0 = ldg4(frame), e1 = ldg4(frame + 1), e2 = ldg4(frame + 2);
+                const bool sky = __float_as_int(e0.w) != 0;
+                cr = sky ? 18.0f : 16.0f; cg = cr; cb = 18.0f;
+                const float sx = u24(w.w0), sy = u24(w.w1);
+                sample_hemisphere(u24(w.w2), u24(w.w3), sky, fn, ldg4(frame + 4), ldg4(frame + 5), dx, dy, dz);
+                roulette = r16(w.w2, w.w3);
+                px = __fadd_rn(__fadd_rn(__fadd_rn(e0.x, __fmul_rn(dx, 1E-5f)), __fmul_rn(e1.x, sx)), __fmul_rn(e2.x, sy));
+                py = __fadd_rn(__fadd_rn(__fadd_rn(e0.y, __fmul_rn(dy, 1E-5f)), __fmul_rn(e1.y, sx)), __fmul_rn(e2.y, sy));
+                pz = __fadd_rn(__fadd_rn(__fadd_rn(e0.z, __fmul_rn(dz, 1E-5f)), __fmul_rn(e1.z, sx)), __fmul_rn(e2.z, sy));
+            } else {
+                if (mirror) {                                   // photonmap.c:230
+                    const float k2 = 2.0f * (fn.x * dx + fn.y * dy + fn.z * dz);
+                    dx = fmaf(-k2, fn.x, dx); dy = fmaf(-k2, fn.y, dy); dz = fmaf(-k2, fn.z, dz);
+                } else {                                        // photonmap.c:233
+                    sample_hemisphere(u24(w.w0), u24(w.w1), false, fn, ldg4(frame + 4), ldg4(frame + 5), dx, dy, dz);
+                }
+                roulette = r16(w.w0, w.w1);
+                px = __fadd_rn(px, __fmul_rn(dx, 1E-5f));       // photonmap.c:254
+                py = __fadd_rn(py, __fmul_rn(dy, 1E-5f));
+                pz = __fadd_rn(pz, __fmul_rn(dz, 1E-5f));
+            }
+
+            // ---- C. closest hit (photonmap.c:198 / photonmap.cl:194-206) ---------------------------
+            float t;
+            hit_id = closest_hit_soup(soup, px, py, pz, dx, dy, dz, t);
+            n_rays++;
+
+            // ---- D. bounce: texel, roulette, attenuation (photonmap.c:200-247) ------------------------
+            if (hit_id < 0) {
+                alive = false;                                   // photonmap.c:200-201: photon leaves the flat
+            } else {
+                px = __fadd_rn(px, __fmul_rn(dx, t));            // photonmap.c:208
+                py = __fadd_rn(py, __fmul_rn(dy, t));
+                pz = __fadd_rn(pz, __fmul_rn(dz, t));
+                const float4 *sh = p.shade + 6 * hit_id;
+                const float4 q0 = ldg4(sh), q1 = ldg4(sh + 1), q2 = ldg4(sh + 2), q3 = ldg4(sh + 3);
+                idx = tile_index(q0, q1, q2, __float_as_int(q3.w), px, py, pz);   // photonmap.c:210-211
+                // floor is slightly reflective: photonmap.c:228 (0.0005 is a double there; for a float
+                // z the comparison is equivalent to z < 0.0005f)
+                mirror = pz < 0.0005f && roulette < 0.75f;
+                if (!mirror) {
+                    if (pz < 1E-5f) { cg *= 0.85f; cb *= 0.7f; } // photonmap.c:236-246
+                    cr *= 0.9f; cg *= 0.9f; cb *= 0.9f;          // photonmap.c:247
+                } else {
+                    n_mirror++;
+                }
+                dep = true;
+                if (kProbe) p.path_out[(photon - __ldg(p.photon_first + emitter)) * p.max_depth + depth] = idx;
+                depth++;
+                n_deposits++;
+                if (depth == p.max_depth) alive = false;         // photonmap.c:187
+            }
+        }
+        // photonmap.c:251 — texels[idx] += colour, after attenuation
+        if (!kProbe) deposit<kDeposit>(p.atlas, idx, cr, cg, cb, dep);
+    }
+
+    // ---- counters: warp reduce, one atomic per warp and counter --------------------------------------
+    unsigned long long c0 = n_photons, c1 = n_rays, c2 = n_deposits, c3 = n_mirror;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        c0 += __shfl_xor_sync(kFullMask, c0, o);
+        c1 += __shfl_xor_sync(kFullMask, c1, o);
+        c2 += __shfl_xor_sync(kFullMask, c2, o);
+        c3 += __shfl_xor_sync(kFullMask, c3, o);
+    }
+    if (lane == 0) {
+        atomicAdd(p.counters + 0, c0);
+        atomicAdd(p.counters + 1, c1);
+        atomicAdd(p.counters + 2, c2);
+        atomicAdd(p.counters + 3, c3);
+    }
+}
+
+// ---- probe kernels: the same device functions, one item per thread --------------------------------------
+
+__global__ void k_probe_closest_hit(const TraceParams p, const float *__restrict__ origins,
+                                    const float *__restrict__ dirs, int num_rays, int32_t *hit_index, float *hit_dist)
+{
+    extern __shared__ float4 smem[];
+    const int n_axis4 = 2 * p.group_begin[kNumAxisGroups];
+    const int n_gen4 = 4 * p.num_general;
+    for (int i = threadIdx.x; i < n_axis4; i += blockDim.x) smem[i] = p.axis[i];
+    for (int i = threadIdx.x; i < n_gen4; i += blockDim.x) smem[n_axis4 + i] = p.general[i];
+    __syncthreads();
+    SoupTables soup;
+    soup.axis = smem;
+    soup.general = smem + n_axis4;
+    for (int g = 0; g <= kNumAxisGroups; g++) soup.group_begin[g] = p.group_begin[g];
+    soup.num_general = p.num_general;
+    for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < num_rays; r += gridDim.x * blockDim.x) {
+        float t;
+        const int id = closest_hit_soup(soup, origins[3 * r], origins[3 * r + 1], origins[3 * r + 2],
+                                        dirs[3 * r], dirs[3 * r + 1], dirs[3 * r + 2], t);
+        hit_index[r] = id;
+        hit_dist[r] = t;
+    }
+}
+
+__global__ void k_probe_tile_ids(const float4 *__restrict__ shade, const int32_t *__restrict__ rect_index,
+                                 const float *__restrict__ points, int n, int32_t *tile_ids)
+{
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const float4 *sh = shade + 6 * rect_index[i];
+        const float4 q0 = sh[0], q1 = sh[1], q2 = sh[2], q3 = sh[3];
+        tile_ids[i] = tile_index(q0, q1, q2, __float_as_int(q3.w), points[3 * i], points[3 * i + 1], points[3 * i + 2])
+                      - __float_as_int(q0.w);
+    }
+}
+
+__global__ void k_probe_philox(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1, uint32_t *out)
+{
+    const Philox4 w = philox4x32_10(c0, c1, c2, c3, k0, k1);
+    out[0] = w.w0; out[1] = w.w1; out[2] = w.w2; out[3] = w.w3;
+}
+
+// Directions as the emission event draws them: photon i of a one-emitter scene, words w2/w3.
+__global__ void k_probe_sample_dirs(float4 n, float4 u, float4 v, int sky, uint32_t seed, int count, float *out)
+{
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < count; i += gridDim.x * blockDim.x) {
+        const Philox4 w = philox4x32_10((uint32_t)i, 0u, 0u, 0u, seed, 0u);
+        float dx, dy, dz;
+        sample_hemisphere(u24(w.w2), u24(w.w3), sky != 0, n, u, v, dx, dy, dz);
+        out[3 * i] = dx; out[3 * i + 1] = dy; out[3 * i + 2] = dz;
+    }
+}
+
+// atlas0 += sum of the peers' atlases, read straight over NVLink peer mappings (multi-GPU fold).
+__global__ void k_fold_peers(float4 *__restrict__ dst, const float4 *const *__restrict__ peers, int num_peers, size_t n)
+{
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        float4 a = dst[i];
+        for (int g = 0; g < num_peers; g++) {
+            const float4 b = peers[g][i];
+            a.x += b.x; a.y += b.y; a.z += b.z;
+        }
+        dst[i] = a;
+    }
+}
+
+}  // namespace fmgi

@@ -1,0 +1,250 @@
+"""Python host-side mirror of libfmgi_cuda.so (include/fmgi.h).
+
+This is plumbing for harnesses (tests/, bench.py): ctypes over the C ABI, numpy for host
+buffers, optional torch tensors for device-resident atlases and streams.  All compute happens
+in the CUDA library; there is no Python or CPU fallback — if the library is missing or no GPU
+is visible, the calls raise.
+
+Names follow the reference: ``Geometry`` (geometry.h:7-15), ``Rectangle`` records
+(rectangle.h:19-26), ``perform_global_illumination_cl`` (global_illumination_cl.h:10).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from pathlib import Path
+
+import numpy as np
+
+_PKG = Path(__file__).resolve().parent.parent
+LIB_PATH = _PKG / "lib" / "libfmgi_cuda.so"
+
+# rectangle.h:19-26 — 80 bytes, 16-byte aligned
+RECT_DTYPE = np.dtype(
+    {
+        "names": ["pos", "width", "height", "n", "lightmapSetup"],
+        "formats": [("<f4", 4), ("<f4", 4), ("<f4", 4), ("<f4", 4), ("<i4", 4)],
+        "offsets": [0, 16, 32, 48, 64],
+        "itemsize": 80,
+    }
+)
+
+DEPOSIT_VEC4, DEPOSIT_SCALAR, DEPOSIT_WARP_AGG = 0, 1, 2
+TIER_AUTO, TIER_SOUP, TIER_GRID = 0, 1, 2
+
+
+class Geometry(C.Structure):
+    """geometry.h:7-15 (same bytes as fmgi_geometry)."""
+
+    _fields_ = [
+        ("windows", C.c_void_p), ("lights", C.c_void_p), ("walls", C.c_void_p), ("boxWalls", C.c_void_p),
+        ("numWindows", C.c_int32), ("numLights", C.c_int32), ("numWalls", C.c_int32), ("numBoxWalls", C.c_int32),
+        ("width", C.c_int32), ("height", C.c_int32),
+        ("startingPositionX", C.c_float), ("startingPositionY", C.c_float),
+        ("numTexels", C.c_int32), ("texels", C.c_void_p),
+    ]
+
+
+class Options(C.Structure):
+    _fields_ = [
+        ("struct_size", C.c_uint32), ("max_depth", C.c_int32), ("seed", C.c_uint32), ("num_gpus", C.c_int32),
+        ("shard", C.c_int32), ("num_shards", C.c_int32), ("tier", C.c_int32), ("deposit", C.c_int32),
+        ("device", C.c_int32), ("reserved", C.c_int32 * 7),
+    ]
+
+
+class Stats(C.Structure):
+    _fields_ = [
+        ("photons", C.c_uint64), ("rays", C.c_uint64), ("deposits", C.c_uint64), ("mirror_bounces", C.c_uint64),
+        ("rect_tests", C.c_uint64), ("kernel_launches", C.c_uint64),
+        ("trace_ms", C.c_double), ("h2d_ms", C.c_double), ("d2h_ms", C.c_double), ("reduce_ms", C.c_double),
+        ("total_ms", C.c_double),
+        ("num_gpus", C.c_int32), ("tier", C.c_int32), ("num_sms", C.c_int32), ("sm_clock_khz", C.c_int32),
+    ]
+
+    def as_dict(self):
+        return {n: getattr(self, n) for n, _ in self._fields_}
+
+
+EXPORTS = [
+    "performGlobalIlluminationCl", "fmgi_default_options", "fmgi_last_error", "fmgi_version", "fmgi_device_count",
+    "fmgi_bake", "fmgi_scene_create", "fmgi_scene_destroy", "fmgi_scene_trace", "fmgi_scene_sync",
+    "fmgi_scene_photon_count", "fmgi_probe_closest_hit", "fmgi_probe_tile_ids", "fmgi_probe_philox",
+    "fmgi_probe_sample_dirs", "fmgi_probe_paths",
+]
+
+_lib = None
+
+
+class FmgiError(RuntimeError):
+    pass
+
+
+def lib() -> C.CDLL:
+    """Loads lib/libfmgi_cuda.so (built by __graft_entry__.build() / make).  Fails loudly if absent."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not LIB_PATH.exists():
+        raise FmgiError(f"{LIB_PATH} not built - run `python -c 'import __graft_entry__ as g; g.build()'`")
+    L = C.CDLL(str(LIB_PATH))
+    L.fmgi_last_error.restype = C.c_char_p
+    L.fmgi_version.restype = C.c_char_p
+    L.fmgi_default_options.argtypes = [C.POINTER(Options)]
+    L.performGlobalIlluminationCl.restype = None
+    L.performGlobalIlluminationCl.argtypes = [C.POINTER(Geometry), C.c_int]
+    L.fmgi_bake.argtypes = [C.POINTER(Geometry), C.c_int, C.POINTER(Options), C.POINTER(Stats)]
+    L.fmgi_scene_create.argtypes = [C.POINTER(C.c_void_p), C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p,
+                                    C.c_int, C.c_int, C.POINTER(Options)]
+    L.fmgi_scene_destroy.restype = None
+    L.fmgi_scene_destroy.argtypes = [C.c_void_p]
+    L.fmgi_scene_trace.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.POINTER(Options), C.c_void_p]
+    L.fmgi_scene_sync.argtypes = [C.c_void_p, C.POINTER(Stats)]
+    L.fmgi_scene_photon_count.restype = C.c_uint64
+    L.fmgi_scene_photon_count.argtypes = [C.c_void_p, C.c_int, C.POINTER(Options)]
+    L.fmgi_probe_closest_hit.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+    L.fmgi_probe_tile_ids.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+    L.fmgi_probe_philox.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+    L.fmgi_probe_sample_dirs.argtypes = [C.c_void_p, C.c_int, C.c_uint32, C.c_int, C.c_void_p]
+    L.fmgi_probe_paths.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_uint32, C.c_uint64, C.c_int, C.c_void_p]
+    _lib = L
+    return L
+
+
+def _check(rc: int):
+    if rc != 0:
+        raise FmgiError(f"fmgi error {rc}: {lib().fmgi_last_error().decode()}")
+
+
+def options(**kw) -> Options:
+    o = Options()
+    lib().fmgi_default_options(C.byref(o))
+    for k, v in kw.items():
+        if not hasattr(o, k):
+            raise TypeError(f"unknown option {k}")
+        setattr(o, k, v)
+    return o
+
+
+def aligned_rects(arr) -> np.ndarray:
+    """16-byte-aligned copy of a Rectangle table (Rectangle is __attribute__((aligned(16))))."""
+    arr = np.asarray(arr, dtype=RECT_DTYPE)
+    n = len(arr)
+    raw = np.zeros(80 * max(n, 1) + 16, dtype=np.uint8)
+    off = (-raw.ctypes.data) % 16
+    out = raw[off: off + 80 * n].view(RECT_DTYPE)
+    out[...] = arr
+    return out
+
+
+def aligned_texels(num_texels: int) -> np.ndarray:
+    """Zeroed (numTexels, 4) float32 atlas, 16-byte aligned like parseLayout.c:526-533 allocates it."""
+    raw = np.zeros(16 * max(num_texels, 1) + 16, dtype=np.uint8)
+    off = (-raw.ctypes.data) % 16
+    return raw[off: off + 16 * num_texels].view("<f4").reshape(num_texels, 4)
+
+
+def make_geometry(walls, windows, lights, texels, box_walls=None) -> Geometry:
+    """A reference-layout Geometry over caller-owned, 16-byte-aligned numpy buffers."""
+    g = Geometry()
+    for name, arr in (("walls", walls), ("windows", windows), ("lights", lights)):
+        assert arr.dtype == RECT_DTYPE and arr.ctypes.data % 16 == 0, name
+    assert texels.dtype == np.float32 and texels.ndim == 2 and texels.shape[1] == 4 and texels.flags.c_contiguous
+    g.walls, g.numWalls = walls.ctypes.data, len(walls)
+    g.windows, g.numWindows = windows.ctypes.data, len(windows)
+    g.lights, g.numLights = lights.ctypes.data, len(lights)
+    if box_walls is not None and len(box_walls):
+        g.boxWalls, g.numBoxWalls = box_walls.ctypes.data, len(box_walls)
+    g.numTexels = texels.shape[0]
+    g.texels = texels.ctypes.data
+    return g
+
+
+def perform_global_illumination_cl(geo: Geometry, num_samples_per_area: int) -> None:
+    """The reference boundary: geo.texels += raw deposits (global_illumination_cl.h:10)."""
+    lib().performGlobalIlluminationCl(C.byref(geo), int(num_samples_per_area))
+
+
+def bake(geo: Geometry, num_samples_per_area: int, **opts) -> dict:
+    """fmgi_bake: host-buffer bake with options; returns the counters."""
+    o = options(**opts)
+    st = Stats()
+    _check(lib().fmgi_bake(C.byref(geo), int(num_samples_per_area), C.byref(o), C.byref(st)))
+    return st.as_dict()
+
+
+class DeviceScene:
+    """fmgi_scene: collider + emitter tables resident on one GPU."""
+
+    def __init__(self, walls, windows, lights, num_texels: int, device: int = 0):
+        self._h = C.c_void_p()
+        self.walls = aligned_rects(walls)
+        self.windows = aligned_rects(windows)
+        self.lights = aligned_rects(lights)
+        self.num_texels = int(num_texels)
+        self.device = device
+        o = options(device=device)
+        _check(lib().fmgi_scene_create(C.byref(self._h), self.walls.ctypes.data, len(self.walls),
+                                       self.windows.ctypes.data, len(self.windows), self.lights.ctypes.data,
+                                       len(self.lights), self.num_texels, C.byref(o)))
+
+    def close(self):
+        if self._h:
+            lib().fmgi_scene_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def photon_count(self, spa: int, **opts) -> int:
+        o = options(device=self.device, **opts)
+        return int(lib().fmgi_scene_photon_count(self._h, int(spa), C.byref(o)))
+
+    def trace(self, atlas_ptr: int, spa: int, stream: int = 0, **opts) -> None:
+        """Enqueue the bake on a CUDA stream, accumulating into the device atlas at atlas_ptr."""
+        o = options(device=self.device, **opts)
+        _check(lib().fmgi_scene_trace(self._h, C.c_void_p(atlas_ptr), int(spa), C.byref(o), C.c_void_p(stream)))
+
+    def sync(self) -> dict:
+        st = Stats()
+        _check(lib().fmgi_scene_sync(self._h, C.byref(st)))
+        return st.as_dict()
+
+    # -- parity probes ---------------------------------------------------------------------------
+    def closest_hit(self, origins, dirs):
+        o = np.ascontiguousarray(origins, dtype=np.float32)
+        d = np.ascontiguousarray(dirs, dtype=np.float32)
+        n = len(o)
+        idx = np.empty(n, dtype=np.int32)
+        t = np.empty(n, dtype=np.float32)
+        _check(lib().fmgi_probe_closest_hit(self._h, o.ctypes.data, d.ctypes.data, n, idx.ctypes.data, t.ctypes.data))
+        return idx, t
+
+    def tile_ids(self, rect_index, points):
+        r = np.ascontiguousarray(rect_index, dtype=np.int32)
+        p = np.ascontiguousarray(points, dtype=np.float32)
+        out = np.empty(len(r), dtype=np.int32)
+        _check(lib().fmgi_probe_tile_ids(self._h, r.ctypes.data, p.ctypes.data, len(r), out.ctypes.data))
+        return out
+
+    def paths(self, emitter_index: int, max_depth: int, seed: int, first: int, count: int):
+        out = np.empty((count, max_depth), dtype=np.int32)
+        _check(lib().fmgi_probe_paths(self._h, emitter_index, max_depth, seed, first, count, out.ctypes.data))
+        return out
+
+
+def philox(ctr, key) -> np.ndarray:
+    c = np.asarray(ctr, dtype=np.uint32)
+    k = np.asarray(key, dtype=np.uint32)
+    out = np.empty(4, dtype=np.uint32)
+    _check(lib().fmgi_probe_philox(c.ctypes.data, k.ctypes.data, out.ctypes.data))
+    return out
+
+
+def sample_dirs(normal, sky: bool, seed: int, n: int) -> np.ndarray:
+    nn = np.ascontiguousarray(normal, dtype=np.float32)
+    out = np.empty((n, 3), dtype=np.float32)
+    _check(lib().fmgi_probe_sample_dirs(nn.ctypes.data, int(sky), seed, n, out.ctypes.data))
+    return out

@@ -115,13 +115,22 @@ void orc_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t ou
 
 /* ------------------------------------------------------------------------------------------
  * Random source.  LIBC: rand()/(double)RAND_MAX in call order (photonmap.c:175-176,228;
- * vector3_cl.c:107-108,131-132).  PHILOX: one 4-word block per event, fixed slot per draw.
+ * vector3_cl.c:107-108,131-132).
+ * PHILOX (the CUDA path's stream, see DESIGN.md "Random stream"): one block per event,
+ *   key = {seed, emitter}, counter = {photon lo, photon hi, event, 0};
+ *   u24(w) = (w >> 8) * 2^-24;  r16(a, b) = (((a & 255) << 8) | (b & 255)) * 2^-16;
+ *   event 0 (emission):  dx = u24(w0), dy = u24(w1), xi1 = u24(w2), xi2 = u24(w3),
+ *                        roulette of bounce 1 = r16(w2, w3);
+ *   event b (after bounce b): xi1 = u24(w0), xi2 = u24(w1), roulette of bounce b+1 = r16(w0, w1).
+ * The roulette draw of a bounce is therefore known before the bounce happens, which lets the
+ * kernel finish a photon's last deposit without another generator call.
  * ---------------------------------------------------------------------------------------- */
 typedef struct {
     int mode;
     uint32_t key[2];
     uint32_t photon_lo, photon_hi;
     uint32_t block[4];
+    double roulette_next;
 } rng_t;
 
 static void rng_event(rng_t *g, uint32_t event)
@@ -129,6 +138,9 @@ static void rng_event(rng_t *g, uint32_t event)
     if (g->mode == ORC_RNG_PHILOX) {
         uint32_t ctr[4] = {g->photon_lo, g->photon_hi, event, 0};
         orc_philox4x32_10(ctr, g->key, g->block);
+        uint32_t a = event == 0 ? g->block[2] : g->block[0];
+        uint32_t b = event == 0 ? g->block[3] : g->block[1];
+        g->roulette_next = (double)((float)(((a & 255u) << 8) | (b & 255u)) * (1.0f / 65536.0f));
     }
 }
 
@@ -360,12 +372,14 @@ static void trace_photon(const scene_t *s, const orc_rect *src, int is_window, r
         int idx = obj->lm[0] + tile_id_v(obj, pos);                  /* :210-211 */
         v3 n = ld(obj->n);
 
+        double roulette = g->roulette_next;            /* PHILOX: drawn by the previous event */
         rng_event(g, (uint32_t)depth + 1);
-        if (pos.z < 0.0005 && rng_u01(g, 0) < 0.75) {                /* :228 mirror, unattenuated */
+        if (pos.z < 0.0005 &&                                        /* :228 mirror, unattenuated */
+            (g->mode == ORC_RNG_LIBC ? rng_u01(g, 0) : roulette) < 0.75) {
             dir = vsub(dir, vmul(n, 2 * vdot(n, dir)));              /* :230 */
             st->mirror_bounces++;
         } else {
-            dir = sample_hemisphere(g, n, 0, 1);                     /* :233 */
+            dir = sample_hemisphere(g, n, 0, 0);                     /* :233 */
             if (pos.z < 1E-5f) {                                     /* :236-246 floor tint */
                 colour.x *= 1.0f; colour.y *= 0.85f; colour.z *= 0.7f;
             }

@@ -48,10 +48,10 @@ void orc_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t ou
  * texels: numTexels x float4, accumulated in place.
  * rng = ORC_RNG_LIBC   : libc rand() in the reference's draw order; caller seeds with srand().
  * rng = ORC_RNG_PHILOX : the CUDA path's stream (key = {seed, emitter}, counter =
- *                        {photon lo, photon hi, event, 0}; event 0 = emission (dx, dy, xi1, xi2),
- *                        event b>=1 = bounce b (roulette, xi1, xi2)); xi = (word >> 8) * 2^-24.
- * photon_first/photon_count select a sub-range of every emitter's photons in PHILOX mode
- * (count 0 = all), mirroring the multi-GPU sharding; ignored in LIBC mode. */
+ *                        {photon lo, photon hi, event, 0}; word layout in photon_oracle.c).
+ * shard/num_shards select the contiguous sub-range [N*shard/num_shards, N*(shard+1)/num_shards)
+ * of every emitter's N photons in PHILOX mode, mirroring the multi-GPU sharding; ignored in
+ * LIBC mode (one sequential rand() stream cannot be split). */
 void orc_bake(const orc_rect *walls, int num_walls,
               const orc_rect *windows, int num_windows,
               const orc_rect *lights, int num_lights,
