@@ -78,7 +78,7 @@ struct fmgi_scene {
     int device = 0;
     HostScene host;
     // device tables
-    AxisRect *d_axis = nullptr;
+    AxisPairBlock *d_axis = nullptr;
     GeneralRect *d_general = nullptr;
     ShadeRect *d_shade = nullptr;
     EmitterRec *d_emitters = nullptr;
@@ -94,6 +94,7 @@ struct fmgi_scene {
     int tier = FMGI_TIER_SOUP;
     uint64_t launches = 0;
     uint64_t tests_per_ray = 0;
+    int min_blocks = 4;                         // resident CTAs per SM the trace kernel is compiled for
 };
 
 namespace {
@@ -104,7 +105,7 @@ TraceParams base_params(const fmgi_scene *s)
     memset(&p, 0, sizeof p);
     p.axis = reinterpret_cast<const float4 *>(s->d_axis);
     p.general = reinterpret_cast<const float4 *>(s->d_general);
-    for (int g = 0; g <= kNumAxisGroups; g++) p.group_begin[g] = s->host.group_begin[g];
+    for (int g = 0; g < 4; g++) p.pair_begin[g] = s->host.pair_begin[g];
     p.num_general = (int)s->host.general.size();
     p.shade = reinterpret_cast<const float4 *>(s->d_shade);
     p.emitters = reinterpret_cast<const float4 *>(s->d_emitters);
@@ -146,11 +147,18 @@ cudaError_t launch_trace(fmgi_scene *s, const TraceParams &p, int deposit, int b
         s->launches++;
         return cudaGetLastError();
     };
-    if (kProbe) return go(k_trace_soup<FMGI_DEPOSIT_VEC4, true>);
+    if (kProbe) return go(k_trace_soup<FMGI_DEPOSIT_VEC4, true, 3>);
+    if (s->min_blocks == 3) {
+        switch (deposit) {
+            case FMGI_DEPOSIT_SCALAR: return go(k_trace_soup<FMGI_DEPOSIT_SCALAR, false, 3>);
+            case FMGI_DEPOSIT_WARP_AGG: return go(k_trace_soup<FMGI_DEPOSIT_WARP_AGG, false, 3>);
+            default: return go(k_trace_soup<FMGI_DEPOSIT_VEC4, false, 3>);
+        }
+    }
     switch (deposit) {
-        case FMGI_DEPOSIT_SCALAR: return go(k_trace_soup<FMGI_DEPOSIT_SCALAR, false>);
-        case FMGI_DEPOSIT_WARP_AGG: return go(k_trace_soup<FMGI_DEPOSIT_WARP_AGG, false>);
-        default: return go(k_trace_soup<FMGI_DEPOSIT_VEC4, false>);
+        case FMGI_DEPOSIT_SCALAR: return go(k_trace_soup<FMGI_DEPOSIT_SCALAR, false, 4>);
+        case FMGI_DEPOSIT_WARP_AGG: return go(k_trace_soup<FMGI_DEPOSIT_WARP_AGG, false, 4>);
+        default: return go(k_trace_soup<FMGI_DEPOSIT_VEC4, false, 4>);
     }
 }
 
@@ -205,10 +213,11 @@ int fmgi_scene_create(fmgi_scene **out, const fmgi_rect *walls, int num_walls, c
     s->num_sms = prop.multiProcessorCount;
     FMGI_CUDA(cudaDeviceGetAttribute(&s->clock_khz, cudaDevAttrClockRate, o.device));
 
-    s->smem_bytes = s->host.axis.size() * sizeof(AxisRect) + s->host.general.size() * sizeof(GeneralRect);
+    s->smem_bytes = s->host.axis.size() * sizeof(AxisPairBlock) + s->host.general.size() * sizeof(GeneralRect);
     s->tier = FMGI_TIER_SOUP;
     if (s->smem_bytes > (size_t)prop.sharedMemPerBlockOptin)
         return fail(FMGI_ERR_UNSUPPORTED, "rectangle soup does not fit in shared memory (grid tier required)");
+    // each lane walks one of the two blocks of every pair: two rectangle tests per pair
     s->tests_per_ray = s->host.axis.size() + s->host.general.size();
 
     FMGI_CUDA(upload(&s->d_axis, s->host.axis));
@@ -224,11 +233,17 @@ int fmgi_scene_create(fmgi_scene **out, const fmgi_rect *walls, int num_walls, c
     FMGI_CUDA(cudaEventCreate(&s->ev_start));
     FMGI_CUDA(cudaEventCreate(&s->ev_stop));
 
-    if (s->smem_bytes > 48 * 1024)
-        FMGI_CUDA(cudaFuncSetAttribute(k_trace_soup<FMGI_DEPOSIT_VEC4, false>,
-                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->smem_bytes));
-    FMGI_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&s->blocks_per_sm, k_trace_soup<FMGI_DEPOSIT_VEC4, false>,
-                                                            kTraceThreads, s->smem_bytes));
+    if (const char *v = getenv("FMGI_TUNE_BLOCKS")) s->min_blocks = atoi(v) == 3 ? 3 : 4;   // tuning knob
+    auto occupancy = [&](auto kernel) {
+        cudaError_t e = cudaSuccess;
+        if (s->smem_bytes > 48 * 1024)
+            e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->smem_bytes);
+        if (e == cudaSuccess)
+            e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&s->blocks_per_sm, kernel, kTraceThreads, s->smem_bytes);
+        return e;
+    };
+    if (s->min_blocks == 3) FMGI_CUDA(occupancy(k_trace_soup<FMGI_DEPOSIT_VEC4, false, 3>));
+    else FMGI_CUDA(occupancy(k_trace_soup<FMGI_DEPOSIT_VEC4, false, 4>));
     if (s->blocks_per_sm < 1) return fail(FMGI_ERR_CUDA, "trace kernel does not fit on an SM");
     *out = s.release();
     return FMGI_OK;

@@ -6,6 +6,7 @@
 // getCosineDistributedRandomRay builds (vector3_cl.c:139-144), so each expression below keeps
 // the reference's operation order: length() = sqrtf(x*x + y*y + z*z) (vector3_cl.c:93),
 // div_vec3() = multiply by 1.0f/len (vector3_cl.c:53-58), normalized() likewise (:95-100).
+#include <algorithm>
 #include <cmath>
 #include <cstring>
 
@@ -71,7 +72,8 @@ const char *prepare_scene(HostScene &out, const fmgi_rect *walls, int num_walls,
     if (num_walls < 0 || num_windows < 0 || num_lights < 0 || num_texels < 0)
         return "negative count";
 
-    std::vector<AxisRect> groups[kNumAxisGroups];
+    struct Axis1 { float c, mid_i, half_i, mid_j, half_j; int id; };
+    std::vector<Axis1> groups[6];         // 2*k + (normal sign > 0 ? 0 : 1)
     out.shade.resize(num_walls);
 
     for (int r = 0; r < num_walls; r++) {
@@ -105,12 +107,15 @@ const char *prepare_scene(HostScene &out, const fmgi_rect *walls, int num_walls,
             // in-plane axes in ascending order, whichever of width/height they belong to
             int i = ai < aj ? ai : aj, j = ai < aj ? aj : ai;
             V3 far = {pos.x + wd.x + ht.x, pos.y + wd.y + ht.y, pos.z + wd.z + ht.z};
-            AxisRect a;
+            const float lo_i = fminf(comp(pos, i), comp(far, i)), hi_i = fmaxf(comp(pos, i), comp(far, i));
+            const float lo_j = fminf(comp(pos, j), comp(far, j)), hi_j = fmaxf(comp(pos, j), comp(far, j));
+            Axis1 a;
             a.c = comp(pos, ak);
-            a.lo_i = fminf(comp(pos, i), comp(far, i)); a.hi_i = fmaxf(comp(pos, i), comp(far, i));
-            a.lo_j = fminf(comp(pos, j), comp(far, j)); a.hi_j = fmaxf(comp(pos, j), comp(far, j));
-            a.id = r; a.pad0 = a.pad1 = 0;
+            a.mid_i = 0.5f * (lo_i + hi_i); a.half_i = 0.5f * (hi_i - lo_i);
+            a.mid_j = 0.5f * (lo_j + hi_j); a.half_j = 0.5f * (hi_j - lo_j);
+            a.id = r;
             groups[2 * ak + (comp(n, ak) > 0 ? 0 : 1)].push_back(a);
+            out.num_axis_rects++;
         } else {
             GeneralRect g;
             g.nx = n.x; g.ny = n.y; g.nz = n.z; g.nd = dot(n, pos);
@@ -121,11 +126,26 @@ const char *prepare_scene(HostScene &out, const fmgi_rect *walls, int num_walls,
             out.general.push_back(g);
         }
     }
-    for (int g = 0; g < kNumAxisGroups; g++) {
-        out.group_begin[g] = (int)out.axis.size();
-        out.axis.insert(out.axis.end(), groups[g].begin(), groups[g].end());
+    // interleave the P and M list of every axis in blocks of two rectangles, padded with
+    // entries that can never be hit (plane coordinate NaN)
+    const float nanv = std::nanf("");
+    const Axis1 pad = {nanv, 0.0f, -1.0f, 0.0f, -1.0f, -1};
+    for (int k = 0; k < 3; k++) {
+        const std::vector<Axis1> &P = groups[2 * k], &M = groups[2 * k + 1];
+        const size_t len = std::max(P.size(), M.size());
+        const size_t pairs = (len + 1) / 2;
+        out.pair_begin[k] = (int)(out.axis.size() / 2);
+        for (size_t j = 0; j < pairs; j++)
+            for (int sgn = 0; sgn < 2; sgn++) {
+                const std::vector<Axis1> &L = sgn ? M : P;
+                const Axis1 &a = 2 * j < L.size() ? L[2 * j] : pad;
+                const Axis1 &b = 2 * j + 1 < L.size() ? L[2 * j + 1] : pad;
+                AxisPairBlock blk = {a.c, a.mid_i, a.half_i, a.mid_j, b.c, b.mid_i, b.half_i, b.mid_j,
+                                     a.half_j, b.half_j, a.id, b.id};
+                out.axis.push_back(blk);
+            }
     }
-    out.group_begin[kNumAxisGroups] = (int)out.axis.size();
+    out.pair_begin[3] = (int)(out.axis.size() / 2);
 
     // emitters: windows first, then lights (photonmap.c:412-431)
     for (int e = 0; e < num_windows + num_lights; e++) {

@@ -11,17 +11,23 @@ namespace fmgi {
 
 // ---- closest-hit tables -------------------------------------------------------------------
 
-// One collider whose width/height/normal are axis parallel (everything parseLayout.c emits).
-// Stored in the group of its normal axis k and normal sign; (i, j) are the two in-plane axes
-// in ascending order.  32 bytes = two 16-byte shared-memory broadcasts per test.
-struct AxisRect {
-    float c;            // plane coordinate pos[k]
-    float lo_i, hi_i;   // extent along in-plane axis i (edges inclusive, rectangle.c:93)
-    float lo_j;
-    float hi_j;
-    int32_t id;         // index into the caller's wall table
-    int32_t pad0, pad1;
+// Colliders whose width/height/normal are axis parallel (everything parseLayout.c emits) are
+// stored per normal axis k as two lists: P (normal +k, hit only by rays with d[k] < 0) and
+// M (normal -k, d[k] > 0) - back-face culling (rectangle.c:70-72) becomes "each lane walks the
+// list its ray can face".  The lists are padded to the same even length and interleaved in
+// blocks of two rectangles, so that a warp executes one uniform loop while every lane reads the
+// block of its own sign: block(k, j, s) = blocks[(pair_begin[k] + j) * 2 + s].
+// (i, j) are the two in-plane axes in ascending order; extents are kept as centre and
+// half-width so that containment is |p - mid| <= half (edges inclusive, rectangle.c:93).
+// 48 bytes = three 16-byte shared-memory loads per two tests; the P and M block of one j are
+// 48 bytes apart, i.e. in disjoint banks.
+struct AxisPairBlock {
+    float c_a, mid_i_a, half_i_a, mid_j_a;    // rectangle a: plane coordinate pos[k], extents
+    float c_b, mid_i_b, half_i_b, mid_j_b;    // rectangle b
+    float half_j_a, half_j_b;
+    int32_t id_a, id_b;                       // index into the caller's wall table (-1: padding)
 };
+static_assert(sizeof(AxisPairBlock) == 48, "AxisPairBlock is three float4");
 
 // Arbitrarily oriented collider: the full plane + two projections of rectangle.c:67-95.
 struct GeneralRect {
@@ -31,10 +37,6 @@ struct GeneralRect {
     float px, py, pz;           // pos
     int32_t id;
 };
-
-// Group g = 2*k + (normal sign > 0 ? 0 : 1).  A ray can only hit group g if d[k] has the
-// opposite sign of the normal (back-face culling, rectangle.c:70-72).
-enum { kNumAxisGroups = 6 };
 
 // ---- shading tables (read once per hit / per emission) ---------------------------------------
 
@@ -72,8 +74,9 @@ struct GridDesc {
 
 struct HostScene {
     int num_walls = 0, num_windows = 0, num_lights = 0, num_texels = 0;
-    std::vector<AxisRect> axis;           // grouped: group_begin[g] .. group_begin[g+1]
-    int group_begin[kNumAxisGroups + 1] = {0};
+    std::vector<AxisPairBlock> axis;      // 2 blocks (P, M) per pair; pairs of axis k: pair_begin[k] .. pair_begin[k+1]
+    int pair_begin[4] = {0, 0, 0, 0};
+    int num_axis_rects = 0;               // real (unpadded) axis-parallel colliders
     std::vector<GeneralRect> general;
     std::vector<ShadeRect> shade;         // per wall
     std::vector<EmitterRec> emitters;     // windows then lights

@@ -8,11 +8,14 @@
 //     dies (miss, or last allowed bounce) the warp's dead lanes are found with a ballot and
 //     refilled from the warp's chunk of the global photon index space, so the closest-hit loop
 //     always runs with full warps ("wavefront" compaction done in registers);
-//   * the rectangle soup lives in shared memory as plane-grouped axis-aligned records; every
-//     lane of a warp reads the same record (broadcast), the loop trip count is warp uniform;
-//   * back-face culling (rectangle.c:70-72) costs nothing per test: for a group whose normal the
-//     ray cannot face, the lane's reciprocal direction is replaced by NaN, which fails the
-//     single unsigned compare that also implements 0 <= t < best;
+//   * the rectangle soup lives in shared memory as per-axis lists of axis-parallel records; the
+//     loop trip count is warp uniform and the loads are broadcasts;
+//   * back-face culling (rectangle.c:70-72) halves the work instead of costing a test: the
+//     records of one normal axis are split by normal sign into two interleaved lists and every
+//     lane walks only the list its ray can face (two distinct, bank-disjoint addresses per warp);
+//   * 0 <= t < best is one unsigned compare (negative and NaN floats are large unsigned
+//     integers); containment is |p - mid| <= half, which moves half of the compare work from the
+//     ALU pipe to the FMA pipe (the ALU pipe was the top pipe of the first version, see profiles/);
 //   * deposits are one 16-byte vector reduction (RED.E.ADD.F32x4) per bounce into the L2-resident
 //     atlas, optionally warp-aggregated with __match_any_sync;
 //   * per-photon Philox4x32-10 sub-streams (philox.cuh) replace the sequential libc stream.
@@ -31,9 +34,9 @@ constexpr unsigned kFullMask = 0xffffffffu;
 
 struct TraceParams {
     // closest-hit tables (global memory; staged into shared memory by the soup kernel)
-    const float4 *axis;          // 2 float4 per AxisRect, grouped
+    const float4 *axis;          // 3 float4 per AxisPairBlock, 2 blocks (P, M) per pair
     const float4 *general;       // 4 float4 per GeneralRect
-    int group_begin[kNumAxisGroups + 1];
+    int pair_begin[4];           // pairs of axis k: pair_begin[k] .. pair_begin[k+1]
     int num_general;
     // shading tables
     const float4 *shade;         // 6 float4 per wall
@@ -55,24 +58,56 @@ struct TraceParams {
 
 // ---- closest hit against the shared-memory soup ----------------------------------------------
 
-struct HitRec { float t; int slot; };   // slot: >= 0 position in the axis table, < -1: ~position in general table, -1 miss
+// Hit code: >= 0: 2 * (global pair index) + (0: rectangle a, 1: rectangle b) of the list the ray
+// faces on that axis; <= -2: -(index into the general table) - 2; -1: miss.
 
-// One (axis, sign) group.  a = 1/d[k] if the ray can face the group else NaN; b = -o[k]*a.
-__device__ __forceinline__ void scan_axis_group(const float4 *__restrict__ tab, int begin, int end,
-                                                float a, float b, float oi, float di, float oj, float dj,
-                                                float &best, int &slot)
+// One axis-parallel rectangle test, written in PTX so that it stays the ten instructions it needs:
+// three FFMA + two FADD on the FMA pipe, one unsigned and two float compares chained through one
+// predicate, and two selects on the ALU pipe.
+//   t  = c * a + b                      (ray parameter on the plane)
+//   pi = t * di + oi - mid_i, pj alike  (hit point relative to the rectangle centre)
+//   ok = (0 <= t < best) && |pi| <= half_i && |pj| <= half_j
+__device__ __forceinline__ void axis_test(float c, float mid_i, float half_i, float mid_j, float half_j,
+                                          float a, float b, float oi, float di, float oj, float dj,
+                                          int cur, float &best, int &code)
 {
-#pragma unroll 4
-    for (int r = begin; r < end; r++) {
-        const float4 q0 = tab[2 * r];
-        const float4 q1 = tab[2 * r + 1];
-        const float t = fmaf(q0.x, a, b);
-        const float pi = fmaf(t, di, oi);
-        const float pj = fmaf(t, dj, oj);
-        // 0 <= t < best in one compare: negative and NaN floats are large unsigned integers
-        const bool ok = (__float_as_uint(t) < __float_as_uint(best)) &&
-                        pi >= q0.y && pi <= q0.z && pj >= q0.w && pj <= q1.x;
-        if (ok) { best = t; slot = r; }
+    asm("{\n\t"
+        ".reg .pred p;\n\t"
+        ".reg .f32 t, pi, pj;\n\t"
+        ".reg .b32 tb, bb;\n\t"
+        "fma.rn.f32 t, %2, %7, %8;\n\t"
+        "fma.rn.f32 pi, t, %10, %9;\n\t"
+        "fma.rn.f32 pj, t, %12, %11;\n\t"
+        "sub.rn.f32 pi, pi, %3;\n\t"
+        "sub.rn.f32 pj, pj, %5;\n\t"
+        "abs.f32 pi, pi;\n\t"
+        "abs.f32 pj, pj;\n\t"
+        "mov.b32 tb, t;\n\t"
+        "mov.b32 bb, %0;\n\t"
+        "setp.lt.u32 p, tb, bb;\n\t"
+        "setp.le.and.f32 p, pi, %4, p;\n\t"
+        "setp.le.and.f32 p, pj, %6, p;\n\t"
+        "selp.f32 %0, t, %0, p;\n\t"
+        "selp.b32 %1, %13, %1, p;\n\t"
+        "}"
+        : "+f"(best), "+r"(code)
+        : "f"(c), "f"(mid_i), "f"(half_i), "f"(mid_j), "f"(half_j), "f"(a), "f"(b), "f"(oi), "f"(di), "f"(oj),
+          "f"(dj), "r"(cur));
+}
+
+// One normal axis.  blk points at the lane's own first block (P or M list); a = 1/d[k], b = -o[k]*a.
+__device__ __forceinline__ void scan_axis(const float4 *__restrict__ blk, int pair0, int pair1,
+                                          float a, float b, float oi, float di, float oj, float dj,
+                                          float &best, int &code)
+{
+    blk += 6 * pair0;
+#pragma unroll 2
+    for (int j = pair0; j < pair1; j++, blk += 6) {
+        const float4 qa = blk[0];
+        const float4 qb = blk[1];
+        const float4 qc = blk[2];
+        axis_test(qa.x, qa.y, qa.z, qa.w, qc.x, a, b, oi, di, oj, dj, 2 * j, best, code);
+        axis_test(qb.x, qb.y, qb.z, qb.w, qc.y, a, b, oi, di, oj, dj, 2 * j + 1, best, code);
     }
 }
 
@@ -91,14 +126,14 @@ __device__ __forceinline__ void scan_general(const float4 *__restrict__ tab, int
         const float v = g2.x * ex + g2.y * ey + g2.z * ez;
         const bool ok = denom < 0.0f && (__float_as_uint(t) < __float_as_uint(best)) &&
                         u >= 0.0f && v >= 0.0f && u <= g1.w && v <= g2.w;
-        if (ok) { best = t; slot = ~r - 1; }     // -2, -3, ...
+        if (ok) { best = t; slot = -r - 2; }
     }
 }
 
 struct SoupTables {
     const float4 *axis;
     const float4 *general;
-    int group_begin[kNumAxisGroups + 1];
+    int pair_begin[4];
     int num_general;
 };
 
@@ -108,41 +143,34 @@ __device__ __forceinline__ int closest_hit_soup(const SoupTables &s, float ox, f
                                                 float dx, float dy, float dz, float &t_out)
 {
     const float nanv = __int_as_float(0x7fc00000);
-    const float ix = __frcp_rn(dx), iy = __frcp_rn(dy), iz = __frcp_rn(dz);
     float best = __int_as_float(0x7f800000);
-    int slot = -1;
-    // group 2k: normal +k, hit by rays with d[k] < 0; group 2k+1: normal -k, d[k] > 0
-    {
-        const float a0 = dx < 0.0f ? ix : nanv, a1 = dx > 0.0f ? ix : nanv;
-        scan_axis_group(s.axis, s.group_begin[0], s.group_begin[1], a0, -ox * a0, oy, dy, oz, dz, best, slot);
-        scan_axis_group(s.axis, s.group_begin[1], s.group_begin[2], a1, -ox * a1, oy, dy, oz, dz, best, slot);
-    }
-    {
-        const float a0 = dy < 0.0f ? iy : nanv, a1 = dy > 0.0f ? iy : nanv;
-        scan_axis_group(s.axis, s.group_begin[2], s.group_begin[3], a0, -oy * a0, ox, dx, oz, dz, best, slot);
-        scan_axis_group(s.axis, s.group_begin[3], s.group_begin[4], a1, -oy * a1, ox, dx, oz, dz, best, slot);
-    }
-    {
-        const float a0 = dz < 0.0f ? iz : nanv, a1 = dz > 0.0f ? iz : nanv;
-        scan_axis_group(s.axis, s.group_begin[4], s.group_begin[5], a0, -oz * a0, ox, dx, oy, dy, best, slot);
-        scan_axis_group(s.axis, s.group_begin[5], s.group_begin[6], a1, -oz * a1, ox, dx, oy, dy, best, slot);
-    }
+    int code = -1;
+    // a lane whose d[k] is exactly zero can face neither list of axis k
+    const float ax = dx != 0.0f ? __frcp_rn(dx) : nanv;
+    const float ay = dy != 0.0f ? __frcp_rn(dy) : nanv;
+    const float az = dz != 0.0f ? __frcp_rn(dz) : nanv;
+    // list P (normal +k) is block 0 of a pair, list M (normal -k) block 1; d[k] > 0 faces M
+    const int sx = dx > 0.0f ? 3 : 0, sy = dy > 0.0f ? 3 : 0, sz = dz > 0.0f ? 3 : 0;
+    scan_axis(s.axis + sx, s.pair_begin[0], s.pair_begin[1], ax, -ox * ax, oy, dy, oz, dz, best, code);
+    scan_axis(s.axis + sy, s.pair_begin[1], s.pair_begin[2], ay, -oy * ay, ox, dx, oz, dz, best, code);
+    scan_axis(s.axis + sz, s.pair_begin[2], s.pair_begin[3], az, -oz * az, ox, dx, oy, dy, best, code);
     if (s.num_general)
-        scan_general(s.general, s.num_general, ox, oy, oz, dx, dy, dz, best, slot);
+        scan_general(s.general, s.num_general, ox, oy, oz, dx, dy, dz, best, code);
 
     int id = -1;
     t_out = best;
-    if (slot >= 0) {
-        const float4 q0 = s.axis[2 * slot];
-        const float4 q1 = s.axis[2 * slot + 1];
-        id = __float_as_int(q1.y);
-        const int k = slot < s.group_begin[2] ? 0 : (slot < s.group_begin[4] ? 1 : 2);
+    if (code >= 0) {
+        const int pair = code >> 1;
+        const int k = pair < s.pair_begin[1] ? 0 : (pair < s.pair_begin[2] ? 1 : 2);
         const float ok = k == 0 ? ox : (k == 1 ? oy : oz);
         const float dk = k == 0 ? dx : (k == 1 ? dy : dz);
-        t_out = __fdiv_rn(__fsub_rn(q0.x, ok), dk);
-    } else if (slot < -1) {
+        const float4 *blk = s.axis + 6 * pair + (dk > 0.0f ? 3 : 0);
+        const float c = (code & 1) ? blk[1].x : blk[0].x;
+        id = __float_as_int((code & 1) ? blk[2].w : blk[2].z);
+        t_out = __fdiv_rn(__fsub_rn(c, ok), dk);
+    } else if (code < -1) {
         // rectangle.c:70-75 for the winner: t = n.(pos - o) / n.d with IEEE operations
-        const float4 *g = s.general + 4 * (~(slot + 1));
+        const float4 *g = s.general + 4 * (-code - 2);
         const float4 g0 = g[0], g3 = g[3];
         id = __float_as_int(g3.w);
         const float denom = __fadd_rn(__fadd_rn(__fmul_rn(g0.x, dx), __fmul_rn(g0.y, dy)), __fmul_rn(g0.z, dz));

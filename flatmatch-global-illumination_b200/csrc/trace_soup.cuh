@@ -19,11 +19,11 @@ __device__ __forceinline__ int find_emitter(const unsigned long long *__restrict
     return lo;
 }
 
-template <int kDeposit, bool kProbe>
-__global__ void __launch_bounds__(kTraceThreads, 3) k_trace_soup(const TraceParams p)
+template <int kDeposit, bool kProbe, int kMinBlocks>
+__global__ void __launch_bounds__(kTraceThreads, kMinBlocks) k_trace_soup(const TraceParams p)
 {
     extern __shared__ float4 smem[];
-    const int n_axis4 = 2 * p.group_begin[kNumAxisGroups];
+    const int n_axis4 = 6 * p.pair_begin[3];
     const int n_gen4 = 4 * p.num_general;
     for (int i = threadIdx.x; i < n_axis4; i += blockDim.x) smem[i] = p.axis[i];
     for (int i = threadIdx.x; i < n_gen4; i += blockDim.x) smem[n_axis4 + i] = p.general[i];
@@ -33,7 +33,7 @@ __global__ void __launch_bounds__(kTraceThreads, 3) k_trace_soup(const TracePara
     soup.axis = smem;
     soup.general = smem + n_axis4;
 #pragma unroll
-    for (int g = 0; g <= kNumAxisGroups; g++) soup.group_begin[g] = p.group_begin[g];
+    for (int g = 0; g < 4; g++) soup.pair_begin[g] = p.pair_begin[g];
     soup.num_general = p.num_general;
 
     const int lane = threadIdx.x & 31;
@@ -175,7 +175,7 @@ __global__ void k_probe_closest_hit(const TraceParams p, const float *__restrict
                                     const float *__restrict__ dirs, int num_rays, int32_t *hit_index, float *hit_dist)
 {
     extern __shared__ float4 smem[];
-    const int n_axis4 = 2 * p.group_begin[kNumAxisGroups];
+    const int n_axis4 = 6 * p.pair_begin[3];
     const int n_gen4 = 4 * p.num_general;
     for (int i = threadIdx.x; i < n_axis4; i += blockDim.x) smem[i] = p.axis[i];
     for (int i = threadIdx.x; i < n_gen4; i += blockDim.x) smem[n_axis4 + i] = p.general[i];
@@ -183,7 +183,7 @@ __global__ void k_probe_closest_hit(const TraceParams p, const float *__restrict
     SoupTables soup;
     soup.axis = smem;
     soup.general = smem + n_axis4;
-    for (int g = 0; g <= kNumAxisGroups; g++) soup.group_begin[g] = p.group_begin[g];
+    for (int g = 0; g < 4; g++) soup.pair_begin[g] = p.pair_begin[g];
     soup.num_general = p.num_general;
     for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < num_rays; r += gridDim.x * blockDim.x) {
         float t;
