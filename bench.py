@@ -223,14 +223,17 @@ def run_ours(args):
     atlas = torch.zeros((num_texels, 4), dtype=torch.float32, device="cuda")
     flush = torch.empty(192 * 1024 * 1024 // 4, dtype=torch.float32, device="cuda")   # > 126 MB L2
     stream = torch.cuda.current_stream()
-    opts = dict(max_depth=depth, seed=args.seed, shard=rank, num_shards=world, deposit=args.deposit)
+
+    from fmgi.distributed import bake_sharded
+
+    def trace(buf, spa, shard, num_shards):
+        scene.trace(buf.data_ptr(), spa, stream=stream.cuda_stream, max_depth=depth, seed=args.seed,
+                    shard=shard, num_shards=num_shards, deposit=args.deposit)
 
     def step():
         atlas.zero_()
         flush.fill_(1.0)                           # L2 flush between timed iterations
-        scene.trace(atlas.data_ptr(), spa_job, stream=stream.cuda_stream, **opts)
-        if world > 1:
-            dist.reduce(atlas, dst=0, op=dist.ReduceOp.SUM)
+        bake_sharded(trace, atlas, spa_job, rank, world, dist=dist)   # trace + one NCCL reduce onto rank 0
 
     def barrier():
         if world > 1:

@@ -304,3 +304,22 @@ def test_general_rectangles(fmgi, oracle, scene):
     assert abs(st["deposits"] / so["deposits"] - 1) < 2e-3
     assert abs(atlas[:, :3].sum(dtype=np.float64) / want[:, :3].sum(dtype=np.float64) - 1) < 2e-3
     s.close()
+
+
+def test_in_library_multi_gpu_bake(fmgi, scene):
+    """fmgi_bake with num_gpus > 1: one host thread per GPU, disjoint photon ranges, peer atlases
+    folded into GPU 0 by a kernel reading them over NVLink peer mappings."""
+    n = fmgi.lib().fmgi_device_count()
+    if n < 2:
+        pytest.skip("needs at least 2 GPUs")
+    spa, depth = 200000, 5
+    tex1 = fmgi.aligned_texels(scene.num_texels)
+    st1 = fmgi.bake(fmgi.make_geometry(scene.walls, scene.windows, scene.lights, tex1), spa, max_depth=depth, seed=5)
+    for g in sorted({2, min(n, 4), n}):
+        texg = fmgi.aligned_texels(scene.num_texels)
+        stg = fmgi.bake(fmgi.make_geometry(scene.walls, scene.windows, scene.lights, texg), spa, max_depth=depth,
+                        seed=5, num_gpus=g)
+        assert stg["num_gpus"] == g
+        for k in ("photons", "rays", "deposits", "mirror_bounces"):
+            assert stg[k] == st1[k], (g, k)
+        assert np.allclose(texg, tex1, rtol=1e-5, atol=5e-2)
