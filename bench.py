@@ -34,6 +34,8 @@ WORKLOADS = {
     "example_1e8x3": ("example_scene.npz", 1.0e8, 3),          # BASELINE.json configs[1]
     "example_default_x8": ("example_scene.npz", 1.538e9, 8),   # configs[0]: reference default density
     "example_1e9x4": ("example_scene.npz", 1.0e9, 4),          # north_star target
+    "synth4000_1e9x4": ("synth4000_scene.npz", 1.0e9, 4),      # configs[2]: ~21.5k rectangles, 0.46 GB atlas
+    "synth800_1e8x4": ("synth800_scene.npz", 1.0e8, 4),
 }
 METRIC = "photon-bounces/sec (device-timed)"
 UNIT = "bounces/s"

@@ -12,7 +12,7 @@
 #include <thread>
 #include <vector>
 
-#include "trace_soup.cuh"
+#include "trace_core.cuh"
 
 using namespace fmgi;
 
@@ -82,6 +82,8 @@ struct fmgi_scene {
     GeneralRect *d_general = nullptr;
     ShadeRect *d_shade = nullptr;
     EmitterRec *d_emitters = nullptr;
+    GridRec *d_grid_recs = nullptr;             // grid tier
+    int32_t *d_grid_ranges = nullptr;
     unsigned long long *d_jobs = nullptr;       // job_begin[E+1] then photon_first[E]
     unsigned long long *d_counters = nullptr;   // 4 counters + work counter
     unsigned long long *h_jobs = nullptr;       // pinned staging
@@ -107,6 +109,9 @@ TraceParams base_params(const fmgi_scene *s)
     p.general = reinterpret_cast<const float4 *>(s->d_general);
     for (int g = 0; g < 4; g++) p.pair_begin[g] = s->host.pair_begin[g];
     p.num_general = (int)s->host.general.size();
+    p.grid_recs = reinterpret_cast<const float4 *>(s->d_grid_recs);
+    p.grid_ranges = reinterpret_cast<const int2 *>(s->d_grid_ranges);
+    p.grid = s->host.grid;
     p.shade = reinterpret_cast<const float4 *>(s->d_shade);
     p.emitters = reinterpret_cast<const float4 *>(s->d_emitters);
     p.num_emitters = (int)s->host.emitters.size();
@@ -135,10 +140,32 @@ unsigned long long fill_jobs(const fmgi_scene *s, int spa, const fmgi_options &o
     return total;
 }
 
-template <bool kProbe>
-cudaError_t launch_trace(fmgi_scene *s, const TraceParams &p, int deposit, int blocks, cudaStream_t st)
+// Picks the instantiation for (tier, deposit, probe, resident CTAs per SM) and applies `fn` to it.
+template <typename Fn>
+cudaError_t with_trace_kernel(int tier, int deposit, bool probe, int min_blocks, Fn fn)
 {
-    auto go = [&](auto kernel) {
+#define FMGI_PICK(T, D, P, B) return fn(k_trace<T, D, P, B>)
+#define FMGI_PICK_DEPOSIT(T, B)                                                   \
+    switch (deposit) {                                                            \
+        case FMGI_DEPOSIT_SCALAR: FMGI_PICK(T, FMGI_DEPOSIT_SCALAR, false, B);    \
+        case FMGI_DEPOSIT_WARP_AGG: FMGI_PICK(T, FMGI_DEPOSIT_WARP_AGG, false, B);\
+        default: FMGI_PICK(T, FMGI_DEPOSIT_VEC4, false, B);                       \
+    }
+    if (tier == FMGI_TIER_GRID) {
+        if (probe) FMGI_PICK(FMGI_TIER_GRID, FMGI_DEPOSIT_VEC4, true, 3);
+        if (min_blocks == 3) { FMGI_PICK_DEPOSIT(FMGI_TIER_GRID, 3) }
+        FMGI_PICK_DEPOSIT(FMGI_TIER_GRID, 4)
+    }
+    if (probe) FMGI_PICK(FMGI_TIER_SOUP, FMGI_DEPOSIT_VEC4, true, 3);
+    if (min_blocks == 3) { FMGI_PICK_DEPOSIT(FMGI_TIER_SOUP, 3) }
+    FMGI_PICK_DEPOSIT(FMGI_TIER_SOUP, 4)
+#undef FMGI_PICK_DEPOSIT
+#undef FMGI_PICK
+}
+
+cudaError_t launch_trace(fmgi_scene *s, const TraceParams &p, int deposit, bool probe, int blocks, cudaStream_t st)
+{
+    return with_trace_kernel(s->tier, deposit, probe, s->min_blocks, [&](auto kernel) {
         cudaError_t e = cudaSuccess;
         if (s->smem_bytes > 48 * 1024)
             e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->smem_bytes);
@@ -146,20 +173,7 @@ cudaError_t launch_trace(fmgi_scene *s, const TraceParams &p, int deposit, int b
         kernel<<<blocks, kTraceThreads, s->smem_bytes, st>>>(p);
         s->launches++;
         return cudaGetLastError();
-    };
-    if (kProbe) return go(k_trace_soup<FMGI_DEPOSIT_VEC4, true, 3>);
-    if (s->min_blocks == 3) {
-        switch (deposit) {
-            case FMGI_DEPOSIT_SCALAR: return go(k_trace_soup<FMGI_DEPOSIT_SCALAR, false, 3>);
-            case FMGI_DEPOSIT_WARP_AGG: return go(k_trace_soup<FMGI_DEPOSIT_WARP_AGG, false, 3>);
-            default: return go(k_trace_soup<FMGI_DEPOSIT_VEC4, false, 3>);
-        }
-    }
-    switch (deposit) {
-        case FMGI_DEPOSIT_SCALAR: return go(k_trace_soup<FMGI_DEPOSIT_SCALAR, false, 4>);
-        case FMGI_DEPOSIT_WARP_AGG: return go(k_trace_soup<FMGI_DEPOSIT_WARP_AGG, false, 4>);
-        default: return go(k_trace_soup<FMGI_DEPOSIT_VEC4, false, 4>);
-    }
+    });
 }
 
 }  // namespace
@@ -213,12 +227,28 @@ int fmgi_scene_create(fmgi_scene **out, const fmgi_rect *walls, int num_walls, c
     s->num_sms = prop.multiProcessorCount;
     FMGI_CUDA(cudaDeviceGetAttribute(&s->clock_khz, cudaDevAttrClockRate, o.device));
 
-    s->smem_bytes = s->host.axis.size() * sizeof(AxisPairBlock) + s->host.general.size() * sizeof(GeneralRect);
-    s->tier = FMGI_TIER_SOUP;
-    if (s->smem_bytes > (size_t)prop.sharedMemPerBlockOptin)
-        return fail(FMGI_ERR_UNSUPPORTED, "rectangle soup does not fit in shared memory (grid tier required)");
-    // each lane walks one of the two blocks of every pair: two rectangle tests per pair
-    s->tests_per_ray = s->host.axis.size() + s->host.general.size();
+    // tier: brute force over the shared-memory soup for small scenes, floor-plan grid otherwise
+    const size_t soup_bytes = s->host.axis.size() * sizeof(AxisPairBlock) + s->host.general.size() * sizeof(GeneralRect);
+    const int colliders = s->host.num_axis_rects + (int)s->host.general.size();
+    int tier = o.tier;
+    if (const char *v = getenv("FMGI_TIER")) tier = atoi(v);
+    if (tier != FMGI_TIER_SOUP && tier != FMGI_TIER_GRID)
+        tier = (colliders <= 1024 && soup_bytes <= (size_t)prop.sharedMemPerBlockOptin) ? FMGI_TIER_SOUP : FMGI_TIER_GRID;
+    if (tier == FMGI_TIER_SOUP && soup_bytes > (size_t)prop.sharedMemPerBlockOptin)
+        return fail(FMGI_ERR_UNSUPPORTED, "rectangle soup does not fit in shared memory; use FMGI_TIER_GRID");
+    s->tier = tier;
+    if (tier == FMGI_TIER_SOUP) {
+        s->smem_bytes = soup_bytes;
+        // each lane walks one of the two blocks of every pair: two rectangle tests per pair
+        s->tests_per_ray = s->host.axis.size() + s->host.general.size();
+    } else {
+        s->smem_bytes = 0;
+        float cell = 0.0f;
+        if (const char *v = getenv("FMGI_GRID_CELL")) cell = (float)atof(v);
+        build_grid(s->host, walls, num_walls, windows, num_windows, lights, num_lights, cell);
+        FMGI_CUDA(upload(&s->d_grid_recs, s->host.grid_recs));
+        FMGI_CUDA(upload(&s->d_grid_ranges, s->host.grid_ranges));
+    }
 
     FMGI_CUDA(upload(&s->d_axis, s->host.axis));
     FMGI_CUDA(upload(&s->d_general, s->host.general));
@@ -234,16 +264,15 @@ int fmgi_scene_create(fmgi_scene **out, const fmgi_rect *walls, int num_walls, c
     FMGI_CUDA(cudaEventCreate(&s->ev_stop));
 
     if (const char *v = getenv("FMGI_TUNE_BLOCKS")) s->min_blocks = atoi(v) == 3 ? 3 : 4;   // tuning knob
-    auto occupancy = [&](auto kernel) {
+    fmgi_scene *sp = s.get();
+    FMGI_CUDA(with_trace_kernel(s->tier, FMGI_DEPOSIT_VEC4, false, s->min_blocks, [&](auto kernel) {
         cudaError_t e = cudaSuccess;
-        if (s->smem_bytes > 48 * 1024)
-            e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->smem_bytes);
+        if (sp->smem_bytes > 48 * 1024)
+            e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sp->smem_bytes);
         if (e == cudaSuccess)
-            e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&s->blocks_per_sm, kernel, kTraceThreads, s->smem_bytes);
+            e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&sp->blocks_per_sm, kernel, kTraceThreads, sp->smem_bytes);
         return e;
-    };
-    if (s->min_blocks == 3) FMGI_CUDA(occupancy(k_trace_soup<FMGI_DEPOSIT_VEC4, false, 3>));
-    else FMGI_CUDA(occupancy(k_trace_soup<FMGI_DEPOSIT_VEC4, false, 4>));
+    }));
     if (s->blocks_per_sm < 1) return fail(FMGI_ERR_CUDA, "trace kernel does not fit on an SM");
     *out = s.release();
     return FMGI_OK;
@@ -254,6 +283,7 @@ void fmgi_scene_destroy(fmgi_scene *s)
     if (!s) return;
     DeviceGuard guard(s->device);
     cudaFree(s->d_axis); cudaFree(s->d_general); cudaFree(s->d_shade); cudaFree(s->d_emitters);
+    cudaFree(s->d_grid_recs); cudaFree(s->d_grid_ranges);
     cudaFree(s->d_jobs); cudaFree(s->d_counters);
     cudaFreeHost(s->h_jobs); cudaFreeHost(s->h_counters);
     if (s->ev_start) cudaEventDestroy(s->ev_start);
@@ -297,7 +327,7 @@ int fmgi_scene_trace(fmgi_scene *s, void *atlas_dev, int spa, const fmgi_options
         want = (want * 32 + kTraceThreads - 1) / kTraceThreads;
         const unsigned long long wave = (unsigned long long)s->num_sms * s->blocks_per_sm;
         const int blocks = (int)(want < wave ? (want ? want : 1) : wave);
-        FMGI_CUDA(launch_trace<false>(s, p, o.deposit, blocks, st));
+        FMGI_CUDA(launch_trace(s, p, o.deposit, false, blocks, st));
     }
     FMGI_CUDA(cudaEventRecord(s->ev_stop, st));
     FMGI_CUDA(cudaMemcpyAsync(s->h_counters, s->d_counters, 8 * sizeof(unsigned long long),
@@ -318,7 +348,7 @@ int fmgi_scene_sync(fmgi_scene *s, fmgi_stats *stats)
         stats->rays = s->h_counters[1];
         stats->deposits = s->h_counters[2];
         stats->mirror_bounces = s->h_counters[3];
-        stats->rect_tests = s->h_counters[1] * s->tests_per_ray;
+        stats->rect_tests = s->tier == FMGI_TIER_SOUP ? s->h_counters[1] * s->tests_per_ray : s->h_counters[5];
         stats->kernel_launches = s->launches;
         if (s->traced) {
             float ms = 0;
@@ -525,13 +555,17 @@ int fmgi_probe_closest_hit(fmgi_scene *s, const float *origins, const float *dir
     FMGI_CUDA(cudaMalloc((void **)&d_i, (size_t)n * sizeof(int32_t)));
     FMGI_CUDA(cudaMemcpy(d_o, origins, vb, cudaMemcpyHostToDevice));
     FMGI_CUDA(cudaMemcpy(d_d, dirs, vb, cudaMemcpyHostToDevice));
-    if (s->smem_bytes > 48 * 1024)
-        FMGI_CUDA(cudaFuncSetAttribute(k_probe_closest_hit, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       (int)s->smem_bytes));
     const TraceParams p = base_params(s);
     int blocks = (n + 255) / 256;
     if (blocks > s->num_sms * 4) blocks = s->num_sms * 4;
-    k_probe_closest_hit<<<blocks, 256, s->smem_bytes>>>(p, d_o, d_d, n, d_i, d_t);
+    if (s->tier == FMGI_TIER_SOUP) {
+        if (s->smem_bytes > 48 * 1024)
+            FMGI_CUDA(cudaFuncSetAttribute(k_probe_closest_hit<FMGI_TIER_SOUP>,
+                                           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->smem_bytes));
+        k_probe_closest_hit<FMGI_TIER_SOUP><<<blocks, 256, s->smem_bytes>>>(p, d_o, d_d, n, d_i, d_t);
+    } else {
+        k_probe_closest_hit<FMGI_TIER_GRID><<<blocks, 256>>>(p, d_o, d_d, n, d_i, d_t);
+    }
     s->launches++;
     FMGI_CUDA(cudaGetLastError());
     FMGI_CUDA(cudaMemcpy(hit_index, d_i, (size_t)n * sizeof(int32_t), cudaMemcpyDeviceToHost));
@@ -623,7 +657,7 @@ int fmgi_probe_paths(fmgi_scene *s, int emitter_index, int max_depth, uint32_t s
     p.path_out = d_path;
     int blocks = (count + kTraceThreads - 1) / kTraceThreads;
     if (blocks > s->num_sms) blocks = s->num_sms;
-    FMGI_CUDA(launch_trace<true>(s, p, 0, blocks, nullptr));
+    FMGI_CUDA(launch_trace(s, p, 0, true, blocks, nullptr));
     FMGI_CUDA(cudaMemcpy(texel_out, d_path, pb, cudaMemcpyDeviceToHost));
     cudaFree(d_path);
     return FMGI_OK;

@@ -166,4 +166,114 @@ const char *prepare_scene(HostScene &out, const fmgi_rect *walls, int num_walls,
     return "";
 }
 
+// ---- grid tier --------------------------------------------------------------------------------------
+
+void build_grid(HostScene &out, const fmgi_rect *walls, int num_walls, const fmgi_rect *windows, int num_windows,
+                const fmgi_rect *lights, int num_lights, float cell_hint)
+{
+    GridDesc &g = out.grid;
+    g = GridDesc();
+    out.grid_ranges.clear();
+    out.grid_recs.clear();
+
+    // bounding box of everything a ray can start from or hit
+    float xmin = INFINITY, xmax = -INFINITY, ymin = INFINITY, ymax = -INFINITY;
+    auto grow = [&](const fmgi_rect &r) {
+        for (int c = 0; c < 4; c++) {
+            const float x = r.pos[0] + (c & 1 ? r.width[0] : 0.0f) + (c & 2 ? r.height[0] : 0.0f);
+            const float y = r.pos[1] + (c & 1 ? r.width[1] : 0.0f) + (c & 2 ? r.height[1] : 0.0f);
+            xmin = fminf(xmin, x); xmax = fmaxf(xmax, x); ymin = fminf(ymin, y); ymax = fmaxf(ymax, y);
+        }
+    };
+    for (int i = 0; i < num_walls; i++) grow(walls[i]);
+    for (int i = 0; i < num_windows; i++) grow(windows[i]);
+    for (int i = 0; i < num_lights; i++) grow(lights[i]);
+    if (!(xmax >= xmin)) { xmin = ymin = 0; xmax = ymax = 1; }
+
+    const float w = fmaxf(xmax - xmin, 1e-3f), h = fmaxf(ymax - ymin, 1e-3f);
+    float cell = cell_hint;
+    if (!(cell > 0)) cell = sqrtf(w * h / fmaxf(1.0f, 0.5f * (float)num_walls));
+    // keep the grid below 4M cells whatever the hint
+    while ((double)(w / cell + 3) * (double)(h / cell + 3) > 4.0e6) cell *= 1.5f;
+    g.cell = cell; g.inv_cell = 1.0f / cell;
+    g.x0 = xmin - cell; g.y0 = ymin - cell;                 // one cell of margin all around
+    g.nx = (int)ceilf(w / cell) + 2; g.ny = (int)ceilf(h / cell) + 2;
+    const int ncell = g.nx * g.ny;
+
+    // classify: which list does each wall go to, and with which record
+    struct Item { int list; int cx0, cx1, cy0, cy1; GridRec rec; };
+    std::vector<Item> items;
+    std::vector<float> up, down;
+    const float eps = 1e-3f * cell;
+    int general_index = 0;
+    for (int r = 0; r < num_walls; r++) {
+        const fmgi_rect &q = walls[r];
+        V3 pos = ld(q.pos), wd = ld(q.width), ht = ld(q.height), n = ld(q.n);
+        if (!(length(wd) > 0) || !(length(ht) > 0) || !(length(n) > 0)) continue;     // as prepare_scene
+        Item it;
+        memset(&it, 0, sizeof it);
+        const int ai = single_axis(wd), aj = single_axis(ht), ak = single_axis(n);
+        const bool axis = ai >= 0 && aj >= 0 && ak >= 0 && ai != aj && ak != ai && ak != aj;
+        V3 far = {pos.x + wd.x + ht.x, pos.y + wd.y + ht.y, pos.z + wd.z + ht.z};
+        it.list = -1;                                       // -1: walk list
+        if (axis) {
+            const int i = ai < aj ? ai : aj, j = ai < aj ? aj : ai;
+            const float lo_i = fminf(comp(pos, i), comp(far, i)), hi_i = fmaxf(comp(pos, i), comp(far, i));
+            const float lo_j = fminf(comp(pos, j), comp(far, j)), hi_j = fmaxf(comp(pos, j), comp(far, j));
+            it.rec.c = comp(pos, ak);
+            it.rec.mid_i = 0.5f * (lo_i + hi_i); it.rec.half_i = 0.5f * (hi_i - lo_i);
+            it.rec.mid_j = 0.5f * (lo_j + hi_j); it.rec.half_j = 0.5f * (hi_j - lo_j);
+            const int neg = comp(n, ak) > 0 ? 0 : 1;
+            it.rec.tag = r | (ak << 28) | (neg << 30);
+            if (ak == 2) {                                  // horizontal: try the plane table
+                std::vector<float> &pl = neg ? down : up;
+                size_t p = 0;
+                while (p < pl.size() && pl[p] != it.rec.c) p++;
+                if (p == pl.size() && pl.size() < (size_t)kMaxPlanesPerSign) pl.push_back(it.rec.c);
+                if (p < pl.size()) it.list = (neg ? kMaxPlanesPerSign : 0) + (int)p;
+            }
+        } else {
+            it.rec.tag = general_index | (3 << 28);
+        }
+        if (!axis) general_index++;                         // same order as HostScene::general
+        // (x, y) bounding box over the four corners
+        float bx0 = INFINITY, bx1 = -INFINITY, by0 = INFINITY, by1 = -INFINITY;
+        for (int c = 0; c < 4; c++) {
+            const float x = pos.x + (c & 1 ? wd.x : 0.0f) + (c & 2 ? ht.x : 0.0f);
+            const float y = pos.y + (c & 1 ? wd.y : 0.0f) + (c & 2 ? ht.y : 0.0f);
+            bx0 = fminf(bx0, x); bx1 = fmaxf(bx1, x); by0 = fminf(by0, y); by1 = fmaxf(by1, y);
+        }
+        auto cellx = [&](float x) { int c = (int)floorf((x - g.x0) * g.inv_cell); return c < 0 ? 0 : (c >= g.nx ? g.nx - 1 : c); };
+        auto celly = [&](float y) { int c = (int)floorf((y - g.y0) * g.inv_cell); return c < 0 ? 0 : (c >= g.ny ? g.ny - 1 : c); };
+        it.cx0 = cellx(bx0 - eps); it.cx1 = cellx(bx1 + eps);
+        it.cy0 = celly(by0 - eps); it.cy1 = celly(by1 + eps);
+        items.push_back(it);
+    }
+    g.planes_up = (int)up.size(); g.planes_down = (int)down.size();
+    for (size_t p = 0; p < up.size(); p++) g.plane_z[p] = up[p];
+    for (size_t p = 0; p < down.size(); p++) g.plane_z[kMaxPlanesPerSign + p] = down[p];
+
+    // lists are numbered: [0, 8) planes +z, [8, 16) planes -z, 16 = walk list
+    const int num_lists = 2 * kMaxPlanesPerSign + 1;
+    auto list_of = [&](const Item &it) { return it.list < 0 ? 2 * kMaxPlanesPerSign : it.list; };
+    std::vector<int32_t> count((size_t)num_lists * ncell + 1, 0);
+    for (const Item &it : items)
+        for (int cy = it.cy0; cy <= it.cy1; cy++)
+            for (int cx = it.cx0; cx <= it.cx1; cx++)
+                count[(size_t)list_of(it) * ncell + cy * g.nx + cx]++;
+    std::vector<int32_t> begin((size_t)num_lists * ncell + 1, 0);
+    for (size_t i = 0; i < (size_t)num_lists * ncell; i++) begin[i + 1] = begin[i] + count[i];
+    out.grid_recs.resize((size_t)begin[(size_t)num_lists * ncell]);
+    std::vector<int32_t> fill(begin.begin(), begin.end() - 1);
+    for (const Item &it : items)
+        for (int cy = it.cy0; cy <= it.cy1; cy++)
+            for (int cx = it.cx0; cx <= it.cx1; cx++)
+                out.grid_recs[(size_t)fill[(size_t)list_of(it) * ncell + cy * g.nx + cx]++] = it.rec;
+    out.grid_ranges.resize((size_t)2 * num_lists * ncell);
+    for (size_t i = 0; i < (size_t)num_lists * ncell; i++) {
+        out.grid_ranges[2 * i] = begin[i];
+        out.grid_ranges[2 * i + 1] = begin[i + 1];
+    }
+}
+
 }  // namespace fmgi

@@ -64,12 +64,36 @@ struct EmitterRec {
 static_assert(sizeof(EmitterRec) == 96, "EmitterRec is six float4");
 
 // ---- uniform grid over the floor plan (grid tier) --------------------------------------------
+//
+// parseLayout.c extrudes a 2-D floor plan, so a 2-D grid over (x, y) is the natural index:
+//   * horizontal rectangles (floors, ceilings, sills, lintels) live on a handful of z planes.
+//     For every distinct (z, normal sign) plane there is one cell list per grid cell; a ray finds
+//     its crossing point with the plane, looks up that one cell and tests only its candidates;
+//   * everything else (vertical walls, arbitrarily oriented rectangles, horizontal rectangles
+//     beyond the plane table) is binned by its (x, y) bounding box into the "walk" list of every
+//     cell it overlaps and found by a 2-D DDA from the ray origin, which stops as soon as the
+//     next cell starts beyond the best hit so far.
+// Cell lists hold the 32-byte records inline (no index indirection): list (l, cell) is
+// recs[ranges[l * ncell + cell].x .. .y).
+
+enum { kMaxPlanesPerSign = 8 };
+
+struct GridRec {
+    float c;                // plane coordinate pos[k]
+    float mid_i, half_i;    // extent along in-plane axis i (centre, half width)
+    float mid_j;
+    float half_j;
+    int32_t tag;            // wall id | k << 28 | (normal negative) << 30;  k == 3: index into `general`
+    int32_t pad0, pad1;
+};
+static_assert(sizeof(GridRec) == 32, "GridRec is two float4");
 
 struct GridDesc {
     float x0, y0;           // world position of cell (0,0)'s corner
     float cell, inv_cell;   // cell edge, 1/edge
     int32_t nx, ny;
-    float zmin, zmax;       // vertical extent of all colliders
+    int32_t planes_up, planes_down;         // number of z planes with normal +z / -z
+    float plane_z[2 * kMaxPlanesPerSign];   // [0, planes_up): normal +z; [kMaxPlanesPerSign, +planes_down): normal -z
 };
 
 struct HostScene {
@@ -81,10 +105,10 @@ struct HostScene {
     std::vector<ShadeRect> shade;         // per wall
     std::vector<EmitterRec> emitters;     // windows then lights
     std::vector<float> emitter_area;      // |w|*|h| in float (photonmap.c:417)
-    // grid tier
+    // grid tier (filled by build_grid)
     GridDesc grid = {};
-    std::vector<int32_t> cell_begin;      // nx*ny + 1 offsets into cell_items
-    std::vector<int32_t> cell_items;      // per cell: indices into `axis` (>= 0) or ~index into `general`
+    std::vector<int32_t> grid_ranges;     // 2 ints (begin, end) per (list, cell); lists: planes_up, planes_down, walk
+    std::vector<GridRec> grid_recs;
 };
 
 // photonmap.c:414-418: N = (uint64)(int spa * float area)
@@ -94,6 +118,13 @@ uint64_t photon_budget(float area, int samples_per_area);
 const char *prepare_scene(HostScene &out, const fmgi_rect *walls, int num_walls,
                           const fmgi_rect *windows, int num_windows,
                           const fmgi_rect *lights, int num_lights, int num_texels);
+
+// Builds the floor-plan grid of the grid tier.  cell_hint <= 0 picks the cell edge from the scene
+// (about two colliders per cell).  Needs the wall table again because HostScene keeps only
+// derived records.
+void build_grid(HostScene &scene, const fmgi_rect *walls, int num_walls,
+                const fmgi_rect *windows, int num_windows, const fmgi_rect *lights, int num_lights,
+                float cell_hint);
 
 // vector3_cl.c:139-144: the basis both hemisphere samplers build around a normal.
 void sampler_basis(const float n[3], float u[3], float v[3]);

@@ -1,5 +1,6 @@
-// Soup tier: persistent photon-tracing kernel with the whole rectangle soup in shared memory,
-// plus the probe kernels that expose its device functions to the parity tests.
+// The persistent photon-tracing kernel (soup tier: whole rectangle soup in shared memory; grid tier:
+// floor-plan grid walked from L2) plus the probe kernels that expose its device functions to the
+// parity tests.
 #pragma once
 #include "trace_kernels.cuh"
 
@@ -19,22 +20,30 @@ __device__ __forceinline__ int find_emitter(const unsigned long long *__restrict
     return lo;
 }
 
-template <int kDeposit, bool kProbe, int kMinBlocks>
-__global__ void __launch_bounds__(kTraceThreads, kMinBlocks) k_trace_soup(const TraceParams p)
+// Stages the soup into shared memory (whole CTA) and returns the table view.
+__device__ __forceinline__ SoupTables stage_soup(const TraceParams &p, float4 *smem)
 {
-    extern __shared__ float4 smem[];
     const int n_axis4 = 6 * p.pair_begin[3];
     const int n_gen4 = 4 * p.num_general;
     for (int i = threadIdx.x; i < n_axis4; i += blockDim.x) smem[i] = p.axis[i];
     for (int i = threadIdx.x; i < n_gen4; i += blockDim.x) smem[n_axis4 + i] = p.general[i];
     __syncthreads();
-
     SoupTables soup;
     soup.axis = smem;
     soup.general = smem + n_axis4;
 #pragma unroll
     for (int g = 0; g < 4; g++) soup.pair_begin[g] = p.pair_begin[g];
     soup.num_general = p.num_general;
+    return soup;
+}
+
+// kTier: FMGI_TIER_SOUP (brute force over the shared-memory soup) or FMGI_TIER_GRID (floor-plan grid in L2).
+template <int kTier, int kDeposit, bool kProbe, int kMinBlocks>
+__global__ void __launch_bounds__(kTraceThreads, kMinBlocks) k_trace(const TraceParams p)
+{
+    extern __shared__ float4 smem[];
+    SoupTables soup;
+    if (kTier == FMGI_TIER_SOUP) soup = stage_soup(p, smem);
 
     const int lane = threadIdx.x & 31;
     const unsigned lt_mask = (1u << lane) - 1u;
@@ -49,7 +58,7 @@ __global__ void __launch_bounds__(kTraceThreads, kMinBlocks) k_trace_soup(const 
     unsigned long long w_next = 0, w_end = 0;
     int w_emitter = 0;
     bool exhausted = false;
-    unsigned n_photons = 0, n_rays = 0, n_deposits = 0, n_mirror = 0;
+    unsigned n_photons = 0, n_rays = 0, n_deposits = 0, n_mirror = 0, n_tests = 0;
 
     for (;;) {
         // ---- A. refill dead lanes from the warp's chunk of the photon index space ---------------
@@ -119,7 +128,8 @@ __global__ void __launch_bounds__(kTraceThreads, kMinBlocks) k_trace_soup(const 
 
             // ---- C. closest hit (photonmap.c:198 / photonmap.cl:194-206) ---------------------------
             float t;
-            hit_id = closest_hit_soup(soup, px, py, pz, dx, dy, dz, t);
+            if (kTier == FMGI_TIER_SOUP) hit_id = closest_hit_soup(soup, px, py, pz, dx, dy, dz, t);
+            else hit_id = closest_hit_grid(p, px, py, pz, dx, dy, dz, t, n_tests);
             n_rays++;
 
             // ---- D. bounce: texel, roulette, attenuation (photonmap.c:200-247) ------------------------
@@ -153,42 +163,40 @@ __global__ void __launch_bounds__(kTraceThreads, kMinBlocks) k_trace_soup(const 
     }
 
     // ---- counters: warp reduce, one atomic per warp and counter --------------------------------------
-    unsigned long long c0 = n_photons, c1 = n_rays, c2 = n_deposits, c3 = n_mirror;
+    unsigned long long c0 = n_photons, c1 = n_rays, c2 = n_deposits, c3 = n_mirror, c5 = n_tests;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
         c0 += __shfl_xor_sync(kFullMask, c0, o);
         c1 += __shfl_xor_sync(kFullMask, c1, o);
         c2 += __shfl_xor_sync(kFullMask, c2, o);
         c3 += __shfl_xor_sync(kFullMask, c3, o);
+        if (kTier == FMGI_TIER_GRID) c5 += __shfl_xor_sync(kFullMask, c5, o);
     }
     if (lane == 0) {
         atomicAdd(p.counters + 0, c0);
         atomicAdd(p.counters + 1, c1);
         atomicAdd(p.counters + 2, c2);
         atomicAdd(p.counters + 3, c3);
+        if (kTier == FMGI_TIER_GRID) atomicAdd(p.counters + 5, c5);
     }
 }
 
 // ---- probe kernels: the same device functions, one item per thread --------------------------------------
 
+template <int kTier>
 __global__ void k_probe_closest_hit(const TraceParams p, const float *__restrict__ origins,
                                     const float *__restrict__ dirs, int num_rays, int32_t *hit_index, float *hit_dist)
 {
     extern __shared__ float4 smem[];
-    const int n_axis4 = 6 * p.pair_begin[3];
-    const int n_gen4 = 4 * p.num_general;
-    for (int i = threadIdx.x; i < n_axis4; i += blockDim.x) smem[i] = p.axis[i];
-    for (int i = threadIdx.x; i < n_gen4; i += blockDim.x) smem[n_axis4 + i] = p.general[i];
-    __syncthreads();
     SoupTables soup;
-    soup.axis = smem;
-    soup.general = smem + n_axis4;
-    for (int g = 0; g < 4; g++) soup.pair_begin[g] = p.pair_begin[g];
-    soup.num_general = p.num_general;
+    if (kTier == FMGI_TIER_SOUP) soup = stage_soup(p, smem);
+    unsigned tests = 0;
     for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < num_rays; r += gridDim.x * blockDim.x) {
         float t;
-        const int id = closest_hit_soup(soup, origins[3 * r], origins[3 * r + 1], origins[3 * r + 2],
-                                        dirs[3 * r], dirs[3 * r + 1], dirs[3 * r + 2], t);
+        const float ox = origins[3 * r], oy = origins[3 * r + 1], oz = origins[3 * r + 2];
+        const float dx = dirs[3 * r], dy = dirs[3 * r + 1], dz = dirs[3 * r + 2];
+        const int id = kTier == FMGI_TIER_SOUP ? closest_hit_soup(soup, ox, oy, oz, dx, dy, dz, t)
+                                               : closest_hit_grid(p, ox, oy, oz, dx, dy, dz, t, tests);
         hit_index[r] = id;
         hit_dist[r] = t;
     }

@@ -38,6 +38,10 @@ struct TraceParams {
     const float4 *general;       // 4 float4 per GeneralRect
     int pair_begin[4];           // pairs of axis k: pair_begin[k] .. pair_begin[k+1]
     int num_general;
+    // grid tier (scene_tables.h): inline cell-list records and (begin, end) per (list, cell)
+    const float4 *grid_recs;     // 2 float4 per GridRec
+    const int2 *grid_ranges;
+    GridDesc grid;
     // shading tables
     const float4 *shade;         // 6 float4 per wall
     const float4 *emitters;      // 6 float4 per emitter
@@ -50,7 +54,7 @@ struct TraceParams {
     unsigned long long *work_counter;
     // output
     float4 *atlas;
-    unsigned long long *counters;   // photons, rays, deposits, mirror bounces
+    unsigned long long *counters;   // photons, rays, deposits, mirror bounces, (work counter), rectangle tests (grid tier)
     int32_t *path_out;              // probe builds only
     int max_depth;
     uint32_t seed;
@@ -177,6 +181,124 @@ __device__ __forceinline__ int closest_hit_soup(const SoupTables &s, float ox, f
         const float num = __fadd_rn(__fadd_rn(__fmul_rn(g0.x, __fsub_rn(g3.x, ox)), __fmul_rn(g0.y, __fsub_rn(g3.y, oy))),
                                     __fmul_rn(g0.z, __fsub_rn(g3.z, oz)));
         t_out = __fdiv_rn(num, denom);
+    }
+    return id;
+}
+
+// ---- closest hit through the floor-plan grid (grid tier) ---------------------------------------------
+
+struct GridHit { float best; int rec; };      // rec: index of the winning inline record, -1 = miss
+
+// One record of a walk list: axis-parallel rectangle with any normal axis, or a general rectangle.
+__device__ __forceinline__ void grid_test_walk(const TraceParams &p, int r, float ox, float oy, float oz,
+                                               float dx, float dy, float dz, float ix, float iy, float iz,
+                                               float &best, int &win)
+{
+    const float4 q0 = __ldg(p.grid_recs + 2 * r);
+    const float4 q1 = __ldg(p.grid_recs + 2 * r + 1);
+    const int tag = __float_as_int(q1.y);
+    const int k = (tag >> 28) & 3;
+    if (k == 3) {
+        // rectangle.c:67-95 for an arbitrarily oriented rectangle
+        const float4 *g = p.general + 4 * (tag & 0x0fffffff);
+        const float4 g0 = __ldg(g), g1 = __ldg(g + 1), g2 = __ldg(g + 2), g3 = __ldg(g + 3);
+        const float denom = g0.x * dx + g0.y * dy + g0.z * dz;
+        const float num = g0.w - (g0.x * ox + g0.y * oy + g0.z * oz);
+        const float t = __fdividef(num, denom);
+        const float ex = fmaf(t, dx, ox) - g3.x, ey = fmaf(t, dy, oy) - g3.y, ez = fmaf(t, dz, oz) - g3.z;
+        const float u = g1.x * ex + g1.y * ey + g1.z * ez;
+        const float v = g2.x * ex + g2.y * ey + g2.z * ez;
+        if (denom < 0.0f && (__float_as_uint(t) < __float_as_uint(best)) && u >= 0.0f && v >= 0.0f && u <= g1.w &&
+            v <= g2.w) {
+            best = t; win = r;
+        }
+        return;
+    }
+    const float ok = k == 0 ? ox : (k == 1 ? oy : oz);
+    const float dk = k == 0 ? dx : (k == 1 ? dy : dz);
+    const float ik = k == 0 ? ix : (k == 1 ? iy : iz);
+    const float oi = k == 0 ? oy : ox, di = k == 0 ? dy : dx;          // in-plane axes in ascending order
+    const float oj = k == 2 ? oy : oz, dj = k == 2 ? dy : dz;
+    const bool facing = (tag & (1 << 30)) ? dk > 0.0f : dk < 0.0f;    // back-face culling, rectangle.c:70-72
+    const float t = (q0.x - ok) * ik;
+    const float pi = fmaf(t, di, oi) - q0.y;
+    const float pj = fmaf(t, dj, oj) - q0.w;
+    if (facing && (__float_as_uint(t) < __float_as_uint(best)) && fabsf(pi) <= q0.z && fabsf(pj) <= q1.x) {
+        best = t; win = r;
+    }
+}
+
+__device__ __forceinline__ int closest_hit_grid(const TraceParams &p, float ox, float oy, float oz,
+                                                float dx, float dy, float dz, float &t_out, unsigned &tests)
+{
+    const GridDesc &g = p.grid;
+    const int ncell = g.nx * g.ny;
+    const float inf = __int_as_float(0x7f800000);
+    float best = inf;
+    int win = -1;
+    const float ix = __frcp_rn(dx), iy = __frcp_rn(dy), iz = __frcp_rn(dz);
+
+    // 1. horizontal planes the ray can face: one cell lookup per plane at the crossing point
+    if (dz != 0.0f) {
+        const int first = dz < 0.0f ? 0 : kMaxPlanesPerSign;                 // d.z < 0 faces normals +z
+        const int count = dz < 0.0f ? g.planes_up : g.planes_down;
+        for (int pl = 0; pl < count; pl++) {
+            const float t = (g.plane_z[first + pl] - oz) * iz;
+            if (!(__float_as_uint(t) < __float_as_uint(best))) continue;
+            const float x = fmaf(t, dx, ox), y = fmaf(t, dy, oy);
+            const int cx = __float2int_rd((x - g.x0) * g.inv_cell), cy = __float2int_rd((y - g.y0) * g.inv_cell);
+            if (cx < 0 || cy < 0 || cx >= g.nx || cy >= g.ny) continue;
+            const int2 range = __ldg(p.grid_ranges + (first + pl) * ncell + cy * g.nx + cx);
+            for (int r = range.x; r < range.y; r++) {
+                const float4 q0 = __ldg(p.grid_recs + 2 * r);
+                const float4 q1 = __ldg(p.grid_recs + 2 * r + 1);
+                tests++;
+                if (fabsf(x - q0.y) <= q0.z && fabsf(y - q0.w) <= q1.x) { best = t; win = r; break; }
+            }
+        }
+    }
+
+    // 2. everything else: 2-D DDA through the walk lists, until the next cell starts beyond the best hit
+    {
+        int cx = __float2int_rd((ox - g.x0) * g.inv_cell), cy = __float2int_rd((oy - g.y0) * g.inv_cell);
+        cx = min(max(cx, 0), g.nx - 1); cy = min(max(cy, 0), g.ny - 1);
+        const int sx = dx > 0.0f ? 1 : -1, sy = dy > 0.0f ? 1 : -1;
+        float tmx = inf, tmy = inf, tdx = inf, tdy = inf;
+        if (dx != 0.0f) { tmx = (g.x0 + (float)(cx + (dx > 0.0f ? 1 : 0)) * g.cell - ox) * ix; tdx = g.cell * fabsf(ix); }
+        if (dy != 0.0f) { tmy = (g.y0 + (float)(cy + (dy > 0.0f ? 1 : 0)) * g.cell - oy) * iy; tdy = g.cell * fabsf(iy); }
+        const int2 *walk = p.grid_ranges + 2 * kMaxPlanesPerSign * ncell;
+        for (int guard = g.nx + g.ny + 2; guard > 0; guard--) {
+            const int2 range = __ldg(walk + cy * g.nx + cx);
+            tests += (unsigned)(range.y - range.x);
+            for (int r = range.x; r < range.y; r++)
+                grid_test_walk(p, r, ox, oy, oz, dx, dy, dz, ix, iy, iz, best, win);
+            const float t_next = fminf(tmx, tmy);
+            if (!(t_next < best)) break;
+            if (tmx < tmy) { cx += sx; tmx += tdx; } else { cy += sy; tmy += tdy; }
+            if (cx < 0 || cy < 0 || cx >= g.nx || cy >= g.ny) break;
+        }
+    }
+
+    int id = -1;
+    t_out = best;
+    if (win >= 0) {
+        const float4 q0 = __ldg(p.grid_recs + 2 * win);
+        const int tag = __float_as_int(__ldg(p.grid_recs + 2 * win + 1).y);
+        const int k = (tag >> 28) & 3;
+        if (k == 3) {
+            const float4 *gg = p.general + 4 * (tag & 0x0fffffff);
+            const float4 g0 = __ldg(gg), g3 = __ldg(gg + 3);
+            id = __float_as_int(g3.w);
+            const float denom = __fadd_rn(__fadd_rn(__fmul_rn(g0.x, dx), __fmul_rn(g0.y, dy)), __fmul_rn(g0.z, dz));
+            const float num = __fadd_rn(__fadd_rn(__fmul_rn(g0.x, __fsub_rn(g3.x, ox)), __fmul_rn(g0.y, __fsub_rn(g3.y, oy))),
+                                        __fmul_rn(g0.z, __fsub_rn(g3.z, oz)));
+            t_out = __fdiv_rn(num, denom);
+        } else {
+            id = tag & 0x0fffffff;
+            const float ok = k == 0 ? ox : (k == 1 ? oy : oz);
+            const float dk = k == 0 ? dx : (k == 1 ? dy : dz);
+            t_out = __fdiv_rn(__fsub_rn(q0.x, ok), dk);
+        }
     }
     return id;
 }

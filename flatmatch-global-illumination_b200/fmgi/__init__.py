@@ -175,14 +175,14 @@ def bake(geo: Geometry, num_samples_per_area: int, **opts) -> dict:
 class DeviceScene:
     """fmgi_scene: collider + emitter tables resident on one GPU."""
 
-    def __init__(self, walls, windows, lights, num_texels: int, device: int = 0):
+    def __init__(self, walls, windows, lights, num_texels: int, device: int = 0, tier: int = TIER_AUTO):
         self._h = C.c_void_p()
         self.walls = aligned_rects(walls)
         self.windows = aligned_rects(windows)
         self.lights = aligned_rects(lights)
         self.num_texels = int(num_texels)
         self.device = device
-        o = options(device=device)
+        o = options(device=device, tier=tier)
         _check(lib().fmgi_scene_create(C.byref(self._h), self.walls.ctypes.data, len(self.walls),
                                        self.windows.ctypes.data, len(self.windows), self.lights.ctypes.data,
                                        len(self.lights), self.num_texels, C.byref(o)))

@@ -5,6 +5,7 @@ UNMODIFIED reference (oracle/_ref/libfmgi_ref*.so, built from /root/reference by
 Run here (where /root/reference exists); the GPU box only reads the fixtures.
 
     python oracle/make_golden.py scene            # example_scene.npz + example_facts.json
+    python oracle/make_golden.py synth            # synth800_scene.npz, synth4000_scene.npz
     python oracle/make_golden.py atlas --depth 8 --spa 5000000 --procs 8
     python oracle/make_golden.py atlas --depth 3 --spa 5000000 --procs 8
 
@@ -102,14 +103,32 @@ def cmd_atlas(args):
           f"per-process {np.mean(out['cpu_seconds']):.0f} s")
 
 
+def cmd_synth(_args):
+    """Synthetic layouts (BASELINE.json configs[2]): pixels from our generator, rectangles from the
+    reference's parseLayout (parseLayout.c:359), scale 30 px/m, TILE_SIZE 200."""
+    sys.path.insert(0, str(HERE.parent / "flatmatch-global-illumination_b200"))
+    from fmgi import synth
+
+    ref = rb.RefLib()
+    for name, kw in (("synth800", dict(size_px=800, seed=1)),
+                     ("synth4000", dict(size_px=4000, seed=1, room_min_m=2.4, room_max_m=5.0))):
+        img = synth.make_layout(**kw)
+        scene, _ = ref.parse_rgba(img, 30.0, 200.0)
+        scene.meta["generator"] = json.dumps(kw, sort_keys=True)
+        scene.save(GOLDEN / f"{name}_scene.npz")
+        print(name, len(scene.walls), "walls", len(scene.windows), "windows", len(scene.lights), "lights",
+              scene.num_texels, "texels", hashlib.sha256(scene.walls.tobytes()).hexdigest()[:16])
+
+
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     sub = ap.add_subparsers(dest="cmd", required=True)
     sub.add_parser("scene")
+    sub.add_parser("synth")
     a = sub.add_parser("atlas")
     a.add_argument("--depth", type=int, default=8)
     a.add_argument("--spa", type=int, default=5_000_000)
     a.add_argument("--procs", type=int, default=8)
     a.add_argument("--seed0", type=int, default=1000)
     args = ap.parse_args()
-    {"scene": cmd_scene, "atlas": cmd_atlas}[args.cmd](args)
+    {"scene": cmd_scene, "atlas": cmd_atlas, "synth": cmd_synth}[args.cmd](args)

@@ -68,6 +68,28 @@ def dev_scene(fmgi, scene):
     s.close()
 
 
+@pytest.fixture(scope="session")
+def dev_scene_grid(fmgi, scene):
+    """The same flat traced through the floor-plan grid instead of the shared-memory soup."""
+    s = fmgi.DeviceScene(scene.walls, scene.windows, scene.lights, scene.num_texels, tier=fmgi.TIER_GRID)
+    yield s
+    s.close()
+
+
+@pytest.fixture(scope="session")
+def synth800():
+    import refbind
+
+    return refbind.Scene.load(GOLDEN / "synth800_scene.npz")
+
+
+@pytest.fixture(scope="session")
+def synth4000():
+    import refbind
+
+    return refbind.Scene.load(GOLDEN / "synth4000_scene.npz")
+
+
 def random_rays(scene, n, seed):
     """Rays as the path produces them: half start inside the flat's bounding box with uniform
     directions, half start on a wall (offset 1e-5 along the new direction, photonmap.c:254)."""

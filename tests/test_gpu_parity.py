@@ -52,11 +52,16 @@ def test_philox_on_device(fmgi, oracle):
         assert np.array_equal(fmgi.philox(ctr, key), oracle.philox(ctr, key))
 
 
-def test_closest_hit_matches_oracle(dev_scene, oracle, scene):
+@pytest.fixture(params=["soup", "grid"])
+def any_tier_scene(request, dev_scene, dev_scene_grid):
+    return dev_scene if request.param == "soup" else dev_scene_grid
+
+
+def test_closest_hit_matches_oracle(any_tier_scene, oracle, scene):
     """>= 1e6 rays: same wall index as the reference's linear scan with intersects()
     (rectangle.c:67, photonmap.cl:194-206); distance within 1e-4 relative."""
     o, d = random_rays(scene, 1_000_000, 11)
-    gi, gt = dev_scene.closest_hit(o, d)
+    gi, gt = any_tier_scene.closest_hit(o, d)
     ci, ct = oracle.closest_hit(scene.walls, o, d, oracle.ACCEL_LINEAR)
     mism = gi != ci
     assert mism.mean() < 5e-6, f"{mism.sum()} index mismatches"
@@ -106,7 +111,8 @@ def test_sampler_moments_and_sky_fold(fmgi):
         assert abs((d.astype(np.float64) @ np.array(normal) / np.linalg.norm(normal)).mean() - 2 / 3) < 2e-3
 
 
-def test_photon_paths_match_oracle(dev_scene, oracle, scene):
+def test_photon_paths_match_oracle(any_tier_scene, oracle, scene):
+    dev_scene = any_tier_scene
     """Same Philox sub-streams -> the same sequence of deposited texels, photon by photon.  The
     oracle evaluates sqrt/sin/cos in double like the reference, the kernel in float with SFU
     sin/cos, so a tiny share of paths may part ways at a texel border."""
@@ -120,7 +126,8 @@ def test_photon_paths_match_oracle(dev_scene, oracle, scene):
         assert (got[:, 0] == want[:, 0]).mean() > 0.9995
 
 
-def test_budgets_and_counters_are_exact(dev_scene, oracle, scene):
+def test_budgets_and_counters_are_exact(any_tier_scene, oracle, scene):
+    dev_scene = any_tier_scene
     """Photon budget per emitter follows photonmap.c:414-418; counters agree with the oracle run
     on the same Philox streams (rays/deposits may differ by the few border paths above)."""
     spa, depth = 20000, 8
@@ -323,3 +330,50 @@ def test_in_library_multi_gpu_bake(fmgi, scene):
         for k in ("photons", "rays", "deposits", "mirror_bounces"):
             assert stg[k] == st1[k], (g, k)
         assert np.allclose(texg, tex1, rtol=1e-5, atol=5e-2)
+
+
+# ---- grid tier on the synthetic multi-room layouts (BASELINE.json configs[2]) -------------------------------
+
+
+@pytest.mark.parametrize("tier", ["soup", "grid"])
+def test_synth800_closest_hit_and_bake(fmgi, oracle, synth800, tier):
+    sc = synth800
+    s = fmgi.DeviceScene(sc.walls, sc.windows, sc.lights, sc.num_texels,
+                         tier=fmgi.TIER_SOUP if tier == "soup" else fmgi.TIER_GRID)
+    o, d = random_rays(sc, 300_000, 21)
+    gi, gt = s.closest_hit(o, d)
+    ci, ct = oracle.closest_hit(sc.walls, o, d, oracle.ACCEL_LINEAR)
+    assert (gi != ci).mean() < 1e-5
+    both = (gi >= 0) & (gi == ci)
+    assert np.max(np.abs(gt[both] - ct[both]) / np.maximum(ct[both], 1e-4)) < 1e-4
+    spa, depth = 3000, 5
+    atlas, st = gpu_bake(s, spa, max_depth=depth, seed=3)
+    want, so = oracle.bake(sc, spa, depth, oracle.ACCEL_LINEAR, oracle.RNG_PHILOX, 3)
+    assert st["photons"] == so["photons"]
+    assert abs(st["deposits"] - so["deposits"]) <= 3e-4 * so["deposits"]
+    assert abs(atlas[:, :3].sum(dtype=np.float64) / want[:, :3].sum(dtype=np.float64) - 1) < 3e-4
+    e = len(sc.windows) + 2                     # a ceiling light
+    got = s.paths(e, depth, 9, 0, 8000)
+    ref = oracle.trace_paths(sc, e, depth, 9, 0, 8000)
+    assert np.all(got == ref, axis=1).mean() > 0.995
+    s.close()
+
+
+def test_synth4000_grid_tier(fmgi, oracle, synth4000):
+    """~21.5k rectangles, 1228 emitters, 0.46 GB atlas: AUTO picks the grid tier."""
+    sc = synth4000
+    s = fmgi.DeviceScene(sc.walls, sc.windows, sc.lights, sc.num_texels)
+    o, d = random_rays(sc, 40_000, 5)
+    gi, gt = s.closest_hit(o, d)
+    ci, ct = oracle.closest_hit(sc.walls, o, d, oracle.ACCEL_LINEAR)
+    assert (gi != ci).mean() < 5e-5
+    both = (gi >= 0) & (gi == ci)
+    assert np.max(np.abs(gt[both] - ct[both]) / np.maximum(ct[both], 1e-4)) < 1e-4
+    spa, depth = 25, 4                         # the oracle's linear scan costs 21.5k tests per ray
+    atlas, st = gpu_bake(s, spa, max_depth=depth, seed=3)
+    assert st["tier"] == fmgi.TIER_GRID
+    assert st["photons"] == sum(sc.photon_counts(spa))
+    want, so = oracle.bake(sc, spa, depth, oracle.ACCEL_LINEAR, oracle.RNG_PHILOX, 3)
+    assert abs(st["deposits"] - so["deposits"]) <= 1e-3 * so["deposits"] + 2
+    assert abs(atlas[:, :3].sum(dtype=np.float64) / want[:, :3].sum(dtype=np.float64) - 1) < 1e-3
+    s.close()
