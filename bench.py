@@ -30,26 +30,33 @@ ROOT = Path(__file__).resolve().parent
 sys.path.insert(0, str(ROOT / "flatmatch-global-illumination_b200"))
 
 WORKLOADS = {
-    # name: (scene fixture, total photons per GPU, depth)
-    "example_1e8x3": ("example_scene.npz", 1.0e8, 3),          # BASELINE.json configs[1]
-    "example_default_x8": ("example_scene.npz", 1.538e9, 8),   # configs[0]: reference default density
-    "example_1e9x4": ("example_scene.npz", 1.0e9, 4),          # north_star target
-    "synth4000_1e9x4": ("synth4000_scene.npz", 1.0e9, 4),      # configs[2]: ~21.5k rectangles, 0.46 GB atlas
-    "synth800_1e8x4": ("synth800_scene.npz", 1.0e8, 4),
+    # name: (scene fixture, total photons per GPU, depth, lightmap texels per m^2 (0 = as parsed, 200))
+    "example_1e8x3": ("example_scene.npz", 1.0e8, 3, 0),          # BASELINE.json configs[1]
+    "example_default_x8": ("example_scene.npz", 1.538e9, 8, 0),   # configs[0]: reference default density
+    "example_1e9x4": ("example_scene.npz", 1.0e9, 4, 0),          # north_star target
+    "synth4000_1e9x4": ("synth4000_scene.npz", 1.0e9, 4, 0),      # configs[2]: ~21.5k rectangles, 0.46 GB atlas
+    "synth4000_hires_1e9x4": ("synth4000_scene.npz", 1.0e9, 4, 800),  # configs[3]: 4x texel density, 1.8 GB atlas
+    "synth800_1e8x4": ("synth800_scene.npz", 1.0e8, 4, 0),
 }
 METRIC = "photon-bounces/sec (device-timed)"
 UNIT = "bounces/s"
 
 
-def load_scene(name):
-    """Rect tables of the fixture as plain numpy (no oracle code involved)."""
+def load_scene(name, tile_size=0):
+    """Rect tables of the fixture as plain numpy (no oracle code involved).  tile_size > 0 rebuilds
+    the lightmap layout at that texel density (fmgi.layout.retile)."""
     import fmgi
+    from fmgi import layout
 
     z = np.load(ROOT / "tests" / "golden" / name)
-    walls = fmgi.aligned_rects(z["walls"].view(fmgi.RECT_DTYPE))
+    walls = z["walls"].view(fmgi.RECT_DTYPE)
+    num_texels = int(z["num_texels"])
+    if tile_size:
+        walls, num_texels = layout.retile(walls, float(tile_size))
+    walls = fmgi.aligned_rects(walls)
     windows = fmgi.aligned_rects(z["windows"].view(fmgi.RECT_DTYPE))
     lights = fmgi.aligned_rects(z["lights"].view(fmgi.RECT_DTYPE))
-    return walls, windows, lights, int(z["num_texels"])
+    return walls, windows, lights, num_texels
 
 
 def emitter_area(windows, lights):
@@ -168,9 +175,10 @@ def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    fixture, _photons, depth = WORKLOADS[args.workload]
+    fixture, _photons, depth, _tile = WORKLOADS[args.workload]
     cores = os.cpu_count() or 1
-    spa = args.cpu_spa
+    _w, windows, lights, _n = load_scene(fixture)
+    spa = max(int(args.cpu_photons / emitter_area(windows, lights)), 1)
     for _ in range(args.warmup):
         cpu_reference_rate(fixture, depth, max(spa // 10, 1000), cores)
     t_total, d_total, kind = 0.0, 0, "port"
@@ -179,7 +187,8 @@ def run_reference_arm(args):
         t_total += secs
         d_total += dep
     value = d_total / t_total
-    sample = f"{cores} processes x spa={spa} ({spa * 15.38:.3g} photons each) per step, depth {depth}, srand seeds distinct"
+    sample = (f"{cores} processes x spa={spa} ({args.cpu_photons:.3g} photons each) per step, depth {depth}, "
+              f"distinct srand seeds, BSP build included")
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_total / max(args.steps, 1),
@@ -212,12 +221,12 @@ def run_ours(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
-    fixture, photons, depth = WORKLOADS[args.workload]
+    fixture, photons, depth, tile_size = WORKLOADS[args.workload]
     if args.photons:
         photons = args.photons
     if args.depth:
         depth = args.depth
-    walls, windows, lights, num_texels = load_scene(fixture)
+    walls, windows, lights, num_texels = load_scene(fixture, tile_size)
     area = emitter_area(windows, lights)
     spa_gpu = int(photons / area)                 # per-GPU density
     spa_job = spa_gpu * world                     # weak scaling: the job grows with N
@@ -313,7 +322,9 @@ def run_ours(args):
                        "emitters": int(len(windows) + len(lights)), "atlas_texels": num_texels,
                        "photons_per_gpu_per_step": photons_all / world / args.steps, "depth": depth,
                        "samples_per_area_per_gpu": spa_gpu, "parallelism": f"photon-range shards x{world}",
-                       "l2": "flushed between steps (192 MiB fill); atlas (1.8 MB) is L2-resident by design",
+                       "atlas_bytes": atlas_bytes, "texels_per_m2": tile_size or 200,
+                       "tier": ["auto", "soup", "grid"][st["tier"]],
+                       "l2": "flushed between steps (192 MiB fill)",
                        "deposit": ["vec4", "scalar", "warp_agg"][args.deposit]},
             "rays_per_s": rays_all / (ms * 1e-3), "photons_per_s": photons_all / (ms * 1e-3),
             "kernel_ms_per_step": kms,
@@ -330,11 +341,12 @@ def run_ours(args):
         }
         if world == 1 and not args.no_cpu:
             cores = os.cpu_count() or 1
-            rate, kind, dep, secs = cpu_reference_rate(fixture, depth, args.cpu_spa, cores)
+            cpu_spa = max(int(args.cpu_photons / area), 1)
+            rate, kind, dep, secs = cpu_reference_rate(fixture, depth, cpu_spa, cores)
             line["cpu_baseline"] = {
                 "value": rate, "unit": UNIT, "cores": cores, "kind": kind,
-                "sample": f"{cores} processes x spa={args.cpu_spa} of the same scene/depth "
-                          f"({dep:.3g} bounces, {secs:.1f} s)"}
+                "sample": f"{cores} processes x {args.cpu_photons:.3g} photons (spa={cpu_spa}) of the same "
+                          f"scene/depth, BSP build included ({dep:.3g} bounces, {secs:.1f} s)"}
         print(json.dumps(line))
     scene.close()
     if world > 1:
@@ -353,7 +365,7 @@ def main():
     ap.add_argument("--seed", type=int, default=1)
     ap.add_argument("--deposit", type=int, default=0)
     ap.add_argument("--e2e-steps", type=int, default=3)
-    ap.add_argument("--cpu-spa", type=int, default=100_000, help="CPU legs: density per process per step")
+    ap.add_argument("--cpu-photons", type=float, default=1.5e6, help="CPU legs: photons per process per step")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -12,6 +12,7 @@
 #include <thread>
 #include <vector>
 
+#include "mem_pool.h"
 #include "trace_core.cuh"
 
 using namespace fmgi;
@@ -66,7 +67,7 @@ cudaError_t upload(T **dst, const std::vector<T> &src)
 {
     *dst = nullptr;
     size_t bytes = src.size() * sizeof(T);
-    cudaError_t e = cudaMalloc((void **)dst, bytes ? bytes : sizeof(T));
+    cudaError_t e = MemPool::get().alloc((void **)dst, bytes ? bytes : sizeof(T), false);
     if (e != cudaSuccess) return e;
     if (bytes) e = cudaMemcpy(*dst, src.data(), bytes, cudaMemcpyHostToDevice);
     return e;
@@ -196,6 +197,8 @@ void fmgi_default_options(fmgi_options *opt)
 const char *fmgi_last_error(void) { return g_last_error.c_str(); }
 const char *fmgi_version(void) { return "fmgi-b200 0.1 (sm_100a)"; }
 
+void fmgi_release_cache(void) { MemPool::get().release(); }
+
 int fmgi_device_count(void)
 {
     int n = 0;
@@ -255,10 +258,11 @@ int fmgi_scene_create(fmgi_scene **out, const fmgi_rect *walls, int num_walls, c
     FMGI_CUDA(upload(&s->d_shade, s->host.shade));
     FMGI_CUDA(upload(&s->d_emitters, s->host.emitters));
     const size_t E = s->host.emitters.size();
-    FMGI_CUDA(cudaMalloc((void **)&s->d_jobs, (2 * E + 2) * sizeof(unsigned long long)));
-    FMGI_CUDA(cudaMalloc((void **)&s->d_counters, 8 * sizeof(unsigned long long)));
-    FMGI_CUDA(cudaMallocHost((void **)&s->h_jobs, (2 * E + 2) * sizeof(unsigned long long)));
-    FMGI_CUDA(cudaMallocHost((void **)&s->h_counters, 8 * sizeof(unsigned long long)));
+    MemPool &pool = MemPool::get();
+    FMGI_CUDA(pool.alloc((void **)&s->d_jobs, (2 * E + 2) * sizeof(unsigned long long), false));
+    FMGI_CUDA(pool.alloc((void **)&s->d_counters, 8 * sizeof(unsigned long long), false));
+    FMGI_CUDA(pool.alloc((void **)&s->h_jobs, (2 * E + 2) * sizeof(unsigned long long), true));
+    FMGI_CUDA(pool.alloc((void **)&s->h_counters, 8 * sizeof(unsigned long long), true));
     memset(s->h_counters, 0, 8 * sizeof(unsigned long long));
     FMGI_CUDA(cudaEventCreate(&s->ev_start));
     FMGI_CUDA(cudaEventCreate(&s->ev_stop));
@@ -282,10 +286,13 @@ void fmgi_scene_destroy(fmgi_scene *s)
 {
     if (!s) return;
     DeviceGuard guard(s->device);
-    cudaFree(s->d_axis); cudaFree(s->d_general); cudaFree(s->d_shade); cudaFree(s->d_emitters);
-    cudaFree(s->d_grid_recs); cudaFree(s->d_grid_ranges);
-    cudaFree(s->d_jobs); cudaFree(s->d_counters);
-    cudaFreeHost(s->h_jobs); cudaFreeHost(s->h_counters);
+    if (s->traced) cudaEventSynchronize(s->ev_stop);      // blocks go back to the pool: nothing may still use them
+    if (s->last_stream || s->traced) cudaStreamSynchronize(s->last_stream);
+    MemPool &pool = MemPool::get();
+    pool.free(s->d_axis); pool.free(s->d_general); pool.free(s->d_shade); pool.free(s->d_emitters);
+    pool.free(s->d_grid_recs); pool.free(s->d_grid_ranges);
+    pool.free(s->d_jobs); pool.free(s->d_counters);
+    pool.free(s->h_jobs); pool.free(s->h_counters);
     if (s->ev_start) cudaEventDestroy(s->ev_start);
     if (s->ev_stop) cudaEventDestroy(s->ev_stop);
     delete s;
@@ -403,7 +410,7 @@ int fmgi_bake(struct Geometry *geo_, int spa, const fmgi_options *opt, fmgi_stat
         if (rc) return bail(rc);
         cudaSetDevice(og.device);
         if (cudaStreamCreateWithFlags(&me.stream, cudaStreamNonBlocking) != cudaSuccess ||
-            cudaMalloc((void **)&me.atlas, atlas_bytes ? atlas_bytes : 16) != cudaSuccess)
+            MemPool::get().alloc((void **)&me.atlas, atlas_bytes ? atlas_bytes : 16, false) != cudaSuccess)
             return bail(fail(FMGI_ERR_CUDA, "atlas allocation failed"));
         const double t0 = now_ms();
         cudaError_t e;
@@ -451,7 +458,7 @@ int fmgi_bake(struct Geometry *geo_, int spa, const fmgi_options *opt, fmgi_stat
                 if (can) peers.push_back(gpus[g].atlas);
                 else {
                     float4 *tmp = nullptr;
-                    e = cudaMalloc((void **)&tmp, atlas_bytes ? atlas_bytes : 16);
+                    e = MemPool::get().alloc((void **)&tmp, atlas_bytes ? atlas_bytes : 16, false);
                     if (e == cudaSuccess)
                         e = cudaMemcpyPeer(tmp, dev0, gpus[g].atlas, gpus[g].scene->device, atlas_bytes);
                     staged.push_back(tmp);
@@ -459,7 +466,7 @@ int fmgi_bake(struct Geometry *geo_, int spa, const fmgi_options *opt, fmgi_stat
                 }
             }
             const float4 **d_peers = nullptr;
-            if (e == cudaSuccess) e = cudaMalloc((void **)&d_peers, peers.size() * sizeof(float4 *));
+            if (e == cudaSuccess) e = MemPool::get().alloc((void **)&d_peers, peers.size() * sizeof(float4 *), false);
             if (e == cudaSuccess)
                 e = cudaMemcpy(d_peers, peers.data(), peers.size() * sizeof(float4 *), cudaMemcpyHostToDevice);
             if (e == cudaSuccess && geo->numTexels > 0) {
@@ -470,8 +477,8 @@ int fmgi_bake(struct Geometry *geo_, int spa, const fmgi_options *opt, fmgi_stat
                 e = cudaGetLastError();
                 if (e == cudaSuccess) e = cudaStreamSynchronize(gpus[0].stream);
             }
-            cudaFree(d_peers);
-            for (float4 *t : staged) cudaFree(t);
+            MemPool::get().free(d_peers);
+            for (float4 *t : staged) MemPool::get().free(t);
             reduce_ms = now_ms() - t0;
         }
         if (e == cudaSuccess) {
@@ -502,9 +509,10 @@ int fmgi_bake(struct Geometry *geo_, int spa, const fmgi_options *opt, fmgi_stat
     }
     for (int g = 0; g < G; g++) {
         if (gpus[g].scene) cudaSetDevice(gpus[g].scene->device);
-        if (gpus[g].atlas) cudaFree(gpus[g].atlas);
-        if (gpus[g].stream) cudaStreamDestroy(gpus[g].stream);
+        if (gpus[g].stream) cudaStreamSynchronize(gpus[g].stream);
         fmgi_scene_destroy(gpus[g].scene);
+        if (gpus[g].atlas) MemPool::get().free(gpus[g].atlas);
+        if (gpus[g].stream) cudaStreamDestroy(gpus[g].stream);
     }
     if (stats) stats->total_ms = now_ms() - t_begin;
     return rc;

@@ -67,6 +67,7 @@ class Stats(C.Structure):
 
 EXPORTS = [
     "performGlobalIlluminationCl", "fmgi_default_options", "fmgi_last_error", "fmgi_version", "fmgi_device_count",
+    "fmgi_release_cache",
     "fmgi_bake", "fmgi_scene_create", "fmgi_scene_destroy", "fmgi_scene_trace", "fmgi_scene_sync",
     "fmgi_scene_photon_count", "fmgi_probe_closest_hit", "fmgi_probe_tile_ids", "fmgi_probe_philox",
     "fmgi_probe_sample_dirs", "fmgi_probe_paths",

@@ -110,6 +110,9 @@ void        fmgi_default_options(fmgi_options *opt);
 const char *fmgi_last_error(void);
 const char *fmgi_version(void);
 int         fmgi_device_count(void);
+/* The library keeps freed device / pinned blocks in a process-wide cache so that repeated bakes do
+ * not pay cudaMalloc/cudaFree again; this returns the cached blocks to the driver. */
+void        fmgi_release_cache(void);
 
 /* Host-buffer bake with options: what performGlobalIlluminationCl wraps. */
 int fmgi_bake(struct Geometry *geo, int numSamplesPerArea, const fmgi_options *opt, fmgi_stats *stats);

@@ -142,3 +142,18 @@ def test_product_never_touches_the_oracle():
     for f in list(pkg.rglob("*.py")) + list(pkg.rglob("*.cu*")) + list(pkg.rglob("*.cpp")) + list(pkg.rglob("*.h")):
         txt = f.read_text()
         assert "refbind" not in txt and "photon_oracle" not in txt and "libfmgi_ref" not in txt, f
+
+
+@pytest.mark.parametrize("fixture", ["example_scene.npz", "synth800_scene.npz", "synth4000_scene.npz"])
+def test_retile_reproduces_the_reference_layout(fixture):
+    """fmgi.layout.retile at TILE_SIZE 200 must give exactly the tile grids and atlas offsets
+    parseLayout/createRectangleV produced (rectangle.c:24-42, parseLayout.c:512-517)."""
+    import refbind
+    from fmgi import layout
+
+    sc = refbind.Scene.load(GOLDEN / fixture)
+    walls, num_texels = layout.retile(sc.walls, 200.0)
+    assert num_texels == sc.num_texels
+    assert np.array_equal(walls["lightmapSetup"], sc.walls["lightmapSetup"])
+    hi, n_hi = layout.retile(sc.walls[:200], 800.0)
+    assert n_hi > 3.5 * layout.retile(sc.walls[:200], 200.0)[1]
