@@ -8,6 +8,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <memory>
+#include <mutex>
 #include <string>
 #include <thread>
 #include <vector>
@@ -225,10 +226,24 @@ int fmgi_scene_create(fmgi_scene **out, const fmgi_rect *walls, int num_walls, c
     if (why[0]) return fail(FMGI_ERR_ARG, why);
 
     DeviceGuard guard(o.device);
-    cudaDeviceProp prop;
-    FMGI_CUDA(cudaGetDeviceProperties(&prop, o.device));
-    s->num_sms = prop.multiProcessorCount;
-    FMGI_CUDA(cudaDeviceGetAttribute(&s->clock_khz, cudaDevAttrClockRate, o.device));
+    // cudaGetDeviceProperties costs about a millisecond per call: query the three attributes we need
+    struct { size_t sharedMemPerBlockOptin; } prop;
+    {
+        // device attributes do not change; cudaDevAttrClockRate in particular is slow to query
+        struct Attr { int valid, sms, smem_optin, clock_khz; };
+        static Attr cache[64];
+        static std::mutex mu;
+        std::lock_guard<std::mutex> lock(mu);
+        Attr &a = cache[o.device & 63];
+        if (!a.valid) {
+            FMGI_CUDA(cudaDeviceGetAttribute(&a.sms, cudaDevAttrMultiProcessorCount, o.device));
+            FMGI_CUDA(cudaDeviceGetAttribute(&a.smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, o.device));
+            FMGI_CUDA(cudaDeviceGetAttribute(&a.clock_khz, cudaDevAttrClockRate, o.device));
+            a.valid = 1;
+        }
+        s->num_sms = a.sms; s->clock_khz = a.clock_khz;
+        prop.sharedMemPerBlockOptin = (size_t)a.smem_optin;
+    }
 
     // tier: brute force over the shared-memory soup for small scenes, floor-plan grid otherwise
     const size_t soup_bytes = s->host.axis.size() * sizeof(AxisPairBlock) + s->host.general.size() * sizeof(GeneralRect);
@@ -236,7 +251,7 @@ int fmgi_scene_create(fmgi_scene **out, const fmgi_rect *walls, int num_walls, c
     int tier = o.tier;
     if (const char *v = getenv("FMGI_TIER")) tier = atoi(v);
     if (tier != FMGI_TIER_SOUP && tier != FMGI_TIER_GRID)
-        tier = (colliders <= 1024 && soup_bytes <= (size_t)prop.sharedMemPerBlockOptin) ? FMGI_TIER_SOUP : FMGI_TIER_GRID;
+        tier = (colliders <= 256 && soup_bytes <= (size_t)prop.sharedMemPerBlockOptin) ? FMGI_TIER_SOUP : FMGI_TIER_GRID;
     if (tier == FMGI_TIER_SOUP && soup_bytes > (size_t)prop.sharedMemPerBlockOptin)
         return fail(FMGI_ERR_UNSUPPORTED, "rectangle soup does not fit in shared memory; use FMGI_TIER_GRID");
     s->tier = tier;
@@ -392,7 +407,7 @@ int fmgi_bake(struct Geometry *geo_, int spa, const fmgi_options *opt, fmgi_stat
         fmgi_stats st;
         int rc = FMGI_OK;
         std::string err;
-        double h2d_ms = 0;
+        double h2d_ms = 0, create_ms = 0, sync_ms = 0;
     };
     std::vector<PerGpu> gpus(G);
 
@@ -405,9 +420,11 @@ int fmgi_bake(struct Geometry *geo_, int spa, const fmgi_options *opt, fmgi_stat
         og.num_shards = o.num_shards * G;
         og.shard = o.shard * G + g;
         if (cudaSetDevice(og.device) != cudaSuccess) return bail(fail(FMGI_ERR_CUDA, "cudaSetDevice failed"));
+        const double tc0 = now_ms();
         int rc = fmgi_scene_create(&me.scene, geo->walls, geo->numWalls, geo->windows, geo->numWindows, geo->lights,
                                    geo->numLights, geo->numTexels, &og);
         if (rc) return bail(rc);
+        me.create_ms = now_ms() - tc0;
         cudaSetDevice(og.device);
         if (cudaStreamCreateWithFlags(&me.stream, cudaStreamNonBlocking) != cudaSuccess ||
             MemPool::get().alloc((void **)&me.atlas, atlas_bytes ? atlas_bytes : 16, false) != cudaSuccess)
@@ -420,10 +437,12 @@ int fmgi_bake(struct Geometry *geo_, int spa, const fmgi_options *opt, fmgi_stat
         if (e == cudaSuccess) e = cudaStreamSynchronize(me.stream);
         if (e != cudaSuccess) return bail(fail(FMGI_ERR_CUDA, std::string("atlas upload: ") + cudaGetErrorString(e)));
         me.h2d_ms = now_ms() - t0;
+        const double ts0 = now_ms();
         rc = fmgi_scene_trace(me.scene, me.atlas, spa, &og, me.stream);
         if (rc) return bail(rc);
         rc = fmgi_scene_sync(me.scene, &me.st);
         if (rc) return bail(rc);
+        me.sync_ms = now_ms() - ts0;
     };
 
     if (G == 1) worker(0);
@@ -515,6 +534,10 @@ int fmgi_bake(struct Geometry *geo_, int spa, const fmgi_options *opt, fmgi_stat
         if (gpus[g].stream) cudaStreamDestroy(gpus[g].stream);
     }
     if (stats) stats->total_ms = now_ms() - t_begin;
+    if (getenv("FMGI_DEBUG_TIMING"))
+        fprintf(stderr, "[fmgi] bake: total %.3f ms (scene %.3f, h2d %.3f, trace+sync host %.3f [device %.3f], fold %.3f, "
+                        "d2h %.3f)\n", now_ms() - t_begin, gpus[0].create_ms, gpus[0].h2d_ms, gpus[0].sync_ms,
+                gpus[0].st.trace_ms, reduce_ms, d2h_ms);
     return rc;
 }
 

@@ -253,22 +253,36 @@ void build_grid(HostScene &out, const fmgi_rect *walls, int num_walls, const fmg
     for (size_t p = 0; p < up.size(); p++) g.plane_z[p] = up[p];
     for (size_t p = 0; p < down.size(); p++) g.plane_z[kMaxPlanesPerSign + p] = down[p];
 
-    // lists are numbered: [0, 8) planes +z, [8, 16) planes -z, 16 = walk list
-    const int num_lists = 2 * kMaxPlanesPerSign + 1;
-    auto list_of = [&](const Item &it) { return it.list < 0 ? 2 * kMaxPlanesPerSign : it.list; };
+    // lists are numbered: [0, 8) planes +z, [8, 16) planes -z, 16 + combo = walk lists, where
+    // combo = (d.x > 0) + 2 * (d.y > 0) is the sign combination of the rays that walk the list
+    const int num_lists = kNumGridLists;
+    auto for_each_list = [&](const Item &it, auto &&fn) {
+        if (it.list >= 0) { fn(it.list); return; }
+        const int k = (it.rec.tag >> 28) & 3, neg = (it.rec.tag >> 30) & 1;
+        for (int combo = 0; combo < 4; combo++) {
+            // normal +x is faced by d.x < 0 (combo bit 0 clear), normal -x by d.x > 0; same for y
+            if (k == 0 && ((combo & 1) != 0) != (neg != 0)) continue;
+            if (k == 1 && ((combo & 2) != 0) != (neg != 0)) continue;
+            fn(kWalkListBase + combo);
+        }
+    };
     std::vector<int32_t> count((size_t)num_lists * ncell + 1, 0);
     for (const Item &it : items)
-        for (int cy = it.cy0; cy <= it.cy1; cy++)
-            for (int cx = it.cx0; cx <= it.cx1; cx++)
-                count[(size_t)list_of(it) * ncell + cy * g.nx + cx]++;
+        for_each_list(it, [&](int l) {
+            for (int cy = it.cy0; cy <= it.cy1; cy++)
+                for (int cx = it.cx0; cx <= it.cx1; cx++)
+                    count[(size_t)l * ncell + cy * g.nx + cx]++;
+        });
     std::vector<int32_t> begin((size_t)num_lists * ncell + 1, 0);
     for (size_t i = 0; i < (size_t)num_lists * ncell; i++) begin[i + 1] = begin[i] + count[i];
     out.grid_recs.resize((size_t)begin[(size_t)num_lists * ncell]);
     std::vector<int32_t> fill(begin.begin(), begin.end() - 1);
     for (const Item &it : items)
-        for (int cy = it.cy0; cy <= it.cy1; cy++)
-            for (int cx = it.cx0; cx <= it.cx1; cx++)
-                out.grid_recs[(size_t)fill[(size_t)list_of(it) * ncell + cy * g.nx + cx]++] = it.rec;
+        for_each_list(it, [&](int l) {
+            for (int cy = it.cy0; cy <= it.cy1; cy++)
+                for (int cx = it.cx0; cx <= it.cx1; cx++)
+                    out.grid_recs[(size_t)fill[(size_t)l * ncell + cy * g.nx + cx]++] = it.rec;
+        });
     out.grid_ranges.resize((size_t)2 * num_lists * ncell);
     for (size_t i = 0; i < (size_t)num_lists * ncell; i++) {
         out.grid_ranges[2 * i] = begin[i];

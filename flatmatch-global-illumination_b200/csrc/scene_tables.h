@@ -70,13 +70,15 @@ static_assert(sizeof(EmitterRec) == 96, "EmitterRec is six float4");
 //     For every distinct (z, normal sign) plane there is one cell list per grid cell; a ray finds
 //     its crossing point with the plane, looks up that one cell and tests only its candidates;
 //   * everything else (vertical walls, arbitrarily oriented rectangles, horizontal rectangles
-//     beyond the plane table) is binned by its (x, y) bounding box into the "walk" list of every
+//     beyond the plane table) is binned by its (x, y) bounding box into the "walk" lists of every
 //     cell it overlaps and found by a 2-D DDA from the ray origin, which stops as soon as the
-//     next cell starts beyond the best hit so far.
+//     next cell starts beyond the best hit so far.  There are four walk lists per cell, one per
+//     sign combination (d.x > 0, d.y > 0) of the ray: a vertical wall is stored only in the two
+//     lists whose rays can face it (back-face culling, rectangle.c:70-72, done at build time).
 // Cell lists hold the 32-byte records inline (no index indirection): list (l, cell) is
-// recs[ranges[l * ncell + cell].x .. .y).
+// recs[ranges[l * ncell + cell].x .. .y); l < 16: planes, l = 16 + combo: walk lists.
 
-enum { kMaxPlanesPerSign = 8 };
+enum { kMaxPlanesPerSign = 8, kWalkListBase = 2 * kMaxPlanesPerSign, kNumGridLists = kWalkListBase + 4 };
 
 struct GridRec {
     float c;                // plane coordinate pos[k]
@@ -107,7 +109,7 @@ struct HostScene {
     std::vector<float> emitter_area;      // |w|*|h| in float (photonmap.c:417)
     // grid tier (filled by build_grid)
     GridDesc grid = {};
-    std::vector<int32_t> grid_ranges;     // 2 ints (begin, end) per (list, cell); lists: planes_up, planes_down, walk
+    std::vector<int32_t> grid_ranges;     // 2 ints (begin, end) per (list, cell); kNumGridLists lists
     std::vector<GridRec> grid_recs;
 };
 

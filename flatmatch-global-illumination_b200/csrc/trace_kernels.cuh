@@ -189,16 +189,13 @@ __device__ __forceinline__ int closest_hit_soup(const SoupTables &s, float ox, f
 
 struct GridHit { float best; int rec; };      // rec: index of the winning inline record, -1 = miss
 
-// One record of a walk list: axis-parallel rectangle with any normal axis, or a general rectangle.
-__device__ __forceinline__ void grid_test_walk(const TraceParams &p, int r, float ox, float oy, float oz,
-                                               float dx, float dy, float dz, float ix, float iy, float iz,
-                                               float &best, int &win)
+// Rare walk-list records: a horizontal rectangle beyond the plane table (k == 2) or an arbitrarily
+// oriented rectangle (k == 3).  These sit in all four walk lists, so facing is tested here.
+__device__ __noinline__ void grid_test_misc(const TraceParams &p, int r, float4 q0, float4 q1, float ox, float oy, float oz,
+                                            float dx, float dy, float dz, float &best, int &win)
 {
-    const float4 q0 = __ldg(p.grid_recs + 2 * r);
-    const float4 q1 = __ldg(p.grid_recs + 2 * r + 1);
     const int tag = __float_as_int(q1.y);
-    const int k = (tag >> 28) & 3;
-    if (k == 3) {
+    if (((tag >> 28) & 3) == 3) {
         // rectangle.c:67-95 for an arbitrarily oriented rectangle
         const float4 *g = p.general + 4 * (tag & 0x0fffffff);
         const float4 g0 = __ldg(g), g1 = __ldg(g + 1), g2 = __ldg(g + 2), g3 = __ldg(g + 3);
@@ -214,15 +211,10 @@ __device__ __forceinline__ void grid_test_walk(const TraceParams &p, int r, floa
         }
         return;
     }
-    const float ok = k == 0 ? ox : (k == 1 ? oy : oz);
-    const float dk = k == 0 ? dx : (k == 1 ? dy : dz);
-    const float ik = k == 0 ? ix : (k == 1 ? iy : iz);
-    const float oi = k == 0 ? oy : ox, di = k == 0 ? dy : dx;          // in-plane axes in ascending order
-    const float oj = k == 2 ? oy : oz, dj = k == 2 ? dy : dz;
-    const bool facing = (tag & (1 << 30)) ? dk > 0.0f : dk < 0.0f;    // back-face culling, rectangle.c:70-72
-    const float t = (q0.x - ok) * ik;
-    const float pi = fmaf(t, di, oi) - q0.y;
-    const float pj = fmaf(t, dj, oj) - q0.w;
+    const bool facing = (tag & (1 << 30)) ? dz > 0.0f : dz < 0.0f;    // back-face culling, rectangle.c:70-72
+    const float t = __fdividef(q0.x - oz, dz);
+    const float pi = fmaf(t, dx, ox) - q0.y;
+    const float pj = fmaf(t, dy, oy) - q0.w;
     if (facing && (__float_as_uint(t) < __float_as_uint(best)) && fabsf(pi) <= q0.z && fabsf(pj) <= q1.x) {
         best = t; win = r;
     }
@@ -258,7 +250,12 @@ __device__ __forceinline__ int closest_hit_grid(const TraceParams &p, float ox, 
         }
     }
 
-    // 2. everything else: 2-D DDA through the walk lists, until the next cell starts beyond the best hit
+    // 2. everything else: 2-D DDA through the walk lists of the ray's sign combination, until the
+    //    next cell starts beyond the best hit.  Cell stepping and record testing are flattened into
+    //    ONE loop in which every lane does exactly one thing per iteration (test its next record,
+    //    or step to its next cell): lanes with long lists and lanes crossing many empty cells keep
+    //    each other busy instead of waiting at the exit of nested loops (the nested version ran
+    //    with 4 of 32 lanes active, profiles/r1_v1_grid_ncu_summary.csv).
     {
         int cx = __float2int_rd((ox - g.x0) * g.inv_cell), cy = __float2int_rd((oy - g.y0) * g.inv_cell);
         cx = min(max(cx, 0), g.nx - 1); cy = min(max(cy, 0), g.ny - 1);
@@ -266,16 +263,46 @@ __device__ __forceinline__ int closest_hit_grid(const TraceParams &p, float ox, 
         float tmx = inf, tmy = inf, tdx = inf, tdy = inf;
         if (dx != 0.0f) { tmx = (g.x0 + (float)(cx + (dx > 0.0f ? 1 : 0)) * g.cell - ox) * ix; tdx = g.cell * fabsf(ix); }
         if (dy != 0.0f) { tmy = (g.y0 + (float)(cy + (dy > 0.0f ? 1 : 0)) * g.cell - oy) * iy; tdy = g.cell * fabsf(iy); }
-        const int2 *walk = p.grid_ranges + 2 * kMaxPlanesPerSign * ncell;
-        for (int guard = g.nx + g.ny + 2; guard > 0; guard--) {
-            const int2 range = __ldg(walk + cy * g.nx + cx);
-            tests += (unsigned)(range.y - range.x);
-            for (int r = range.x; r < range.y; r++)
-                grid_test_walk(p, r, ox, oy, oz, dx, dy, dz, ix, iy, iz, best, win);
-            const float t_next = fminf(tmx, tmy);
-            if (!(t_next < best)) break;
-            if (tmx < tmy) { cx += sx; tmx += tdx; } else { cy += sy; tmy += tdy; }
-            if (cx < 0 || cy < 0 || cx >= g.nx || cy >= g.ny) break;
+        const int combo = (dx > 0.0f ? 1 : 0) + (dy > 0.0f ? 2 : 0);
+        const int2 *walk = p.grid_ranges + (kWalkListBase + combo) * ncell;
+        int2 range = __ldg(walk + cy * g.nx + cx);
+        int r = range.x;
+        int guard = 4 * (g.nx + g.ny) + 64;
+        bool more = true;
+        while (more) {
+            if (r < range.y) {
+                const float4 q0 = __ldg(p.grid_recs + 2 * r);
+                const float4 q1 = __ldg(p.grid_recs + 2 * r + 1);
+                const int tag = __float_as_int(q1.y);
+                tests++;
+                if (tag & (2 << 28)) {
+                    grid_test_misc(p, r, q0, q1, ox, oy, oz, dx, dy, dz, best, win);
+                } else {
+                    // vertical wall, normal along x (k = 0) or y (k = 1); the list only holds walls this
+                    // ray can face.  In-plane axes: the other horizontal axis and z.
+                    const bool ky = (tag & (1 << 28)) != 0;
+                    const float t = (q0.x - (ky ? oy : ox)) * (ky ? iy : ix);
+                    const float pi = fmaf(t, ky ? dx : dy, ky ? ox : oy) - q0.y;
+                    const float pj = fmaf(t, dz, oz) - q0.w;
+                    if ((__float_as_uint(t) < __float_as_uint(best)) && fabsf(pi) <= q0.z && fabsf(pj) <= q1.x) {
+                        best = t; win = r;
+                    }
+                }
+                r++;
+            } else {
+                const float t_next = fminf(tmx, tmy);
+                if (!(t_next < best) || --guard < 0) {
+                    more = false;
+                } else {
+                    if (tmx < tmy) { cx += sx; tmx += tdx; } else { cy += sy; tmy += tdy; }
+                    if (cx < 0 || cy < 0 || cx >= g.nx || cy >= g.ny) {
+                        more = false;
+                    } else {
+                        range = __ldg(walk + cy * g.nx + cx);
+                        r = range.x;
+                    }
+                }
+            }
         }
     }
 

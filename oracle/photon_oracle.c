@@ -131,6 +131,7 @@ typedef struct {
     uint32_t photon_lo, photon_hi;
     uint32_t block[4];
     double roulette_next;
+    uint64_t seq;              /* ORC_RNG_SEQ31 state */
 } rng_t;
 
 static void rng_event(rng_t *g, uint32_t event)
@@ -148,6 +149,13 @@ static double rng_u01(rng_t *g, int slot)
 {
     if (g->mode == ORC_RNG_LIBC)
         return rand() / (double)RAND_MAX;
+    if (g->mode == ORC_RNG_SEQ31) {            /* splitmix64 (Steele, Lea, Flood 2014), top 31 bits */
+        uint64_t z = (g->seq += 0x9E3779B97F4A7C15ull);
+        z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+        z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+        z ^= z >> 31;
+        return (double)(z >> 33) / 2147483647.0;
+    }
     return (double)((float)(g->block[slot] >> 8) * (1.0f / 16777216.0f));
 }
 
@@ -375,7 +383,7 @@ static void trace_photon(const scene_t *s, const orc_rect *src, int is_window, r
         double roulette = g->roulette_next;            /* PHILOX: drawn by the previous event */
         rng_event(g, (uint32_t)depth + 1);
         if (pos.z < 0.0005 &&                                        /* :228 mirror, unattenuated */
-            (g->mode == ORC_RNG_LIBC ? rng_u01(g, 0) : roulette) < 0.75) {
+            (g->mode != ORC_RNG_PHILOX ? rng_u01(g, 0) : roulette) < 0.75) {
             dir = vsub(dir, vmul(n, 2 * vdot(n, dir)));              /* :230 */
             st->mirror_bounces++;
         } else {
@@ -408,6 +416,7 @@ void orc_bake(const orc_rect *walls, int num_walls, const orc_rect *windows, int
     rng_t g;
     memset(&g, 0, sizeof g);
     g.mode = rng;
+    g.seq = 0x1234567ull * (seed + 1);
     if (num_shards < 1) { num_shards = 1; shard = 0; }
 
     for (int e = 0; e < num_windows + num_lights; e++) {

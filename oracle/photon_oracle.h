@@ -27,7 +27,10 @@ typedef struct __attribute__((aligned(16))) orc_rect {
     int32_t lm[4];
 } orc_rect;
 
-enum { ORC_RNG_LIBC = 0, ORC_RNG_PHILOX = 1 };
+/* ORC_RNG_SEQ31: a sequential splitmix64 stream drawn in the reference's order and resolution
+ * (31-bit value / 2147483647, like rand()/(double)RAND_MAX) - isolates effects of glibc's additive
+ * lagged-Fibonacci rand() from effects of the draw order. */
+enum { ORC_RNG_LIBC = 0, ORC_RNG_PHILOX = 1, ORC_RNG_SEQ31 = 2 };
 enum { ORC_ACCEL_BSP = 0, ORC_ACCEL_LINEAR = 1 };
 
 typedef struct orc_stats {
