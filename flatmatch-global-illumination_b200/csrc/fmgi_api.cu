@@ -17,6 +17,7 @@
 #include "trace_core.cuh"
 
 using namespace fmgi;
+#define COMMA ,
 
 namespace {
 
@@ -99,6 +100,8 @@ struct fmgi_scene {
     uint64_t launches = 0;
     uint64_t tests_per_ray = 0;
     int min_blocks = 4;                         // resident CTAs per SM the trace kernel is compiled for
+    int shade_eighths = 4;                      // k_trace_grid refill threshold (FMGI_TUNE_THRESH)
+    bool grid_nested = false;                   // grid tier: one-ray-at-a-time kernel instead of the interleaved one
 };
 
 namespace {
@@ -121,6 +124,7 @@ TraceParams base_params(const fmgi_scene *s)
     p.photon_first = s->d_jobs + (p.num_emitters + 1);
     p.work_counter = s->d_counters + 4;
     p.counters = s->d_counters;
+    p.shade_eighths = s->shade_eighths;
     return p;
 }
 
@@ -143,31 +147,36 @@ unsigned long long fill_jobs(const fmgi_scene *s, int spa, const fmgi_options &o
 }
 
 // Picks the instantiation for (tier, deposit, probe, resident CTAs per SM) and applies `fn` to it.
+// Grid tier: k_trace_grid (walk steps of different rays interleaved) unless `nested` asks for the
+// one-ray-at-a-time k_trace<GRID> kept for comparison (FMGI_GRID_KERNEL=0).
 template <typename Fn>
-cudaError_t with_trace_kernel(int tier, int deposit, bool probe, int min_blocks, Fn fn)
+cudaError_t with_trace_kernel(int tier, int deposit, bool probe, int min_blocks, bool nested, Fn fn)
 {
-#define FMGI_PICK(T, D, P, B) return fn(k_trace<T, D, P, B>)
-#define FMGI_PICK_DEPOSIT(T, B)                                                   \
-    switch (deposit) {                                                            \
-        case FMGI_DEPOSIT_SCALAR: FMGI_PICK(T, FMGI_DEPOSIT_SCALAR, false, B);    \
-        case FMGI_DEPOSIT_WARP_AGG: FMGI_PICK(T, FMGI_DEPOSIT_WARP_AGG, false, B);\
-        default: FMGI_PICK(T, FMGI_DEPOSIT_VEC4, false, B);                       \
+#define FMGI_PICK_DEPOSIT(KERNEL_PREFIX, B)                                                          \
+    switch (deposit) {                                                                               \
+        case FMGI_DEPOSIT_SCALAR: return fn(KERNEL_PREFIX FMGI_DEPOSIT_SCALAR, false, B>);           \
+        case FMGI_DEPOSIT_WARP_AGG: return fn(KERNEL_PREFIX FMGI_DEPOSIT_WARP_AGG, false, B>);       \
+        default: return fn(KERNEL_PREFIX FMGI_DEPOSIT_VEC4, false, B>);                              \
+    }
+    if (tier == FMGI_TIER_GRID && !nested) {
+        if (probe) return fn(k_trace_grid<FMGI_DEPOSIT_VEC4, true, 3>);
+        if (min_blocks == 3) { FMGI_PICK_DEPOSIT(k_trace_grid<, 3) }
+        FMGI_PICK_DEPOSIT(k_trace_grid<, 4)
     }
     if (tier == FMGI_TIER_GRID) {
-        if (probe) FMGI_PICK(FMGI_TIER_GRID, FMGI_DEPOSIT_VEC4, true, 3);
-        if (min_blocks == 3) { FMGI_PICK_DEPOSIT(FMGI_TIER_GRID, 3) }
-        FMGI_PICK_DEPOSIT(FMGI_TIER_GRID, 4)
+        if (probe) return fn(k_trace<FMGI_TIER_GRID, FMGI_DEPOSIT_VEC4, true, 3>);
+        if (min_blocks == 3) { FMGI_PICK_DEPOSIT(k_trace<FMGI_TIER_GRID COMMA, 3) }
+        FMGI_PICK_DEPOSIT(k_trace<FMGI_TIER_GRID COMMA, 4)
     }
-    if (probe) FMGI_PICK(FMGI_TIER_SOUP, FMGI_DEPOSIT_VEC4, true, 3);
-    if (min_blocks == 3) { FMGI_PICK_DEPOSIT(FMGI_TIER_SOUP, 3) }
-    FMGI_PICK_DEPOSIT(FMGI_TIER_SOUP, 4)
+    if (probe) return fn(k_trace<FMGI_TIER_SOUP, FMGI_DEPOSIT_VEC4, true, 3>);
+    if (min_blocks == 3) { FMGI_PICK_DEPOSIT(k_trace<FMGI_TIER_SOUP COMMA, 3) }
+    FMGI_PICK_DEPOSIT(k_trace<FMGI_TIER_SOUP COMMA, 4)
 #undef FMGI_PICK_DEPOSIT
-#undef FMGI_PICK
 }
 
 cudaError_t launch_trace(fmgi_scene *s, const TraceParams &p, int deposit, bool probe, int blocks, cudaStream_t st)
 {
-    return with_trace_kernel(s->tier, deposit, probe, s->min_blocks, [&](auto kernel) {
+    return with_trace_kernel(s->tier, deposit, probe, s->min_blocks, s->grid_nested, [&](auto kernel) {
         cudaError_t e = cudaSuccess;
         if (s->smem_bytes > 48 * 1024)
             e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->smem_bytes);
@@ -284,7 +293,9 @@ int fmgi_scene_create(fmgi_scene **out, const fmgi_rect *walls, int num_walls, c
 
     if (const char *v = getenv("FMGI_TUNE_BLOCKS")) s->min_blocks = atoi(v) == 3 ? 3 : 4;   // tuning knob
     fmgi_scene *sp = s.get();
-    FMGI_CUDA(with_trace_kernel(s->tier, FMGI_DEPOSIT_VEC4, false, s->min_blocks, [&](auto kernel) {
+    if (const char *v = getenv("FMGI_GRID_KERNEL")) s->grid_nested = atoi(v) == 0;           // tuning knob
+    if (const char *v = getenv("FMGI_TUNE_THRESH")) s->shade_eighths = atoi(v);
+    FMGI_CUDA(with_trace_kernel(s->tier, FMGI_DEPOSIT_VEC4, false, s->min_blocks, s->grid_nested, [&](auto kernel) {
         cudaError_t e = cudaSuccess;
         if (sp->smem_bytes > 48 * 1024)
             e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sp->smem_bytes);

@@ -58,6 +58,7 @@ struct TraceParams {
     int32_t *path_out;              // probe builds only
     int max_depth;
     uint32_t seed;
+    int shade_eighths;              // k_trace_grid: shade when 8 * waiting >= shade_eighths * live lanes
 };
 
 // ---- closest hit against the shared-memory soup ----------------------------------------------
@@ -191,13 +192,16 @@ struct GridHit { float best; int rec; };      // rec: index of the winning inlin
 
 // Rare walk-list records: a horizontal rectangle beyond the plane table (k == 2) or an arbitrarily
 // oriented rectangle (k == 3).  These sit in all four walk lists, so facing is tested here.
-__device__ __noinline__ void grid_test_misc(const TraceParams &p, int r, float4 q0, float4 q1, float ox, float oy, float oz,
-                                            float dx, float dy, float dz, float &best, int &win)
+// Returns the ray parameter of a valid hit closer than `best`, else +inf (by value: the caller's
+// running minimum stays in registers).
+__device__ __noinline__ float grid_test_misc(const float4 *__restrict__ general, float4 q0, float4 q1, float ox, float oy,
+                                             float oz, float dx, float dy, float dz, float best)
 {
+    const float inf = __int_as_float(0x7f800000);
     const int tag = __float_as_int(q1.y);
     if (((tag >> 28) & 3) == 3) {
         // rectangle.c:67-95 for an arbitrarily oriented rectangle
-        const float4 *g = p.general + 4 * (tag & 0x0fffffff);
+        const float4 *g = general + 4 * (tag & 0x0fffffff);
         const float4 g0 = __ldg(g), g1 = __ldg(g + 1), g2 = __ldg(g + 2), g3 = __ldg(g + 3);
         const float denom = g0.x * dx + g0.y * dy + g0.z * dz;
         const float num = g0.w - (g0.x * ox + g0.y * oy + g0.z * oz);
@@ -205,129 +209,151 @@ __device__ __noinline__ void grid_test_misc(const TraceParams &p, int r, float4 
         const float ex = fmaf(t, dx, ox) - g3.x, ey = fmaf(t, dy, oy) - g3.y, ez = fmaf(t, dz, oz) - g3.z;
         const float u = g1.x * ex + g1.y * ey + g1.z * ez;
         const float v = g2.x * ex + g2.y * ey + g2.z * ez;
-        if (denom < 0.0f && (__float_as_uint(t) < __float_as_uint(best)) && u >= 0.0f && v >= 0.0f && u <= g1.w &&
-            v <= g2.w) {
-            best = t; win = r;
-        }
-        return;
+        const bool ok = denom < 0.0f && (__float_as_uint(t) < __float_as_uint(best)) && u >= 0.0f && v >= 0.0f &&
+                        u <= g1.w && v <= g2.w;
+        return ok ? t : inf;
     }
     const bool facing = (tag & (1 << 30)) ? dz > 0.0f : dz < 0.0f;    // back-face culling, rectangle.c:70-72
     const float t = __fdividef(q0.x - oz, dz);
     const float pi = fmaf(t, dx, ox) - q0.y;
     const float pj = fmaf(t, dy, oy) - q0.w;
-    if (facing && (__float_as_uint(t) < __float_as_uint(best)) && fabsf(pi) <= q0.z && fabsf(pj) <= q1.x) {
-        best = t; win = r;
-    }
+    const bool ok = facing && (__float_as_uint(t) < __float_as_uint(best)) && fabsf(pi) <= q0.z && fabsf(pj) <= q1.x;
+    return ok ? t : inf;
 }
+
+// Closest-hit query through the grid, split into begin / step / finish so that the trace kernel
+// can interleave the steps of different rays (see k_trace_grid).
+struct GridWalk {
+    float best;            // ray parameter of the best hit so far (+inf: none)
+    int win;               // inline record index of the best hit, -1: none
+    float ix, iy;          // 1/d.x, 1/d.y
+    float tmx, tmy;        // ray parameter at which the walk leaves the current cell along x / y
+    int cx, cy;            // current cell
+    int r, rend;           // pending records of the current cell
+    int guard;
+
+    // Phase 1 (horizontal planes the ray can face: one cell lookup per plane at the crossing point)
+    // and DDA set-up.  Returns false if the walk has nothing to do.
+    __device__ __forceinline__ void begin(const TraceParams &p, float ox, float oy, float oz, float dx, float dy,
+                                          float dz, unsigned &tests)
+    {
+        const GridDesc &g = p.grid;
+        const int ncell = g.nx * g.ny;
+        const float inf = __int_as_float(0x7f800000);
+        best = inf;
+        win = -1;
+        ix = __frcp_rn(dx); iy = __frcp_rn(dy);
+        if (dz != 0.0f) {
+            const float iz = __frcp_rn(dz);
+            const int first = dz < 0.0f ? 0 : kMaxPlanesPerSign;             // d.z < 0 faces normals +z
+            const int count = dz < 0.0f ? g.planes_up : g.planes_down;
+            for (int pl = 0; pl < count; pl++) {
+                const float t = (g.plane_z[first + pl] - oz) * iz;
+                if (!(__float_as_uint(t) < __float_as_uint(best))) continue;
+                const float x = fmaf(t, dx, ox), y = fmaf(t, dy, oy);
+                const int px = __float2int_rd((x - g.x0) * g.inv_cell), py = __float2int_rd((y - g.y0) * g.inv_cell);
+                if (px < 0 || py < 0 || px >= g.nx || py >= g.ny) continue;
+                const int2 range = __ldg(p.grid_ranges + (first + pl) * ncell + py * g.nx + px);
+                for (int q = range.x; q < range.y; q++) {
+                    const float4 q0 = __ldg(p.grid_recs + 2 * q);
+                    const float4 q1 = __ldg(p.grid_recs + 2 * q + 1);
+                    tests++;
+                    if (fabsf(x - q0.y) <= q0.z && fabsf(y - q0.w) <= q1.x) { best = t; win = q; break; }
+                }
+            }
+        }
+        cx = __float2int_rd((ox - g.x0) * g.inv_cell); cy = __float2int_rd((oy - g.y0) * g.inv_cell);
+        cx = min(max(cx, 0), g.nx - 1); cy = min(max(cy, 0), g.ny - 1);
+        tmx = inf; tmy = inf;
+        if (dx != 0.0f) tmx = (g.x0 + (float)(cx + (dx > 0.0f ? 1 : 0)) * g.cell - ox) * ix;
+        if (dy != 0.0f) tmy = (g.y0 + (float)(cy + (dy > 0.0f ? 1 : 0)) * g.cell - oy) * iy;
+        const int combo = (dx > 0.0f ? 1 : 0) + (dy > 0.0f ? 2 : 0);
+        const int2 range = __ldg(p.grid_ranges + (kWalkListBase + combo) * ncell + cy * g.nx + cx);
+        r = range.x; rend = range.y;
+        guard = 4 * (g.nx + g.ny) + 64;
+    }
+
+    // Phase 2, one step of the 2-D DDA through the walk lists of the ray's sign combination: test the
+    // next pending record, or move to the next cell.  Cell stepping and record testing are
+    // flattened into one loop in which every lane does exactly one thing per step, so lanes with
+    // long lists and lanes crossing empty cells keep each other busy (the nested-loop version ran
+    // with 4 of 32 lanes active, profiles/r1_v1_grid_ncu_summary.csv).  Returns false when the walk
+    // is over: the next cell starts beyond the best hit, or the ray left the grid.
+    __device__ __forceinline__ bool step(const TraceParams &p, float ox, float oy, float oz, float dx, float dy,
+                                         float dz, unsigned &tests)
+    {
+        const GridDesc &g = p.grid;
+        if (r < rend) {
+            const float4 q0 = __ldg(p.grid_recs + 2 * r);
+            const float4 q1 = __ldg(p.grid_recs + 2 * r + 1);
+            const int tag = __float_as_int(q1.y);
+            tests++;
+            if (tag & (2 << 28)) {
+                const float t = grid_test_misc(p.general, q0, q1, ox, oy, oz, dx, dy, dz, best);
+                if (t < best) { best = t; win = r; }
+            } else {
+                // vertical wall, normal along x (k = 0) or y (k = 1); the list only holds walls this ray
+                // can face (back-face culling done at build time).  In-plane axes: the other horizontal
+                // axis and z.
+                const bool ky = (tag & (1 << 28)) != 0;
+                const float t = (q0.x - (ky ? oy : ox)) * (ky ? iy : ix);
+                const float pi = fmaf(t, ky ? dx : dy, ky ? ox : oy) - q0.y;
+                const float pj = fmaf(t, dz, oz) - q0.w;
+                if ((__float_as_uint(t) < __float_as_uint(best)) && fabsf(pi) <= q0.z && fabsf(pj) <= q1.x) {
+                    best = t; win = r;
+                }
+            }
+            r++;
+            return true;
+        }
+        const float t_next = fminf(tmx, tmy);
+        if (!(t_next < best) || --guard < 0) return false;
+        if (tmx < tmy) { cx += dx > 0.0f ? 1 : -1; tmx += g.cell * fabsf(ix); }
+        else { cy += dy > 0.0f ? 1 : -1; tmy += g.cell * fabsf(iy); }
+        if (cx < 0 || cy < 0 || cx >= g.nx || cy >= g.ny) return false;
+        const int combo = (dx > 0.0f ? 1 : 0) + (dy > 0.0f ? 2 : 0);
+        const int2 range = __ldg(p.grid_ranges + (kWalkListBase + combo) * (g.nx * g.ny) + cy * g.nx + cx);
+        r = range.x; rend = range.y;
+        return true;
+    }
+
+    // Wall index of the winner (-1: miss) and its distance recomputed with the reference's formula.
+    __device__ __forceinline__ int finish(const TraceParams &p, float ox, float oy, float oz, float dx, float dy,
+                                          float dz, float &t_out) const
+    {
+        int id = -1;
+        t_out = best;
+        if (win >= 0) {
+            const float4 q0 = __ldg(p.grid_recs + 2 * win);
+            const int tag = __float_as_int(__ldg(p.grid_recs + 2 * win + 1).y);
+            const int k = (tag >> 28) & 3;
+            if (k == 3) {
+                const float4 *gg = p.general + 4 * (tag & 0x0fffffff);
+                const float4 g0 = __ldg(gg), g3 = __ldg(gg + 3);
+                id = __float_as_int(g3.w);
+                const float denom = __fadd_rn(__fadd_rn(__fmul_rn(g0.x, dx), __fmul_rn(g0.y, dy)), __fmul_rn(g0.z, dz));
+                const float num = __fadd_rn(__fadd_rn(__fmul_rn(g0.x, __fsub_rn(g3.x, ox)),
+                                                      __fmul_rn(g0.y, __fsub_rn(g3.y, oy))),
+                                            __fmul_rn(g0.z, __fsub_rn(g3.z, oz)));
+                t_out = __fdiv_rn(num, denom);
+            } else {
+                id = tag & 0x0fffffff;
+                const float ok = k == 0 ? ox : (k == 1 ? oy : oz);
+                const float dk = k == 0 ? dx : (k == 1 ? dy : dz);
+                t_out = __fdiv_rn(__fsub_rn(q0.x, ok), dk);
+            }
+        }
+        return id;
+    }
+};
 
 __device__ __forceinline__ int closest_hit_grid(const TraceParams &p, float ox, float oy, float oz,
                                                 float dx, float dy, float dz, float &t_out, unsigned &tests)
 {
-    const GridDesc &g = p.grid;
-    const int ncell = g.nx * g.ny;
-    const float inf = __int_as_float(0x7f800000);
-    float best = inf;
-    int win = -1;
-    const float ix = __frcp_rn(dx), iy = __frcp_rn(dy), iz = __frcp_rn(dz);
-
-    // 1. horizontal planes the ray can face: one cell lookup per plane at the crossing point
-    if (dz != 0.0f) {
-        const int first = dz < 0.0f ? 0 : kMaxPlanesPerSign;                 // d.z < 0 faces normals +z
-        const int count = dz < 0.0f ? g.planes_up : g.planes_down;
-        for (int pl = 0; pl < count; pl++) {
-            const float t = (g.plane_z[first + pl] - oz) * iz;
-            if (!(__float_as_uint(t) < __float_as_uint(best))) continue;
-            const float x = fmaf(t, dx, ox), y = fmaf(t, dy, oy);
-            const int cx = __float2int_rd((x - g.x0) * g.inv_cell), cy = __float2int_rd((y - g.y0) * g.inv_cell);
-            if (cx < 0 || cy < 0 || cx >= g.nx || cy >= g.ny) continue;
-            const int2 range = __ldg(p.grid_ranges + (first + pl) * ncell + cy * g.nx + cx);
-            for (int r = range.x; r < range.y; r++) {
-                const float4 q0 = __ldg(p.grid_recs + 2 * r);
-                const float4 q1 = __ldg(p.grid_recs + 2 * r + 1);
-                tests++;
-                if (fabsf(x - q0.y) <= q0.z && fabsf(y - q0.w) <= q1.x) { best = t; win = r; break; }
-            }
-        }
-    }
-
-    // 2. everything else: 2-D DDA through the walk lists of the ray's sign combination, until the
-    //    next cell starts beyond the best hit.  Cell stepping and record testing are flattened into
-    //    ONE loop in which every lane does exactly one thing per iteration (test its next record,
-    //    or step to its next cell): lanes with long lists and lanes crossing many empty cells keep
-    //    each other busy instead of waiting at the exit of nested loops (the nested version ran
-    //    with 4 of 32 lanes active, profiles/r1_v1_grid_ncu_summary.csv).
-    {
-        int cx = __float2int_rd((ox - g.x0) * g.inv_cell), cy = __float2int_rd((oy - g.y0) * g.inv_cell);
-        cx = min(max(cx, 0), g.nx - 1); cy = min(max(cy, 0), g.ny - 1);
-        const int sx = dx > 0.0f ? 1 : -1, sy = dy > 0.0f ? 1 : -1;
-        float tmx = inf, tmy = inf, tdx = inf, tdy = inf;
-        if (dx != 0.0f) { tmx = (g.x0 + (float)(cx + (dx > 0.0f ? 1 : 0)) * g.cell - ox) * ix; tdx = g.cell * fabsf(ix); }
-        if (dy != 0.0f) { tmy = (g.y0 + (float)(cy + (dy > 0.0f ? 1 : 0)) * g.cell - oy) * iy; tdy = g.cell * fabsf(iy); }
-        const int combo = (dx > 0.0f ? 1 : 0) + (dy > 0.0f ? 2 : 0);
-        const int2 *walk = p.grid_ranges + (kWalkListBase + combo) * ncell;
-        int2 range = __ldg(walk + cy * g.nx + cx);
-        int r = range.x;
-        int guard = 4 * (g.nx + g.ny) + 64;
-        bool more = true;
-        while (more) {
-            if (r < range.y) {
-                const float4 q0 = __ldg(p.grid_recs + 2 * r);
-                const float4 q1 = __ldg(p.grid_recs + 2 * r + 1);
-                const int tag = __float_as_int(q1.y);
-                tests++;
-                if (tag & (2 << 28)) {
-                    grid_test_misc(p, r, q0, q1, ox, oy, oz, dx, dy, dz, best, win);
-                } else {
-                    // vertical wall, normal along x (k = 0) or y (k = 1); the list only holds walls this
-                    // ray can face.  In-plane axes: the other horizontal axis and z.
-                    const bool ky = (tag & (1 << 28)) != 0;
-                    const float t = (q0.x - (ky ? oy : ox)) * (ky ? iy : ix);
-                    const float pi = fmaf(t, ky ? dx : dy, ky ? ox : oy) - q0.y;
-                    const float pj = fmaf(t, dz, oz) - q0.w;
-                    if ((__float_as_uint(t) < __float_as_uint(best)) && fabsf(pi) <= q0.z && fabsf(pj) <= q1.x) {
-                        best = t; win = r;
-                    }
-                }
-                r++;
-            } else {
-                const float t_next = fminf(tmx, tmy);
-                if (!(t_next < best) || --guard < 0) {
-                    more = false;
-                } else {
-                    if (tmx < tmy) { cx += sx; tmx += tdx; } else { cy += sy; tmy += tdy; }
-                    if (cx < 0 || cy < 0 || cx >= g.nx || cy >= g.ny) {
-                        more = false;
-                    } else {
-                        range = __ldg(walk + cy * g.nx + cx);
-                        r = range.x;
-                    }
-                }
-            }
-        }
-    }
-
-    int id = -1;
-    t_out = best;
-    if (win >= 0) {
-        const float4 q0 = __ldg(p.grid_recs + 2 * win);
-        const int tag = __float_as_int(__ldg(p.grid_recs + 2 * win + 1).y);
-        const int k = (tag >> 28) & 3;
-        if (k == 3) {
-            const float4 *gg = p.general + 4 * (tag & 0x0fffffff);
-            const float4 g0 = __ldg(gg), g3 = __ldg(gg + 3);
-            id = __float_as_int(g3.w);
-            const float denom = __fadd_rn(__fadd_rn(__fmul_rn(g0.x, dx), __fmul_rn(g0.y, dy)), __fmul_rn(g0.z, dz));
-            const float num = __fadd_rn(__fadd_rn(__fmul_rn(g0.x, __fsub_rn(g3.x, ox)), __fmul_rn(g0.y, __fsub_rn(g3.y, oy))),
-                                        __fmul_rn(g0.z, __fsub_rn(g3.z, oz)));
-            t_out = __fdiv_rn(num, denom);
-        } else {
-            id = tag & 0x0fffffff;
-            const float ok = k == 0 ? ox : (k == 1 ? oy : oz);
-            const float dk = k == 0 ? dx : (k == 1 ? dy : dz);
-            t_out = __fdiv_rn(__fsub_rn(q0.x, ok), dk);
-        }
-    }
-    return id;
+    GridWalk w;
+    w.begin(p, ox, oy, oz, dx, dy, dz, tests);
+    while (w.step(p, ox, oy, oz, dx, dy, dz, tests)) {}
+    return w.finish(p, ox, oy, oz, dx, dy, dz, t_out);
 }
 
 // ---- texel index: rectangle.c:205-230, same operations in the same order, no contraction ----------
