@@ -17,9 +17,11 @@
 #include "trace_core.cuh"
 
 using namespace fmgi;
-#define COMMA ,
 
 namespace {
+
+// photons per fp32 accumulation pass (see fmgi_scene_trace)
+constexpr unsigned long long kAccumPhotons = 1ull << 28;
 
 thread_local std::string g_last_error;
 
@@ -87,7 +89,9 @@ struct fmgi_scene {
     EmitterRec *d_emitters = nullptr;
     GridRec *d_grid_recs = nullptr;             // grid tier
     int32_t *d_grid_ranges = nullptr;
-    unsigned long long *d_jobs = nullptr;       // job_begin[E+1] then photon_first[E]
+    unsigned long long *d_jobs = nullptr;       // per accumulation pass: job_begin[E+1] then photon_first[E]
+    size_t job_tables = 0;                      // passes the job-table buffers have room for
+    float4 *d_scratch = nullptr;                // per-pass fp32 atlas when a bake needs several passes
     unsigned long long *d_counters = nullptr;   // 4 counters + work counter
     unsigned long long *h_jobs = nullptr;       // pinned staging
     unsigned long long *h_counters = nullptr;   // pinned
@@ -100,8 +104,6 @@ struct fmgi_scene {
     uint64_t launches = 0;
     uint64_t tests_per_ray = 0;
     int min_blocks = 4;                         // resident CTAs per SM the trace kernel is compiled for
-    int shade_eighths = 4;                      // k_trace_grid refill threshold (FMGI_TUNE_THRESH)
-    bool grid_nested = false;                   // grid tier: one-ray-at-a-time kernel instead of the interleaved one
 };
 
 namespace {
@@ -124,7 +126,6 @@ TraceParams base_params(const fmgi_scene *s)
     p.photon_first = s->d_jobs + (p.num_emitters + 1);
     p.work_counter = s->d_counters + 4;
     p.counters = s->d_counters;
-    p.shade_eighths = s->shade_eighths;
     return p;
 }
 
@@ -147,36 +148,29 @@ unsigned long long fill_jobs(const fmgi_scene *s, int spa, const fmgi_options &o
 }
 
 // Picks the instantiation for (tier, deposit, probe, resident CTAs per SM) and applies `fn` to it.
-// Grid tier: k_trace_grid (walk steps of different rays interleaved) unless `nested` asks for the
-// one-ray-at-a-time k_trace<GRID> kept for comparison (FMGI_GRID_KERNEL=0).
 template <typename Fn>
-cudaError_t with_trace_kernel(int tier, int deposit, bool probe, int min_blocks, bool nested, Fn fn)
+cudaError_t with_trace_kernel(int tier, int deposit, bool probe, int min_blocks, Fn fn)
 {
-#define FMGI_PICK_DEPOSIT(KERNEL_PREFIX, B)                                                          \
-    switch (deposit) {                                                                               \
-        case FMGI_DEPOSIT_SCALAR: return fn(KERNEL_PREFIX FMGI_DEPOSIT_SCALAR, false, B>);           \
-        case FMGI_DEPOSIT_WARP_AGG: return fn(KERNEL_PREFIX FMGI_DEPOSIT_WARP_AGG, false, B>);       \
-        default: return fn(KERNEL_PREFIX FMGI_DEPOSIT_VEC4, false, B>);                              \
-    }
-    if (tier == FMGI_TIER_GRID && !nested) {
-        if (probe) return fn(k_trace_grid<FMGI_DEPOSIT_VEC4, true, 3>);
-        if (min_blocks == 3) { FMGI_PICK_DEPOSIT(k_trace_grid<, 3) }
-        FMGI_PICK_DEPOSIT(k_trace_grid<, 4)
+#define FMGI_PICK_DEPOSIT(T, B)                                                                  \
+    switch (deposit) {                                                                           \
+        case FMGI_DEPOSIT_SCALAR: return fn(k_trace<T, FMGI_DEPOSIT_SCALAR, false, B>);          \
+        case FMGI_DEPOSIT_WARP_AGG: return fn(k_trace<T, FMGI_DEPOSIT_WARP_AGG, false, B>);      \
+        default: return fn(k_trace<T, FMGI_DEPOSIT_VEC4, false, B>);                             \
     }
     if (tier == FMGI_TIER_GRID) {
         if (probe) return fn(k_trace<FMGI_TIER_GRID, FMGI_DEPOSIT_VEC4, true, 3>);
-        if (min_blocks == 3) { FMGI_PICK_DEPOSIT(k_trace<FMGI_TIER_GRID COMMA, 3) }
-        FMGI_PICK_DEPOSIT(k_trace<FMGI_TIER_GRID COMMA, 4)
+        if (min_blocks == 3) { FMGI_PICK_DEPOSIT(FMGI_TIER_GRID, 3) }
+        FMGI_PICK_DEPOSIT(FMGI_TIER_GRID, 4)
     }
     if (probe) return fn(k_trace<FMGI_TIER_SOUP, FMGI_DEPOSIT_VEC4, true, 3>);
-    if (min_blocks == 3) { FMGI_PICK_DEPOSIT(k_trace<FMGI_TIER_SOUP COMMA, 3) }
-    FMGI_PICK_DEPOSIT(k_trace<FMGI_TIER_SOUP COMMA, 4)
+    if (min_blocks == 3) { FMGI_PICK_DEPOSIT(FMGI_TIER_SOUP, 3) }
+    FMGI_PICK_DEPOSIT(FMGI_TIER_SOUP, 4)
 #undef FMGI_PICK_DEPOSIT
 }
 
 cudaError_t launch_trace(fmgi_scene *s, const TraceParams &p, int deposit, bool probe, int blocks, cudaStream_t st)
 {
-    return with_trace_kernel(s->tier, deposit, probe, s->min_blocks, s->grid_nested, [&](auto kernel) {
+    return with_trace_kernel(s->tier, deposit, probe, s->min_blocks, [&](auto kernel) {
         cudaError_t e = cudaSuccess;
         if (s->smem_bytes > 48 * 1024)
             e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->smem_bytes);
@@ -284,6 +278,7 @@ int fmgi_scene_create(fmgi_scene **out, const fmgi_rect *walls, int num_walls, c
     const size_t E = s->host.emitters.size();
     MemPool &pool = MemPool::get();
     FMGI_CUDA(pool.alloc((void **)&s->d_jobs, (2 * E + 2) * sizeof(unsigned long long), false));
+    s->job_tables = 1;
     FMGI_CUDA(pool.alloc((void **)&s->d_counters, 8 * sizeof(unsigned long long), false));
     FMGI_CUDA(pool.alloc((void **)&s->h_jobs, (2 * E + 2) * sizeof(unsigned long long), true));
     FMGI_CUDA(pool.alloc((void **)&s->h_counters, 8 * sizeof(unsigned long long), true));
@@ -293,9 +288,7 @@ int fmgi_scene_create(fmgi_scene **out, const fmgi_rect *walls, int num_walls, c
 
     if (const char *v = getenv("FMGI_TUNE_BLOCKS")) s->min_blocks = atoi(v) == 3 ? 3 : 4;   // tuning knob
     fmgi_scene *sp = s.get();
-    if (const char *v = getenv("FMGI_GRID_KERNEL")) s->grid_nested = atoi(v) == 0;           // tuning knob
-    if (const char *v = getenv("FMGI_TUNE_THRESH")) s->shade_eighths = atoi(v);
-    FMGI_CUDA(with_trace_kernel(s->tier, FMGI_DEPOSIT_VEC4, false, s->min_blocks, s->grid_nested, [&](auto kernel) {
+    FMGI_CUDA(with_trace_kernel(s->tier, FMGI_DEPOSIT_VEC4, false, s->min_blocks, [&](auto kernel) {
         cudaError_t e = cudaSuccess;
         if (sp->smem_bytes > 48 * 1024)
             e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sp->smem_bytes);
@@ -317,7 +310,7 @@ void fmgi_scene_destroy(fmgi_scene *s)
     MemPool &pool = MemPool::get();
     pool.free(s->d_axis); pool.free(s->d_general); pool.free(s->d_shade); pool.free(s->d_emitters);
     pool.free(s->d_grid_recs); pool.free(s->d_grid_ranges);
-    pool.free(s->d_jobs); pool.free(s->d_counters);
+    pool.free(s->d_jobs); pool.free(s->d_counters); pool.free(s->d_scratch);
     pool.free(s->h_jobs); pool.free(s->h_counters);
     if (s->ev_start) cudaEventDestroy(s->ev_start);
     if (s->ev_stop) cudaEventDestroy(s->ev_stop);
@@ -340,27 +333,70 @@ int fmgi_scene_trace(fmgi_scene *s, void *atlas_dev, int spa, const fmgi_options
     DeviceGuard guard(s->device);
     cudaStream_t st = (cudaStream_t)cuda_stream;
     const int E = (int)s->host.emitters.size();
+    const size_t table_words = (size_t)(2 * E + 2);
 
     if (s->traced) FMGI_CUDA(cudaEventSynchronize(s->ev_stop));   // pinned staging is reused
-    const unsigned long long total = fill_jobs(s, spa, o, s->h_jobs);
-    FMGI_CUDA(cudaMemcpyAsync(s->d_jobs, s->h_jobs, (2 * E + 2) * sizeof(unsigned long long),
+
+    // fp32 accumulation passes.  Every texel is a float sum of deposits of about 16; once a hot texel
+    // passes ~1e7 a single deposit is a few ulps and the sum drifts (measured: -0.054 % total energy at
+    // 4e9 photons on example.png; the reference has the same flaw, photonmap.c:251, at 1e3 x fewer
+    // photons per hour).  Above kAccumPhotons the shard is therefore traced in several passes into a
+    // zeroed scratch atlas that is added to the caller's atlas after each pass.  A pass is just a finer
+    // shard of the photon index space, so the sample set does not change.
+    std::vector<unsigned long long> whole(table_words);
+    const unsigned long long total_all = fill_jobs(s, spa, o, whole.data());
+    int passes = (int)((total_all + kAccumPhotons - 1) / kAccumPhotons);
+    if (const char *v = getenv("FMGI_ACCUM_PASSES")) passes = atoi(v);     // tuning / test knob
+    if (passes < 1) passes = 1;
+    MemPool &pool = MemPool::get();
+    if ((size_t)passes > s->job_tables) {
+        pool.free(s->d_jobs); pool.free(s->h_jobs);
+        s->d_jobs = nullptr; s->h_jobs = nullptr;
+        FMGI_CUDA(pool.alloc((void **)&s->d_jobs, passes * table_words * sizeof(unsigned long long), false));
+        FMGI_CUDA(pool.alloc((void **)&s->h_jobs, passes * table_words * sizeof(unsigned long long), true));
+        s->job_tables = (size_t)passes;
+    }
+    const size_t atlas_bytes = (size_t)s->host.num_texels * sizeof(float4);
+    if (passes > 1 && !s->d_scratch)
+        FMGI_CUDA(pool.alloc((void **)&s->d_scratch, atlas_bytes ? atlas_bytes : 16, false));
+
+    fmgi_options op = o;
+    op.num_shards = o.num_shards * passes;
+    std::vector<unsigned long long> totals(passes);
+    for (int c = 0; c < passes; c++) {
+        op.shard = o.shard * passes + c;
+        totals[c] = fill_jobs(s, spa, op, s->h_jobs + c * table_words);
+    }
+    FMGI_CUDA(cudaMemcpyAsync(s->d_jobs, s->h_jobs, passes * table_words * sizeof(unsigned long long),
                               cudaMemcpyHostToDevice, st));
     FMGI_CUDA(cudaMemsetAsync(s->d_counters, 0, 8 * sizeof(unsigned long long), st));
 
-    TraceParams p = base_params(s);
-    p.total_jobs = total;
-    p.atlas = reinterpret_cast<float4 *>(atlas_dev);
-    p.max_depth = o.max_depth;
-    p.seed = o.seed;
-
     FMGI_CUDA(cudaEventRecord(s->ev_start, st));
-    if (total > 0) {
+    for (int c = 0; c < passes; c++) {
+        if (totals[c] == 0) continue;
+        TraceParams p = base_params(s);
+        p.job_begin = s->d_jobs + c * table_words;
+        p.photon_first = p.job_begin + (E + 1);
+        p.total_jobs = totals[c];
+        p.atlas = reinterpret_cast<float4 *>(passes > 1 ? (void *)s->d_scratch : atlas_dev);
+        p.max_depth = o.max_depth;
+        p.seed = o.seed;
+        if (passes > 1) {
+            FMGI_CUDA(cudaMemsetAsync(s->d_scratch, 0, atlas_bytes, st));
+            FMGI_CUDA(cudaMemsetAsync(s->d_counters + 4, 0, sizeof(unsigned long long), st));   // work counter
+        }
         // persistent grid: one wave of resident CTAs, never more warps than chunks of work
-        unsigned long long want = (total + kChunkPhotons - 1) / kChunkPhotons;
+        unsigned long long want = (totals[c] + kChunkPhotons - 1) / kChunkPhotons;
         want = (want * 32 + kTraceThreads - 1) / kTraceThreads;
         const unsigned long long wave = (unsigned long long)s->num_sms * s->blocks_per_sm;
         const int blocks = (int)(want < wave ? (want ? want : 1) : wave);
         FMGI_CUDA(launch_trace(s, p, o.deposit, false, blocks, st));
+        if (passes > 1 && s->host.num_texels > 0) {
+            k_accumulate<<<s->num_sms * 8, 256, 0, st>>>(reinterpret_cast<float4 *>(atlas_dev), s->d_scratch,
+                                                         (size_t)s->host.num_texels);
+            s->launches++;
+            FMGI_CUDA(cudaGetLastError());
+        }
     }
     FMGI_CUDA(cudaEventRecord(s->ev_stop, st));
     FMGI_CUDA(cudaMemcpyAsync(s->h_counters, s->d_counters, 8 * sizeof(unsigned long long),

@@ -181,172 +181,6 @@ __global__ void __launch_bounds__(kTraceThreads, kMinBlocks) k_trace(const Trace
     }
 }
 
-// ---- grid tier, interleaved: k_trace_grid ------------------------------------------------------------
-//
-// Rays through the grid take very different numbers of steps (1 .. 20+ cells and records), so with
-// "every lane traces its ray to the end, then all lanes shade" the warp waits for its slowest ray
-// (11 of 32 lanes alive in the walk loop, profiles/r1_v2_grid_ncu_summary.csv).  Here the warp runs ONE loop
-// whose body is a single walk step; lanes whose walk is over wait until at least half of the warp's
-// live lanes are waiting (or nobody walks any more), and only then does the warp run the expensive,
-// warp-uniform "shade + refill + emit + begin next walk" block for exactly those lanes.  Both the
-// walk step and the shade block therefore run with at least about half of the lanes active.
-template <int kDeposit, bool kProbe, int kMinBlocks>
-__global__ void __launch_bounds__(kTraceThreads, kMinBlocks) k_trace_grid(const TraceParams p)
-{
-    const int lane = threadIdx.x & 31;
-    const unsigned lt_mask = (1u << lane) - 1u;
-    enum { kWalking = 0, kWaiting = 1, kIdle = 2 };      // kIdle: dead and no photons left to take
-
-    bool alive = false, is_new = false, mirror = false, has_ray = false;
-    int state = kWaiting;
-    float px = 0, py = 0, pz = 0, dx = 0, dy = 0, dz = 1;
-    float cr = 0, cg = 0, cb = 0, roulette = 0;
-    int depth = 0, emitter = 0, hit_id = 0;
-    unsigned long long photon = 0;
-    unsigned long long w_next = 0, w_end = 0;
-    int w_emitter = 0;
-    bool exhausted = false;
-    unsigned n_photons = 0, n_rays = 0, n_deposits = 0, n_mirror = 0, n_tests = 0;
-    GridWalk walk;
-
-    for (;;) {
-        const unsigned waiting = __ballot_sync(kFullMask, state == kWaiting);
-        const unsigned walking = __ballot_sync(kFullMask, state == kWalking);
-        if ((waiting | walking) == 0u) break;
-
-        if (waiting != 0u && (walking == 0u || 8 * __popc(waiting) >= p.shade_eighths * __popc(waiting | walking))) {
-            const bool me = state == kWaiting;
-
-            // ---- D. finish the ray that was walking: bounce bookkeeping (photonmap.c:200-247) ---------
-            bool dep = false;
-            int idx = 0;
-            if (me && has_ray) {
-                float t;
-                hit_id = walk.finish(p, px, py, pz, dx, dy, dz, t);
-                has_ray = false;
-                if (hit_id < 0) {
-                    alive = false;                               // photonmap.c:200-201
-                } else {
-                    px = __fadd_rn(px, __fmul_rn(dx, t));        // photonmap.c:208
-                    py = __fadd_rn(py, __fmul_rn(dy, t));
-                    pz = __fadd_rn(pz, __fmul_rn(dz, t));
-                    const float4 *sh = p.shade + 6 * hit_id;
-                    const float4 q0 = ldg4(sh), q1 = ldg4(sh + 1), q2 = ldg4(sh + 2), q3 = ldg4(sh + 3);
-                    idx = tile_index(q0, q1, q2, __float_as_int(q3.w), px, py, pz);   // photonmap.c:210-211
-                    mirror = pz < 0.0005f && roulette < 0.75f;   // photonmap.c:228
-                    if (!mirror) {
-                        if (pz < 1E-5f) { cg *= 0.85f; cb *= 0.7f; } // photonmap.c:236-246
-                        cr *= 0.9f; cg *= 0.9f; cb *= 0.9f;          // photonmap.c:247
-                    } else {
-                        n_mirror++;
-                    }
-                    dep = true;
-                    if (kProbe) p.path_out[(photon - __ldg(p.photon_first + emitter)) * p.max_depth + depth] = idx;
-                    depth++;
-                    n_deposits++;
-                    if (depth == p.max_depth) alive = false;     // photonmap.c:187
-                }
-            }
-            if (!kProbe) deposit<kDeposit>(p.atlas, idx, cr, cg, cb, dep);   // photonmap.c:251
-
-            // ---- A. refill the waiting lanes whose photon is finished -------------------------------------
-            is_new = false;
-            if (!exhausted) {
-                unsigned dead = __ballot_sync(kFullMask, me && !alive);
-                while (dead) {
-                    if (w_next == w_end) {
-                        unsigned long long base = 0;
-                        if (lane == 0) base = atomicAdd(p.work_counter, (unsigned long long)kChunkPhotons);
-                        base = __shfl_sync(kFullMask, base, 0);
-                        if (base >= p.total_jobs) { exhausted = true; break; }
-                        w_next = base;
-                        w_end = min(base + (unsigned long long)kChunkPhotons, p.total_jobs);
-                        w_emitter = find_emitter(p.job_begin, p.num_emitters, w_next);
-                    }
-                    const unsigned long long avail = w_end - w_next;
-                    const int rank = __popc(dead & lt_mask);
-                    if (me && !alive && (unsigned long long)rank < avail) {
-                        const unsigned long long job = w_next + (unsigned long long)rank;
-                        int e = w_emitter;
-                        while (job >= __ldg(p.job_begin + e + 1)) e++;
-                        emitter = e;
-                        photon = __ldg(p.photon_first + e) + (job - __ldg(p.job_begin + e));
-                        alive = true; is_new = true; depth = 0;
-                        n_photons++;
-                    }
-                    const unsigned long long want = (unsigned long long)__popc(dead);
-                    w_next += want < avail ? want : avail;
-                    dead = __ballot_sync(kFullMask, me && !alive);
-                }
-            }
-
-            // ---- P/S. next direction and the start of the next walk ----------------------------------------
-            if (me) {
-                if (!alive) {
-                    state = kIdle;             // no photon to take (work exhausted); may be revived never
-                    if (!exhausted) state = kWaiting;
-                } else {
-                    const Philox4 w = philox4x32_10((uint32_t)photon, (uint32_t)(photon >> 32), (uint32_t)depth, 0u,
-                                                    p.seed, (uint32_t)emitter);
-                    const float4 *frame = is_new ? p.emitters + 6 * emitter : p.shade + 6 * hit_id;
-                    const float4 fn = ldg4(frame + 3);
-                    if (is_new) {                                    // photonmap.c:169-185
-                        const float4 e0 = ldg4(frame), e1 = ldg4(frame + 1), e2 = ldg4(frame + 2);
-                        const bool sky = __float_as_int(e0.w) != 0;
-                        cr = sky ? 18.0f : 16.0f; cg = cr; cb = 18.0f;
-                        const float sx = u24(w.w0), sy = u24(w.w1);
-                        sample_hemisphere(u24(w.w2), u24(w.w3), sky, fn, ldg4(frame + 4), ldg4(frame + 5), dx, dy, dz);
-                        roulette = r16(w.w2, w.w3);
-                        px = __fadd_rn(__fadd_rn(__fadd_rn(e0.x, __fmul_rn(dx, 1E-5f)), __fmul_rn(e1.x, sx)), __fmul_rn(e2.x, sy));
-                        py = __fadd_rn(__fadd_rn(__fadd_rn(e0.y, __fmul_rn(dy, 1E-5f)), __fmul_rn(e1.y, sx)), __fmul_rn(e2.y, sy));
-                        pz = __fadd_rn(__fadd_rn(__fadd_rn(e0.z, __fmul_rn(dz, 1E-5f)), __fmul_rn(e1.z, sx)), __fmul_rn(e2.z, sy));
-                    } else {
-                        if (mirror) {                                // photonmap.c:230
-                            const float k2 = 2.0f * (fn.x * dx + fn.y * dy + fn.z * dz);
-                            dx = fmaf(-k2, fn.x, dx); dy = fmaf(-k2, fn.y, dy); dz = fmaf(-k2, fn.z, dz);
-                        } else {                                     // photonmap.c:233
-                            sample_hemisphere(u24(w.w0), u24(w.w1), false, fn, ldg4(frame + 4), ldg4(frame + 5), dx, dy, dz);
-                        }
-                        roulette = r16(w.w0, w.w1);
-                        px = __fadd_rn(px, __fmul_rn(dx, 1E-5f));    // photonmap.c:254
-                        py = __fadd_rn(py, __fmul_rn(dy, 1E-5f));
-                        pz = __fadd_rn(pz, __fmul_rn(dz, 1E-5f));
-                    }
-                    walk.begin(p, px, py, pz, dx, dy, dz, n_tests);  // photonmap.c:198 starts here
-                    n_rays++;
-                    has_ray = true;
-                    state = kWalking;
-                }
-            }
-        }
-
-        // ---- C. a few walk steps for every lane that has a ray in flight -------------------------------
-#pragma unroll 1
-        for (int rep = 0; rep < 4; rep++) {
-            if (state == kWalking) {
-                if (!walk.step(p, px, py, pz, dx, dy, dz, n_tests)) state = kWaiting;
-            }
-        }
-    }
-
-    unsigned long long c0 = n_photons, c1 = n_rays, c2 = n_deposits, c3 = n_mirror, c5 = n_tests;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        c0 += __shfl_xor_sync(kFullMask, c0, o);
-        c1 += __shfl_xor_sync(kFullMask, c1, o);
-        c2 += __shfl_xor_sync(kFullMask, c2, o);
-        c3 += __shfl_xor_sync(kFullMask, c3, o);
-        c5 += __shfl_xor_sync(kFullMask, c5, o);
-    }
-    if (lane == 0) {
-        atomicAdd(p.counters + 0, c0);
-        atomicAdd(p.counters + 1, c1);
-        atomicAdd(p.counters + 2, c2);
-        atomicAdd(p.counters + 3, c3);
-        atomicAdd(p.counters + 5, c5);
-    }
-}
-
 // ---- probe kernels: the same device functions, one item per thread --------------------------------------
 
 template <int kTier>
@@ -393,6 +227,17 @@ __global__ void k_probe_sample_dirs(float4 n, float4 u, float4 v, int sky, uint3
         float dx, dy, dz;
         sample_hemisphere(u24(w.w2), u24(w.w3), sky != 0, n, u, v, dx, dy, dz);
         out[3 * i] = dx; out[3 * i + 1] = dy; out[3 * i + 2] = dz;
+    }
+}
+
+// atlas += scratch (colour lanes only): folds one fp32 accumulation pass into the caller's atlas.
+__global__ void k_accumulate(float4 *__restrict__ atlas, const float4 *__restrict__ scratch, size_t n)
+{
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        float4 a = atlas[i];
+        const float4 b = scratch[i];
+        a.x += b.x; a.y += b.y; a.z += b.z;
+        atlas[i] = a;
     }
 }
 

@@ -377,3 +377,18 @@ def test_synth4000_grid_tier(fmgi, oracle, synth4000):
     assert abs(st["deposits"] - so["deposits"]) <= 1e-3 * so["deposits"] + 2
     assert abs(atlas[:, :3].sum(dtype=np.float64) / want[:, :3].sum(dtype=np.float64) - 1) < 1e-3
     s.close()
+
+
+def test_accumulation_passes_keep_the_sample_set(dev_scene, monkeypatch):
+    """Big bakes are traced in several fp32 accumulation passes (finer shards into a scratch atlas
+    that is folded into the caller's atlas): same photons, same counters, same sums."""
+    spa, depth = 60000, 6
+    monkeypatch.setenv("FMGI_ACCUM_PASSES", "1")
+    one, s1 = gpu_bake(dev_scene, spa, max_depth=depth, seed=17)
+    monkeypatch.setenv("FMGI_ACCUM_PASSES", "5")
+    five, s5 = gpu_bake(dev_scene, spa, max_depth=depth, seed=17)
+    for k in ("photons", "rays", "deposits", "mirror_bounces"):
+        assert s1[k] == s5[k]
+    assert s5["kernel_launches"] - s1["kernel_launches"] >= 9
+    assert np.allclose(one, five, rtol=1e-5, atol=1e-2)
+    assert np.all(five[:, 3] == 0)
