@@ -206,6 +206,39 @@ def run_reference_arm(args):
 # our arm
 # ---------------------------------------------------------------------------------------------------
 
+def ncu_facts(workload):
+    """Counters of the dominant kernel for this workload from the committed `ncu --set full` capture
+    (profiles/ncu_facts.json, written by profiles/summarize_ncu.py --facts); None if not captured."""
+    p = ROOT / "profiles" / "ncu_facts.json"
+    if not p.exists():
+        return None
+    return json.loads(p.read_text()).get(workload)
+
+
+def reference_app_wall_time():
+    """The other half of the BASELINE metric: wall time of the reference's untouched main.c linked
+    against libfmgi_cuda.so (process start -> last tile PNG written) on example.png with its default
+    1e8 photons/m^2 and 8 bounces.  None if the prebuilt binary or the layout is missing."""
+    import subprocess
+    import tempfile
+
+    app = ROOT / "flatmatch-global-illumination_b200" / "build" / "globalIllumination"
+    png = ROOT / "tests" / "golden" / "example.png"
+    if not app.exists() or not png.exists():
+        return None
+    with tempfile.TemporaryDirectory() as tmp:
+        os.mkdir(os.path.join(tmp, "tiles"))
+        best = None
+        for _ in range(2):
+            t0 = time.perf_counter()
+            r = subprocess.run([str(app), str(png)], cwd=tmp, capture_output=True)
+            dt = time.perf_counter() - t0
+            if r.returncode != 0:
+                return None
+            best = dt if best is None else min(best, dt)
+        return best
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -254,7 +287,8 @@ def run_ours(args):
     for _ in range(args.warmup):
         step()
     barrier()
-    kernel_ms, deposits, rays, photons_done, launches = [], 0, 0, 0, 0
+    kernel_ms, deposits, rays, photons_done = [], 0, 0, 0
+    launches0 = scene.sync()["kernel_launches"]
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     with ClockSampler(local) as clk:
         barrier()
@@ -264,10 +298,10 @@ def run_ours(args):
             st = scene.sync()                       # counters + CUDA-event time of the trace kernel
             kernel_ms.append(st["trace_ms"])
             deposits += st["deposits"]; rays += st["rays"]; photons_done += st["photons"]
-            launches += 1
         ev1.record(stream)
         barrier()
     ms = ev0.elapsed_time(ev1)
+    launches = st["kernel_launches"] - launches0          # our kernels inside the timed region (this rank)
     tests_per_ray = st["rect_tests"] / max(st["rays"], 1)
 
     tot = torch.tensor([float(deposits), float(rays), float(photons_done), ms, float(np.mean(kernel_ms))],
@@ -283,7 +317,7 @@ def run_ours(args):
     value = deposits_all / (ms * 1e-3)
 
     # ---- e2e: host buffers through the C-ABI call performGlobalIlluminationCl wraps ----------------
-    tex = fmgi.aligned_texels(num_texels)
+    tex = torch.zeros((num_texels, 4), dtype=torch.float32).pin_memory().numpy()    # pinned host atlas
     geo = fmgi.make_geometry(walls, windows, lights, tex)
     e2e_opts = dict(max_depth=depth, seed=args.seed, shard=rank, num_shards=world, device=local, deposit=args.deposit)
     fmgi.bake(geo, spa_job, **e2e_opts)            # warm-up (context, module load)
@@ -335,10 +369,19 @@ def run_ours(args):
                          "note": "algorithmic FP32 work per SURVEY.md 8(d): 13*T+150 flops per ray"},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": atlas_bytes + rect_bytes,
                     "d2h_bytes_per_step": atlas_bytes, "steps": args.e2e_steps,
-                    "api": "fmgi_bake (host Geometry in, host atlas out; what performGlobalIlluminationCl runs)"},
+                    "api": "fmgi_bake (host Geometry + pinned host atlas in, host atlas out; what "
+                           "performGlobalIlluminationCl runs: table build, H2D, trace, D2H every call)"},
             "gpu_launches": launches,
             "clocks": clk.summary(),
         }
+        facts = ncu_facts(args.workload) if not (args.photons or args.depth) else None
+        if facts and facts.get("tier") == line["config"]["tier"]:
+            line["roofline"]["traffic"] = facts.get("dram_bytes_per_launch")
+            line["roofline"]["ncu"] = facts
+        if world == 1 and args.workload.startswith("example") and not args.no_app:
+            wall = reference_app_wall_time()
+            if wall is not None:
+                line["example_bake_wall_s"] = wall
         if world == 1 and not args.no_cpu:
             cores = os.cpu_count() or 1
             cpu_spa = max(int(args.cpu_photons / area), 1)
@@ -367,6 +410,7 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--cpu-photons", type=float, default=1.5e6, help="CPU legs: photons per process per step")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-app", action="store_true", help="skip the example.png end-to-end wall-time run")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference_arm(args)

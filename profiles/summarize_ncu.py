@@ -35,7 +35,42 @@ KEEP = [
 ]
 
 
+def facts(rep, workload, tier, out_json, source):
+    """Adds the per-launch counters bench.py quotes (DRAM traffic, issue-slot and pipe utilisation) to
+    profiles/ncu_facts.json under `workload`."""
+    import json
+    import os
+
+    txt = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True, check=True).stdout
+    rows = list(csv.reader(io.StringIO(txt)))
+    d = dict(zip(rows[0], rows[2]))
+    u = dict(zip(rows[0], rows[1]))
+
+    def bytes_of(k):
+        scale = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}[u[k]]
+        return float(d[k]) * scale
+
+    entry = {
+        "kernel": d["Kernel Name"], "tier": tier, "source": source,
+        "duration_ms": float(d["gpu__time_duration.sum"]) * {"ms": 1, "us": 1e-3, "s": 1e3, "ns": 1e-6}[u["gpu__time_duration.sum"]],
+        "dram_bytes_per_launch": bytes_of("dram__bytes_read.sum") + bytes_of("dram__bytes_write.sum"),
+        "issue_active_pct": float(d["smsp__issue_active.avg.pct_of_peak_sustained_active"]),
+        "pipe_alu_pct": float(d["sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active"]),
+        "pipe_fma_pct": float(d["sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active"]),
+        "pipe_lsu_pct": float(d["sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active"]),
+        "smem_wavefronts_pct": float(d["l1tex__data_pipe_lsu_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed"]),
+        "threads_per_instruction": float(d["smsp__thread_inst_executed_per_inst_executed.ratio"]),
+        "registers_per_thread": int(float(d["launch__registers_per_thread"])),
+    }
+    allf = json.load(open(out_json)) if os.path.exists(out_json) else {}
+    allf[workload] = entry
+    json.dump(allf, open(out_json, "w"), indent=1, sort_keys=True)
+    print(json.dumps(entry, indent=1))
+
+
 def main():
+    if sys.argv[1] == "--facts":            # --facts <rep> <workload> <tier> <source label>
+        return facts(sys.argv[2], sys.argv[3], sys.argv[4], "profiles/ncu_facts.json", sys.argv[5])
     rep, out = sys.argv[1], sys.argv[2]
     launch = int(sys.argv[3]) if len(sys.argv) > 3 else 0
     txt = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True, check=True).stdout
