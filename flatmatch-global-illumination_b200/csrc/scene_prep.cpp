@@ -194,10 +194,12 @@ void build_grid(HostScene &out, const fmgi_rect *walls, int num_walls, const fmg
     float cell = cell_hint;
     if (!(cell > 0)) cell = sqrtf(w * h / fmaxf(1.0f, 0.5f * (float)num_walls));
     // keep the grid below 4M cells whatever the hint
-    while ((double)(w / cell + 3) * (double)(h / cell + 3) > 4.0e6) cell *= 1.5f;
+    while ((double)(w / cell + 5) * (double)(h / cell + 5) > 4.0e6) cell *= 1.5f;
     g.cell = cell; g.inv_cell = 1.0f / cell;
-    g.x0 = xmin - cell; g.y0 = ymin - cell;                 // one cell of margin all around
-    g.nx = (int)ceilf(w / cell) + 2; g.ny = (int)ceilf(h / cell) + 2;
+    // two cells of margin all around: the walk stops where the ray leaves the box that excludes the
+    // outermost ring (GridWalk::t_exit), so a step taken on a rounding error still lands on a cell
+    g.x0 = xmin - 2 * cell; g.y0 = ymin - 2 * cell;
+    g.nx = (int)ceilf(w / cell) + 4; g.ny = (int)ceilf(h / cell) + 4;
     const int ncell = g.nx * g.ny;
 
     // classify: which list does each wall go to, and with which record

@@ -229,12 +229,15 @@ struct GridWalk {
     int win;               // inline record index of the best hit, -1: none
     float ix, iy;          // 1/d.x, 1/d.y
     float tmx, tmy;        // ray parameter at which the walk leaves the current cell along x / y
-    int cx, cy;            // current cell
+    float tdx, tdy;        // ray parameter per cell along x / y
+    float t_exit;          // ray parameter at which the ray leaves the grid minus its outermost ring of cells
+    int ci;                // current cell, linear index cy * nx + cx
+    int sx, sy;            // linear-index step along x (+-1) and y (+-nx)
     int r, rend;           // pending records of the current cell
-    int guard;
+    const int2 *walk;      // the walk list ranges of this ray's sign combination
 
     // Phase 1 (horizontal planes the ray can face: one cell lookup per plane at the crossing point)
-    // and DDA set-up.  Returns false if the walk has nothing to do.
+    // and DDA set-up.
     __device__ __forceinline__ void begin(const TraceParams &p, float ox, float oy, float oz, float dx, float dy,
                                           float dz, unsigned &tests)
     {
@@ -263,15 +266,28 @@ struct GridWalk {
                 }
             }
         }
-        cx = __float2int_rd((ox - g.x0) * g.inv_cell); cy = __float2int_rd((oy - g.y0) * g.inv_cell);
+        int cx = __float2int_rd((ox - g.x0) * g.inv_cell), cy = __float2int_rd((oy - g.y0) * g.inv_cell);
         cx = min(max(cx, 0), g.nx - 1); cy = min(max(cy, 0), g.ny - 1);
-        tmx = inf; tmy = inf;
-        if (dx != 0.0f) tmx = (g.x0 + (float)(cx + (dx > 0.0f ? 1 : 0)) * g.cell - ox) * ix;
-        if (dy != 0.0f) tmy = (g.y0 + (float)(cy + (dy > 0.0f ? 1 : 0)) * g.cell - oy) * iy;
+        // per-axis DDA constants; an axis the ray does not move along never triggers a step.  t_exit
+        // replaces the per-step bounds check: the walk ends where the ray leaves the grid's box.
+        tmx = inf; tmy = inf; tdx = inf; tdy = inf; t_exit = inf;
+        if (dx != 0.0f) {
+            tmx = (g.x0 + (float)(cx + (dx > 0.0f ? 1 : 0)) * g.cell - ox) * ix;
+            tdx = g.cell * fabsf(ix);
+            t_exit = (g.x0 + (dx > 0.0f ? (float)(g.nx - 1) : 1.0f) * g.cell - ox) * ix;
+        }
+        if (dy != 0.0f) {
+            tmy = (g.y0 + (float)(cy + (dy > 0.0f ? 1 : 0)) * g.cell - oy) * iy;
+            tdy = g.cell * fabsf(iy);
+            t_exit = fminf(t_exit, (g.y0 + (dy > 0.0f ? (float)(g.ny - 1) : 1.0f) * g.cell - oy) * iy);
+        }
+        sx = dx > 0.0f ? 1 : -1;
+        sy = dy > 0.0f ? g.nx : -g.nx;
+        ci = cy * g.nx + cx;
         const int combo = (dx > 0.0f ? 1 : 0) + (dy > 0.0f ? 2 : 0);
-        const int2 range = __ldg(p.grid_ranges + (kWalkListBase + combo) * ncell + cy * g.nx + cx);
+        walk = p.grid_ranges + (kWalkListBase + combo) * ncell;
+        const int2 range = __ldg(walk + ci);
         r = range.x; rend = range.y;
-        guard = 4 * (g.nx + g.ny) + 64;
     }
 
     // Phase 2, one step of the 2-D DDA through the walk lists of the ray's sign combination: test the
@@ -279,14 +295,14 @@ struct GridWalk {
     // flattened into one loop in which every lane does exactly one thing per step, so lanes with
     // long lists and lanes crossing empty cells keep each other busy (the nested-loop version ran
     // with 4 of 32 lanes active, profiles/r1_v1_grid_ncu_summary.csv).  Returns false when the walk
-    // is over: the next cell starts beyond the best hit, or the ray left the grid.
+    // is over: the next cell starts beyond the best hit, or the ray leaves the grid.
     __device__ __forceinline__ bool step(const TraceParams &p, float ox, float oy, float oz, float dx, float dy,
                                          float dz, unsigned &tests)
     {
-        const GridDesc &g = p.grid;
         if (r < rend) {
-            const float4 q0 = __ldg(p.grid_recs + 2 * r);
-            const float4 q1 = __ldg(p.grid_recs + 2 * r + 1);
+            const float4 *rec = p.grid_recs + 2 * r;
+            const float4 q0 = __ldg(rec);
+            const float4 q1 = __ldg(rec + 1);
             const int tag = __float_as_int(q1.y);
             tests++;
             if (tag & (2 << 28)) {
@@ -308,12 +324,9 @@ struct GridWalk {
             return true;
         }
         const float t_next = fminf(tmx, tmy);
-        if (!(t_next < best) || --guard < 0) return false;
-        if (tmx < tmy) { cx += dx > 0.0f ? 1 : -1; tmx += g.cell * fabsf(ix); }
-        else { cy += dy > 0.0f ? 1 : -1; tmy += g.cell * fabsf(iy); }
-        if (cx < 0 || cy < 0 || cx >= g.nx || cy >= g.ny) return false;
-        const int combo = (dx > 0.0f ? 1 : 0) + (dy > 0.0f ? 2 : 0);
-        const int2 range = __ldg(p.grid_ranges + (kWalkListBase + combo) * (g.nx * g.ny) + cy * g.nx + cx);
+        if (!(t_next < fminf(best, t_exit))) return false;
+        if (tmx < tmy) { ci += sx; tmx += tdx; } else { ci += sy; tmy += tdy; }
+        const int2 range = __ldg(walk + ci);
         r = range.x; rend = range.y;
         return true;
     }
