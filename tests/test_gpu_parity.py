@@ -292,12 +292,14 @@ def rotated_scene(scene, angle_deg=27.0):
     return turn(scene.walls), turn(scene.windows), turn(scene.lights)
 
 
-def test_general_rectangles(fmgi, oracle, scene):
+@pytest.mark.parametrize("tier", ["soup", "grid"])
+def test_general_rectangles(fmgi, oracle, scene, tier):
     import refbind
 
     walls, windows, lights = rotated_scene(scene)
     rs = refbind.Scene(walls, windows, lights, scene.num_texels)
-    s = fmgi.DeviceScene(rs.walls, rs.windows, rs.lights, rs.num_texels)
+    s = fmgi.DeviceScene(rs.walls, rs.windows, rs.lights, rs.num_texels,
+                         tier=fmgi.TIER_SOUP if tier == "soup" else fmgi.TIER_GRID)
     o, d = random_rays(rs, 200_000, 4)
     gi, gt = s.closest_hit(o, d)
     ci, ct = oracle.closest_hit(rs.walls, o, d, oracle.ACCEL_LINEAR)
@@ -392,3 +394,65 @@ def test_accumulation_passes_keep_the_sample_set(dev_scene, monkeypatch):
     assert s5["kernel_launches"] - s1["kernel_launches"] >= 9
     assert np.allclose(one, five, rtol=1e-5, atol=1e-2)
     assert np.all(five[:, 3] == 0)
+
+
+def staircase_scene(fmgi):
+    """A closed 6 x 4 x 3 m room with a 12-step staircase of horizontal slabs, each at its own height, top and
+    bottom faces: 12 + 1 distinct z planes per normal sign, more than the grid tier's 8 + 8 plane table, so some
+    horizontal rectangles have to ride in the walk lists."""
+    def rect(px, py, pz, w, h, n, base, tw, th):
+        r = np.zeros(1, dtype=fmgi.RECT_DTYPE)[0]
+        r["pos"][:3] = (px, py, pz); r["width"][:3] = w; r["height"][:3] = h; r["n"][:3] = n
+        r["lightmapSetup"][:3] = (base, tw, th)
+        return r
+
+    walls, base = [], 0
+
+    def add(px, py, pz, w, h):
+        nonlocal base
+        n = np.cross(np.array(h, dtype=np.float32), np.array(w, dtype=np.float32))     # rectangle.c:22
+        n = (n / np.linalg.norm(n)).astype(np.float32)
+        walls.append(rect(px, py, pz, w, h, n, base, 8, 8))
+        base += 8 * 8 + 16 + 4 + 1                     # full mip chain of an 8 x 8 tile (rectangle.c:166-192)
+
+    X, Y, Z = 6.0, 4.0, 3.0
+    add(X, 0, 0, (-X, 0, 0), (0, Y, 0))                # floor, normal +z (parseLayout.c:466 orientation)
+    add(0, 0, Z, (X, 0, 0), (0, Y, 0))                 # ceiling, normal -z
+    add(0, 0, 0, (X, 0, 0), (0, 0, Z))                 # wall y = 0, normal +y
+    add(X, Y, 0, (-X, 0, 0), (0, 0, Z))                # wall y = Y, normal -y
+    add(0, Y, 0, (0, -Y, 0), (0, 0, Z))                # wall x = 0, normal +x
+    add(X, 0, 0, (0, Y, 0), (0, 0, Z))                 # wall x = X, normal -x
+    for i in range(12):
+        x0, z = 0.4 * i + 0.3, 0.2 * (i + 1)
+        add(x0 + 0.4, 1.0, z, (-0.4, 0, 0), (0, 2.0, 0))          # tread, top face (normal +z)
+        add(x0, 1.0, z - 0.05, (0.4, 0, 0), (0, 2.0, 0))          # underside (normal -z)
+    light = rect(2.5, 1.5, Z - 0.001, (1.0, 0, 0), (0, 1.0, 0), (0, 0, -1), 0, 1, 1)
+    walls = np.array(walls, dtype=fmgi.RECT_DTYPE)
+    return walls, np.zeros(0, dtype=fmgi.RECT_DTYPE), np.array([light], dtype=fmgi.RECT_DTYPE), base
+
+
+@pytest.mark.parametrize("tier", ["soup", "grid"])
+def test_more_z_planes_than_the_plane_table(fmgi, oracle, tier):
+    import refbind
+
+    walls, windows, lights, num_texels = staircase_scene(fmgi)
+    sc = refbind.Scene(walls, windows, lights, num_texels)
+    s = fmgi.DeviceScene(sc.walls, sc.windows, sc.lights, sc.num_texels,
+                         tier=fmgi.TIER_SOUP if tier == "soup" else fmgi.TIER_GRID)
+    o, d = random_rays(sc, 200_000, 9)
+    gi, gt = s.closest_hit(o, d)
+    ci, ct = oracle.closest_hit(sc.walls, o, d, oracle.ACCEL_LINEAR)
+    assert (gi != ci).mean() < 2e-5
+    both = (gi >= 0) & (gi == ci)
+    assert both.mean() > 0.9                            # closed room: almost every ray hits something
+    assert np.max(np.abs(gt[both] - ct[both]) / np.maximum(ct[both], 1e-4)) < 1e-4
+    spa, depth = 200000, 8
+    atlas, st = gpu_bake(s, spa, max_depth=depth, seed=2)
+    want, so = oracle.bake(sc, spa, depth, oracle.ACCEL_LINEAR, oracle.RNG_PHILOX, 2)
+    assert st["photons"] == so["photons"] > 100000
+    assert abs(st["deposits"] - so["deposits"]) <= 3e-4 * so["deposits"]
+    assert abs(atlas[:, :3].sum(dtype=np.float64) / want[:, :3].sum(dtype=np.float64) - 1) < 3e-4
+    got = s.paths(0, depth, 4, 0, 20000)
+    ref = oracle.trace_paths(sc, 0, depth, 4, 0, 20000)
+    assert np.all(got == ref, axis=1).mean() > 0.995
+    s.close()
