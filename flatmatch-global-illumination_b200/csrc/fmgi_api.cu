@@ -101,6 +101,7 @@ struct fmgi_scene {
     int num_sms = 0, clock_khz = 0, blocks_per_sm = 0;
     size_t smem_bytes = 0;
     int tier = FMGI_TIER_SOUP;
+    int kernel_tier = FMGI_TIER_SOUP;           // tier, or kTierSoupPlanes (soup + the grid's plane tables)
     uint64_t launches = 0;
     uint64_t tests_per_ray = 0;
     int min_blocks = 4;                         // resident CTAs per SM the trace kernel is compiled for
@@ -162,6 +163,11 @@ cudaError_t with_trace_kernel(int tier, int deposit, bool probe, int min_blocks,
         if (min_blocks == 3) { FMGI_PICK_DEPOSIT(FMGI_TIER_GRID, 3) }
         FMGI_PICK_DEPOSIT(FMGI_TIER_GRID, 4)
     }
+    if (tier == kTierSoupPlanes) {
+        if (probe) return fn(k_trace<kTierSoupPlanes, FMGI_DEPOSIT_VEC4, true, 3>);
+        if (min_blocks == 3) { FMGI_PICK_DEPOSIT(kTierSoupPlanes, 3) }
+        FMGI_PICK_DEPOSIT(kTierSoupPlanes, 4)
+    }
     if (probe) return fn(k_trace<FMGI_TIER_SOUP, FMGI_DEPOSIT_VEC4, true, 3>);
     if (min_blocks == 3) { FMGI_PICK_DEPOSIT(FMGI_TIER_SOUP, 3) }
     FMGI_PICK_DEPOSIT(FMGI_TIER_SOUP, 4)
@@ -170,7 +176,7 @@ cudaError_t with_trace_kernel(int tier, int deposit, bool probe, int min_blocks,
 
 cudaError_t launch_trace(fmgi_scene *s, const TraceParams &p, int deposit, bool probe, int blocks, cudaStream_t st)
 {
-    return with_trace_kernel(s->tier, deposit, probe, s->min_blocks, [&](auto kernel) {
+    return with_trace_kernel(s->kernel_tier, deposit, probe, s->min_blocks, [&](auto kernel) {
         cudaError_t e = cudaSuccess;
         if (s->smem_bytes > 48 * 1024)
             e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->smem_bytes);
@@ -258,15 +264,25 @@ int fmgi_scene_create(fmgi_scene **out, const fmgi_rect *walls, int num_walls, c
     if (tier == FMGI_TIER_SOUP && soup_bytes > (size_t)prop.sharedMemPerBlockOptin)
         return fail(FMGI_ERR_UNSUPPORTED, "rectangle soup does not fit in shared memory; use FMGI_TIER_GRID");
     s->tier = tier;
+    s->kernel_tier = tier;
+    float cell = 0.0f;
+    if (const char *v = getenv("FMGI_GRID_CELL")) cell = (float)atof(v);
+    build_grid(s->host, walls, num_walls, windows, num_windows, lights, num_lights, cell);
     if (tier == FMGI_TIER_SOUP) {
         s->smem_bytes = soup_bytes;
         // each lane walks one of the two blocks of every pair: two rectangle tests per pair
         s->tests_per_ray = s->host.axis.size() + s->host.general.size();
+        // horizontal rectangles through the plane tables when all of them fit (and there are any)
+        bool planes = s->host.grid_overflow_horizontal == 0 && s->host.pair_begin[3] > s->host.pair_begin[2];
+        if (const char *v = getenv("FMGI_SOUP_PLANES")) planes = planes && atoi(v) != 0;       // tuning knob
+        if (planes) {
+            s->kernel_tier = kTierSoupPlanes;
+            s->tests_per_ray = 2 * (size_t)s->host.pair_begin[2] + s->host.general.size();   // x and y lists only
+        }
     } else {
         s->smem_bytes = 0;
-        float cell = 0.0f;
-        if (const char *v = getenv("FMGI_GRID_CELL")) cell = (float)atof(v);
-        build_grid(s->host, walls, num_walls, windows, num_windows, lights, num_lights, cell);
+    }
+    if (s->kernel_tier != FMGI_TIER_SOUP) {
         FMGI_CUDA(upload(&s->d_grid_recs, s->host.grid_recs));
         FMGI_CUDA(upload(&s->d_grid_ranges, s->host.grid_ranges));
     }
@@ -288,7 +304,7 @@ int fmgi_scene_create(fmgi_scene **out, const fmgi_rect *walls, int num_walls, c
 
     if (const char *v = getenv("FMGI_TUNE_BLOCKS")) s->min_blocks = atoi(v) == 3 ? 3 : 4;   // tuning knob
     fmgi_scene *sp = s.get();
-    FMGI_CUDA(with_trace_kernel(s->tier, FMGI_DEPOSIT_VEC4, false, s->min_blocks, [&](auto kernel) {
+    FMGI_CUDA(with_trace_kernel(s->kernel_tier, FMGI_DEPOSIT_VEC4, false, s->min_blocks, [&](auto kernel) {
         cudaError_t e = cudaSuccess;
         if (sp->smem_bytes > 48 * 1024)
             e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sp->smem_bytes);
@@ -417,7 +433,7 @@ int fmgi_scene_sync(fmgi_scene *s, fmgi_stats *stats)
         stats->rays = s->h_counters[1];
         stats->deposits = s->h_counters[2];
         stats->mirror_bounces = s->h_counters[3];
-        stats->rect_tests = s->tier == FMGI_TIER_SOUP ? s->h_counters[1] * s->tests_per_ray : s->h_counters[5];
+        stats->rect_tests = s->h_counters[1] * s->tests_per_ray + s->h_counters[5];   // static scan + counted lookups
         stats->kernel_launches = s->launches;
         if (s->traced) {
             float ms = 0;
@@ -636,7 +652,12 @@ int fmgi_probe_closest_hit(fmgi_scene *s, const float *origins, const float *dir
     const TraceParams p = base_params(s);
     int blocks = (n + 255) / 256;
     if (blocks > s->num_sms * 4) blocks = s->num_sms * 4;
-    if (s->tier == FMGI_TIER_SOUP) {
+    if (s->kernel_tier == kTierSoupPlanes) {
+        if (s->smem_bytes > 48 * 1024)
+            FMGI_CUDA(cudaFuncSetAttribute(k_probe_closest_hit<kTierSoupPlanes>,
+                                           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->smem_bytes));
+        k_probe_closest_hit<kTierSoupPlanes><<<blocks, 256, s->smem_bytes>>>(p, d_o, d_d, n, d_i, d_t);
+    } else if (s->tier == FMGI_TIER_SOUP) {
         if (s->smem_bytes > 48 * 1024)
             FMGI_CUDA(cudaFuncSetAttribute(k_probe_closest_hit<FMGI_TIER_SOUP>,
                                            cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->smem_bytes));

@@ -175,6 +175,7 @@ void build_grid(HostScene &out, const fmgi_rect *walls, int num_walls, const fmg
     g = GridDesc();
     out.grid_ranges.clear();
     out.grid_recs.clear();
+    out.grid_overflow_horizontal = 0;
 
     // bounding box of everything a ray can start from or hit
     float xmin = INFINITY, xmax = -INFINITY, ymin = INFINITY, ymax = -INFINITY;
@@ -233,6 +234,7 @@ void build_grid(HostScene &out, const fmgi_rect *walls, int num_walls, const fmg
                 while (p < pl.size() && pl[p] != it.rec.c) p++;
                 if (p == pl.size() && pl.size() < (size_t)kMaxPlanesPerSign) pl.push_back(it.rec.c);
                 if (p < pl.size()) it.list = (neg ? kMaxPlanesPerSign : 0) + (int)p;
+                else out.grid_overflow_horizontal++;
             }
         } else {
             it.rec.tag = general_index | (3 << 28);

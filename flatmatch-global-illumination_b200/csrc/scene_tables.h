@@ -111,6 +111,7 @@ struct HostScene {
     GridDesc grid = {};
     std::vector<int32_t> grid_ranges;     // 2 ints (begin, end) per (list, cell); kNumGridLists lists
     std::vector<GridRec> grid_recs;
+    int grid_overflow_horizontal = 0;     // horizontal rectangles that did not fit the plane table
 };
 
 // photonmap.c:414-418: N = (uint64)(int spa * float area)

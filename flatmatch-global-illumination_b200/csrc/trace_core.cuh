@@ -37,13 +37,14 @@ __device__ __forceinline__ SoupTables stage_soup(const TraceParams &p, float4 *s
     return soup;
 }
 
-// kTier: FMGI_TIER_SOUP (brute force over the shared-memory soup) or FMGI_TIER_GRID (floor-plan grid in L2).
+// kTier: FMGI_TIER_SOUP (brute force over the shared-memory soup), kTierSoupPlanes (the same with the
+// horizontal rectangles looked up through the grid's plane tables) or FMGI_TIER_GRID (floor-plan grid in L2).
 template <int kTier, int kDeposit, bool kProbe, int kMinBlocks>
 __global__ void __launch_bounds__(kTraceThreads, kMinBlocks) k_trace(const TraceParams p)
 {
     extern __shared__ float4 smem[];
     SoupTables soup;
-    if (kTier == FMGI_TIER_SOUP) soup = stage_soup(p, smem);
+    if (kTier != FMGI_TIER_GRID) soup = stage_soup(p, smem);
 
     const int lane = threadIdx.x & 31;
     const unsigned lt_mask = (1u << lane) - 1u;
@@ -129,6 +130,7 @@ __global__ void __launch_bounds__(kTraceThreads, kMinBlocks) k_trace(const Trace
             // ---- C. closest hit (photonmap.c:198 / photonmap.cl:194-206) ---------------------------
             float t;
             if (kTier == FMGI_TIER_SOUP) hit_id = closest_hit_soup(soup, px, py, pz, dx, dy, dz, t);
+            else if (kTier == kTierSoupPlanes) hit_id = closest_hit_soup_planes(soup, p, px, py, pz, dx, dy, dz, t, n_tests);
             else hit_id = closest_hit_grid(p, px, py, pz, dx, dy, dz, t, n_tests);
             n_rays++;
 
@@ -170,14 +172,14 @@ __global__ void __launch_bounds__(kTraceThreads, kMinBlocks) k_trace(const Trace
         c1 += __shfl_xor_sync(kFullMask, c1, o);
         c2 += __shfl_xor_sync(kFullMask, c2, o);
         c3 += __shfl_xor_sync(kFullMask, c3, o);
-        if (kTier == FMGI_TIER_GRID) c5 += __shfl_xor_sync(kFullMask, c5, o);
+        if (kTier != FMGI_TIER_SOUP) c5 += __shfl_xor_sync(kFullMask, c5, o);
     }
     if (lane == 0) {
         atomicAdd(p.counters + 0, c0);
         atomicAdd(p.counters + 1, c1);
         atomicAdd(p.counters + 2, c2);
         atomicAdd(p.counters + 3, c3);
-        if (kTier == FMGI_TIER_GRID) atomicAdd(p.counters + 5, c5);
+        if (kTier != FMGI_TIER_SOUP) atomicAdd(p.counters + 5, c5);
     }
 }
 
@@ -189,14 +191,15 @@ __global__ void k_probe_closest_hit(const TraceParams p, const float *__restrict
 {
     extern __shared__ float4 smem[];
     SoupTables soup;
-    if (kTier == FMGI_TIER_SOUP) soup = stage_soup(p, smem);
+    if (kTier != FMGI_TIER_GRID) soup = stage_soup(p, smem);
     unsigned tests = 0;
     for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < num_rays; r += gridDim.x * blockDim.x) {
         float t;
         const float ox = origins[3 * r], oy = origins[3 * r + 1], oz = origins[3 * r + 2];
         const float dx = dirs[3 * r], dy = dirs[3 * r + 1], dz = dirs[3 * r + 2];
         const int id = kTier == FMGI_TIER_SOUP ? closest_hit_soup(soup, ox, oy, oz, dx, dy, dz, t)
-                                               : closest_hit_grid(p, ox, oy, oz, dx, dy, dz, t, tests);
+                     : kTier == kTierSoupPlanes ? closest_hit_soup_planes(soup, p, ox, oy, oz, dx, dy, dz, t, tests)
+                                                : closest_hit_grid(p, ox, oy, oz, dx, dy, dz, t, tests);
         hit_index[r] = id;
         hit_dist[r] = t;
     }

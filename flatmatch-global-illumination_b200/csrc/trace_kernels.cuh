@@ -31,6 +31,8 @@ namespace fmgi {
 constexpr int kTraceThreads = 256;
 constexpr int kChunkPhotons = 256;          // photon indices a warp claims per global atomic
 constexpr unsigned kFullMask = 0xffffffffu;
+// internal kernel variant: soup tier whose horizontal rectangles go through the grid's plane tables
+constexpr int kTierSoupPlanes = 3;
 
 struct TraceParams {
     // closest-hit tables (global memory; staged into shared memory by the soup kernel)
@@ -141,26 +143,11 @@ struct SoupTables {
     int num_general;
 };
 
-// Closest front-facing hit.  Returns the wall index (or -1) and the distance recomputed from the
-// winning plane as (c - o[k]) / d[k], the reference's formulation for an axis-parallel normal.
-__device__ __forceinline__ int closest_hit_soup(const SoupTables &s, float ox, float oy, float oz,
-                                                float dx, float dy, float dz, float &t_out)
+// Wall index of the soup winner `code` (-1: miss) and its distance recomputed from the winning plane
+// as (c - o[k]) / d[k], the reference's formulation for an axis-parallel normal.
+__device__ __forceinline__ int soup_winner(const SoupTables &s, int code, float best, float ox, float oy, float oz,
+                                           float dx, float dy, float dz, float &t_out)
 {
-    const float nanv = __int_as_float(0x7fc00000);
-    float best = __int_as_float(0x7f800000);
-    int code = -1;
-    // a lane whose d[k] is exactly zero can face neither list of axis k
-    const float ax = dx != 0.0f ? __frcp_rn(dx) : nanv;
-    const float ay = dy != 0.0f ? __frcp_rn(dy) : nanv;
-    const float az = dz != 0.0f ? __frcp_rn(dz) : nanv;
-    // list P (normal +k) is block 0 of a pair, list M (normal -k) block 1; d[k] > 0 faces M
-    const int sx = dx > 0.0f ? 3 : 0, sy = dy > 0.0f ? 3 : 0, sz = dz > 0.0f ? 3 : 0;
-    scan_axis(s.axis + sx, s.pair_begin[0], s.pair_begin[1], ax, -ox * ax, oy, dy, oz, dz, best, code);
-    scan_axis(s.axis + sy, s.pair_begin[1], s.pair_begin[2], ay, -oy * ay, ox, dx, oz, dz, best, code);
-    scan_axis(s.axis + sz, s.pair_begin[2], s.pair_begin[3], az, -oz * az, ox, dx, oy, dy, best, code);
-    if (s.num_general)
-        scan_general(s.general, s.num_general, ox, oy, oz, dx, dy, dz, best, code);
-
     int id = -1;
     t_out = best;
     if (code >= 0) {
@@ -183,6 +170,29 @@ __device__ __forceinline__ int closest_hit_soup(const SoupTables &s, float ox, f
         t_out = __fdiv_rn(num, denom);
     }
     return id;
+}
+
+// Closest front-facing hit.  Returns the wall index (or -1) and the distance recomputed from the
+// winning plane as (c - o[k]) / d[k], the reference's formulation for an axis-parallel normal.
+__device__ __forceinline__ int closest_hit_soup(const SoupTables &s, float ox, float oy, float oz,
+                                                float dx, float dy, float dz, float &t_out)
+{
+    const float nanv = __int_as_float(0x7fc00000);
+    float best = __int_as_float(0x7f800000);
+    int code = -1;
+    // a lane whose d[k] is exactly zero can face neither list of axis k
+    const float ax = dx != 0.0f ? __frcp_rn(dx) : nanv;
+    const float ay = dy != 0.0f ? __frcp_rn(dy) : nanv;
+    const float az = dz != 0.0f ? __frcp_rn(dz) : nanv;
+    // list P (normal +k) is block 0 of a pair, list M (normal -k) block 1; d[k] > 0 faces M
+    const int sx = dx > 0.0f ? 3 : 0, sy = dy > 0.0f ? 3 : 0, sz = dz > 0.0f ? 3 : 0;
+    scan_axis(s.axis + sx, s.pair_begin[0], s.pair_begin[1], ax, -ox * ax, oy, dy, oz, dz, best, code);
+    scan_axis(s.axis + sy, s.pair_begin[1], s.pair_begin[2], ay, -oy * ay, ox, dx, oz, dz, best, code);
+    scan_axis(s.axis + sz, s.pair_begin[2], s.pair_begin[3], az, -oz * az, ox, dx, oy, dy, best, code);
+    if (s.num_general)
+        scan_general(s.general, s.num_general, ox, oy, oz, dx, dy, dz, best, code);
+
+    return soup_winner(s, code, best, ox, oy, oz, dx, dy, dz, t_out);
 }
 
 // ---- closest hit through the floor-plan grid (grid tier) ---------------------------------------------
@@ -236,17 +246,14 @@ struct GridWalk {
     int r, rend;           // pending records of the current cell
     const int2 *walk;      // the walk list ranges of this ray's sign combination
 
-    // Phase 1 (horizontal planes the ray can face: one cell lookup per plane at the crossing point)
-    // and DDA set-up.
-    __device__ __forceinline__ void begin(const TraceParams &p, float ox, float oy, float oz, float dx, float dy,
-                                          float dz, unsigned &tests)
+    // Phase 1: horizontal planes the ray can face - one cell lookup per plane at the crossing point.
+    __device__ __forceinline__ void planes(const TraceParams &p, float ox, float oy, float oz, float dx, float dy,
+                                           float dz, unsigned &tests)
     {
         const GridDesc &g = p.grid;
         const int ncell = g.nx * g.ny;
-        const float inf = __int_as_float(0x7f800000);
-        best = inf;
+        best = __int_as_float(0x7f800000);
         win = -1;
-        ix = __frcp_rn(dx); iy = __frcp_rn(dy);
         if (dz != 0.0f) {
             const float iz = __frcp_rn(dz);
             const int first = dz < 0.0f ? 0 : kMaxPlanesPerSign;             // d.z < 0 faces normals +z
@@ -266,6 +273,17 @@ struct GridWalk {
                 }
             }
         }
+    }
+
+    // Phase 1 + DDA set-up.
+    __device__ __forceinline__ void begin(const TraceParams &p, float ox, float oy, float oz, float dx, float dy,
+                                          float dz, unsigned &tests)
+    {
+        const GridDesc &g = p.grid;
+        const int ncell = g.nx * g.ny;
+        const float inf = __int_as_float(0x7f800000);
+        planes(p, ox, oy, oz, dx, dy, dz, tests);
+        ix = __frcp_rn(dx); iy = __frcp_rn(dy);
         int cx = __float2int_rd((ox - g.x0) * g.inv_cell), cy = __float2int_rd((oy - g.y0) * g.inv_cell);
         cx = min(max(cx, 0), g.nx - 1); cy = min(max(cy, 0), g.ny - 1);
         // per-axis DDA constants; an axis the ray does not move along never triggers a step.  t_exit
@@ -368,6 +386,35 @@ __device__ __forceinline__ int closest_hit_grid(const TraceParams &p, float ox, 
     w.begin(p, ox, oy, oz, dx, dy, dz, tests);
     while (w.step(p, ox, oy, oz, dx, dy, dz, tests)) {}
     return w.finish(p, ox, oy, oz, dx, dy, dz, t_out);
+}
+
+// Soup tier with the grid's plane tables: horizontal rectangles (floors, ceilings, sills: about a third
+// of a flat's soup) are found by one cell lookup per z plane exactly as in the grid tier, which also
+// bounds `best` before the shared-memory scan of the vertical walls (x and y lists only).  Used when
+// every horizontal rectangle fits the plane table.
+__device__ __forceinline__ int closest_hit_soup_planes(const SoupTables &s, const TraceParams &p, float ox, float oy,
+                                                       float oz, float dx, float dy, float dz, float &t_out,
+                                                       unsigned &tests)
+{
+    GridWalk w;
+    w.planes(p, ox, oy, oz, dx, dy, dz, tests);
+    const float nanv = __int_as_float(0x7fc00000);
+    float best = w.best;
+    int code = -1;
+    const float ax = dx != 0.0f ? __frcp_rn(dx) : nanv;
+    const float ay = dy != 0.0f ? __frcp_rn(dy) : nanv;
+    const int sx = dx > 0.0f ? 3 : 0, sy = dy > 0.0f ? 3 : 0;
+    scan_axis(s.axis + sx, s.pair_begin[0], s.pair_begin[1], ax, -ox * ax, oy, dy, oz, dz, best, code);
+    scan_axis(s.axis + sy, s.pair_begin[1], s.pair_begin[2], ay, -oy * ay, ox, dx, oz, dz, best, code);
+    if (s.num_general)
+        scan_general(s.general, s.num_general, ox, oy, oz, dx, dy, dz, best, code);
+    if (code != -1) return soup_winner(s, code, best, ox, oy, oz, dx, dy, dz, t_out);
+    t_out = best;
+    if (w.win < 0) return -1;
+    const float4 q0 = __ldg(p.grid_recs + 2 * w.win);
+    const int tag = __float_as_int(__ldg(p.grid_recs + 2 * w.win + 1).y);
+    t_out = __fdiv_rn(__fsub_rn(q0.x, oz), dz);
+    return tag & 0x0fffffff;
 }
 
 // ---- texel index: rectangle.c:205-230, same operations in the same order, no contraction ----------
