@@ -257,6 +257,9 @@ def run_ours(args):
     fixture, photons, depth, tile_size = WORKLOADS[args.workload]
     if args.photons:
         photons = args.photons
+    strong = args.total_photons > 0          # configs[4]: fixed total budget split over the GPUs
+    if strong:
+        photons = args.total_photons / world
     if args.depth:
         depth = args.depth
     walls, windows, lights, num_texels = load_scene(fixture, tile_size)
@@ -350,7 +353,8 @@ def run_ours(args):
         achieved = rays_per_s_kernel * flops_per_ray / 1e12
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+            "scaling": "strong" if strong else "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": args.workload, "scene": fixture, "rectangles": int(len(walls)),
                        "emitters": int(len(windows) + len(lights)), "atlas_texels": num_texels,
@@ -374,7 +378,7 @@ def run_ours(args):
             "gpu_launches": launches,
             "clocks": clk.summary(),
         }
-        facts = ncu_facts(args.workload) if not (args.photons or args.depth) else None
+        facts = ncu_facts(args.workload) if not (args.photons or args.depth or strong) else None
         if facts and facts.get("tier") == line["config"]["tier"]:
             line["roofline"]["traffic"] = facts.get("dram_bytes_per_launch")
             line["roofline"]["ncu"] = facts
@@ -404,6 +408,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="example_1e8x3", choices=sorted(WORKLOADS))
     ap.add_argument("--photons", type=float, default=0.0, help="override photons per GPU per step")
+    ap.add_argument("--total-photons", type=float, default=0.0,
+                    help="strong scaling: total photons per step over all GPUs (photon-count sweeps)")
     ap.add_argument("--depth", type=int, default=0)
     ap.add_argument("--seed", type=int, default=1)
     ap.add_argument("--deposit", type=int, default=0)
