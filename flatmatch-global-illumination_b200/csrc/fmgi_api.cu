@@ -92,6 +92,10 @@ struct fmgi_scene {
     unsigned long long *d_jobs = nullptr;       // per accumulation pass: job_begin[E+1] then photon_first[E]
     size_t job_tables = 0;                      // passes the job-table buffers have room for
     float4 *d_scratch = nullptr;                // per-pass fp32 atlas when a bake needs several passes
+    TileWall *d_tile_walls = nullptr;           // tone-map wall table (fmgi_scene_tonemap)
+    TileWall *h_tile_walls = nullptr;           // pinned staging for it
+    std::vector<float> wall_area;               // |width| * |height| per wall, float (rectangle.c:194-197)
+    std::vector<int> wall_floor;                // rectangle.c:317
     unsigned long long *d_counters = nullptr;   // 4 counters + work counter
     unsigned long long *h_jobs = nullptr;       // pinned staging
     unsigned long long *h_counters = nullptr;   // pinned
@@ -234,6 +238,13 @@ int fmgi_scene_create(fmgi_scene **out, const fmgi_rect *walls, int num_walls, c
     const char *why = prepare_scene(s->host, walls, num_walls, windows, num_windows, lights, num_lights, num_texels);
     if (why[0]) return fail(FMGI_ERR_ARG, why);
 
+    s->wall_area.resize(num_walls);
+    s->wall_floor.resize(num_walls);
+    for (int i = 0; i < num_walls; i++) {
+        const ShadeRect &sh = s->host.shade[i];
+        s->wall_area[i] = sh.wlen * sh.hlen;                                            // getArea, rectangle.c:194-197
+        s->wall_floor[i] = walls[i].pos[2] == 0 && walls[i].width[2] == 0 && walls[i].height[2] == 0;
+    }
     DeviceGuard guard(o.device);
     // cudaGetDeviceProperties costs about a millisecond per call: query the three attributes we need
     struct { size_t sharedMemPerBlockOptin; } prop;
@@ -327,6 +338,7 @@ void fmgi_scene_destroy(fmgi_scene *s)
     pool.free(s->d_axis); pool.free(s->d_general); pool.free(s->d_shade); pool.free(s->d_emitters);
     pool.free(s->d_grid_recs); pool.free(s->d_grid_ranges);
     pool.free(s->d_jobs); pool.free(s->d_counters); pool.free(s->d_scratch);
+    pool.free(s->d_tile_walls); pool.free(s->h_tile_walls);
     pool.free(s->h_jobs); pool.free(s->h_counters);
     if (s->ev_start) cudaEventDestroy(s->ev_start);
     if (s->ev_stop) cudaEventDestroy(s->ev_stop);
@@ -450,7 +462,14 @@ int fmgi_scene_sync(fmgi_scene *s, fmgi_stats *stats)
 
 // ---- host-buffer bake ---------------------------------------------------------------------------------
 
-int fmgi_bake(struct Geometry *geo_, int spa, const fmgi_options *opt, fmgi_stats *stats)
+} // extern "C"
+
+namespace {
+
+// Host-buffer bake.  tiles_out == NULL: geo->texels receives the float atlas (fmgi_bake); otherwise the
+// atlas is tone-mapped on GPU 0 and only the packed RGB tiles come back (fmgi_bake_tiles).
+int bake_impl(struct Geometry *geo_, int spa, const fmgi_options *opt, fmgi_stats *stats, uint8_t *tiles_out,
+              int tint_extra)
 {
     fmgi_geometry *geo = reinterpret_cast<fmgi_geometry *>(geo_);
     if (!geo) return fail(FMGI_ERR_ARG, "geo is NULL");
@@ -563,10 +582,26 @@ int fmgi_bake(struct Geometry *geo_, int spa, const fmgi_options *opt, fmgi_stat
             for (float4 *t : staged) MemPool::get().free(t);
             reduce_ms = now_ms() - t0;
         }
-        if (e == cudaSuccess) {
+        if (e == cudaSuccess && !tiles_out) {
             const double t0 = now_ms();
             e = cudaMemcpyAsync(geo->texels, gpus[0].atlas, atlas_bytes, cudaMemcpyDeviceToHost, gpus[0].stream);
             if (e == cudaSuccess) e = cudaStreamSynchronize(gpus[0].stream);
+            d2h_ms = now_ms() - t0;
+        }
+        if (e == cudaSuccess && tiles_out) {
+            // normalise + tone-map + pack on the device, read back 3 bytes per texel
+            const double t0 = now_ms();
+            const uint64_t tile_bytes = fmgi_tile_bytes(geo->walls, geo->numWalls);
+            unsigned char *d_rgb = nullptr;
+            e = MemPool::get().alloc((void **)&d_rgb, tile_bytes ? tile_bytes : 16, false);
+            if (e == cudaSuccess) {
+                if (fmgi_scene_tonemap(gpus[0].scene, gpus[0].atlas, spa, tint_extra, d_rgb, gpus[0].stream) != FMGI_OK)
+                    e = cudaErrorUnknown;
+                cudaSetDevice(dev0);
+            }
+            if (e == cudaSuccess) e = cudaMemcpyAsync(tiles_out, d_rgb, tile_bytes, cudaMemcpyDeviceToHost, gpus[0].stream);
+            if (e == cudaSuccess) e = cudaStreamSynchronize(gpus[0].stream);
+            MemPool::get().free(d_rgb);
             d2h_ms = now_ms() - t0;
         }
         if (e != cudaSuccess) rc = fail(FMGI_ERR_CUDA, std::string("atlas fold/read-back: ") + cudaGetErrorString(e));
@@ -604,6 +639,22 @@ int fmgi_bake(struct Geometry *geo_, int spa, const fmgi_options *opt, fmgi_stat
     return rc;
 }
 
+}  // namespace
+
+extern "C" {
+
+int fmgi_bake(struct Geometry *geo, int spa, const fmgi_options *opt, fmgi_stats *stats)
+{
+    return bake_impl(geo, spa, opt, stats, nullptr, 0);
+}
+
+int fmgi_bake_tiles(struct Geometry *geo, int spa, const fmgi_options *opt, int tint_extra, uint8_t *rgb_out,
+                    fmgi_stats *stats)
+{
+    if (!rgb_out) return fail(FMGI_ERR_ARG, "rgb_out is NULL");
+    return bake_impl(geo, spa, opt, stats, rgb_out, tint_extra);
+}
+
 // ---- the reference boundary (global_illumination_cl.h:10) -------------------------------------------------
 
 void performGlobalIlluminationCl(struct Geometry *geo, int numSamplesPerArea)
@@ -630,6 +681,52 @@ void performGlobalIlluminationCl(struct Geometry *geo, int numSamplesPerArea)
                    (unsigned long long)st.rays, (unsigned long long)st.mirror_bounces,
                    (unsigned long long)st.rect_tests, st.h2d_ms, st.d2h_ms, st.reduce_ms,
                    (unsigned long long)st.kernel_launches);
+}
+
+// ---- tile post-processing ----------------------------------------------------------------
+
+uint64_t fmgi_tile_bytes(const fmgi_rect *walls, int num_walls)
+{
+    uint64_t n = 0;
+    for (int i = 0; walls && i < num_walls; i++) n += 3ull * (uint64_t)walls[i].lightmap[1] * (uint64_t)walls[i].lightmap[2];
+    return n;
+}
+
+int fmgi_scene_tonemap(fmgi_scene *s, const void *atlas_dev, int spa, int tint_extra, void *rgb_dev, void *cuda_stream)
+{
+    if (!s || !atlas_dev || !rgb_dev) return fail(FMGI_ERR_ARG, "scene, atlas or output is NULL");
+    DeviceGuard guard(s->device);
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    const int W = s->host.num_walls;
+    MemPool &pool = MemPool::get();
+    if (!s->d_tile_walls) {
+        FMGI_CUDA(pool.alloc((void **)&s->d_tile_walls, (W ? W : 1) * sizeof(TileWall), false));
+        FMGI_CUDA(pool.alloc((void **)&s->h_tile_walls, (W ? W : 1) * sizeof(TileWall), true));
+    } else {
+        FMGI_CUDA(cudaStreamSynchronize(st));                     // pinned staging is reused
+    }
+    long long pixels = 0;
+    for (int i = 0; i < W; i++) {
+        const ShadeRect &sh = s->host.shade[i];
+        const int tiles = (sh.tiles & 0xffff) * (sh.tiles >> 16);
+        TileWall &t = s->h_tile_walls[i];
+        t.base = sh.base;
+        t.first = (int32_t)pixels;
+        const float tiles_per_sample = tiles / (s->wall_area[i] * spa);            // main.c:73 (int / (float * int))
+        t.scale = (float)(0.35 * tiles_per_sample);                                // main.c:77: double product, float arg
+        t.is_floor = s->wall_floor[i];
+        pixels += tiles;
+    }
+    if (pixels > 0x7fffffffLL) return fail(FMGI_ERR_UNSUPPORTED, "more than 2^31 tile pixels");
+    if (pixels == 0) return FMGI_OK;
+    FMGI_CUDA(cudaMemcpyAsync(s->d_tile_walls, s->h_tile_walls, W * sizeof(TileWall), cudaMemcpyHostToDevice, st));
+    long long blocks = (pixels + 255) / 256;
+    if (blocks > (long long)s->num_sms * 16) blocks = (long long)s->num_sms * 16;
+    k_tonemap<<<(int)blocks, 256, 0, st>>>(reinterpret_cast<const float4 *>(atlas_dev), s->d_tile_walls, W, pixels,
+                                         tint_extra, reinterpret_cast<unsigned char *>(rgb_dev));
+    s->launches++;
+    FMGI_CUDA(cudaGetLastError());
+    return FMGI_OK;
 }
 
 // ---- parity probes ---------------------------------------------------------------------------------------------

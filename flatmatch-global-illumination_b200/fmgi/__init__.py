@@ -67,7 +67,7 @@ class Stats(C.Structure):
 
 EXPORTS = [
     "performGlobalIlluminationCl", "fmgi_default_options", "fmgi_last_error", "fmgi_version", "fmgi_device_count",
-    "fmgi_release_cache",
+    "fmgi_release_cache", "fmgi_tile_bytes", "fmgi_scene_tonemap", "fmgi_bake_tiles",
     "fmgi_bake", "fmgi_scene_create", "fmgi_scene_destroy", "fmgi_scene_trace", "fmgi_scene_sync",
     "fmgi_scene_photon_count", "fmgi_probe_closest_hit", "fmgi_probe_tile_ids", "fmgi_probe_philox",
     "fmgi_probe_sample_dirs", "fmgi_probe_paths",
@@ -102,6 +102,10 @@ def lib() -> C.CDLL:
     L.fmgi_scene_sync.argtypes = [C.c_void_p, C.POINTER(Stats)]
     L.fmgi_scene_photon_count.restype = C.c_uint64
     L.fmgi_scene_photon_count.argtypes = [C.c_void_p, C.c_int, C.POINTER(Options)]
+    L.fmgi_tile_bytes.restype = C.c_uint64
+    L.fmgi_tile_bytes.argtypes = [C.c_void_p, C.c_int]
+    L.fmgi_scene_tonemap.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+    L.fmgi_bake_tiles.argtypes = [C.POINTER(Geometry), C.c_int, C.POINTER(Options), C.c_int, C.c_void_p, C.POINTER(Stats)]
     L.fmgi_probe_closest_hit.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
     L.fmgi_probe_tile_ids.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
     L.fmgi_probe_philox.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
@@ -173,6 +177,18 @@ def bake(geo: Geometry, num_samples_per_area: int, **opts) -> dict:
     return st.as_dict()
 
 
+def bake_tiles(geo: Geometry, walls: np.ndarray, num_samples_per_area: int, tint_extra: int = 0, **opts):
+    """fmgi_bake_tiles: bake, then normalise + tone-map + pack on the device (main.c:68-79 +
+    rectangle.c:293-336).  Returns (packed RGB bytes in wall order, counters)."""
+    o = options(**opts)
+    st = Stats()
+    n = int(lib().fmgi_tile_bytes(walls.ctypes.data, len(walls)))
+    out = np.zeros(max(n, 1), dtype=np.uint8)
+    _check(lib().fmgi_bake_tiles(C.byref(geo), int(num_samples_per_area), C.byref(o), int(tint_extra),
+                                 out.ctypes.data, C.byref(st)))
+    return out[:n], st.as_dict()
+
+
 class DeviceScene:
     """fmgi_scene: collider + emitter tables resident on one GPU."""
 
@@ -212,6 +228,14 @@ class DeviceScene:
         st = Stats()
         _check(lib().fmgi_scene_sync(self._h, C.byref(st)))
         return st.as_dict()
+
+    def tonemap(self, atlas_ptr: int, spa: int, rgb_ptr: int, tint_extra: int = 0, stream: int = 0) -> None:
+        """fmgi_scene_tonemap: RAW device atlas -> packed RGB tiles on the device."""
+        _check(lib().fmgi_scene_tonemap(self._h, C.c_void_p(atlas_ptr), int(spa), int(tint_extra),
+                                        C.c_void_p(rgb_ptr), C.c_void_p(stream)))
+
+    def tile_bytes(self) -> int:
+        return int(lib().fmgi_tile_bytes(self.walls.ctypes.data, len(self.walls)))
 
     # -- parity probes ---------------------------------------------------------------------------
     def closest_hit(self, origins, dirs):

@@ -140,6 +140,21 @@ int fmgi_scene_sync(fmgi_scene *scene, fmgi_stats *stats);
 /* Photons this shard emits for the given density (sum over emitters). */
 uint64_t fmgi_scene_photon_count(const fmgi_scene *scene, int numSamplesPerArea, const fmgi_options *opt);
 
+/* ---- extension: tile post-processing on the device ------------------------- */
+
+/* Bytes of the packed tile buffer: sum over walls of tilesW * tilesH * 3. */
+uint64_t fmgi_tile_bytes(const fmgi_rect *walls, int num_walls);
+/* Device version of main.c:68-79 (normalisation) + saveAs_core (rectangle.c:293-336): from the RAW
+ * device atlas to, for every wall in order, tilesW * tilesH RGB bytes - the pixel buffer saveAs
+ * hands to write_png_file.  rgb_dev: device buffer of fmgi_tile_bytes() bytes.  Asynchronous on
+ * `cuda_stream`. */
+int fmgi_scene_tonemap(fmgi_scene *scene, const void *atlas_dev, int numSamplesPerArea, int tintExtra,
+                       void *rgb_dev, void *cuda_stream);
+/* fmgi_bake followed by the tone-map on the device: reads back 3 bytes per texel instead of 16.
+ * geo->texels is the initial atlas and is NOT written back; rgb_out receives fmgi_tile_bytes() bytes. */
+int fmgi_bake_tiles(struct Geometry *geo, int numSamplesPerArea, const fmgi_options *opt, int tintExtra,
+                    uint8_t *rgb_out, fmgi_stats *stats);
+
 /* ---- extension: parity probes (each runs the same device functions the trace kernel uses) -- */
 
 /* Closest front-facing hit for num_rays host rays (xyz triples): wall index or -1, distance. */

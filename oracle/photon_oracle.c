@@ -473,3 +473,43 @@ void orc_closest_hit(const orc_rect *walls, int num_walls, int accel, const floa
     }
     bsp_free(s.root);
 }
+
+/* ------------------------------------------------------------------------------------------
+ * main.c:68-79 + rectangle.c:263-336 — normalise, tone-map and pack one wall's base-level tile.
+ * Every implicit promotion of the reference is kept: `0.35 * tilesPerSample` is a double product
+ * narrowed to float by mul()'s parameter; the luminance sum and exp() run in double; the floor
+ * tint multiplies a uint8 by a double and truncates.
+ * ---------------------------------------------------------------------------------------- */
+static uint8_t clamp_u8(float d)                                     /* rectangle.c:287-292 */
+{
+    if (d < 0) d = 0;
+    if (d > 255) d = 255;
+    return d;
+}
+
+void orc_tonemap_tiles(const orc_rect *walls, int num_walls, const float *texels, int spa, int tint_extra,
+                       uint8_t *rgb_out)
+{
+    for (int i = 0; i < num_walls; i++) {
+        const orc_rect *obj = &walls[i];
+        const int base = obj->lm[0], tiles = obj->lm[1] * obj->lm[2];
+        float area = vlen(ld(obj->width)) * vlen(ld(obj->height));                 /* rectangle.c:194-197 */
+        float tiles_per_sample = tiles / (area * spa);                              /* main.c:73 */
+        float scale = 0.35 * tiles_per_sample;                                      /* main.c:77, narrowed by mul() */
+        const int is_floor = obj->pos[2] == 0 && obj->width[2] == 0 && obj->height[2] == 0;   /* rectangle.c:317 */
+        for (int j = 0; j < tiles; j++) {
+            const float *t = texels + 4 * (size_t)(base + j);
+            float r = t[0] * scale, g = t[1] * scale, b = t[2] * scale;            /* main.c:77 */
+            float luminance = 0.2126 * r + 0.7152 * g + 0.0722 * b;                /* rectangle.c:277 */
+            float perceptive = 1 - exp(-2 * luminance);                             /* rectangle.c:269 */
+            r *= perceptive / luminance; g *= perceptive / luminance; b *= perceptive / luminance;
+            uint8_t *d = rgb_out + 3 * (size_t)j;
+            d[0] = clamp_u8(r * 255); d[1] = clamp_u8(g * 255); d[2] = clamp_u8(b * 255);   /* rectangle.c:307-309 */
+            if (is_floor) {                                                         /* rectangle.c:317-334 */
+                d[1] *= 0.95; d[2] *= 0.9;
+                if (tint_extra) { d[0] *= 1.0f; d[1] *= 0.95f; d[2] *= 0.9f; }
+            }
+        }
+        rgb_out += 3 * (size_t)tiles;
+    }
+}

@@ -73,6 +73,14 @@ void orc_closest_hit(const orc_rect *walls, int num_walls, int accel,
                      const float *origins, const float *dirs, int num_rays,
                      int32_t *hit_index, float *hit_dist);
 
+/* The caller-side post-processing the lightmap goes through before it becomes tiles/tile_N.png:
+ * main.c:68-79 (texel *= 0.35 * tiles / (area * samplesPerArea), base level only) followed by
+ * saveAs_core (rectangle.c:293-336: tone-map 1 - exp(-2 L) at constant chroma, x255, clamp, floor
+ * tint).  texels: RAW sums (numTexels x float4, not modified).  rgb_out: for every wall in order,
+ * tilesW * tilesH RGB bytes - the buffer saveAs hands to write_png_file. */
+void orc_tonemap_tiles(const orc_rect *walls, int num_walls, const float *texels, int samples_per_area,
+                       int tint_extra, uint8_t *rgb_out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -53,11 +53,28 @@ void read_png_file(const char *file_name, int *width, int *height, int *color_ty
     exit(2);
 }
 
+/* saveAs (rectangle.c:338-346) hands the tone-mapped tile to write_png_file: capture it instead of
+ * encoding it, so that tests can read the reference's own pixel bytes. */
+static uint8_t *g_capture = NULL;
+static size_t g_capture_size = 0;
+
 void write_png_file(const char *file_name, int width, int height, int color_type,
                     uint8_t *pixel_buffer)
 {
-    /* parseLayout.c:314 dumps ./filled.png as a debugging side effect; drop it. */
-    (void)file_name; (void)width; (void)height; (void)color_type; (void)pixel_buffer;
+    /* parseLayout.c:314 also dumps ./filled.png (RGBA) as a debugging side effect; never kept. */
+    (void)file_name;
+    if (!g_capture || color_type != PNG_COLOR_TYPE_RGB) return;
+    size_t n = (size_t)width * height * 3;
+    if (n > g_capture_size) n = g_capture_size;
+    memcpy(g_capture, pixel_buffer, n);
+}
+
+/* The reference's saveAs on one wall of an already normalised atlas; out receives tilesW*tilesH*3 bytes. */
+void fmgi_ref_save_tile(const Rectangle *rect, const Vector3 *texels, int tint_extra, uint8_t *out, size_t out_size)
+{
+    g_capture = out; g_capture_size = out_size;
+    saveAs(rect, "capture", texels, tint_extra);
+    g_capture = NULL; g_capture_size = 0;
 }
 
 /* ---- layout -> Geometry through the reference's own parser ------------------------- */

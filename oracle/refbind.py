@@ -198,6 +198,8 @@ class RefLib:
             fn.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
         L.fmgi_ref_tile_ids.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
         L.fmgi_ref_sample_dirs.argtypes = [C.c_void_p, C.c_int, C.c_uint, C.c_int, C.c_void_p]
+        L.fmgi_ref_save_tile.restype = None
+        L.fmgi_ref_save_tile.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_size_t]
         assert L.fmgi_ref_sizeof_rectangle() == 80 and L.fmgi_ref_sizeof_geometry() == 80
         assert L.fmgi_ref_sizeof_vector3() == 16
 
@@ -279,6 +281,15 @@ class RefLib:
         self.lib.fmgi_ref_sample_dirs(nn.ctypes.data, int(sky), seed, n, out.ctypes.data)
         return out
 
+    def save_tile(self, rect, normalised_texels: np.ndarray, tint_extra: int) -> np.ndarray:
+        """saveAs (rectangle.c:338) on one wall: the RGB bytes it hands to write_png_file."""
+        r = aligned_rects(np.asarray([rect], dtype=RECT_DTYPE))
+        tw, th = int(rect["lightmapSetup"][1]), int(rect["lightmapSetup"][2])
+        out = np.zeros(tw * th * 3, dtype=np.uint8)
+        assert normalised_texels.dtype == np.float32 and normalised_texels.ctypes.data % 16 == 0
+        self.lib.fmgi_ref_save_tile(r.ctypes.data, normalised_texels.ctypes.data, int(tint_extra), out.ctypes.data, out.size)
+        return out
+
 
 class _quiet_stdout:
     """The reference printf()s progress (photonmap.c:266-270, 398-404); keep test logs readable."""
@@ -340,6 +351,8 @@ class OracleLib:
         L.orc_photon_budget.argtypes = [C.c_void_p, C.c_int]
         L.orc_philox4x32_10.restype = None
         L.orc_philox4x32_10.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        L.orc_tonemap_tiles.restype = None
+        L.orc_tonemap_tiles.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p]
 
     def bake(self, scene: Scene, spa: int, depth: int = 8, accel: int = 0, rng: int = 0, seed: int = 1,
              shard: int = 0, num_shards: int = 1, texels: np.ndarray | None = None):
@@ -377,6 +390,15 @@ class OracleLib:
         p = np.ascontiguousarray(points, dtype=np.float32)
         return np.array([self.lib.orc_tile_id(r.ctypes.data, p[i].ctypes.data) for i in range(len(p))],
                         dtype=np.int32)
+
+    def tonemap_tiles(self, scene: Scene, raw_texels: np.ndarray, spa: int, tint_extra: int = 0) -> np.ndarray:
+        """main.c:68-79 + saveAs_core for every wall: concatenated RGB bytes in wall order."""
+        n = int(sum(int(w["lightmapSetup"][1]) * int(w["lightmapSetup"][2]) for w in scene.walls))
+        out = np.zeros(3 * n, dtype=np.uint8)
+        t = np.ascontiguousarray(raw_texels, dtype=np.float32)
+        self.lib.orc_tonemap_tiles(scene.walls.ctypes.data, len(scene.walls), t.ctypes.data, int(spa), int(tint_extra),
+                                   out.ctypes.data)
+        return out
 
     def philox(self, ctr, key):
         c = np.asarray(ctr, dtype=np.uint32)

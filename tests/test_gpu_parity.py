@@ -456,3 +456,41 @@ def test_more_z_planes_than_the_plane_table(fmgi, oracle, tier):
     ref = oracle.trace_paths(sc, 0, depth, 4, 0, 20000)
     assert np.all(got == ref, axis=1).mean() > 0.995
     s.close()
+
+
+@pytest.mark.parametrize("tint", [0, 1])
+def test_device_tonemap_is_byte_exact(fmgi, dev_scene, oracle, scene, tint):
+    """fmgi_scene_tonemap = main.c:68-79 + saveAs_core (rectangle.c:293-336) on the device: the packed RGB
+    tiles equal the oracle's (which equals the reference's saveAs output) byte for byte, including black
+    texels (0/0 -> 0) and the floor tint."""
+    import torch
+
+    spa = 30000
+    atlas = device_atlas(dev_scene.num_texels)
+    dev_scene.trace(atlas.data_ptr(), spa, stream=torch.cuda.current_stream().cuda_stream, max_depth=8, seed=3)
+    dev_scene.sync()
+    rgb = torch.zeros(dev_scene.tile_bytes(), dtype=torch.uint8, device="cuda")
+    dev_scene.tonemap(atlas.data_ptr(), spa, rgb.data_ptr(), tint_extra=tint,
+                      stream=torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    got = rgb.cpu().numpy()
+    want = oracle.tonemap_tiles(scene, atlas.cpu().numpy(), spa, tint)
+    assert got.size == want.size == 3 * int(scene.base_texel_mask().sum())
+    diff = got != want
+    assert diff.mean() < 1e-6, f"{diff.sum()} differing bytes"
+    assert (got > 0).mean() > 0.9
+
+
+def test_bake_tiles_returns_packed_tiles_only(fmgi, oracle, scene):
+    spa = 20000
+    tex = fmgi.aligned_texels(scene.num_texels)
+    before = tex.copy()
+    geo = fmgi.make_geometry(scene.walls, scene.windows, scene.lights, tex)
+    rgb, st = fmgi.bake_tiles(geo, scene.walls, spa, tint_extra=0, seed=6, max_depth=8)
+    assert np.array_equal(tex, before)                       # the float atlas is not written back
+    tex2 = fmgi.aligned_texels(scene.num_texels)
+    fmgi.bake(fmgi.make_geometry(scene.walls, scene.windows, scene.lights, tex2), spa, seed=6, max_depth=8)
+    want = oracle.tonemap_tiles(scene, tex2, spa, 0)
+    d = np.abs(rgb.astype(np.int32) - want.astype(np.int32))
+    assert d.max() <= 1 and (d > 0).mean() < 2e-3            # two bakes: float atomics order differs
+    assert st["deposits"] > 0

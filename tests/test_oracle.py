@@ -157,3 +157,30 @@ def test_retile_reproduces_the_reference_layout(fixture):
     assert np.array_equal(walls["lightmapSetup"], sc.walls["lightmapSetup"])
     hi, n_hi = layout.retile(sc.walls[:200], 800.0)
     assert n_hi > 3.5 * layout.retile(sc.walls[:200], 200.0)[1]
+
+
+def test_oracle_tonemap_equals_reference_saveas(oracle, reflib, scene):
+    """orc_tonemap_tiles (main.c:68-79 + rectangle.c:263-336 restated) gives byte for byte the pixel
+    buffer the reference's saveAs hands to write_png_file, with and without the extra floor tint."""
+    import refbind
+
+    ref8, _ = reflib
+    spa = 8000
+    raw, _ = oracle.bake(scene, spa, 8, oracle.ACCEL_BSP, oracle.RNG_LIBC, 5)
+    norm = refbind.aligned_texels(scene.num_texels)
+    norm[...] = raw
+    for w in scene.walls:                      # main.c:68-79, float/double promotions as in the reference
+        b, tw, th = (int(x) for x in w["lightmapSetup"][:3])
+        lw = np.sqrt(np.float32((w["width"][:3].astype(np.float32) ** 2).sum(dtype=np.float32)), dtype=np.float32)
+        lh = np.sqrt(np.float32((w["height"][:3].astype(np.float32) ** 2).sum(dtype=np.float32)), dtype=np.float32)
+        tps = np.float32(np.float32(tw * th) / np.float32(np.float32(lw * lh) * np.float32(spa)))
+        norm[b:b + tw * th, :3] = raw[b:b + tw * th, :3] * np.float32(0.35 * float(tps))
+    for tint in (0, 1):
+        mine = oracle.tonemap_tiles(scene, raw, spa, tint)
+        off = 0
+        for w in scene.walls:
+            tw, th = int(w["lightmapSetup"][1]), int(w["lightmapSetup"][2])
+            want = ref8.save_tile(w, norm, tint)
+            assert np.array_equal(mine[off:off + 3 * tw * th], want)
+            off += 3 * tw * th
+        assert off == mine.size and (mine > 0).mean() > 0.9
