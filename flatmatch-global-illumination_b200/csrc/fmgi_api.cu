@@ -94,6 +94,9 @@ struct fmgi_scene {
     float4 *d_scratch = nullptr;                // per-pass fp32 atlas when a bake needs several passes
     TileWall *d_tile_walls = nullptr;           // tone-map wall table (fmgi_scene_tonemap)
     TileWall *h_tile_walls = nullptr;           // pinned staging for it
+    float *d_ao = nullptr;                      // ambient occlusion: widths, heights (3 floats per wall), then float4 directions
+    AoWall *d_ao_walls = nullptr;
+    std::vector<float> wall_wh;                 // the walls' width and height vectors (6 floats per wall)
     std::vector<float> wall_area;               // |width| * |height| per wall, float (rectangle.c:194-197)
     std::vector<int> wall_floor;                // rectangle.c:317
     unsigned long long *d_counters = nullptr;   // 4 counters + work counter
@@ -244,6 +247,12 @@ int fmgi_scene_create(fmgi_scene **out, const fmgi_rect *walls, int num_walls, c
         const ShadeRect &sh = s->host.shade[i];
         s->wall_area[i] = sh.wlen * sh.hlen;                                            // getArea, rectangle.c:194-197
         s->wall_floor[i] = walls[i].pos[2] == 0 && walls[i].width[2] == 0 && walls[i].height[2] == 0;
+        for (int c = 0; c < 3; c++) {
+            s->wall_wh.push_back(walls[i].width[c]);
+        }
+        for (int c = 0; c < 3; c++) {
+            s->wall_wh.push_back(walls[i].height[c]);
+        }
     }
     DeviceGuard guard(o.device);
     // cudaGetDeviceProperties costs about a millisecond per call: query the three attributes we need
@@ -339,6 +348,7 @@ void fmgi_scene_destroy(fmgi_scene *s)
     pool.free(s->d_grid_recs); pool.free(s->d_grid_ranges);
     pool.free(s->d_jobs); pool.free(s->d_counters); pool.free(s->d_scratch);
     pool.free(s->d_tile_walls); pool.free(s->h_tile_walls);
+    pool.free(s->d_ao); pool.free(s->d_ao_walls);
     pool.free(s->h_jobs); pool.free(s->h_counters);
     if (s->ev_start) cudaEventDestroy(s->ev_start);
     if (s->ev_stop) cudaEventDestroy(s->ev_stop);
@@ -727,6 +737,102 @@ int fmgi_scene_tonemap(fmgi_scene *s, const void *atlas_dev, int spa, int tint_e
     s->launches++;
     FMGI_CUDA(cudaGetLastError());
     return FMGI_OK;
+}
+
+// ---- ambient occlusion --------------------------------------------------------------------
+
+int fmgi_geosphere(int iterations, float *xyz_out, int max_directions)
+{
+    const std::vector<float> d = geosphere_directions(iterations);
+    const int n = (int)d.size() / 3;
+    for (int i = 0; xyz_out && i < 3 * (n < max_directions ? n : max_directions); i++) xyz_out[i] = d[i];
+    return n;
+}
+
+int fmgi_scene_ambient_occlusion(fmgi_scene *s, void *atlas_dev, void *cuda_stream)
+{
+    if (!s || !atlas_dev) return fail(FMGI_ERR_ARG, "scene or atlas is NULL");
+    DeviceGuard guard(s->device);
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    const int W = s->host.num_walls;
+    // flat enumeration of the base-level texels
+    std::vector<AoWall> aw(W ? W : 1);
+    long long pixels = 0;
+    for (int i = 0; i < W; i++) {
+        const ShadeRect &sh = s->host.shade[i];
+        aw[i].base = sh.base; aw[i].first = (int32_t)pixels; aw[i].wall = i; aw[i].pad = 0;
+        pixels += (long long)(sh.tiles & 0xffff) * (sh.tiles >> 16);
+    }
+    if (pixels > 0x7fffffffLL) return fail(FMGI_ERR_UNSUPPORTED, "more than 2^31 texels");
+    if (pixels == 0) return FMGI_OK;
+    // the reference's geoSphere4 direction set (photonmap.c:450-453), regenerated (geosphere.cpp)
+    const std::vector<float> dirs = geosphere_directions(4);
+    const int num_dirs = (int)dirs.size() / 3;
+    std::vector<float> blob;                                   // widths | heights | float4 directions
+    blob.reserve((size_t)6 * W + 4 * num_dirs + 4);
+    for (int i = 0; i < W; i++) for (int c = 0; c < 3; c++) blob.push_back(s->wall_wh[6 * i + c]);
+    for (int i = 0; i < W; i++) for (int c = 0; c < 3; c++) blob.push_back(s->wall_wh[6 * i + 3 + c]);
+    while (blob.size() % 4) blob.push_back(0.0f);
+    const size_t dirs_at = blob.size();
+    for (int k = 0; k < num_dirs; k++) {
+        blob.push_back(dirs[3 * k]); blob.push_back(dirs[3 * k + 1]); blob.push_back(dirs[3 * k + 2]); blob.push_back(0.0f);
+    }
+    MemPool &pool = MemPool::get();
+    if (!s->d_ao) {
+        FMGI_CUDA(pool.alloc((void **)&s->d_ao, blob.size() * sizeof(float), false));
+        FMGI_CUDA(pool.alloc((void **)&s->d_ao_walls, aw.size() * sizeof(AoWall), false));
+    }
+    FMGI_CUDA(cudaMemcpyAsync(s->d_ao, blob.data(), blob.size() * sizeof(float), cudaMemcpyHostToDevice, st));
+    FMGI_CUDA(cudaMemcpyAsync(s->d_ao_walls, aw.data(), aw.size() * sizeof(AoWall), cudaMemcpyHostToDevice, st));
+    FMGI_CUDA(cudaStreamSynchronize(st));                      // the staging vectors die with this call
+
+    TraceParams p = base_params(s);
+    p.atlas = reinterpret_cast<float4 *>(atlas_dev);
+    p.ao_width = s->d_ao;
+    p.ao_height = s->d_ao + 3 * (size_t)W;
+    const float4 *d_dirs = reinterpret_cast<const float4 *>(s->d_ao + dirs_at);
+    long long blocks = (pixels + kTraceThreads - 1) / kTraceThreads;
+    if (blocks > (long long)s->num_sms * 8) blocks = (long long)s->num_sms * 8;
+    auto go = [&](auto kernel) {
+        cudaError_t e = cudaSuccess;
+        if (s->smem_bytes > 48 * 1024)
+            e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->smem_bytes);
+        if (e != cudaSuccess) return e;
+        kernel<<<(int)blocks, kTraceThreads, s->smem_bytes, st>>>(p, s->d_ao_walls, W, pixels, d_dirs, num_dirs);
+        s->launches++;
+        return cudaGetLastError();
+    };
+    if (s->kernel_tier == kTierSoupPlanes) FMGI_CUDA(go(k_ambient_occlusion<kTierSoupPlanes>));
+    else if (s->kernel_tier == FMGI_TIER_SOUP) FMGI_CUDA(go(k_ambient_occlusion<FMGI_TIER_SOUP>));
+    else FMGI_CUDA(go(k_ambient_occlusion<FMGI_TIER_GRID>));
+    s->last_stream = st;
+    return FMGI_OK;
+}
+
+int fmgi_ambient_occlusion(struct Geometry *geo_, const fmgi_options *opt)
+{
+    fmgi_geometry *geo = reinterpret_cast<fmgi_geometry *>(geo_);
+    if (!geo || geo->numTexels < 0 || (geo->numTexels && !geo->texels)) return fail(FMGI_ERR_ARG, "bad geometry");
+    fmgi_options o = resolve(opt);
+    fmgi_scene *scene = nullptr;
+    int rc = fmgi_scene_create(&scene, geo->walls, geo->numWalls, geo->windows, geo->numWindows, geo->lights,
+                               geo->numLights, geo->numTexels, &o);
+    if (rc) return rc;
+    DeviceGuard guard(o.device);
+    const size_t bytes = (size_t)geo->numTexels * sizeof(float4);
+    float4 *atlas = nullptr;
+    cudaError_t e = MemPool::get().alloc((void **)&atlas, bytes ? bytes : 16, false);
+    // texels the pass does not write (mip slots) keep their contents, as in the reference
+    if (e == cudaSuccess) e = cudaMemcpy(atlas, geo->texels, bytes, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) {
+        rc = fmgi_scene_ambient_occlusion(scene, atlas, nullptr);
+        cudaSetDevice(o.device);
+        if (rc == FMGI_OK) e = cudaMemcpy(geo->texels, atlas, bytes, cudaMemcpyDeviceToHost);
+    }
+    MemPool::get().free(atlas);
+    fmgi_scene_destroy(scene);
+    if (rc == FMGI_OK && e != cudaSuccess) rc = fail(FMGI_ERR_CUDA, std::string("ambient occlusion: ") + cudaGetErrorString(e));
+    return rc;
 }
 
 // ---- parity probes ---------------------------------------------------------------------------------------------

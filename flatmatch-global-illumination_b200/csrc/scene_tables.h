@@ -129,6 +129,9 @@ void build_grid(HostScene &scene, const fmgi_rect *walls, int num_walls,
                 const fmgi_rect *windows, int num_windows, const fmgi_rect *lights, int num_lights,
                 float cell_hint);
 
+// Geodesic half-sphere direction set (xyz triples); iterations = 4 is the reference's geoSphere4.
+std::vector<float> geosphere_directions(int iterations);
+
 // vector3_cl.c:139-144: the basis both hemisphere samplers build around a normal.
 void sampler_basis(const float n[3], float u[3], float v[3]);
 

@@ -233,6 +233,74 @@ __global__ void k_probe_sample_dirs(float4 n, float4 u, float4 v, int sky, uint3
     }
 }
 
+// ---- ambient occlusion ------------------------------------------------------------------
+//
+// performAmbientOcclusionNative (photonmap.c:436-491) on the closest-hit code of the photon tracer: one
+// thread per base-level texel, num_dirs rays from the texel centre (getTileCenter, rectangle.c:140-153)
+// in the wall's local frame (createBase / transformToOrthoNormalBase, vector3_cl.c:152, photonmap.c:31),
+// d = sum(dist * fac) / (1.5 * sum(fac)) with dist = 10 for a miss; the texel is overwritten with (d, d, d, 0).
+struct AoWall {
+    int32_t base;        // atlas index of the wall's base level
+    int32_t first;       // index of its first texel in the flat texel enumeration
+    int32_t wall;        // wall index (shading record)
+    int32_t pad;
+};
+
+template <int kTier>
+__global__ void __launch_bounds__(kTraceThreads) k_ambient_occlusion(const TraceParams p, const AoWall *__restrict__ walls,
+                                                                     int num_walls, long long num_pixels,
+                                                                     const float4 *__restrict__ dirs, int num_dirs)
+{
+    extern __shared__ float4 smem[];
+    SoupTables soup;
+    if (kTier != FMGI_TIER_GRID) soup = stage_soup(p, smem);
+    unsigned tests = 0;
+    for (long long g = blockIdx.x * (long long)blockDim.x + threadIdx.x; g < num_pixels;
+         g += (long long)gridDim.x * blockDim.x) {
+        int lo = 0, hi = num_walls - 1;
+        while (lo < hi) {
+            const int mid = (lo + hi + 1) >> 1;
+            if ((long long)walls[mid].first <= g) lo = mid; else hi = mid - 1;
+        }
+        const AoWall w = walls[lo];
+        const int j = (int)(g - w.first);
+        const float4 *sh = p.shade + 6 * w.wall;
+        const float4 q0 = ldg4(sh), q1 = ldg4(sh + 1), q2 = ldg4(sh + 2), fn = ldg4(sh + 3), fu = ldg4(sh + 4), fv = ldg4(sh + 5);
+        const int tw = __float_as_int(fn.w) & 0xffff, th = __float_as_int(fn.w) >> 16;
+        // getTileCenter: pos + (width / tilesW) * (tx + 0.5) + (height / tilesH) * (ty + 0.5), with
+        // width = wn * |width| recovered from the shading record
+        const float rw = __fdiv_rn(1.0f, (float)tw), rh = __fdiv_rn(1.0f, (float)th);
+        const float fx = (float)((double)(j % tw) + 0.5), fy = (float)((double)(j / tw) + 0.5);
+        const float wx = __fmul_rn(p.ao_width[3 * w.wall], rw), wy = __fmul_rn(p.ao_width[3 * w.wall + 1], rw),
+                    wz = __fmul_rn(p.ao_width[3 * w.wall + 2], rw);
+        const float hx = __fmul_rn(p.ao_height[3 * w.wall], rh), hy = __fmul_rn(p.ao_height[3 * w.wall + 1], rh),
+                    hz = __fmul_rn(p.ao_height[3 * w.wall + 2], rh);
+        const float cx = __fadd_rn(__fadd_rn(q0.x, __fmul_rn(wx, fx)), __fmul_rn(hx, fy));
+        const float cy = __fadd_rn(__fadd_rn(q0.y, __fmul_rn(wy, fx)), __fmul_rn(hy, fy));
+        const float cz = __fadd_rn(__fadd_rn(q0.z, __fmul_rn(wz, fx)), __fmul_rn(hz, fy));
+        (void)q1; (void)q2; (void)th;
+        float dist_sum = 0.0f, fac_sum = 0.0f;
+        for (int k = 0; k < num_dirs; k++) {
+            const float4 d = __ldg(dirs + k);
+            // photonmap.c:41-45: in.x * b0 + in.y * b1 + in.z * b2, (b0, b1, b2) = (U, V, n)
+            const float dx = __fadd_rn(__fadd_rn(__fmul_rn(d.x, fu.x), __fmul_rn(d.y, fv.x)), __fmul_rn(d.z, fn.x));
+            const float dy = __fadd_rn(__fadd_rn(__fmul_rn(d.x, fu.y), __fmul_rn(d.y, fv.y)), __fmul_rn(d.z, fn.y));
+            const float dz = __fadd_rn(__fadd_rn(__fmul_rn(d.x, fu.z), __fmul_rn(d.y, fv.z)), __fmul_rn(d.z, fn.z));
+            const float ox = __fadd_rn(cx, __fmul_rn(dx, 1E-5f)), oy = __fadd_rn(cy, __fmul_rn(dy, 1E-5f)),
+                        oz = __fadd_rn(cz, __fmul_rn(dz, 1E-5f));                         // photonmap.c:457
+            float t;
+            const int id = kTier == FMGI_TIER_SOUP ? closest_hit_soup(soup, ox, oy, oz, dx, dy, dz, t)
+                         : kTier == kTierSoupPlanes ? closest_hit_soup_planes(soup, p, ox, oy, oz, dx, dy, dz, t, tests)
+                                                    : closest_hit_grid(p, ox, oy, oz, dx, dy, dz, t, tests);
+            if (id < 0) t = 10.0f;                                                       // photonmap.c:462-466
+            dist_sum = __fadd_rn(dist_sum, __fmul_rn(t, d.z));
+            fac_sum = __fadd_rn(fac_sum, d.z);
+        }
+        const float v = (float)((double)dist_sum / ((double)fac_sum * 1.5));              // photonmap.c:473
+        p.atlas[w.base + j] = make_float4(v, v, v, 0.0f);
+    }
+}
+
 // ---- tile post-processing ---------------------------------------------------------------
 //
 // Device version of what the caller does to the lightmap before it becomes tiles/tile_N.png:

@@ -47,6 +47,8 @@ struct TraceParams {
     // shading tables
     const float4 *shade;         // 6 float4 per wall
     const float4 *emitters;      // 6 float4 per emitter
+    const float *ao_width;       // ambient occlusion only: the walls' width / height vectors (3 floats each)
+    const float *ao_height;
     // this shard's photon index space: jobs [job_begin[e], job_begin[e+1]) belong to emitter e and
     // map to photon indices photon_first[e] + (job - job_begin[e])
     const unsigned long long *job_begin;

@@ -68,6 +68,7 @@ class Stats(C.Structure):
 EXPORTS = [
     "performGlobalIlluminationCl", "fmgi_default_options", "fmgi_last_error", "fmgi_version", "fmgi_device_count",
     "fmgi_release_cache", "fmgi_tile_bytes", "fmgi_scene_tonemap", "fmgi_bake_tiles",
+    "fmgi_ambient_occlusion", "fmgi_scene_ambient_occlusion", "fmgi_geosphere",
     "fmgi_bake", "fmgi_scene_create", "fmgi_scene_destroy", "fmgi_scene_trace", "fmgi_scene_sync",
     "fmgi_scene_photon_count", "fmgi_probe_closest_hit", "fmgi_probe_tile_ids", "fmgi_probe_philox",
     "fmgi_probe_sample_dirs", "fmgi_probe_paths",
@@ -106,6 +107,9 @@ def lib() -> C.CDLL:
     L.fmgi_tile_bytes.argtypes = [C.c_void_p, C.c_int]
     L.fmgi_scene_tonemap.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
     L.fmgi_bake_tiles.argtypes = [C.POINTER(Geometry), C.c_int, C.POINTER(Options), C.c_int, C.c_void_p, C.POINTER(Stats)]
+    L.fmgi_ambient_occlusion.argtypes = [C.POINTER(Geometry), C.POINTER(Options)]
+    L.fmgi_geosphere.argtypes = [C.c_int, C.c_void_p, C.c_int]
+    L.fmgi_scene_ambient_occlusion.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
     L.fmgi_probe_closest_hit.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
     L.fmgi_probe_tile_ids.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
     L.fmgi_probe_philox.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
@@ -187,6 +191,19 @@ def bake_tiles(geo: Geometry, walls: np.ndarray, num_samples_per_area: int, tint
     _check(lib().fmgi_bake_tiles(C.byref(geo), int(num_samples_per_area), C.byref(o), int(tint_extra),
                                  out.ctypes.data, C.byref(st)))
     return out[:n], st.as_dict()
+
+
+def geosphere(iterations: int = 4) -> np.ndarray:
+    n = lib().fmgi_geosphere(int(iterations), None, 0)
+    out = np.zeros((n, 3), dtype=np.float32)
+    lib().fmgi_geosphere(int(iterations), out.ctypes.data_as(C.c_void_p), n)
+    return out
+
+
+def ambient_occlusion(geo: Geometry, **opts) -> None:
+    """fmgi_ambient_occlusion: performAmbientOcclusionNative (photonmap.c:480) on the GPU."""
+    o = options(**opts)
+    _check(lib().fmgi_ambient_occlusion(C.byref(geo), C.byref(o)))
 
 
 class DeviceScene:

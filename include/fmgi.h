@@ -155,6 +155,19 @@ int fmgi_scene_tonemap(fmgi_scene *scene, const void *atlas_dev, int numSamplesP
 int fmgi_bake_tiles(struct Geometry *geo, int numSamplesPerArea, const fmgi_options *opt, int tintExtra,
                     uint8_t *rgb_out, fmgi_stats *stats);
 
+/* ---- extension: ambient occlusion on the device ---------------------------- */
+
+/* performAmbientOcclusionNative (global_illumination_native.h:16, photonmap.c:436-491) on the closest-hit
+ * code of the photon tracer: every base-level texel of every wall is OVERWRITTEN with (d, d, d, 0),
+ * d = sum(dist * fac) / (1.5 * sum(fac)) over the reference's 481 geoSphere4 directions (dist = 10 for
+ * a miss).  Other texels keep their contents. */
+int fmgi_ambient_occlusion(struct Geometry *geo, const fmgi_options *opt);
+/* The direction set itself (host only, no GPU needed): geodesic half-sphere with `iterations`
+ * subdivisions; 4 gives the reference's geoSphere4 (geoSphere.c:148) as a set.  Returns the count. */
+int fmgi_geosphere(int iterations, float *xyz_out, int max_directions);
+/* The same on a device-resident atlas; asynchronous on `cuda_stream` after its table upload. */
+int fmgi_scene_ambient_occlusion(fmgi_scene *scene, void *atlas_dev, void *cuda_stream);
+
 /* ---- extension: parity probes (each runs the same device functions the trace kernel uses) -- */
 
 /* Closest front-facing hit for num_rays host rays (xyz triples): wall index or -1, distance. */

@@ -120,15 +120,28 @@ def cmd_synth(_args):
               scene.num_texels, "texels", hashlib.sha256(scene.walls.tobytes()).hexdigest()[:16])
 
 
+def cmd_ao(_args):
+    """performAmbientOcclusionNative (photonmap.c:480) on example.png: base-level texel values."""
+    ref = rb.RefLib()
+    scene = rb.Scene.load(GOLDEN / "example_scene.npz")
+    t0 = time.time()
+    tex = ref.ambient_occlusion_native(scene)
+    mask = scene.base_texel_mask()
+    assert np.array_equal(tex[:, 0], tex[:, 1]) and np.array_equal(tex[:, 0], tex[:, 2]) and not tex[~mask].any()
+    np.savez_compressed(GOLDEN / "example_ao_native.npz", ao=tex[mask, 0], seconds=np.float64(time.time() - t0))
+    print("wrote example_ao_native.npz", tex[mask, 0].mean(), time.time() - t0)
+
+
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     sub = ap.add_subparsers(dest="cmd", required=True)
     sub.add_parser("scene")
     sub.add_parser("synth")
+    sub.add_parser("ao")
     a = sub.add_parser("atlas")
     a.add_argument("--depth", type=int, default=8)
     a.add_argument("--spa", type=int, default=5_000_000)
     a.add_argument("--procs", type=int, default=8)
     a.add_argument("--seed0", type=int, default=1000)
     args = ap.parse_args()
-    {"scene": cmd_scene, "atlas": cmd_atlas, "synth": cmd_synth}[args.cmd](args)
+    {"scene": cmd_scene, "atlas": cmd_atlas, "synth": cmd_synth, "ao": cmd_ao}[args.cmd](args)

@@ -513,3 +513,49 @@ void orc_tonemap_tiles(const orc_rect *walls, int num_walls, const float *texels
         rgb_out += 3 * (size_t)tiles;
     }
 }
+
+/* ------------------------------------------------------------------------------------------
+ * photonmap.c:436-491 — ambient occlusion; rectangle.c:140-153 (getTileCenter);
+ * photonmap.c:31-48 (transformToOrthoNormalBase); vector3_cl.c:152-170 (createBase).
+ * ---------------------------------------------------------------------------------------- */
+void orc_ambient_occlusion(const orc_rect *walls, int num_walls, float *texels, const float *dirs, int num_dirs,
+                           int accel)
+{
+    scene_t s = {walls, num_walls, accel, NULL};
+    if (accel == ORC_ACCEL_BSP)
+        s.root = bsp_build(walls, num_walls);
+    uint64_t tests = 0;
+    for (int i = 0; i < num_walls; i++) {
+        const orc_rect *wall = &walls[i];
+        v3 n = ld(wall->n);
+        /* createBase: c1 starts as z (or y), c2 = normalized(c1 x n), c1 = normalized(c2 x n) */
+        v3 b1 = V(0, 0, 1);
+        if (fabs(vdot(n, b1)) >= 0.999999f) b1 = V(0, 1, 0);
+        v3 b2 = vnormalized(vcross(b1, n));
+        b1 = vnormalized(vcross(b2, n));
+        const int tw = wall->lm[1], th = wall->lm[2];
+        v3 vw = vdiv(ld(wall->width), tw), vh = vdiv(ld(wall->height), th);        /* rectangle.c:144-145 */
+        for (int j = 0; j < tw * th; j++) {
+            float dist_sum = 0, fac_sum = 0;
+            const int tx = j % tw, ty = j / tw;
+            for (int k = 0; k < num_dirs; k++) {
+                v3 g = ld(dirs + 3 * k);
+                float fac = g.z;
+                v3 dir = V(g.x * b1.x + g.y * b2.x + g.z * n.x,                     /* photonmap.c:41-45 */
+                           g.x * b1.y + g.y * b2.y + g.z * n.y,
+                           g.x * b1.z + g.y * b2.z + g.z * n.z);
+                v3 pos = vadd3(ld(wall->pos), vmul(vw, tx + 0.5), vmul(vh, ty + 0.5));   /* rectangle.c:150 */
+                pos = vadd(pos, vmul(dir, 1E-5));                                   /* photonmap.c:457 */
+                float dist; int hit;
+                closest(&s, pos, dir, &dist, &hit, &tests);
+                if (hit < 0) dist = 10;                                             /* photonmap.c:462-466 */
+                dist_sum += dist * fac;
+                fac_sum += fac;
+            }
+            dist_sum /= (fac_sum * 1.5);                                            /* photonmap.c:473 */
+            float *t = texels + 4 * (size_t)(wall->lm[0] + j);
+            t[0] = dist_sum; t[1] = dist_sum; t[2] = dist_sum; t[3] = 0;
+        }
+    }
+    bsp_free(s.root);
+}

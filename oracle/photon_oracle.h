@@ -73,6 +73,13 @@ void orc_closest_hit(const orc_rect *walls, int num_walls, int accel,
                      const float *origins, const float *dirs, int num_rays,
                      int32_t *hit_index, float *hit_dist);
 
+/* performAmbientOcclusionNative (photonmap.c:436-491): every base-level texel of every wall is
+ * OVERWRITTEN with (d, d, d, 0), d = sum_k dist_k * fac_k / (1.5 * sum_k fac_k) over the direction
+ * set dirs (xyz triples in the texel's local frame, fac = z; the reference uses geoSphere4), where
+ * dist_k is the closest-hit distance from the texel centre or 10 for a miss. */
+void orc_ambient_occlusion(const orc_rect *walls, int num_walls, float *texels, const float *dirs, int num_dirs,
+                           int accel);
+
 /* The caller-side post-processing the lightmap goes through before it becomes tiles/tile_N.png:
  * main.c:68-79 (texel *= 0.35 * tiles / (area * samplesPerArea), base level only) followed by
  * saveAs_core (rectangle.c:293-336: tone-map 1 - exp(-2 L) at constant chroma, x255, clamp, floor

@@ -198,6 +198,8 @@ class RefLib:
             fn.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
         L.fmgi_ref_tile_ids.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
         L.fmgi_ref_sample_dirs.argtypes = [C.c_void_p, C.c_int, C.c_uint, C.c_int, C.c_void_p]
+        L.performAmbientOcclusionNative.restype = None
+        L.performAmbientOcclusionNative.argtypes = [C.POINTER(Geometry)]
         L.fmgi_ref_save_tile.restype = None
         L.fmgi_ref_save_tile.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_size_t]
         assert L.fmgi_ref_sizeof_rectangle() == 80 and L.fmgi_ref_sizeof_geometry() == 80
@@ -281,6 +283,20 @@ class RefLib:
         self.lib.fmgi_ref_sample_dirs(nn.ctypes.data, int(sky), seed, n, out.ctypes.data)
         return out
 
+    def ambient_occlusion_native(self, scene: Scene, texels: np.ndarray | None = None):
+        """performAmbientOcclusionNative (photonmap.c:480): overwrites the base-level texels."""
+        tex = aligned_texels(scene.num_texels) if texels is None else texels
+        g = scene.geometry(tex)
+        with _quiet_stdout():
+            self.lib.performAmbientOcclusionNative(C.byref(g))
+        return tex
+
+    def geosphere4(self) -> np.ndarray:
+        """The reference's 481-direction table (geoSphere.c:148), in its own order."""
+        n = C.c_int.in_dll(self.lib, "geoSphere4NumVectors").value
+        arr = (C.c_float * (4 * n)).in_dll(self.lib, "geoSphere4")
+        return np.frombuffer(arr, dtype=np.float32).reshape(n, 4)[:, :3].copy()
+
     def save_tile(self, rect, normalised_texels: np.ndarray, tint_extra: int) -> np.ndarray:
         """saveAs (rectangle.c:338) on one wall: the RGB bytes it hands to write_png_file."""
         r = aligned_rects(np.asarray([rect], dtype=RECT_DTYPE))
@@ -351,6 +367,8 @@ class OracleLib:
         L.orc_photon_budget.argtypes = [C.c_void_p, C.c_int]
         L.orc_philox4x32_10.restype = None
         L.orc_philox4x32_10.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        L.orc_ambient_occlusion.restype = None
+        L.orc_ambient_occlusion.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int]
         L.orc_tonemap_tiles.restype = None
         L.orc_tonemap_tiles.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p]
 
@@ -390,6 +408,13 @@ class OracleLib:
         p = np.ascontiguousarray(points, dtype=np.float32)
         return np.array([self.lib.orc_tile_id(r.ctypes.data, p[i].ctypes.data) for i in range(len(p))],
                         dtype=np.int32)
+
+    def ambient_occlusion(self, scene: Scene, dirs: np.ndarray, accel: int = 0, texels: np.ndarray | None = None):
+        tex = aligned_texels(scene.num_texels) if texels is None else texels
+        d = np.ascontiguousarray(dirs, dtype=np.float32)
+        self.lib.orc_ambient_occlusion(scene.walls.ctypes.data, len(scene.walls), tex.ctypes.data, d.ctypes.data,
+                                       len(d), accel)
+        return tex
 
     def tonemap_tiles(self, scene: Scene, raw_texels: np.ndarray, spa: int, tint_extra: int = 0) -> np.ndarray:
         """main.c:68-79 + saveAs_core for every wall: concatenated RGB bytes in wall order."""

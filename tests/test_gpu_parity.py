@@ -494,3 +494,37 @@ def test_bake_tiles_returns_packed_tiles_only(fmgi, oracle, scene):
     d = np.abs(rgb.astype(np.int32) - want.astype(np.int32))
     assert d.max() <= 1 and (d > 0).mean() < 2e-3            # two bakes: float atomics order differs
     assert st["deposits"] > 0
+
+
+def test_ambient_occlusion_matches_reference(fmgi, scene):
+    """fmgi_ambient_occlusion vs performAmbientOcclusionNative (photonmap.c:480) on example.png (fixture made
+    by the compiled reference).  Float result: the direction set is the same but summed in another order
+    and the distances come from another exact closest-hit search, so texels agree to ~1e-6 relative; a ray
+    grazing a rectangle edge may flip between hit and miss, which moves one texel by up to 1/481 of its range."""
+    want = np.load(GOLDEN / "example_ao_native.npz")["ao"].astype(np.float64)
+    tex = fmgi.aligned_texels(scene.num_texels)
+    tex[...] = 7.0                                            # must be overwritten on the base level only
+    fmgi.ambient_occlusion(fmgi.make_geometry(scene.walls, scene.windows, scene.lights, tex))
+    mask = scene.base_texel_mask()
+    assert np.all(tex[~mask] == 7.0)
+    got = tex[mask]
+    assert np.array_equal(got[:, 0], got[:, 1]) and np.array_equal(got[:, 0], got[:, 2]) and not got[:, 3].any()
+    rel = np.abs(got[:, 0] - want) / np.maximum(want, 1e-3)
+    assert np.mean(rel < 1e-5) > 0.99, np.mean(rel < 1e-5)
+    assert rel.max() < 0.03
+    assert abs(got[:, 0].mean() / want.mean() - 1) < 1e-5
+
+
+@pytest.mark.parametrize("tier", ["soup", "grid"])
+def test_ambient_occlusion_matches_oracle_on_small_room(fmgi, oracle, tier):
+    import refbind
+
+    walls, windows, lights, num_texels = staircase_scene(fmgi)
+    sc = refbind.Scene(walls, windows, lights, num_texels)
+    want = oracle.ambient_occlusion(sc, fmgi.geosphere(4), oracle.ACCEL_LINEAR)
+    tex = fmgi.aligned_texels(num_texels)
+    fmgi.ambient_occlusion(fmgi.make_geometry(sc.walls, sc.windows, sc.lights, tex),
+                           tier=fmgi.TIER_SOUP if tier == "soup" else fmgi.TIER_GRID)
+    mask = sc.base_texel_mask()
+    rel = np.abs(tex[mask, 0] - want[mask, 0]) / np.maximum(want[mask, 0], 1e-3)
+    assert np.mean(rel < 1e-5) > 0.98 and rel.max() < 0.03

@@ -184,3 +184,29 @@ def test_oracle_tonemap_equals_reference_saveas(oracle, reflib, scene):
             assert np.array_equal(mine[off:off + 3 * tw * th], want)
             off += 3 * tw * th
         assert off == mine.size and (mine > 0).mean() > 0.9
+
+
+def test_geosphere_regenerates_the_reference_direction_set(fmgi, reflib):
+    """geosphere.cpp rebuilds geoSphere4 (geoSphere.c:148, the AO direction table) from the generator's
+    construction (geoSphere.py): same 481 float triples as a set, whatever the order."""
+    ref8, _ = reflib
+    want = ref8.geosphere4()
+    got = fmgi.geosphere(4)
+    assert got.shape == want.shape == (481, 3)
+    assert sorted(map(tuple, got.tolist())) == sorted(map(tuple, want.tolist()))
+    assert (got[:, 2] > 0).all() and np.allclose(np.linalg.norm(got.astype(np.float64), axis=1), 1, atol=1e-6)
+
+
+def test_oracle_ambient_occlusion_equals_reference(oracle, reflib, fmgi):
+    """photonmap.c:436-491 restated: bit-equal to performAmbientOcclusionNative on a small closed room
+    (with the reference's own table order, since the sums are float)."""
+    import refbind
+    from test_gpu_parity import staircase_scene
+
+    ref8, _ = reflib
+    walls, windows, lights, num_texels = staircase_scene(fmgi)
+    sc = refbind.Scene(walls, windows, lights, num_texels)
+    want = ref8.ambient_occlusion_native(sc)
+    got = oracle.ambient_occlusion(sc, ref8.geosphere4(), oracle.ACCEL_BSP)
+    assert np.array_equal(want, got)
+    assert 0.1 < want[sc.base_texel_mask(), 0].mean() < 10 and not want[~sc.base_texel_mask()].any()
