@@ -16,8 +16,12 @@
 //   * 0 <= t < best is one unsigned compare (negative and NaN floats are large unsigned
 //     integers); containment is |p - mid| <= half, which moves half of the compare work from the
 //     ALU pipe to the FMA pipe (the ALU pipe was the top pipe of the first version, see profiles/);
-//   * deposits are one 16-byte vector reduction (RED.E.ADD.F32x4) per bounce into the L2-resident
-//     atlas, optionally warp-aggregated with __match_any_sync;
+//   * horizontal rectangles (a third of a flat) are not scanned at all when they fit the grid's
+//     plane tables: one cell lookup per z plane at the ray's crossing point (GridWalk::planes);
+//   * scenes beyond a few hundred rectangles use the floor-plan grid instead of the soup
+//     (GridWalk: plane lookups + a 2-D DDA through per-cell, per-sign-combination wall lists);
+//   * deposits are one 16-byte vector reduction (RED.E.ADD.F32x4) per bounce into the atlas,
+//     optionally warp-aggregated with __match_any_sync (measured: no gain, not the default);
 //   * per-photon Philox4x32-10 sub-streams (philox.cuh) replace the sequential libc stream.
 #pragma once
 #include <cuda_runtime.h>
