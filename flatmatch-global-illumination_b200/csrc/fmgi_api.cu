@@ -66,6 +66,15 @@ fmgi_options resolve(const fmgi_options *in)
     return o;
 }
 
+// Pool-backed device buffer that goes back to the pool on every exit path.
+template <typename T>
+struct DevBuf {
+    T *ptr = nullptr;
+    cudaError_t alloc(size_t count) { return MemPool::get().alloc((void **)&ptr, (count ? count : 1) * sizeof(T), false); }
+    ~DevBuf() { MemPool::get().free(ptr); }
+    operator T *() const { return ptr; }
+};
+
 template <typename T>
 cudaError_t upload(T **dst, const std::vector<T> &src)
 {
@@ -236,7 +245,8 @@ int fmgi_scene_create(fmgi_scene **out, const fmgi_rect *walls, int num_walls, c
     FMGI_CUDA(cudaGetDeviceCount(&ndev));
     if (o.device < 0 || o.device >= ndev) return fail(FMGI_ERR_ARG, "device ordinal out of range");
 
-    std::unique_ptr<fmgi_scene> s(new fmgi_scene);
+    // a scene that fails half-way gives its device blocks back through fmgi_scene_destroy
+    std::unique_ptr<fmgi_scene, void (*)(fmgi_scene *)> s(new fmgi_scene, fmgi_scene_destroy);
     s->device = o.device;
     const char *why = prepare_scene(s->host, walls, num_walls, windows, num_windows, lights, num_lights, num_texels);
     if (why[0]) return fail(FMGI_ERR_ARG, why);
@@ -843,13 +853,13 @@ int fmgi_probe_closest_hit(fmgi_scene *s, const float *origins, const float *dir
     if (!s || !origins || !dirs || !hit_index || !hit_dist || n < 0) return fail(FMGI_ERR_ARG, "bad argument");
     if (n == 0) return FMGI_OK;
     DeviceGuard guard(s->device);
-    float *d_o = nullptr, *d_d = nullptr, *d_t = nullptr;
-    int32_t *d_i = nullptr;
+    DevBuf<float> d_o, d_d, d_t;
+    DevBuf<int32_t> d_i;
     const size_t vb = (size_t)n * 3 * sizeof(float);
-    FMGI_CUDA(cudaMalloc((void **)&d_o, vb));
-    FMGI_CUDA(cudaMalloc((void **)&d_d, vb));
-    FMGI_CUDA(cudaMalloc((void **)&d_t, (size_t)n * sizeof(float)));
-    FMGI_CUDA(cudaMalloc((void **)&d_i, (size_t)n * sizeof(int32_t)));
+    FMGI_CUDA(d_o.alloc((size_t)n * 3));
+    FMGI_CUDA(d_d.alloc((size_t)n * 3));
+    FMGI_CUDA(d_t.alloc((size_t)n));
+    FMGI_CUDA(d_i.alloc((size_t)n));
     FMGI_CUDA(cudaMemcpy(d_o, origins, vb, cudaMemcpyHostToDevice));
     FMGI_CUDA(cudaMemcpy(d_d, dirs, vb, cudaMemcpyHostToDevice));
     const TraceParams p = base_params(s);
@@ -872,7 +882,6 @@ int fmgi_probe_closest_hit(fmgi_scene *s, const float *origins, const float *dir
     FMGI_CUDA(cudaGetLastError());
     FMGI_CUDA(cudaMemcpy(hit_index, d_i, (size_t)n * sizeof(int32_t), cudaMemcpyDeviceToHost));
     FMGI_CUDA(cudaMemcpy(hit_dist, d_t, (size_t)n * sizeof(float), cudaMemcpyDeviceToHost));
-    cudaFree(d_o); cudaFree(d_d); cudaFree(d_t); cudaFree(d_i);
     return FMGI_OK;
 }
 
@@ -883,11 +892,11 @@ int fmgi_probe_tile_ids(fmgi_scene *s, const int32_t *rect_index, const float *p
     for (int i = 0; i < n; i++)
         if (rect_index[i] < 0 || rect_index[i] >= s->host.num_walls) return fail(FMGI_ERR_ARG, "rect index out of range");
     DeviceGuard guard(s->device);
-    float *d_p = nullptr;
-    int32_t *d_r = nullptr, *d_t = nullptr;
-    FMGI_CUDA(cudaMalloc((void **)&d_p, (size_t)n * 3 * sizeof(float)));
-    FMGI_CUDA(cudaMalloc((void **)&d_r, (size_t)n * sizeof(int32_t)));
-    FMGI_CUDA(cudaMalloc((void **)&d_t, (size_t)n * sizeof(int32_t)));
+    DevBuf<float> d_p;
+    DevBuf<int32_t> d_r, d_t;
+    FMGI_CUDA(d_p.alloc((size_t)n * 3));
+    FMGI_CUDA(d_r.alloc((size_t)n));
+    FMGI_CUDA(d_t.alloc((size_t)n));
     FMGI_CUDA(cudaMemcpy(d_p, points, (size_t)n * 3 * sizeof(float), cudaMemcpyHostToDevice));
     FMGI_CUDA(cudaMemcpy(d_r, rect_index, (size_t)n * sizeof(int32_t), cudaMemcpyHostToDevice));
     int blocks = (n + 255) / 256;
@@ -896,19 +905,17 @@ int fmgi_probe_tile_ids(fmgi_scene *s, const int32_t *rect_index, const float *p
     s->launches++;
     FMGI_CUDA(cudaGetLastError());
     FMGI_CUDA(cudaMemcpy(tile_ids, d_t, (size_t)n * sizeof(int32_t), cudaMemcpyDeviceToHost));
-    cudaFree(d_p); cudaFree(d_r); cudaFree(d_t);
     return FMGI_OK;
 }
 
 int fmgi_probe_philox(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4])
 {
     if (!ctr || !key || !out) return fail(FMGI_ERR_ARG, "bad argument");
-    uint32_t *d = nullptr;
-    FMGI_CUDA(cudaMalloc((void **)&d, 4 * sizeof(uint32_t)));
+    DevBuf<uint32_t> d;
+    FMGI_CUDA(d.alloc(4));
     k_probe_philox<<<1, 1>>>(ctr[0], ctr[1], ctr[2], ctr[3], key[0], key[1], d);
     FMGI_CUDA(cudaGetLastError());
     FMGI_CUDA(cudaMemcpy(out, d, 4 * sizeof(uint32_t), cudaMemcpyDeviceToHost));
-    cudaFree(d);
     return FMGI_OK;
 }
 
@@ -918,14 +925,13 @@ int fmgi_probe_sample_dirs(const float normal[3], int sky, uint32_t seed, int n,
     if (n == 0) return FMGI_OK;
     float u[3], v[3];
     sampler_basis(normal, u, v);
-    float *d = nullptr;
-    FMGI_CUDA(cudaMalloc((void **)&d, (size_t)n * 3 * sizeof(float)));
+    DevBuf<float> d;
+    FMGI_CUDA(d.alloc((size_t)n * 3));
     k_probe_sample_dirs<<<(n + 255) / 256, 256>>>(make_float4(normal[0], normal[1], normal[2], 0),
                                                   make_float4(u[0], u[1], u[2], 0), make_float4(v[0], v[1], v[2], 0),
                                                   sky, seed, n, d);
     FMGI_CUDA(cudaGetLastError());
     FMGI_CUDA(cudaMemcpy(dirs_out, d, (size_t)n * 3 * sizeof(float), cudaMemcpyDeviceToHost));
-    cudaFree(d);
     return FMGI_OK;
 }
 
@@ -948,9 +954,9 @@ int fmgi_probe_paths(fmgi_scene *s, int emitter_index, int max_depth, uint32_t s
     s->h_jobs[E] = total;
     FMGI_CUDA(cudaMemcpy(s->d_jobs, s->h_jobs, (2 * E + 2) * sizeof(unsigned long long), cudaMemcpyHostToDevice));
     FMGI_CUDA(cudaMemset(s->d_counters, 0, 8 * sizeof(unsigned long long)));
-    int32_t *d_path = nullptr;
+    DevBuf<int32_t> d_path;
     const size_t pb = (size_t)count * max_depth * sizeof(int32_t);
-    FMGI_CUDA(cudaMalloc((void **)&d_path, pb));
+    FMGI_CUDA(d_path.alloc((size_t)count * max_depth));
     FMGI_CUDA(cudaMemset(d_path, 0xff, pb));
     TraceParams p = base_params(s);
     p.total_jobs = total;
@@ -961,7 +967,6 @@ int fmgi_probe_paths(fmgi_scene *s, int emitter_index, int max_depth, uint32_t s
     if (blocks > s->num_sms) blocks = s->num_sms;
     FMGI_CUDA(launch_trace(s, p, 0, true, blocks, nullptr));
     FMGI_CUDA(cudaMemcpy(texel_out, d_path, pb, cudaMemcpyDeviceToHost));
-    cudaFree(d_path);
     return FMGI_OK;
 }
 
