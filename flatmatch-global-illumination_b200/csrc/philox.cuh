@@ -14,7 +14,9 @@ struct Philox4 { uint32_t w0, w1, w2, w3; };
 __host__ __device__ __forceinline__ Philox4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
                                                           uint32_t k0, uint32_t k1)
 {
+#ifdef __CUDA_ARCH__
 #pragma unroll
+#endif
     for (int r = 0; r < 10; r++) {
 #ifdef __CUDA_ARCH__
         const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
