@@ -533,3 +533,77 @@ def test_ambient_occlusion_matches_oracle_on_small_room(fmgi, oracle, tier):
     rel = np.abs(tex[mask, 0] - want[mask, 0]) / np.maximum(want[mask, 0], 1e-3)
     assert np.mean(rel < 1e-5) > 0.99 and rel.max() < 0.08
     assert abs(tex[mask, 0].mean(dtype=np.float64) / want[mask, 0].mean(dtype=np.float64) - 1) < 2e-3
+
+
+def random_scene(fmgi, seed, n_axis=120, n_general=25):
+    """Random rectangle soup in a 12 x 9 x 3 m box: axis-parallel rectangles of all six orientations at
+    many different plane coordinates (more z planes than the plane table holds) plus arbitrarily
+    oriented ones, with normals as createRectangleV builds them (rectangle.c:22)."""
+    rng = np.random.default_rng(seed)
+    walls = np.zeros(n_axis + n_general, dtype=fmgi.RECT_DTYPE)
+    base = 0
+    for i in range(len(walls)):
+        pos = rng.uniform([0, 0, 0], [12, 9, 3]).astype(np.float32)
+        if i < n_axis:
+            k = rng.integers(0, 3)
+            ai, aj = [a for a in range(3) if a != k]
+            if rng.random() < 0.5:
+                ai, aj = aj, ai
+            w = np.zeros(3, np.float32); h = np.zeros(3, np.float32)
+            w[ai] = rng.uniform(0.3, 4.0) * rng.choice([-1, 1]); h[aj] = rng.uniform(0.3, 3.0) * rng.choice([-1, 1])
+        else:
+            w = rng.normal(size=3).astype(np.float32); w *= rng.uniform(0.5, 3.0) / np.linalg.norm(w)
+            h = np.cross(w, rng.normal(size=3)).astype(np.float32); h *= rng.uniform(0.5, 3.0) / np.linalg.norm(h)
+        n = np.cross(h, w).astype(np.float32)
+        n = (n / np.float32(np.linalg.norm(n))).astype(np.float32)
+        walls[i]["pos"][:3] = pos; walls[i]["width"][:3] = w; walls[i]["height"][:3] = h; walls[i]["n"][:3] = n
+        walls[i]["lightmapSetup"][:3] = (base, 4, 2)
+        base += 8 + 2 + 1
+    light = np.zeros(1, dtype=fmgi.RECT_DTYPE)
+    light[0]["pos"][:3] = (5, 4, 2.9); light[0]["width"][:3] = (1, 0, 0); light[0]["height"][:3] = (0, 1, 0)
+    light[0]["n"][:3] = (0, 0, -1); light[0]["lightmapSetup"][:3] = (0, 1, 1)
+    return walls, np.zeros(0, dtype=fmgi.RECT_DTYPE), light, base
+
+
+@pytest.mark.parametrize("seed", [1, 2, 3])
+@pytest.mark.parametrize("tier", ["soup", "grid"])
+def test_random_soups_closest_hit_and_paths(fmgi, oracle, seed, tier):
+    """Property test of the closest-hit search on scenes parseLayout would never produce."""
+    import refbind
+
+    walls, windows, lights, num_texels = random_scene(fmgi, seed)
+    sc = refbind.Scene(walls, windows, lights, num_texels)
+    s = fmgi.DeviceScene(sc.walls, sc.windows, sc.lights, sc.num_texels,
+                         tier=fmgi.TIER_SOUP if tier == "soup" else fmgi.TIER_GRID)
+    o, d = random_rays(sc, 100_000, seed)
+    gi, gt = s.closest_hit(o, d)
+    ci, ct = oracle.closest_hit(sc.walls, o, d, oracle.ACCEL_LINEAR)
+    assert (gi != ci).mean() < 2e-4, (gi != ci).sum()
+    both = (gi >= 0) & (gi == ci)
+    assert both.mean() > 0.15
+    assert np.max(np.abs(gt[both] - ct[both]) / np.maximum(ct[both], 1e-3)) < 1e-3
+    got = s.paths(0, 6, seed, 0, 20000)
+    ref = oracle.trace_paths(sc, 0, 6, seed, 0, 20000)
+    assert np.all(got == ref, axis=1).mean() > 0.99
+    s.close()
+
+
+def test_hires_retiled_layout_texel_index(fmgi, oracle, synth800):
+    """4x texel density (BASELINE configs[3]): tile grids from fmgi.layout.retile, texel index still the
+    reference's getTileIdAt bit for bit."""
+    import refbind
+    from fmgi import layout
+
+    walls, num_texels = layout.retile(synth800.walls, 800.0)
+    assert num_texels > 3.5 * synth800.num_texels
+    sc = refbind.Scene(walls, synth800.windows, synth800.lights, num_texels)
+    s = fmgi.DeviceScene(sc.walls, sc.windows, sc.lights, sc.num_texels)
+    rng = np.random.default_rng(4)
+    for wi in rng.choice(len(sc.walls), 40, replace=False):
+        w = sc.walls[wi]
+        uv = rng.random((3000, 2), dtype=np.float32)
+        pts = (w["pos"][:3] + uv[:, :1] * w["width"][:3] + uv[:, 1:] * w["height"][:3]).astype(np.float32)
+        assert np.array_equal(s.tile_ids(np.full(len(pts), wi, dtype=np.int32), pts), oracle.tile_ids(w, pts))
+    atlas, st = gpu_bake(s, 2000, max_depth=4, seed=1)
+    assert st["deposits"] > 0 and np.all(atlas[~sc.base_texel_mask()] == 0)
+    s.close()
