@@ -68,16 +68,16 @@ def cmd_scene(_args):
 
 
 def _worker(job):
-    depth, spa, seed = job
+    depth, spa, seed, fixture = job
     ref = rb.RefLib(runtime_depth=(depth != 8))
-    scene = rb.Scene.load(GOLDEN / "example_scene.npz")
+    scene = rb.Scene.load(GOLDEN / f"{fixture}_scene.npz")
     tex, secs = ref.photonmap_native(scene, spa, seed, depth)
     return tex.astype(np.float64), secs
 
 
 def cmd_atlas(args):
-    scene = rb.Scene.load(GOLDEN / "example_scene.npz")
-    jobs = [(args.depth, args.spa, args.seed0 + i) for i in range(args.procs)]
+    scene = rb.Scene.load(GOLDEN / f"{args.fixture}_scene.npz")
+    jobs = [(args.depth, args.spa, args.seed0 + i, args.fixture) for i in range(args.procs)]
     t0 = time.time()
     with mp.Pool(args.procs) as pool:
         res = pool.map(_worker, jobs)
@@ -90,14 +90,18 @@ def cmd_atlas(args):
         spa_total = args.spa * len(part)
         norm = scene.normalisation(spa_total)
         lum = (raw[:, :3] @ LUMA) * norm
-        out[f"lum_{name}"] = lum[mask].astype(np.float32)
+        out[f"lum_{name}"] = lum[mask][:: args.stride].astype(np.float32)
+        # per-wall mean luminance: almost noise-free, catches any per-surface bias
+        out[f"wall_lum_{name}"] = np.array([lum[int(w["lightmapSetup"][0]): int(w["lightmapSetup"][0]) +
+                                               int(w["lightmapSetup"][1]) * int(w["lightmapSetup"][2])].mean()
+                                           for w in scene.walls], dtype=np.float64)
         out[f"rgb_total_{name}"] = raw[:, :3].sum(axis=0)
         out[f"spa_{name}"] = np.int64(spa_total)
     photons = sum(scene.photon_counts(args.spa))
-    out.update(depth=np.int64(args.depth), photons_per_half=np.int64(photons * half),
+    out.update(stride=np.int64(args.stride), depth=np.int64(args.depth), photons_per_half=np.int64(photons * half),
                cpu_seconds=np.array([r[1] for r in res]), wall_seconds=np.float64(wall),
                seeds=np.array([j[2] for j in jobs]))
-    path = GOLDEN / f"example_native_depth{args.depth}.npz"
+    path = GOLDEN / f"{args.fixture}_native_depth{args.depth}.npz"
     np.savez_compressed(path, **out)
     print(f"wrote {path}: {photons * args.procs:.3e} photons in {wall:.0f} s wall, "
           f"per-process {np.mean(out['cpu_seconds']):.0f} s")
@@ -143,5 +147,7 @@ if __name__ == "__main__":
     a.add_argument("--spa", type=int, default=5_000_000)
     a.add_argument("--procs", type=int, default=8)
     a.add_argument("--seed0", type=int, default=1000)
+    a.add_argument("--fixture", default="example")
+    a.add_argument("--stride", type=int, default=1, help="keep every stride-th base texel (fixture size)")
     args = ap.parse_args()
     {"scene": cmd_scene, "atlas": cmd_atlas, "synth": cmd_synth, "ao": cmd_ao}[args.cmd](args)

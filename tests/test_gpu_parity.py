@@ -607,3 +607,40 @@ def test_hires_retiled_layout_texel_index(fmgi, oracle, synth800):
     atlas, st = gpu_bake(s, 2000, max_depth=4, seed=1)
     assert st["deposits"] > 0 and np.all(atlas[~sc.base_texel_mask()] == 0)
     s.close()
+
+
+def test_radiance_parity_grid_tier_synth800(fmgi, synth800):
+    """The same radiance bars on a layout that goes through the GRID tier and is lit mostly by ceiling
+    lights (cosine emitters): 547 rectangles, 31 emitters, against 6.0e8 photons of the compiled reference
+    (fixture: every 8th base texel + per-wall mean luminance, two independent halves)."""
+    sc = synth800
+    z = np.load(GOLDEN / "synth800_native_depth8.npz")
+    stride, depth = int(z["stride"]), int(z["depth"])
+    s = fmgi.DeviceScene(sc.walls, sc.windows, sc.lights, sc.num_texels, tier=fmgi.TIER_GRID)
+    area = sum(sc.photon_counts(1_000_000)) / 1e6
+    spa = int(2.0e9 / area)
+    atlas, st = gpu_bake(s, spa, max_depth=depth, seed=99)
+    s.close()
+    mask = sc.base_texel_mask()
+    lum_all = (atlas[:, :3].astype(np.float64) @ LUMA) * sc.normalisation(spa)
+    lum_gpu = lum_all[mask][::stride]
+    lum_a, lum_b = z["lum_a"].astype(np.float64), z["lum_b"].astype(np.float64)
+    s_ab, sp_ab, _ = parity_stats(lum_a, lum_b)
+    s_g, sp_g, lit = parity_stats(lum_gpu, 0.5 * (lum_a + lum_b))
+    print(f"synth800 depth {depth}: S={s_g:.4%} S'={sp_g:.4%} (lit {lit:.3f}); reference half-vs-half S={s_ab:.4%} "
+          f"S'={sp_ab:.4%}; gpu photons {st['photons']:.3e}")
+    assert sp_g < 0.02 and s_g < 0.02 and sp_g < 1.05 * sp_ab
+    # per-wall mean luminance: noise is negligible at this level, so this is a bias check per surface
+    wall_ref = 0.5 * (z["wall_lum_a"] + z["wall_lum_b"])
+    wall_gpu = np.array([lum_all[int(w["lightmapSetup"][0]): int(w["lightmapSetup"][0]) +
+                                 int(w["lightmapSetup"][1]) * int(w["lightmapSetup"][2])].mean() for w in sc.walls])
+    bright = wall_ref > 0.05 * wall_ref.mean()
+    wall_rel = (wall_gpu[bright] - wall_ref[bright]) / wall_ref[bright]
+    ab_rel = (z["wall_lum_a"][bright] - z["wall_lum_b"][bright]) / wall_ref[bright]
+    print(f"per-wall mean luminance: rel. RMS {np.sqrt(np.mean(wall_rel ** 2)):.4%} (reference half-vs-half "
+          f"{np.sqrt(np.mean(ab_rel ** 2)):.4%}), mean bias {wall_rel.mean():+.4%}")
+    assert np.sqrt(np.mean(wall_rel ** 2)) < 0.01 and abs(wall_rel.mean()) < 2e-3
+    e_ref = 0.5 * (z["rgb_total_a"] / float(z["spa_a"]) + z["rgb_total_b"] / float(z["spa_b"]))
+    e_gpu = atlas[:, :3].sum(axis=0, dtype=np.float64) / spa
+    print(f"energy per unit density rel. diff {e_gpu / e_ref - 1}")
+    assert np.all(np.abs(e_gpu / e_ref - 1) < 1e-3)
