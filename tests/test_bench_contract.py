@@ -17,7 +17,7 @@ def test_reference_arm_prints_one_contract_line():
     assert len(lines) == 1
     d = json.loads(lines[0])
     assert REQUIRED <= set(d) and d["impl"] == "reference"
-    assert d["unit"] == "bounces/s" and d["value"] > 1e5 and d["higher_is_better"] is True
+    assert d["unit"] == "photon-bounces/s" and d["metric"].startswith("photon-bounces/sec") and d["value"] > 1e5 and d["higher_is_better"] is True
     assert d["config"]["workload"] == "example_1e8x3" and d["vs_baseline"] is None
     assert d["cpu_baseline"]["kind"] in ("reference", "port") and d["cpu_baseline"]["cores"] >= 1
     assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
