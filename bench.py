@@ -240,7 +240,9 @@ def reference_app_wall_time():
         best = None
         for _ in range(2):
             t0 = time.perf_counter()
-            r = subprocess.run([str(app), str(png)], cwd=tmp, capture_output=True)
+            # one visible GPU: driver initialisation time grows with the number of GPUs it enumerates
+            env = dict(os.environ, CUDA_VISIBLE_DEVICES=os.environ.get("CUDA_VISIBLE_DEVICES", "0").split(",")[0])
+            r = subprocess.run([str(app), str(png)], cwd=tmp, capture_output=True, env=env)
             dt = time.perf_counter() - t0
             if r.returncode != 0:
                 return None
