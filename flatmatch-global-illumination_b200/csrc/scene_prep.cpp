@@ -287,6 +287,23 @@ void build_grid(HostScene &out, const fmgi_rect *walls, int num_walls, const fmg
                 for (int cx = it.cx0; cx <= it.cx1; cx++)
                     out.grid_recs[(size_t)fill[(size_t)l * ncell + cy * g.nx + cx]++] = it.rec;
         });
+    // plane lists: the lookup stops at the first rectangle that contains the crossing point, so put
+    // the rectangle that covers most of the cell first (floors tile the plane: usually one dominates)
+    for (int l = 0; l < kWalkListBase; l++)
+        for (int cy = 0; cy < g.ny; cy++)
+            for (int cx = 0; cx < g.nx; cx++) {
+                const size_t idx = (size_t)l * ncell + cy * g.nx + cx;
+                const int b = begin[idx], e = begin[idx + 1];
+                if (e - b < 2) continue;
+                const float x0c = g.x0 + cx * cell, y0c = g.y0 + cy * cell;
+                auto overlap = [&](const GridRec &r) {
+                    const float ox = fminf(r.mid_i + r.half_i, x0c + cell) - fmaxf(r.mid_i - r.half_i, x0c);
+                    const float oy = fminf(r.mid_j + r.half_j, y0c + cell) - fmaxf(r.mid_j - r.half_j, y0c);
+                    return fmaxf(ox, 0.0f) * fmaxf(oy, 0.0f);
+                };
+                std::stable_sort(out.grid_recs.begin() + b, out.grid_recs.begin() + e,
+                                 [&](const GridRec &a, const GridRec &c) { return overlap(a) > overlap(c); });
+            }
     out.grid_ranges.resize((size_t)2 * num_lists * ncell);
     for (size_t i = 0; i < (size_t)num_lists * ncell; i++) {
         out.grid_ranges[2 * i] = begin[i];
