@@ -113,7 +113,7 @@ __device__ __forceinline__ void scan_axis(const float4 *__restrict__ blk, int pa
                                           float &best, int &code)
 {
     blk += 6 * pair0;
-#pragma unroll 2
+#pragma unroll 4
     for (int j = pair0; j < pair1; j++, blk += 6) {
         const float4 qa = blk[0];
         const float4 qb = blk[1];
