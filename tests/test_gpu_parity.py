@@ -644,3 +644,34 @@ def test_radiance_parity_grid_tier_synth800(fmgi, synth800):
     e_gpu = atlas[:, :3].sum(axis=0, dtype=np.float64) / spa
     print(f"energy per unit density rel. diff {e_gpu / e_ref - 1}")
     assert np.all(np.abs(e_gpu / e_ref - 1) < 1e-3)
+
+
+def test_full_size_properties(dev_scene, scene):
+    """BASELINE.json configs[1] at full size (example.png, 1e8 photons x 3 bounces): size-independent
+    properties instead of an oracle run - exact budgets, counter identities, determinism of the sample set,
+    additivity over photon shards (what the multi-GPU reduce relies on) and energy per photon equal to a
+    10x smaller bake within Monte-Carlo noise."""
+    area = sum(scene.photon_counts(1_000_000)) / 1e6
+    spa, depth = int(1.0e8 / area), 3
+    whole, sw = gpu_bake(dev_scene, spa, max_depth=depth, seed=12)
+    assert sw["photons"] == sum(scene.photon_counts(spa)) and abs(sw["photons"] - 1e8) < 100
+    # every ray either deposits or ends its photon; a photon makes at most `depth` deposits
+    assert sw["deposits"] <= sw["rays"] <= sw["deposits"] + sw["photons"]
+    assert sw["deposits"] <= depth * sw["photons"] and sw["mirror_bounces"] < sw["deposits"]
+    assert 2.2 < sw["deposits"] / sw["photons"] < 2.3           # SURVEY.md section 6: 2.254 at depth 3
+    again, sa = gpu_bake(dev_scene, spa, max_depth=depth, seed=12)
+    for k in ("photons", "rays", "deposits", "mirror_bounces"):
+        assert sw[k] == sa[k]
+    assert np.allclose(whole, again, rtol=2e-5, atol=0.5)
+    parts = [gpu_bake(dev_scene, spa, max_depth=depth, seed=12, shard=g, num_shards=8) for g in range(8)]
+    for k in ("photons", "rays", "deposits", "mirror_bounces"):
+        assert sum(p[1][k] for p in parts) == sw[k]
+    total = np.sum([p[0].astype(np.float64) for p in parts], axis=0)
+    assert np.allclose(total, whole, rtol=2e-5, atol=0.5)
+    assert np.all(whole[:, 3] == 0) and np.all(whole[~scene.base_texel_mask()] == 0)
+    # colour lanes: every deposit is (18 or 16, ., 18) x 0.9^k x tint -> R >= G >= B-ish ordering never inverts R < 0
+    assert whole.min() >= 0
+    small, ss = gpu_bake(dev_scene, spa // 10, max_depth=depth, seed=13)
+    e_big = whole[:, :3].sum(dtype=np.float64) / sw["photons"]
+    e_small = small[:, :3].sum(dtype=np.float64) / ss["photons"]
+    assert abs(e_big / e_small - 1) < 1e-3
