@@ -662,12 +662,14 @@ def test_full_size_properties(dev_scene, scene):
     again, sa = gpu_bake(dev_scene, spa, max_depth=depth, seed=12)
     for k in ("photons", "rays", "deposits", "mirror_bounces"):
         assert sw[k] == sa[k]
-    assert np.allclose(whole, again, rtol=2e-5, atol=0.5)
+    # same deposits in another order: float atomics round differently (about 3e4 additions per texel)
+    assert np.allclose(whole, again, rtol=1e-4, atol=1.0)
     parts = [gpu_bake(dev_scene, spa, max_depth=depth, seed=12, shard=g, num_shards=8) for g in range(8)]
     for k in ("photons", "rays", "deposits", "mirror_bounces"):
         assert sum(p[1][k] for p in parts) == sw[k]
     total = np.sum([p[0].astype(np.float64) for p in parts], axis=0)
-    assert np.allclose(total, whole, rtol=2e-5, atol=0.5)
+    assert np.allclose(total, whole, rtol=1e-4, atol=1.0)
+    assert abs(total[:, :3].sum() / whole[:, :3].sum(dtype=np.float64) - 1) < 1e-6
     assert np.all(whole[:, 3] == 0) and np.all(whole[~scene.base_texel_mask()] == 0)
     # colour lanes: every deposit is (18 or 16, ., 18) x 0.9^k x tint -> R >= G >= B-ish ordering never inverts R < 0
     assert whole.min() >= 0
