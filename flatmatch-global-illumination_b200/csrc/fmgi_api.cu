@@ -96,9 +96,8 @@ struct fmgi_scene {
     GeneralRect *d_general = nullptr;
     ShadeRect *d_shade = nullptr;
     EmitterRec *d_emitters = nullptr;
-    GridRec *d_grid_recs = nullptr;             // grid tier
-    int32_t *d_grid_ranges = nullptr;
-    unsigned long long *d_jobs = nullptr;       // per accumulation pass: job_begin[E+1] then photon_first[E]
+    GridRec *d_grid_table = nullptr;            // grid tier / plane tables
+    unsigned long long *d_jobs = nullptr;       // per accumulation pass: chunk_begin[E+1], photon_first[E], photon_count[E]
     size_t job_tables = 0;                      // passes the job-table buffers have room for
     float4 *d_scratch = nullptr;                // per-pass fp32 atlas when a bake needs several passes
     TileWall *d_tile_walls = nullptr;           // tone-map wall table (fmgi_scene_tonemap)
@@ -133,34 +132,44 @@ TraceParams base_params(const fmgi_scene *s)
     p.general = reinterpret_cast<const float4 *>(s->d_general);
     for (int g = 0; g < 4; g++) p.pair_begin[g] = s->host.pair_begin[g];
     p.num_general = (int)s->host.general.size();
-    p.grid_recs = reinterpret_cast<const float4 *>(s->d_grid_recs);
-    p.grid_ranges = reinterpret_cast<const int2 *>(s->d_grid_ranges);
+    p.grid_table = reinterpret_cast<const float4 *>(s->d_grid_table);
     p.grid = s->host.grid;
+    p.grid_has_misc = s->host.grid_misc != 0;
     p.shade = reinterpret_cast<const float4 *>(s->d_shade);
     p.emitters = reinterpret_cast<const float4 *>(s->d_emitters);
     p.num_emitters = (int)s->host.emitters.size();
     p.job_begin = s->d_jobs;
     p.photon_first = s->d_jobs + (p.num_emitters + 1);
+    p.photon_count = s->d_jobs + (2 * p.num_emitters + 1);
     p.work_counter = s->d_counters + 4;
     p.counters = s->d_counters;
     return p;
 }
 
-// Fills the pinned job tables for (spa, shard): emitter e's N photons (photonmap.c:414-418) are
-// split into num_shards contiguous index ranges.  Returns the shard's photon total.
-unsigned long long fill_jobs(const fmgi_scene *s, int spa, const fmgi_options &o, unsigned long long *jobs)
+// Job tables, per accumulation pass: chunk_begin[E + 1] (prefix of the emitters' chunk counts; a chunk is
+// kChunkPhotons consecutive photon indices of ONE emitter, the unit a warp claims), photon_first[E],
+// photon_count[E].
+inline size_t job_table_words(size_t E) { return 3 * E + 2; }
+
+// Fills the pinned job tables for (spa, shard): emitter e's N photons (photonmap.c:414-418) are split
+// into num_shards contiguous index ranges.  Returns the shard's photon total; *chunks its chunk total.
+unsigned long long fill_jobs(const fmgi_scene *s, int spa, const fmgi_options &o, unsigned long long *jobs,
+                             unsigned long long *chunks = nullptr)
 {
     const int E = (int)s->host.emitters.size();
-    unsigned long long total = 0;
+    unsigned long long total = 0, total_chunks = 0;
     for (int e = 0; e < E; e++) {
         const unsigned long long n = photon_budget(s->host.emitter_area[e], spa);
         const unsigned long long first = (unsigned long long)((unsigned __int128)n * o.shard / o.num_shards);
         const unsigned long long last = (unsigned long long)((unsigned __int128)n * (o.shard + 1) / o.num_shards);
-        jobs[e] = total;
+        jobs[e] = total_chunks;
         jobs[E + 1 + e] = first;
+        jobs[2 * E + 1 + e] = last - first;
         total += last - first;
+        total_chunks += (last - first + kChunkPhotons - 1) / kChunkPhotons;
     }
-    jobs[E] = total;
+    jobs[E] = total_chunks;
+    if (chunks) *chunks = total_chunks;
     return total;
 }
 
@@ -313,8 +322,7 @@ int fmgi_scene_create(fmgi_scene **out, const fmgi_rect *walls, int num_walls, c
         s->smem_bytes = 0;
     }
     if (s->kernel_tier != FMGI_TIER_SOUP) {
-        FMGI_CUDA(upload(&s->d_grid_recs, s->host.grid_recs));
-        FMGI_CUDA(upload(&s->d_grid_ranges, s->host.grid_ranges));
+        FMGI_CUDA(upload(&s->d_grid_table, s->host.grid_table));
     }
 
     FMGI_CUDA(upload(&s->d_axis, s->host.axis));
@@ -323,10 +331,10 @@ int fmgi_scene_create(fmgi_scene **out, const fmgi_rect *walls, int num_walls, c
     FMGI_CUDA(upload(&s->d_emitters, s->host.emitters));
     const size_t E = s->host.emitters.size();
     MemPool &pool = MemPool::get();
-    FMGI_CUDA(pool.alloc((void **)&s->d_jobs, (2 * E + 2) * sizeof(unsigned long long), false));
+    FMGI_CUDA(pool.alloc((void **)&s->d_jobs, job_table_words(E) * sizeof(unsigned long long), false));
     s->job_tables = 1;
     FMGI_CUDA(pool.alloc((void **)&s->d_counters, 8 * sizeof(unsigned long long), false));
-    FMGI_CUDA(pool.alloc((void **)&s->h_jobs, (2 * E + 2) * sizeof(unsigned long long), true));
+    FMGI_CUDA(pool.alloc((void **)&s->h_jobs, job_table_words(E) * sizeof(unsigned long long), true));
     FMGI_CUDA(pool.alloc((void **)&s->h_counters, 8 * sizeof(unsigned long long), true));
     memset(s->h_counters, 0, 8 * sizeof(unsigned long long));
     FMGI_CUDA(cudaEventCreate(&s->ev_start));
@@ -355,7 +363,7 @@ void fmgi_scene_destroy(fmgi_scene *s)
     if (s->last_stream || s->traced) cudaStreamSynchronize(s->last_stream);
     MemPool &pool = MemPool::get();
     pool.free(s->d_axis); pool.free(s->d_general); pool.free(s->d_shade); pool.free(s->d_emitters);
-    pool.free(s->d_grid_recs); pool.free(s->d_grid_ranges);
+    pool.free(s->d_grid_table);
     pool.free(s->d_jobs); pool.free(s->d_counters); pool.free(s->d_scratch);
     pool.free(s->d_tile_walls); pool.free(s->h_tile_walls);
     pool.free(s->d_ao); pool.free(s->d_ao_walls);
@@ -369,7 +377,7 @@ uint64_t fmgi_scene_photon_count(const fmgi_scene *s, int spa, const fmgi_option
 {
     if (!s) return 0;
     const fmgi_options o = resolve(opt);
-    std::vector<unsigned long long> jobs(2 * s->host.emitters.size() + 2);
+    std::vector<unsigned long long> jobs(job_table_words(s->host.emitters.size()));
     return fill_jobs(s, spa, o, jobs.data());
 }
 
@@ -381,7 +389,7 @@ int fmgi_scene_trace(fmgi_scene *s, void *atlas_dev, int spa, const fmgi_options
     DeviceGuard guard(s->device);
     cudaStream_t st = (cudaStream_t)cuda_stream;
     const int E = (int)s->host.emitters.size();
-    const size_t table_words = (size_t)(2 * E + 2);
+    const size_t table_words = job_table_words((size_t)E);
 
     if (s->traced) FMGI_CUDA(cudaEventSynchronize(s->ev_stop));   // pinned staging is reused
 
@@ -410,10 +418,10 @@ int fmgi_scene_trace(fmgi_scene *s, void *atlas_dev, int spa, const fmgi_options
 
     fmgi_options op = o;
     op.num_shards = o.num_shards * passes;
-    std::vector<unsigned long long> totals(passes);
+    std::vector<unsigned long long> totals(passes), chunks(passes);
     for (int c = 0; c < passes; c++) {
         op.shard = o.shard * passes + c;
-        totals[c] = fill_jobs(s, spa, op, s->h_jobs + c * table_words);
+        totals[c] = fill_jobs(s, spa, op, s->h_jobs + c * table_words, &chunks[c]);
     }
     FMGI_CUDA(cudaMemcpyAsync(s->d_jobs, s->h_jobs, passes * table_words * sizeof(unsigned long long),
                               cudaMemcpyHostToDevice, st));
@@ -425,7 +433,8 @@ int fmgi_scene_trace(fmgi_scene *s, void *atlas_dev, int spa, const fmgi_options
         TraceParams p = base_params(s);
         p.job_begin = s->d_jobs + c * table_words;
         p.photon_first = p.job_begin + (E + 1);
-        p.total_jobs = totals[c];
+        p.photon_count = p.job_begin + (2 * E + 1);
+        p.total_jobs = chunks[c];
         p.atlas = reinterpret_cast<float4 *>(passes > 1 ? (void *)s->d_scratch : atlas_dev);
         p.max_depth = o.max_depth;
         p.seed = o.seed;
@@ -434,8 +443,7 @@ int fmgi_scene_trace(fmgi_scene *s, void *atlas_dev, int spa, const fmgi_options
             FMGI_CUDA(cudaMemsetAsync(s->d_counters + 4, 0, sizeof(unsigned long long), st));   // work counter
         }
         // persistent grid: one wave of resident CTAs, never more warps than chunks of work
-        unsigned long long want = (totals[c] + kChunkPhotons - 1) / kChunkPhotons;
-        want = (want * 32 + kTraceThreads - 1) / kTraceThreads;
+        unsigned long long want = (chunks[c] * 32 + kTraceThreads - 1) / kTraceThreads;
         const unsigned long long wave = (unsigned long long)s->num_sms * s->blocks_per_sm;
         const int blocks = (int)(want < wave ? (want ? want : 1) : wave);
         FMGI_CUDA(launch_trace(s, p, o.deposit, false, blocks, st));
@@ -949,10 +957,11 @@ int fmgi_probe_paths(fmgi_scene *s, int emitter_index, int max_depth, uint32_t s
     for (int e = 0; e < E; e++) {
         s->h_jobs[e] = total;
         s->h_jobs[E + 1 + e] = e == emitter_index ? first : 0;
-        if (e == emitter_index) total += (unsigned long long)count;
+        s->h_jobs[2 * E + 1 + e] = e == emitter_index ? (unsigned long long)count : 0;
+        if (e == emitter_index) total += ((unsigned long long)count + kChunkPhotons - 1) / kChunkPhotons;
     }
     s->h_jobs[E] = total;
-    FMGI_CUDA(cudaMemcpy(s->d_jobs, s->h_jobs, (2 * E + 2) * sizeof(unsigned long long), cudaMemcpyHostToDevice));
+    FMGI_CUDA(cudaMemcpy(s->d_jobs, s->h_jobs, job_table_words(E) * sizeof(unsigned long long), cudaMemcpyHostToDevice));
     FMGI_CUDA(cudaMemset(s->d_counters, 0, 8 * sizeof(unsigned long long)));
     DevBuf<int32_t> d_path;
     const size_t pb = (size_t)count * max_depth * sizeof(int32_t);

@@ -176,6 +176,7 @@ void build_grid(HostScene &out, const fmgi_rect *walls, int num_walls, const fmg
     out.grid_ranges.clear();
     out.grid_recs.clear();
     out.grid_overflow_horizontal = 0;
+    out.grid_misc = 0;
 
     // bounding box of everything a ray can start from or hit
     float xmin = INFINITY, xmax = -INFINITY, ymin = INFINITY, ymax = -INFINITY;
@@ -204,11 +205,12 @@ void build_grid(HostScene &out, const fmgi_rect *walls, int num_walls, const fmg
     const int ncell = g.nx * g.ny;
 
     // classify: which list does each wall go to, and with which record
-    struct Item { int list; int cx0, cx1, cy0, cy1; GridRec rec; };
+    struct Item { int list; int axis, neg; int cx0, cx1, cy0, cy1; GridRec rec; };
     std::vector<Item> items;
     std::vector<float> up, down;
     const float eps = 1e-3f * cell;
     int general_index = 0;
+    float zlo = INFINITY, zhi = -INFINITY;
     for (int r = 0; r < num_walls; r++) {
         const fmgi_rect &q = walls[r];
         V3 pos = ld(q.pos), wd = ld(q.width), ht = ld(q.height), n = ld(q.n);
@@ -227,19 +229,27 @@ void build_grid(HostScene &out, const fmgi_rect *walls, int num_walls, const fmg
             it.rec.mid_i = 0.5f * (lo_i + hi_i); it.rec.half_i = 0.5f * (hi_i - lo_i);
             it.rec.mid_j = 0.5f * (lo_j + hi_j); it.rec.half_j = 0.5f * (hi_j - lo_j);
             const int neg = comp(n, ak) > 0 ? 0 : 1;
-            it.rec.tag = r | (ak << 28) | (neg << 30);
+            it.axis = ak; it.neg = neg;
+            it.rec.tag = (uint32_t)r | (ak == 1 ? kTagAlongY : 0u);
             if (ak == 2) {                                  // horizontal: try the plane table
                 std::vector<float> &pl = neg ? down : up;
                 size_t p = 0;
                 while (p < pl.size() && pl[p] != it.rec.c) p++;
                 if (p == pl.size() && pl.size() < (size_t)kMaxPlanesPerSign) pl.push_back(it.rec.c);
-                if (p < pl.size()) it.list = (neg ? kMaxPlanesPerSign : 0) + (int)p;
-                else out.grid_overflow_horizontal++;
+                if (p < pl.size()) {
+                    it.list = (neg ? kMaxPlanesPerSign : 0) + (int)p;
+                    it.rec.tag = (uint32_t)r | kTagHorizontal;
+                } else {
+                    out.grid_overflow_horizontal++;
+                    it.rec.tag = (uint32_t)r | kTagMisc | (neg ? kTagNegative : 0u);
+                }
             }
         } else {
-            it.rec.tag = general_index | (3 << 28);
+            it.axis = 3; it.neg = 0;
+            it.rec.tag = (uint32_t)general_index | kTagMisc | kTagHorizontal;
         }
         if (!axis) general_index++;                         // same order as HostScene::general
+        if (it.rec.tag & kTagMisc) out.grid_misc++;
         // (x, y) bounding box over the four corners
         float bx0 = INFINITY, bx1 = -INFINITY, by0 = INFINITY, by1 = -INFINITY;
         for (int c = 0; c < 4; c++) {
@@ -249,20 +259,52 @@ void build_grid(HostScene &out, const fmgi_rect *walls, int num_walls, const fmg
         }
         auto cellx = [&](float x) { int c = (int)floorf((x - g.x0) * g.inv_cell); return c < 0 ? 0 : (c >= g.nx ? g.nx - 1 : c); };
         auto celly = [&](float y) { int c = (int)floorf((y - g.y0) * g.inv_cell); return c < 0 ? 0 : (c >= g.ny ? g.ny - 1 : c); };
+        if (it.list < 0)
+            for (int c = 0; c < 4; c++) {
+                const float z = pos.z + (c & 1 ? wd.z : 0.0f) + (c & 2 ? ht.z : 0.0f);
+                zlo = fminf(zlo, z); zhi = fmaxf(zhi, z);
+            }
         it.cx0 = cellx(bx0 - eps); it.cx1 = cellx(bx1 + eps);
         it.cy0 = celly(by0 - eps); it.cy1 = celly(by1 + eps);
         items.push_back(it);
     }
+    // Plane order: a ray travelling down meets the upward-facing planes from the top, a ray travelling up
+    // the downward-facing ones from the bottom; with the nearest plane first a hit bounds the later ones
+    // away (t < best fails) before their cell is looked up.
+    {
+        std::vector<int> remap(2 * kMaxPlanesPerSign, -1);
+        for (int sgn = 0; sgn < 2; sgn++) {
+            std::vector<float> &pl = sgn ? down : up;
+            std::vector<int> order(pl.size());
+            for (size_t p = 0; p < pl.size(); p++) order[p] = (int)p;
+            std::sort(order.begin(), order.end(), [&](int a, int b) { return sgn ? pl[a] < pl[b] : pl[a] > pl[b]; });
+            std::vector<float> sorted(pl.size());
+            for (size_t p = 0; p < pl.size(); p++) {
+                sorted[p] = pl[order[p]];
+                remap[sgn * kMaxPlanesPerSign + order[p]] = sgn * kMaxPlanesPerSign + (int)p;
+            }
+            pl = sorted;
+        }
+        for (Item &it : items)
+            if (it.list >= 0) it.list = remap[it.list];
+    }
     g.planes_up = (int)up.size(); g.planes_down = (int)down.size();
     for (size_t p = 0; p < up.size(); p++) g.plane_z[p] = up[p];
     for (size_t p = 0; p < down.size(); p++) g.plane_z[kMaxPlanesPerSign + p] = down[p];
+    g.ncell = ncell;
+    if (!(zhi >= zlo)) { zlo = 0.0f; zhi = 0.0f; }
+    g.wall_z_lo = zlo; g.wall_z_hi = zhi;
+    g.planes_max = std::max(g.planes_up, g.planes_down);
+    g.bx = -g.x0 * g.inv_cell; g.by = -g.y0 * g.inv_cell;
+    g.exit_lo_x = g.x0 + g.cell; g.exit_hi_x = g.x0 + (float)(g.nx - 1) * g.cell;
+    g.exit_lo_y = g.y0 + g.cell; g.exit_hi_y = g.y0 + (float)(g.ny - 1) * g.cell;
 
     // lists are numbered: [0, 8) planes +z, [8, 16) planes -z, 16 + combo = walk lists, where
     // combo = (d.x > 0) + 2 * (d.y > 0) is the sign combination of the rays that walk the list
     const int num_lists = kNumGridLists;
     auto for_each_list = [&](const Item &it, auto &&fn) {
         if (it.list >= 0) { fn(it.list); return; }
-        const int k = (it.rec.tag >> 28) & 3, neg = (it.rec.tag >> 30) & 1;
+        const int k = it.axis, neg = it.neg;
         for (int combo = 0; combo < 4; combo++) {
             // normal +x is faced by d.x < 0 (combo bit 0 clear), normal -x by d.x > 0; same for y
             if (k == 0 && ((combo & 1) != 0) != (neg != 0)) continue;
@@ -308,6 +350,36 @@ void build_grid(HostScene &out, const fmgi_rect *walls, int num_walls, const fmg
     for (size_t i = 0; i < (size_t)num_lists * ncell; i++) {
         out.grid_ranges[2 * i] = begin[i];
         out.grid_ranges[2 * i + 1] = begin[i + 1];
+    }
+
+    // T: heads (first record inline + continuation range), then the remaining records
+    const int num_used = g.planes_up + g.planes_down + 4;
+    g.down_base = g.planes_up * ncell;
+    g.walk_base = (g.planes_up + g.planes_down) * ncell;
+    auto used_list = [&](int u) {      // compact list number -> CSR list number
+        if (u < g.planes_up) return u;
+        if (u < g.planes_up + g.planes_down) return kMaxPlanesPerSign + (u - g.planes_up);
+        return kWalkListBase + (u - g.planes_up - g.planes_down);
+    };
+    GridRec dummy;
+    memset(&dummy, 0, sizeof dummy);
+    dummy.half_i = -1.0f; dummy.half_j = -1.0f; dummy.c = std::nanf("");
+    out.grid_table.assign((size_t)num_used * ncell, dummy);
+    for (int u = 0; u < num_used; u++) {
+        const int l = used_list(u);
+        for (int cell = 0; cell < ncell; cell++) {
+            const int b = begin[(size_t)l * ncell + cell], e = begin[(size_t)l * ncell + cell + 1];
+            if (b == e) continue;
+            GridRec head = out.grid_recs[b];
+            head.next = (int32_t)out.grid_table.size();
+            for (int q = b + 1; q < e; q++) {
+                GridRec rest = out.grid_recs[q];
+                rest.next = rest.end = 0;
+                out.grid_table.push_back(rest);
+            }
+            head.end = (int32_t)out.grid_table.size();
+            out.grid_table[(size_t)u * ncell + cell] = head;
+        }
     }
 }
 

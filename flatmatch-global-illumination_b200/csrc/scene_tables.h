@@ -75,18 +75,33 @@ static_assert(sizeof(EmitterRec) == 96, "EmitterRec is six float4");
 //     next cell starts beyond the best hit so far.  There are four walk lists per cell, one per
 //     sign combination (d.x > 0, d.y > 0) of the ray: a vertical wall is stored only in the two
 //     lists whose rays can face it (back-face culling, rectangle.c:70-72, done at build time).
-// Cell lists hold the 32-byte records inline (no index indirection): list (l, cell) is
-// recs[ranges[l * ncell + cell].x .. .y); l < 16: planes, l = 16 + combo: walk lists.
+// One table T of 32-byte records serves every list: entry l * ncell + cell is the HEAD of list
+// (l, cell) - its first record stored inline (or a dummy that no ray can hit) together with the index
+// range [next, end) of the list's remaining records, which follow the heads in T.  A cell visit is
+// therefore ONE dependent memory round trip (head = first candidate + continuation) instead of two
+// (range, then record).  Lists are numbered compactly: [0, planes_up) planes with normal +z (highest
+// first), [planes_up, planes_up + planes_down) planes with normal -z (lowest first), then the four
+// walk lists; GridDesc carries the bases.  (build_grid also keeps the CSR form it builds T from:
+// grid_ranges / grid_recs, lists numbered l < 16: planes, l = 16 + combo: walk lists.)
 
 enum { kMaxPlanesPerSign = 8, kWalkListBase = 2 * kMaxPlanesPerSign, kNumGridLists = kWalkListBase + 4 };
 
+// Record tag: wall id in the low 28 bits plus
+//   bit 31       vertical wall whose normal is along y (clear: along x)  - the sign bit, one compare
+//   bit 30       "misc" record that takes the slow path of the walk: bit 29 set = arbitrarily oriented
+//                rectangle (low bits index `general`), bit 29 clear = horizontal rectangle beyond the
+//                plane table (bit 28: normal is -z)
+//   bit 29 alone horizontal rectangle in a plane list
+enum : uint32_t { kTagAlongY = 1u << 31, kTagMisc = 1u << 30, kTagHorizontal = 1u << 29, kTagNegative = 1u << 28,
+                  kTagIdMask = (1u << 28) - 1 };
+
+// The first float4 is all a plane lookup needs (extents); the walk also reads (c, tag).
 struct GridRec {
-    float c;                // plane coordinate pos[k]
     float mid_i, half_i;    // extent along in-plane axis i (centre, half width)
-    float mid_j;
-    float half_j;
-    int32_t tag;            // wall id | k << 28 | (normal negative) << 30;  k == 3: index into `general`
-    int32_t pad0, pad1;
+    float mid_j, half_j;
+    float c;                // plane coordinate pos[k]; NaN in a dummy head
+    uint32_t tag;
+    int32_t next, end;      // heads only: the list's remaining records are T[next .. end)
 };
 static_assert(sizeof(GridRec) == 32, "GridRec is two float4");
 
@@ -96,6 +111,14 @@ struct GridDesc {
     int32_t nx, ny;
     int32_t planes_up, planes_down;         // number of z planes with normal +z / -z
     float plane_z[2 * kMaxPlanesPerSign];   // [0, planes_up): normal +z; [kMaxPlanesPerSign, +planes_down): normal -z
+    // derived constants of the walk
+    int32_t ncell;          // nx * ny
+    int32_t planes_max;     // max(planes_up, planes_down)
+    float bx, by;           // -x0 * inv_cell, -y0 * inv_cell: cell coordinate = fma(x, inv_cell, bx)
+    float exit_lo_x, exit_hi_x, exit_lo_y, exit_hi_y;   // the box without the outermost ring of cells
+    float wall_z_lo, wall_z_hi;                         // z range of everything in the walk lists
+    int32_t down_base;      // T index of the first head of the first plane with normal -z (planes_up * ncell)
+    int32_t walk_base;      // T index of the first head of walk list 0 ((planes_up + planes_down) * ncell)
 };
 
 struct HostScene {
@@ -111,7 +134,9 @@ struct HostScene {
     GridDesc grid = {};
     std::vector<int32_t> grid_ranges;     // 2 ints (begin, end) per (list, cell); kNumGridLists lists
     std::vector<GridRec> grid_recs;
+    std::vector<GridRec> grid_table;      // T: what the device walks
     int grid_overflow_horizontal = 0;     // horizontal rectangles that did not fit the plane table
+    int grid_misc = 0;                    // misc records in the walk lists (those plus arbitrarily oriented rectangles)
 };
 
 // photonmap.c:414-418: N = (uint64)(int spa * float area)

@@ -55,9 +55,9 @@ __global__ void __launch_bounds__(kTraceThreads, kMinBlocks) k_trace(const Trace
     float cr = 0, cg = 0, cb = 0, roulette = 0;
     int depth = 0, emitter = 0, hit_id = 0;
     unsigned long long photon = 0;
-    // warp-uniform work range
-    unsigned long long w_next = 0, w_end = 0;
-    int w_emitter = 0;
+    // the warp's chunk (warp uniform): photon indices w_base + [w_pos, w_cnt) of emitter w_emitter
+    unsigned long long w_base = 0;
+    int w_pos = 0, w_cnt = 0, w_emitter = 0;
     bool exhausted = false;
     unsigned n_photons = 0, n_rays = 0, n_deposits = 0, n_mirror = 0, n_tests = 0;
 
@@ -67,28 +67,27 @@ __global__ void __launch_bounds__(kTraceThreads, kMinBlocks) k_trace(const Trace
         if (!exhausted) {
             unsigned dead = __ballot_sync(kFullMask, !alive);
             while (dead) {
-                if (w_next == w_end) {
-                    unsigned long long base = 0;
-                    if (lane == 0) base = atomicAdd(p.work_counter, (unsigned long long)kChunkPhotons);
-                    base = __shfl_sync(kFullMask, base, 0);
-                    if (base >= p.total_jobs) { exhausted = true; break; }
-                    w_next = base;
-                    w_end = min(base + (unsigned long long)kChunkPhotons, p.total_jobs);
-                    w_emitter = find_emitter(p.job_begin, p.num_emitters, w_next);
+                if (w_pos == w_cnt) {
+                    unsigned long long k = 0;
+                    if (lane == 0) k = atomicAdd(p.work_counter, 1ull);
+                    k = __shfl_sync(kFullMask, k, 0);
+                    if (k >= p.total_jobs) { exhausted = true; break; }
+                    w_emitter = find_emitter(p.job_begin, p.num_emitters, k);
+                    const unsigned long long first = (k - __ldg(p.job_begin + w_emitter)) * kChunkPhotons;
+                    const unsigned long long left = __ldg(p.photon_count + w_emitter) - first;
+                    w_base = __ldg(p.photon_first + w_emitter) + first;
+                    w_cnt = left < (unsigned long long)kChunkPhotons ? (int)left : kChunkPhotons;
+                    w_pos = 0;
                 }
-                const unsigned long long avail = w_end - w_next;
+                const int avail = w_cnt - w_pos;
                 const int rank = __popc(dead & lt_mask);
-                if (!alive && (unsigned long long)rank < avail) {
-                    const unsigned long long job = w_next + (unsigned long long)rank;
-                    int e = w_emitter;
-                    while (job >= __ldg(p.job_begin + e + 1)) e++;     // chunk straddles emitters: rare
-                    emitter = e;
-                    photon = __ldg(p.photon_first + e) + (job - __ldg(p.job_begin + e));
-                    alive = true; is_new = true; depth = 0;
+                if (!alive && rank < avail) {
+                    photon = w_base + (unsigned)(w_pos + rank);
+                    emitter = w_emitter;
+                    alive = true; is_new = true; mirror = false; depth = 0;
                     n_photons++;
                 }
-                const unsigned long long want = (unsigned long long)__popc(dead);
-                w_next += want < avail ? want : avail;
+                w_pos += min(__popc(dead), avail);
                 dead = __ballot_sync(kFullMask, !alive);
             }
         }
@@ -100,31 +99,35 @@ __global__ void __launch_bounds__(kTraceThreads, kMinBlocks) k_trace(const Trace
             // ---- P. one Philox block per event: emission (event 0) or the bounce just done --------
             const Philox4 w = philox4x32_10((uint32_t)photon, (uint32_t)(photon >> 32), (uint32_t)depth, 0u,
                                             p.seed, (uint32_t)emitter);
-            // ---- S. new direction -------------------------------------------------------------------
+            // ---- S. new direction: emission and re-emission share the sampler ------------------------
+            // emission (photonmap.c:169-185) draws dx, dy from words 0, 1 and the direction from words 2, 3;
+            // a bounce (photonmap.c:228-233) draws its direction from words 0, 1
             const float4 *frame = is_new ? p.emitters + 6 * emitter : p.shade + 6 * hit_id;
             const float4 fn = ldg4(frame + 3);
+            const uint32_t wa = is_new ? w.w2 : w.w0, wb = is_new ? w.w3 : w.w1;
+            float4 e0 = make_float4(px, py, pz, 0.0f);
             if (is_new) {
-                // photonmap.c:169-185
-                const float4 e0 = ldg4(frame), e1 = ldg4(frame + 1), e2 = ldg4(frame + 2);
+                e0 = ldg4(frame);
                 const bool sky = __float_as_int(e0.w) != 0;
-                cr = sky ? 18.0f : 16.0f; cg = cr; cb = 18.0f;
+                cr = sky ? 18.0f : 16.0f; cg = cr; cb = 18.0f;   // photonmap.c:169-171
+            }
+            if (mirror) {                                       // photonmap.c:230
+                const float k2 = 2.0f * (fn.x * dx + fn.y * dy + fn.z * dz);
+                dx = fmaf(-k2, fn.x, dx); dy = fmaf(-k2, fn.y, dy); dz = fmaf(-k2, fn.z, dz);
+            } else {                                            // photonmap.c:179-181, :233
+                sample_hemisphere(u24(wa), u24(wb), is_new && __float_as_int(e0.w) != 0, fn, ldg4(frame + 4),
+                                  ldg4(frame + 5), dx, dy, dz);
+            }
+            roulette = r16(wa, wb);
+            px = __fadd_rn(e0.x, __fmul_rn(dx, 1E-5f));         // photonmap.c:183, :254
+            py = __fadd_rn(e0.y, __fmul_rn(dy, 1E-5f));
+            pz = __fadd_rn(e0.z, __fmul_rn(dz, 1E-5f));
+            if (is_new) {                                       // photonmap.c:184-185
+                const float4 e1 = ldg4(frame + 1), e2 = ldg4(frame + 2);
                 const float sx = u24(w.w0), sy = u24(w.w1);
-                sample_hemisphere(u24(w.w2), u24(w.w3), sky, fn, ldg4(frame + 4), ldg4(frame + 5), dx, dy, dz);
-                roulette = r16(w.w2, w.w3);
-                px = __fadd_rn(__fadd_rn(__fadd_rn(e0.x, __fmul_rn(dx, 1E-5f)), __fmul_rn(e1.x, sx)), __fmul_rn(e2.x, sy));
-                py = __fadd_rn(__fadd_rn(__fadd_rn(e0.y, __fmul_rn(dy, 1E-5f)), __fmul_rn(e1.y, sx)), __fmul_rn(e2.y, sy));
-                pz = __fadd_rn(__fadd_rn(__fadd_rn(e0.z, __fmul_rn(dz, 1E-5f)), __fmul_rn(e1.z, sx)), __fmul_rn(e2.z, sy));
-            } else {
-                if (mirror) {                                   // photonmap.c:230
-                    const float k2 = 2.0f * (fn.x * dx + fn.y * dy + fn.z * dz);
-                    dx = fmaf(-k2, fn.x, dx); dy = fmaf(-k2, fn.y, dy); dz = fmaf(-k2, fn.z, dz);
-                } else {                                        // photonmap.c:233
-                    sample_hemisphere(u24(w.w0), u24(w.w1), false, fn, ldg4(frame + 4), ldg4(frame + 5), dx, dy, dz);
-                }
-                roulette = r16(w.w0, w.w1);
-                px = __fadd_rn(px, __fmul_rn(dx, 1E-5f));       // photonmap.c:254
-                py = __fadd_rn(py, __fmul_rn(dy, 1E-5f));
-                pz = __fadd_rn(pz, __fmul_rn(dz, 1E-5f));
+                px = __fadd_rn(__fadd_rn(px, __fmul_rn(e1.x, sx)), __fmul_rn(e2.x, sy));
+                py = __fadd_rn(__fadd_rn(py, __fmul_rn(e1.y, sx)), __fmul_rn(e2.y, sy));
+                pz = __fadd_rn(__fadd_rn(pz, __fmul_rn(e1.z, sx)), __fmul_rn(e2.z, sy));
             }
 
             // ---- C. closest hit (photonmap.c:198 / photonmap.cl:194-206) ---------------------------

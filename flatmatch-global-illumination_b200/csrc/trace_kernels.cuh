@@ -44,21 +44,22 @@ struct TraceParams {
     const float4 *general;       // 4 float4 per GeneralRect
     int pair_begin[4];           // pairs of axis k: pair_begin[k] .. pair_begin[k+1]
     int num_general;
-    // grid tier (scene_tables.h): inline cell-list records and (begin, end) per (list, cell)
-    const float4 *grid_recs;     // 2 float4 per GridRec
-    const int2 *grid_ranges;
+    // grid tier (scene_tables.h): list heads, then the lists' remaining records
+    const float4 *grid_table;    // 2 float4 per GridRec
     GridDesc grid;
     // shading tables
     const float4 *shade;         // 6 float4 per wall
     const float4 *emitters;      // 6 float4 per emitter
     const float *ao_width;       // ambient occlusion only: the walls' width / height vectors (3 floats each)
     const float *ao_height;
-    // this shard's photon index space: jobs [job_begin[e], job_begin[e+1]) belong to emitter e and
-    // map to photon indices photon_first[e] + (job - job_begin[e])
+    // this shard's photon index space in chunks of kChunkPhotons photons of ONE emitter (the unit a warp
+    // claims): chunks [job_begin[e], job_begin[e+1]) belong to emitter e; chunk j of emitter e covers
+    // photon indices photon_first[e] + [j * kChunkPhotons, min((j + 1) * kChunkPhotons, photon_count[e]))
     const unsigned long long *job_begin;
     const unsigned long long *photon_first;
+    const unsigned long long *photon_count;
     int num_emitters;
-    unsigned long long total_jobs;
+    unsigned long long total_jobs;   // chunks
     unsigned long long *work_counter;
     // output
     float4 *atlas;
@@ -66,6 +67,7 @@ struct TraceParams {
     int32_t *path_out;              // probe builds only
     int max_depth;
     uint32_t seed;
+    int grid_has_misc;              // the walk lists hold misc records (scene_tables.h)
 };
 
 // ---- closest hit against the shared-memory soup ----------------------------------------------
@@ -203,20 +205,20 @@ __device__ __forceinline__ int closest_hit_soup(const SoupTables &s, float ox, f
 
 // ---- closest hit through the floor-plan grid (grid tier) ---------------------------------------------
 
-struct GridHit { float best; int rec; };      // rec: index of the winning inline record, -1 = miss
+__device__ __forceinline__ float rcp_fast(float x) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+__device__ __forceinline__ float2 ldg2(const float4 *p) { return __ldg(reinterpret_cast<const float2 *>(p)); }
 
-// Rare walk-list records: a horizontal rectangle beyond the plane table (k == 2) or an arbitrarily
-// oriented rectangle (k == 3).  These sit in all four walk lists, so facing is tested here.
-// Returns the ray parameter of a valid hit closer than `best`, else +inf (by value: the caller's
-// running minimum stays in registers).
-__device__ __noinline__ float grid_test_misc(const float4 *__restrict__ general, float4 q0, float4 q1, float ox, float oy,
-                                             float oz, float dx, float dy, float dz, float best)
+// Rare walk-list records (tag bit 30): a horizontal rectangle beyond the plane table or an arbitrarily
+// oriented rectangle.  These sit in all four walk lists, so facing is tested here.  Returns the ray
+// parameter of a valid hit closer than `best`, else +inf (by value: the caller's running minimum
+// stays in registers).
+__device__ __noinline__ float grid_test_misc(const float4 *__restrict__ general, float4 q0, float c, unsigned tag, float ox,
+                                             float oy, float oz, float dx, float dy, float dz, float best)
 {
     const float inf = __int_as_float(0x7f800000);
-    const int tag = __float_as_int(q1.y);
-    if (((tag >> 28) & 3) == 3) {
+    if (tag & kTagHorizontal) {
         // rectangle.c:67-95 for an arbitrarily oriented rectangle
-        const float4 *g = general + 4 * (tag & 0x0fffffff);
+        const float4 *g = general + 4 * (tag & kTagIdMask);
         const float4 g0 = __ldg(g), g1 = __ldg(g + 1), g2 = __ldg(g + 2), g3 = __ldg(g + 3);
         const float denom = g0.x * dx + g0.y * dy + g0.z * dz;
         const float num = g0.w - (g0.x * ox + g0.y * oy + g0.z * oz);
@@ -228,131 +230,194 @@ __device__ __noinline__ float grid_test_misc(const float4 *__restrict__ general,
                         u <= g1.w && v <= g2.w;
         return ok ? t : inf;
     }
-    const bool facing = (tag & (1 << 30)) ? dz > 0.0f : dz < 0.0f;    // back-face culling, rectangle.c:70-72
-    const float t = __fdividef(q0.x - oz, dz);
-    const float pi = fmaf(t, dx, ox) - q0.y;
-    const float pj = fmaf(t, dy, oy) - q0.w;
-    const bool ok = facing && (__float_as_uint(t) < __float_as_uint(best)) && fabsf(pi) <= q0.z && fabsf(pj) <= q1.x;
+    const bool facing = (tag & kTagNegative) ? dz > 0.0f : dz < 0.0f;    // back-face culling, rectangle.c:70-72
+    const float t = __fdividef(c - oz, dz);
+    const float pi = fmaf(t, dx, ox) - q0.x;
+    const float pj = fmaf(t, dy, oy) - q0.z;
+    const bool ok = facing && (__float_as_uint(t) < __float_as_uint(best)) && fabsf(pi) <= q0.y && fabsf(pj) <= q0.w;
     return ok ? t : inf;
 }
 
-// Closest-hit query through the grid as begin / step / finish.  (A kernel that interleaved the
-// steps of different rays - lanes whose walk was over waited until most of the warp was waiting,
-// then shaded together - was measured and dropped: 54.3 ms vs 53.7 ms for this one-ray-at-a-time
-// form on the 21.5k-rectangle scene; the bookkeeping ate what the fuller warps gained.)
+// Closest-hit query through the grid.  (Shapes that were measured and dropped: a kernel that interleaved
+// the walk steps of different rays - lanes whose walk was over waited until most of the warp was
+// waiting, then shaded together; and, in a CPU replay of the warp, walks capped at M steps per round
+// with unfinished lanes carried over - the shading phase then runs with fewer lanes and eats the gain.)
 struct GridWalk {
     float best;            // ray parameter of the best hit so far (+inf: none)
-    int win;               // inline record index of the best hit, -1: none
-    float ix, iy;          // 1/d.x, 1/d.y
-    float tmx, tmy;        // ray parameter at which the walk leaves the current cell along x / y
-    float tdx, tdy;        // ray parameter per cell along x / y
-    float t_exit;          // ray parameter at which the ray leaves the grid minus its outermost ring of cells
-    int ci;                // current cell, linear index cy * nx + cx
-    int sx, sy;            // linear-index step along x (+-1) and y (+-nx)
-    int r, rend;           // pending records of the current cell
-    const int2 *walk;      // the walk list ranges of this ray's sign combination
+    int win;               // index in T of the best hit's record, -1: none
 
-    // Phase 1: horizontal planes the ray can face - one cell lookup per plane at the crossing point.
+    __device__ __forceinline__ void reset() { best = __int_as_float(0x7f800000); win = -1; }
+
+    // Horizontal planes the ray can face - one head lookup per plane at the crossing point, nearest
+    // plane first (the table is sorted), so that a hit bounds the remaining planes away.  Only planes
+    // crossed before the current best hit are looked up.
     __device__ __forceinline__ void planes(const TraceParams &p, float ox, float oy, float oz, float dx, float dy,
                                            float dz, unsigned &tests)
     {
         const GridDesc &g = p.grid;
-        const int ncell = g.nx * g.ny;
-        best = __int_as_float(0x7f800000);
-        win = -1;
-        if (dz != 0.0f) {
-            const float iz = __frcp_rn(dz);
-            const int first = dz < 0.0f ? 0 : kMaxPlanesPerSign;             // d.z < 0 faces normals +z
-            const int count = dz < 0.0f ? g.planes_up : g.planes_down;
-            for (int pl = 0; pl < count; pl++) {
-                const float t = (g.plane_z[first + pl] - oz) * iz;
-                if (!(__float_as_uint(t) < __float_as_uint(best))) continue;
-                const float x = fmaf(t, dx, ox), y = fmaf(t, dy, oy);
-                const int px = __float2int_rd((x - g.x0) * g.inv_cell), py = __float2int_rd((y - g.y0) * g.inv_cell);
-                if (px < 0 || py < 0 || px >= g.nx || py >= g.ny) continue;
-                const int2 range = __ldg(p.grid_ranges + (first + pl) * ncell + py * g.nx + px);
-                for (int q = range.x; q < range.y; q++) {
-                    const float4 q0 = __ldg(p.grid_recs + 2 * q);
-                    const float4 q1 = __ldg(p.grid_recs + 2 * q + 1);
-                    tests++;
-                    if (fabsf(x - q0.y) <= q0.z && fabsf(y - q0.w) <= q1.x) { best = t; win = q; break; }
+        const bool down = dz < 0.0f;                                   // d.z < 0 faces normals +z
+        const float iz = rcp_fast(dz);                                 // d.z == 0: t = +-inf or NaN, never < best
+        const int count = down ? g.planes_up : g.planes_down;
+        const int base = down ? 0 : g.down_base;
+#pragma unroll 1
+        for (int pl = 0; pl < g.planes_max; pl++) {
+            const float z = down ? g.plane_z[pl] : g.plane_z[kMaxPlanesPerSign + pl];
+            const float t = (z - oz) * iz;
+            const float x = fmaf(t, dx, ox), y = fmaf(t, dy, oy);
+            const int px = __float2int_rd(fmaf(x, g.inv_cell, g.bx)), py = __float2int_rd(fmaf(y, g.inv_cell, g.by));
+            const bool go = pl < count && (__float_as_uint(t) < __float_as_uint(best)) && (unsigned)px < (unsigned)g.nx &&
+                            (unsigned)py < (unsigned)g.ny;
+            if (go) {
+                const int head = base + pl * g.ncell + py * g.nx + px;
+                const float4 h0 = __ldg(p.grid_table + 2 * head);
+                const float4 h1 = __ldg(p.grid_table + 2 * head + 1);
+                tests += h1.x == h1.x ? 1u : 0u;                       // dummy heads (c = NaN) are not tests
+                if (fabsf(x - h0.x) <= h0.y && fabsf(y - h0.z) <= h0.w) { best = t; win = head; }
+                else {
+                    const int end = __float_as_int(h1.w);
+                    for (int q = __float_as_int(h1.z); q < end; q++) {
+                        const float4 q0 = __ldg(p.grid_table + 2 * q);
+                        tests++;
+                        if (fabsf(x - q0.x) <= q0.y && fabsf(y - q0.z) <= q0.w) { best = t; win = q; break; }
+                    }
                 }
             }
         }
     }
 
-    // Phase 1 + DDA set-up.
-    __device__ __forceinline__ void begin(const TraceParams &p, float ox, float oy, float oz, float dx, float dy,
-                                          float dz, unsigned &tests)
-    {
-        const GridDesc &g = p.grid;
-        const int ncell = g.nx * g.ny;
-        const float inf = __int_as_float(0x7f800000);
-        planes(p, ox, oy, oz, dx, dy, dz, tests);
-        ix = __frcp_rn(dx); iy = __frcp_rn(dy);
-        int cx = __float2int_rd((ox - g.x0) * g.inv_cell), cy = __float2int_rd((oy - g.y0) * g.inv_cell);
-        cx = min(max(cx, 0), g.nx - 1); cy = min(max(cy, 0), g.ny - 1);
-        // per-axis DDA constants; an axis the ray does not move along never triggers a step.  t_exit
-        // replaces the per-step bounds check: the walk ends where the ray leaves the grid's box.
-        tmx = inf; tmy = inf; tdx = inf; tdy = inf; t_exit = inf;
-        if (dx != 0.0f) {
-            tmx = (g.x0 + (float)(cx + (dx > 0.0f ? 1 : 0)) * g.cell - ox) * ix;
-            tdx = g.cell * fabsf(ix);
-            t_exit = (g.x0 + (dx > 0.0f ? (float)(g.nx - 1) : 1.0f) * g.cell - ox) * ix;
-        }
-        if (dy != 0.0f) {
-            tmy = (g.y0 + (float)(cy + (dy > 0.0f ? 1 : 0)) * g.cell - oy) * iy;
-            tdy = g.cell * fabsf(iy);
-            t_exit = fminf(t_exit, (g.y0 + (dy > 0.0f ? (float)(g.ny - 1) : 1.0f) * g.cell - oy) * iy);
-        }
-        sx = dx > 0.0f ? 1 : -1;
-        sy = dy > 0.0f ? g.nx : -g.nx;
-        ci = cy * g.nx + cx;
-        const int combo = (dx > 0.0f ? 1 : 0) + (dy > 0.0f ? 2 : 0);
-        walk = p.grid_ranges + (kWalkListBase + combo) * ncell;
-        const int2 range = __ldg(walk + ci);
-        r = range.x; rend = range.y;
-    }
-
-    // Phase 2, one step of the 2-D DDA through the walk lists of the ray's sign combination: test the
-    // next pending record, or move to the next cell.  Cell stepping and record testing are
-    // flattened into one loop in which every lane does exactly one thing per step, so lanes with
-    // long lists and lanes crossing empty cells keep each other busy (the nested-loop version ran
-    // with 4 of 32 lanes active, profiles/r1_v1_grid_ncu_summary.csv).  Returns false when the walk
-    // is over: the next cell starts beyond the best hit, or the ray leaves the grid.
-    __device__ __forceinline__ bool step(const TraceParams &p, float ox, float oy, float oz, float dx, float dy,
+    // Vertical walls by a 2-D DDA from the ray origin through the walk list of the ray's sign
+    // combination (back-face culling was done when the lists were built).  The loop carries one PENDING
+    // record, already loaded; one iteration tests it and fetches the next one: the next record of the
+    // current cell, or - when the cell's list is exhausted - the head of the next cell the DDA steps to
+    // (first record + continuation in one round trip), all in straight-line predicated code.  In the
+    // first version of this loop "test" and "advance" were the two sides of a branch and ran one after
+    // the other with 4.5 and 10 of 32 lanes (profiles/r1_bench_synth4000_ncu_summary.csv).  The walk ends
+    // when the next cell starts beyond the best hit, where the ray leaves the grid, or where it leaves the
+    // z range of the walls (t_exit replaces per-step bounds checks).
+    __device__ __forceinline__ void walk(const TraceParams &p, float ox, float oy, float oz, float dx, float dy,
                                          float dz, unsigned &tests)
     {
-        if (r < rend) {
-            const float4 *rec = p.grid_recs + 2 * r;
-            const float4 q0 = __ldg(rec);
-            const float4 q1 = __ldg(rec + 1);
-            const int tag = __float_as_int(q1.y);
-            tests++;
-            if (tag & (2 << 28)) {
-                const float t = grid_test_misc(p.general, q0, q1, ox, oy, oz, dx, dy, dz, best);
-                if (t < best) { best = t; win = r; }
-            } else {
-                // vertical wall, normal along x (k = 0) or y (k = 1); the list only holds walls this ray
-                // can face (back-face culling done at build time).  In-plane axes: the other horizontal
-                // axis and z.
-                const bool ky = (tag & (1 << 28)) != 0;
-                const float t = (q0.x - (ky ? oy : ox)) * (ky ? iy : ix);
-                const float pi = fmaf(t, ky ? dx : dy, ky ? ox : oy) - q0.y;
-                const float pj = fmaf(t, dz, oz) - q0.w;
-                if ((__float_as_uint(t) < __float_as_uint(best)) && fabsf(pi) <= q0.z && fabsf(pj) <= q1.x) {
-                    best = t; win = r;
+        const GridDesc &g = p.grid;
+        const float inf = __int_as_float(0x7f800000);
+        const bool xp = dx > 0.0f, yp = dy > 0.0f;
+        const bool x0 = dx == 0.0f, y0 = dy == 0.0f;
+        const float ix = rcp_fast(dx), iy = rcp_fast(dy), iz = rcp_fast(dz);
+        int cx = __float2int_rd(fmaf(ox, g.inv_cell, g.bx)), cy = __float2int_rd(fmaf(oy, g.inv_cell, g.by));
+        cx = min(max(cx, 0), g.nx - 1); cy = min(max(cy, 0), g.ny - 1);
+        // per-axis DDA constants; an axis the ray does not move along never triggers a step (tmx = inf),
+        // so its per-cell increment cell * |1/d| is never used
+        float tmx = (fmaf((float)(cx + (xp ? 1 : 0)), g.cell, g.x0) - ox) * ix;
+        float tmy = (fmaf((float)(cy + (yp ? 1 : 0)), g.cell, g.y0) - oy) * iy;
+        const float ex = ((xp ? g.exit_hi_x : g.exit_lo_x) - ox) * ix, ey = ((yp ? g.exit_hi_y : g.exit_lo_y) - oy) * iy;
+        // no wall beyond the z range of the walls (with a little slack for the approximate reciprocal)
+        const float ez = ((dz < 0.0f ? g.wall_z_lo : g.wall_z_hi) - oz) * iz * 1.0001f;
+        tmx = x0 ? inf : tmx; tmy = y0 ? inf : tmy;
+        const float t_exit = fminf(fminf(x0 ? inf : ex, y0 ? inf : ey), dz == 0.0f ? inf : ez);
+        const int sx = xp ? 1 : -1, sy = yp ? g.nx : -g.nx;
+        // current cell as an index into T: the head of the walk list of the ray's sign combination
+        int ci = g.walk_base + ((xp ? 1 : 0) + (yp ? 2 : 0)) * g.ncell + cy * g.nx + cx;
+        // a ray with d.x == 0 faces no wall whose normal is along x: NaN never passes t < best
+        const float nanv = __int_as_float(0x7fc00000);
+        const float ax = x0 ? nanv : ix, ay = y0 ? nanv : iy;
+        const float bx = -ox * ax, by = -oy * ay;
+        // pending record: the head of the origin's cell
+        float4 q0 = __ldg(p.grid_table + 2 * ci);
+        const float4 h1 = __ldg(p.grid_table + 2 * ci + 1);
+        float qc = h1.x;
+        unsigned qtag = __float_as_uint(h1.y);
+        int cur = ci, r = __float_as_int(h1.z), rend = __float_as_int(h1.w);
+        // Written in PTX so that it stays one predicated instruction stream: from the C form nvcc rebuilt
+        // nested loops (inner loop over the records of a cell, reconvergence behind it).
+        //   test the pending record (a dummy head has c = NaN and fails t < best); best / win by select
+        //   adv  = the cell's list is exhausted -> step the DDA unless the next cell starts beyond
+        //          min(best, t_exit), which ends the walk
+        //   fetch T[adv ? next cell's head : r] as the new pending record
+        // MISC (scenes with misc records only): such a record is skipped by the fast test and leaves the
+        // loop with misc = its index.
+#define FMGI_WALK_LOOP(MISC_TEST, MISC_EXIT)                                                                         \
+        asm volatile(                                                                                                \
+            "{\n\t"                                                                                                  \
+            ".reg .pred ky, ok, adv, cont, stepx, go, gx, gy, pm, real, more;\n\t"                                   \
+            ".reg .f32 ak, bk, dh, oh, t, pi, pj, tn, lim, sa;\n\t"                                                  \
+            ".reg .b32 tb, bb, st, idx;\n\t"                                                                         \
+            ".reg .b64 a;\n\t"                                                                                       \
+            "mov.s32 %16, -1;\n\t"                                                                                   \
+            "WALK:\n\t"                                                                                              \
+            "setp.lt.s32 ky, %13, 0;\n\t"                                                                            \
+            "selp.f32 ak, %20, %19, ky;\n\t"                                                                         \
+            "selp.f32 bk, %22, %21, ky;\n\t"                                                                         \
+            "selp.f32 dh, %26, %27, ky;\n\t"                                                                         \
+            "selp.f32 oh, %23, %24, ky;\n\t"                                                                         \
+            "fma.rn.f32 t, %12, ak, bk;\n\t"                                                                         \
+            "fma.rn.f32 pi, t, dh, oh;\n\t"                                                                          \
+            "fma.rn.f32 pj, t, %28, %25;\n\t"                                                                        \
+            "sub.rn.f32 pi, pi, %8;\n\t"                                                                             \
+            "sub.rn.f32 pj, pj, %10;\n\t"                                                                            \
+            "abs.f32 pi, pi;\n\t"                                                                                    \
+            "abs.f32 pj, pj;\n\t"                                                                                    \
+            "mov.b32 tb, t;\n\t"                                                                                     \
+            "mov.b32 bb, %0;\n\t"                                                                                    \
+            "setp.lt.u32 ok, tb, bb;\n\t"                                                                            \
+            "setp.le.and.f32 ok, pi, %9, ok;\n\t"                                                                    \
+            "setp.le.and.f32 ok, pj, %11, ok;\n\t"                                                                   \
+            MISC_TEST                                                                                                \
+            "selp.f32 %0, t, %0, ok;\n\t"                                                                            \
+            "selp.b32 %1, %14, %1, ok;\n\t"                                                                          \
+            "setp.eq.f32 real, %12, %12;\n\t"                                                                        \
+            "@real add.u32 %7, %7, 1;\n\t"                                                                           \
+            "setp.ge.s32 adv, %2, %3;\n\t"                                                                           \
+            "min.f32 tn, %5, %6;\n\t"                                                                                \
+            "min.f32 lim, %0, %30;\n\t"                                                                              \
+            "setp.lt.f32 cont, tn, lim;\n\t"                                                                         \
+            "setp.lt.f32 stepx, %5, %6;\n\t"                                                                         \
+            "and.pred go, adv, cont;\n\t"                                                                            \
+            "and.pred gx, go, stepx;\n\t"                                                                            \
+            "and.pred gy, go, !stepx;\n\t"                                                                           \
+            "or.pred more, cont, !adv;\n\t"                                                                          \
+            "selp.b32 st, %31, %32, stepx;\n\t"                                                                      \
+            "selp.f32 sa, %19, %20, stepx;\n\t"                                                                      \
+            "abs.f32 sa, sa;\n\t"                                                                                    \
+            "@go add.s32 %4, %4, st;\n\t"                                                                            \
+            "@gx fma.rn.f32 %5, sa, %29, %5;\n\t"                                                                    \
+            "@gy fma.rn.f32 %6, sa, %29, %6;\n\t"                                                                    \
+            "selp.b32 idx, %4, %2, go;\n\t"                                                                          \
+            "@!adv add.s32 %2, %2, 1;\n\t"                                                                           \
+            "@more mov.b32 %14, idx;\n\t"                                                                            \
+            "mul.wide.s32 a, idx, 32;\n\t"                                                                           \
+            "add.s64 a, a, %18;\n\t"                                                                                 \
+            "@more ld.global.nc.v4.f32 {%8, %9, %10, %11}, [a];\n\t"                                                 \
+            "@more ld.global.nc.v2.b32 {%12, %13}, [a+16];\n\t"                                                      \
+            "@go ld.global.nc.v2.b32 {%2, %3}, [a+24];\n\t"                                                          \
+            "selp.u32 %15, 1, 0, more;\n\t"                                                                          \
+            MISC_EXIT                                                                                                \
+            "@more bra WALK;\n\t"                                                                                    \
+            "DONE:\n\t"                                                                                              \
+            "}"                                                                                                      \
+            : "+f"(best), "+r"(win), "+r"(r), "+r"(rend), "+r"(ci), "+f"(tmx), "+f"(tmy), "+r"(tests), "+f"(q0.x),   \
+              "+f"(q0.y), "+f"(q0.z), "+f"(q0.w), "+f"(qc), "+r"(qtag), "+r"(cur), "=r"(more), "=r"(misc)            \
+            : "r"(0), "l"(p.grid_table), "f"(ax), "f"(ay), "f"(bx), "f"(by), "f"(ox), "f"(oy), "f"(oz), "f"(dx),     \
+              "f"(dy), "f"(dz), "f"(g.cell), "f"(t_exit), "r"(sx), "r"(sy))
+        int more, misc;
+        if (!p.grid_has_misc) {
+            FMGI_WALK_LOOP("", "");
+        } else {
+            do {
+                FMGI_WALK_LOOP("and.b32 st, %13, 0x40000000;\n\t"
+                               "setp.ne.u32 pm, st, 0;\n\t"
+                               "and.pred ok, ok, !pm;\n\t"
+                               "@pm mov.b32 %16, %14;\n\t",
+                               "@pm bra DONE;\n\t");
+                if (misc >= 0) {
+                    // The fast test skipped misc record `misc`; the next pending record is already loaded.
+                    // The DDA decided with the old best: at worst it visits one cell more than needed.
+                    const float4 m0 = __ldg(p.grid_table + 2 * misc);
+                    const float2 m1 = ldg2(p.grid_table + 2 * misc + 1);
+                    const float t = grid_test_misc(p.general, m0, m1.x, __float_as_uint(m1.y), ox, oy, oz, dx, dy, dz, best);
+                    if (t < best) { best = t; win = misc; }
                 }
-            }
-            r++;
-            return true;
+            } while (misc >= 0 && more);
         }
-        const float t_next = fminf(tmx, tmy);
-        if (!(t_next < fminf(best, t_exit))) return false;
-        if (tmx < tmy) { ci += sx; tmx += tdx; } else { ci += sy; tmy += tdy; }
-        const int2 range = __ldg(walk + ci);
-        r = range.x; rend = range.y;
-        return true;
+#undef FMGI_WALK_LOOP
     }
 
     // Wall index of the winner (-1: miss) and its distance recomputed with the reference's formula.
@@ -362,11 +427,10 @@ struct GridWalk {
         int id = -1;
         t_out = best;
         if (win >= 0) {
-            const float4 q0 = __ldg(p.grid_recs + 2 * win);
-            const int tag = __float_as_int(__ldg(p.grid_recs + 2 * win + 1).y);
-            const int k = (tag >> 28) & 3;
-            if (k == 3) {
-                const float4 *gg = p.general + 4 * (tag & 0x0fffffff);
+            const float2 q1 = ldg2(p.grid_table + 2 * win + 1);
+            const unsigned tag = __float_as_uint(q1.y);
+            if ((tag & (kTagMisc | kTagHorizontal)) == (kTagMisc | kTagHorizontal)) {
+                const float4 *gg = p.general + 4 * (tag & kTagIdMask);
                 const float4 g0 = __ldg(gg), g3 = __ldg(gg + 3);
                 id = __float_as_int(g3.w);
                 const float denom = __fadd_rn(__fadd_rn(__fmul_rn(g0.x, dx), __fmul_rn(g0.y, dy)), __fmul_rn(g0.z, dz));
@@ -375,10 +439,11 @@ struct GridWalk {
                                             __fmul_rn(g0.z, __fsub_rn(g3.z, oz)));
                 t_out = __fdiv_rn(num, denom);
             } else {
-                id = tag & 0x0fffffff;
-                const float ok = k == 0 ? ox : (k == 1 ? oy : oz);
-                const float dk = k == 0 ? dx : (k == 1 ? dy : dz);
-                t_out = __fdiv_rn(__fsub_rn(q0.x, ok), dk);
+                id = (int)(tag & kTagIdMask);
+                const bool kz = (tag & (kTagMisc | kTagHorizontal)) != 0, ky = (int)tag < 0;
+                const float ok = kz ? oz : (ky ? oy : ox);
+                const float dk = kz ? dz : (ky ? dy : dx);
+                t_out = __fdiv_rn(__fsub_rn(q1.x, ok), dk);
             }
         }
         return id;
@@ -388,9 +453,12 @@ struct GridWalk {
 __device__ __forceinline__ int closest_hit_grid(const TraceParams &p, float ox, float oy, float oz,
                                                 float dx, float dy, float dz, float &t_out, unsigned &tests)
 {
+    // walls first: the walk is bounded by the z range of the walls, and only the planes crossed before
+    // the wall hit need a lookup
     GridWalk w;
-    w.begin(p, ox, oy, oz, dx, dy, dz, tests);
-    while (w.step(p, ox, oy, oz, dx, dy, dz, tests)) {}
+    w.reset();
+    w.walk(p, ox, oy, oz, dx, dy, dz, tests);
+    w.planes(p, ox, oy, oz, dx, dy, dz, tests);
     return w.finish(p, ox, oy, oz, dx, dy, dz, t_out);
 }
 
@@ -403,6 +471,7 @@ __device__ __forceinline__ int closest_hit_soup_planes(const SoupTables &s, cons
                                                        unsigned &tests)
 {
     GridWalk w;
+    w.reset();
     w.planes(p, ox, oy, oz, dx, dy, dz, tests);
     const float nanv = __int_as_float(0x7fc00000);
     float best = w.best;
@@ -417,10 +486,9 @@ __device__ __forceinline__ int closest_hit_soup_planes(const SoupTables &s, cons
     if (code != -1) return soup_winner(s, code, best, ox, oy, oz, dx, dy, dz, t_out);
     t_out = best;
     if (w.win < 0) return -1;
-    const float4 q0 = __ldg(p.grid_recs + 2 * w.win);
-    const int tag = __float_as_int(__ldg(p.grid_recs + 2 * w.win + 1).y);
-    t_out = __fdiv_rn(__fsub_rn(q0.x, oz), dz);
-    return tag & 0x0fffffff;
+    const float2 q1 = ldg2(p.grid_table + 2 * w.win + 1);
+    t_out = __fdiv_rn(__fsub_rn(q1.x, oz), dz);
+    return (int)(__float_as_uint(q1.y) & kTagIdMask);
 }
 
 // ---- texel index: rectangle.c:205-230, same operations in the same order, no contraction ----------
