@@ -298,6 +298,14 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    # rectangle tests per ray (the T of the algorithmic flop count): a scene property, measured once by a
+    # short untimed trace with the counting kernel variant (the timed kernel does not count, two
+    # instructions less per walk step)
+    scene.trace(atlas.data_ptr(), max(1, int(2.0e6 / area)), stream=stream.cuda_stream, max_depth=depth, seed=args.seed,
+                count_tests=1)
+    st = scene.sync()
+    tests_per_ray = st["rect_tests"] / max(st["rays"], 1)
+
     for _ in range(args.warmup):
         step()
     barrier()
@@ -316,7 +324,6 @@ def run_ours(args):
         barrier()
     ms = ev0.elapsed_time(ev1)
     launches = st["kernel_launches"] - launches0          # our kernels inside the timed region (this rank)
-    tests_per_ray = st["rect_tests"] / max(st["rays"], 1)
 
     tot = torch.tensor([float(deposits), float(rays), float(photons_done), ms, float(np.mean(kernel_ms))],
                        dtype=torch.float64, device="cuda")

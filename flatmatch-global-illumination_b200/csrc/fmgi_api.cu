@@ -175,8 +175,12 @@ unsigned long long fill_jobs(const fmgi_scene *s, int spa, const fmgi_options &o
 
 // Picks the instantiation for (tier, deposit, probe, resident CTAs per SM) and applies `fn` to it.
 template <typename Fn>
-cudaError_t with_trace_kernel(int tier, int deposit, bool probe, int min_blocks, Fn fn)
+cudaError_t with_trace_kernel(int tier, int deposit, bool probe, int min_blocks, bool count, Fn fn)
 {
+    if (count && !probe) {      // counting variant: one instantiation per tier
+        if (tier == FMGI_TIER_GRID) return fn(k_trace<FMGI_TIER_GRID, FMGI_DEPOSIT_VEC4, false, 4, true>);
+        if (tier == kTierSoupPlanes) return fn(k_trace<kTierSoupPlanes, FMGI_DEPOSIT_VEC4, false, 4, true>);
+    }
 #define FMGI_PICK_DEPOSIT(T, B)                                                                  \
     switch (deposit) {                                                                           \
         case FMGI_DEPOSIT_SCALAR: return fn(k_trace<T, FMGI_DEPOSIT_SCALAR, false, B>);          \
@@ -199,9 +203,10 @@ cudaError_t with_trace_kernel(int tier, int deposit, bool probe, int min_blocks,
 #undef FMGI_PICK_DEPOSIT
 }
 
-cudaError_t launch_trace(fmgi_scene *s, const TraceParams &p, int deposit, bool probe, int blocks, cudaStream_t st)
+cudaError_t launch_trace(fmgi_scene *s, const TraceParams &p, int deposit, bool probe, int blocks, cudaStream_t st,
+                         bool count = false)
 {
-    return with_trace_kernel(s->kernel_tier, deposit, probe, s->min_blocks, [&](auto kernel) {
+    return with_trace_kernel(s->kernel_tier, deposit, probe, s->min_blocks, count, [&](auto kernel) {
         cudaError_t e = cudaSuccess;
         if (s->smem_bytes > 48 * 1024)
             e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->smem_bytes);
@@ -342,7 +347,7 @@ int fmgi_scene_create(fmgi_scene **out, const fmgi_rect *walls, int num_walls, c
 
     if (const char *v = getenv("FMGI_TUNE_BLOCKS")) s->min_blocks = atoi(v) == 3 ? 3 : 4;   // tuning knob
     fmgi_scene *sp = s.get();
-    FMGI_CUDA(with_trace_kernel(s->kernel_tier, FMGI_DEPOSIT_VEC4, false, s->min_blocks, [&](auto kernel) {
+    FMGI_CUDA(with_trace_kernel(s->kernel_tier, FMGI_DEPOSIT_VEC4, false, s->min_blocks, false, [&](auto kernel) {
         cudaError_t e = cudaSuccess;
         if (sp->smem_bytes > 48 * 1024)
             e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sp->smem_bytes);
@@ -404,6 +409,8 @@ int fmgi_scene_trace(fmgi_scene *s, void *atlas_dev, int spa, const fmgi_options
     int passes = (int)((total_all + kAccumPhotons - 1) / kAccumPhotons);
     if (const char *v = getenv("FMGI_ACCUM_PASSES")) passes = atoi(v);     // tuning / test knob
     if (passes < 1) passes = 1;
+    bool count_tests = o.count_tests != 0;
+    if (const char *v = getenv("FMGI_COUNT_TESTS")) count_tests = atoi(v) != 0;
     MemPool &pool = MemPool::get();
     if ((size_t)passes > s->job_tables) {
         pool.free(s->d_jobs); pool.free(s->h_jobs);
@@ -446,7 +453,7 @@ int fmgi_scene_trace(fmgi_scene *s, void *atlas_dev, int spa, const fmgi_options
         unsigned long long want = (chunks[c] * 32 + kTraceThreads - 1) / kTraceThreads;
         const unsigned long long wave = (unsigned long long)s->num_sms * s->blocks_per_sm;
         const int blocks = (int)(want < wave ? (want ? want : 1) : wave);
-        FMGI_CUDA(launch_trace(s, p, o.deposit, false, blocks, st));
+        FMGI_CUDA(launch_trace(s, p, o.deposit, false, blocks, st, count_tests));
         if (passes > 1 && s->host.num_texels > 0) {
             k_accumulate<<<s->num_sms * 8, 256, 0, st>>>(reinterpret_cast<float4 *>(atlas_dev), s->d_scratch,
                                                          (size_t)s->host.num_texels);

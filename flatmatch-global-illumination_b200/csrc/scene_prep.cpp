@@ -370,14 +370,16 @@ void build_grid(HostScene &out, const fmgi_rect *walls, int num_walls, const fmg
         for (int cell = 0; cell < ncell; cell++) {
             const int b = begin[(size_t)l * ncell + cell], e = begin[(size_t)l * ncell + cell + 1];
             if (b == e) continue;
+            // every record says what follows it: [next, end) of its list, empty after the last one
             GridRec head = out.grid_recs[b];
             head.next = (int32_t)out.grid_table.size();
+            head.end = head.next + (e - b - 1);
             for (int q = b + 1; q < e; q++) {
                 GridRec rest = out.grid_recs[q];
-                rest.next = rest.end = 0;
+                rest.next = (int32_t)out.grid_table.size() + 1;
+                rest.end = head.end;
                 out.grid_table.push_back(rest);
             }
-            head.end = (int32_t)out.grid_table.size();
             out.grid_table[(size_t)u * ncell + cell] = head;
         }
     }

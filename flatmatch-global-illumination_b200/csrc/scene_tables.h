@@ -77,7 +77,8 @@ static_assert(sizeof(EmitterRec) == 96, "EmitterRec is six float4");
 //     lists whose rays can face it (back-face culling, rectangle.c:70-72, done at build time).
 // One table T of 32-byte records serves every list: entry l * ncell + cell is the HEAD of list
 // (l, cell) - its first record stored inline (or a dummy that no ray can hit) together with the index
-// range [next, end) of the list's remaining records, which follow the heads in T.  A cell visit is
+// range [next, end) of the list's remaining records, which follow the heads in T; every record carries
+// the range of what follows IT, so that fetching a record also fetches the walk's continuation state.  A cell visit is
 // therefore ONE dependent memory round trip (head = first candidate + continuation) instead of two
 // (range, then record).  Lists are numbered compactly: [0, planes_up) planes with normal +z (highest
 // first), [planes_up, planes_up + planes_down) planes with normal -z (lowest first), then the four
@@ -101,7 +102,7 @@ struct GridRec {
     float mid_j, half_j;
     float c;                // plane coordinate pos[k]; NaN in a dummy head
     uint32_t tag;
-    int32_t next, end;      // heads only: the list's remaining records are T[next .. end)
+    int32_t next, end;      // the records that follow this one in its list: T[next .. end) (next == end: none)
 };
 static_assert(sizeof(GridRec) == 32, "GridRec is two float4");
 

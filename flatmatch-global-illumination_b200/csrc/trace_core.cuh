@@ -39,7 +39,9 @@ __device__ __forceinline__ SoupTables stage_soup(const TraceParams &p, float4 *s
 
 // kTier: FMGI_TIER_SOUP (brute force over the shared-memory soup), kTierSoupPlanes (the same with the
 // horizontal rectangles looked up through the grid's plane tables) or FMGI_TIER_GRID (floor-plan grid in L2).
-template <int kTier, int kDeposit, bool kProbe, int kMinBlocks>
+// kCount: also count the rectangle tests the grid lookups execute (fmgi_options.count_tests; two more
+// instructions in the walk loop, so not the default).
+template <int kTier, int kDeposit, bool kProbe, int kMinBlocks, bool kCount = false>
 __global__ void __launch_bounds__(kTraceThreads, kMinBlocks) k_trace(const TraceParams p)
 {
     extern __shared__ float4 smem[];
@@ -115,8 +117,9 @@ __global__ void __launch_bounds__(kTraceThreads, kMinBlocks) k_trace(const Trace
                 const float k2 = 2.0f * (fn.x * dx + fn.y * dy + fn.z * dz);
                 dx = fmaf(-k2, fn.x, dx); dy = fmaf(-k2, fn.y, dy); dz = fmaf(-k2, fn.z, dz);
             } else {                                            // photonmap.c:179-181, :233
-                sample_hemisphere(u24(wa), u24(wb), is_new && __float_as_int(e0.w) != 0, fn, ldg4(frame + 4),
-                                  ldg4(frame + 5), dx, dy, dz);
+                float4 fu, fv;
+                ldg256(frame + 4, fu, fv);
+                sample_hemisphere(u24(wa), u24(wb), is_new && __float_as_int(e0.w) != 0, fn, fu, fv, dx, dy, dz);
             }
             roulette = r16(wa, wb);
             px = __fadd_rn(e0.x, __fmul_rn(dx, 1E-5f));         // photonmap.c:183, :254
@@ -133,8 +136,8 @@ __global__ void __launch_bounds__(kTraceThreads, kMinBlocks) k_trace(const Trace
             // ---- C. closest hit (photonmap.c:198 / photonmap.cl:194-206) ---------------------------
             float t;
             if (kTier == FMGI_TIER_SOUP) hit_id = closest_hit_soup(soup, px, py, pz, dx, dy, dz, t);
-            else if (kTier == kTierSoupPlanes) hit_id = closest_hit_soup_planes(soup, p, px, py, pz, dx, dy, dz, t, n_tests);
-            else hit_id = closest_hit_grid(p, px, py, pz, dx, dy, dz, t, n_tests);
+            else if (kTier == kTierSoupPlanes) hit_id = closest_hit_soup_planes<kCount>(soup, p, px, py, pz, dx, dy, dz, t, n_tests);
+            else hit_id = closest_hit_grid<kCount>(p, px, py, pz, dx, dy, dz, t, n_tests);
             n_rays++;
 
             // ---- D. bounce: texel, roulette, attenuation (photonmap.c:200-247) ------------------------
@@ -145,7 +148,9 @@ __global__ void __launch_bounds__(kTraceThreads, kMinBlocks) k_trace(const Trace
                 py = __fadd_rn(py, __fmul_rn(dy, t));
                 pz = __fadd_rn(pz, __fmul_rn(dz, t));
                 const float4 *sh = p.shade + 6 * hit_id;
-                const float4 q0 = ldg4(sh), q1 = ldg4(sh + 1), q2 = ldg4(sh + 2), q3 = ldg4(sh + 3);
+                float4 q0, q1, q2, q3;
+                ldg256(sh, q0, q1);
+                ldg256(sh + 2, q2, q3);
                 idx = tile_index(q0, q1, q2, __float_as_int(q3.w), px, py, pz);   // photonmap.c:210-211
                 // floor is slightly reflective: photonmap.c:228 (0.0005 is a double there; for a float
                 // z the comparison is equivalent to z < 0.0005f)
@@ -201,8 +206,8 @@ __global__ void k_probe_closest_hit(const TraceParams p, const float *__restrict
         const float ox = origins[3 * r], oy = origins[3 * r + 1], oz = origins[3 * r + 2];
         const float dx = dirs[3 * r], dy = dirs[3 * r + 1], dz = dirs[3 * r + 2];
         const int id = kTier == FMGI_TIER_SOUP ? closest_hit_soup(soup, ox, oy, oz, dx, dy, dz, t)
-                     : kTier == kTierSoupPlanes ? closest_hit_soup_planes(soup, p, ox, oy, oz, dx, dy, dz, t, tests)
-                                                : closest_hit_grid(p, ox, oy, oz, dx, dy, dz, t, tests);
+                     : kTier == kTierSoupPlanes ? closest_hit_soup_planes<false>(soup, p, ox, oy, oz, dx, dy, dz, t, tests)
+                                                : closest_hit_grid<false>(p, ox, oy, oz, dx, dy, dz, t, tests);
         hit_index[r] = id;
         hit_dist[r] = t;
     }
@@ -293,8 +298,8 @@ __global__ void __launch_bounds__(kTraceThreads) k_ambient_occlusion(const Trace
                         oz = __fadd_rn(cz, __fmul_rn(dz, 1E-5f));                         // photonmap.c:457
             float t;
             const int id = kTier == FMGI_TIER_SOUP ? closest_hit_soup(soup, ox, oy, oz, dx, dy, dz, t)
-                         : kTier == kTierSoupPlanes ? closest_hit_soup_planes(soup, p, ox, oy, oz, dx, dy, dz, t, tests)
-                                                    : closest_hit_grid(p, ox, oy, oz, dx, dy, dz, t, tests);
+                         : kTier == kTierSoupPlanes ? closest_hit_soup_planes<false>(soup, p, ox, oy, oz, dx, dy, dz, t, tests)
+                                                    : closest_hit_grid<false>(p, ox, oy, oz, dx, dy, dz, t, tests);
             if (id < 0) t = 10.0f;                                                       // photonmap.c:462-466
             dist_sum = __fadd_rn(dist_sum, __fmul_rn(t, d.z));
             fac_sum = __fadd_rn(fac_sum, d.z);

@@ -207,6 +207,14 @@ __device__ __forceinline__ int closest_hit_soup(const SoupTables &s, float ox, f
 
 __device__ __forceinline__ float rcp_fast(float x) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
 __device__ __forceinline__ float2 ldg2(const float4 *p) { return __ldg(reinterpret_cast<const float2 *>(p)); }
+// One 256-bit read-only load (sm_100: LDG.E.256) of a 32-byte aligned pair of float4: one request to
+// L1 instead of two.  The trace kernel's lanes read scattered 32-byte records, which made the L1
+// data pipe (wavefronts, one per distinct line and request) the busiest unit of the grid tier.
+__device__ __forceinline__ void ldg256(const float4 *p, float4 &a, float4 &b)
+{
+    asm("ld.global.nc.v8.f32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+        : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w), "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w) : "l"(p));
+}
 
 // Rare walk-list records (tag bit 30): a horizontal rectangle beyond the plane table or an arbitrarily
 // oriented rectangle.  These sit in all four walk lists, so facing is tested here.  Returns the ray
@@ -251,6 +259,7 @@ struct GridWalk {
     // Horizontal planes the ray can face - one head lookup per plane at the crossing point, nearest
     // plane first (the table is sorted), so that a hit bounds the remaining planes away.  Only planes
     // crossed before the current best hit are looked up.
+    template <bool kCount>
     __device__ __forceinline__ void planes(const TraceParams &p, float ox, float oy, float oz, float dx, float dy,
                                            float dz, unsigned &tests)
     {
@@ -269,15 +278,15 @@ struct GridWalk {
                             (unsigned)py < (unsigned)g.ny;
             if (go) {
                 const int head = base + pl * g.ncell + py * g.nx + px;
-                const float4 h0 = __ldg(p.grid_table + 2 * head);
-                const float4 h1 = __ldg(p.grid_table + 2 * head + 1);
-                tests += h1.x == h1.x ? 1u : 0u;                       // dummy heads (c = NaN) are not tests
+                float4 h0, h1;
+                ldg256(p.grid_table + 2 * head, h0, h1);
+                if (kCount) tests += h1.x == h1.x ? 1u : 0u;           // dummy heads (c = NaN) are not tests
                 if (fabsf(x - h0.x) <= h0.y && fabsf(y - h0.z) <= h0.w) { best = t; win = head; }
                 else {
                     const int end = __float_as_int(h1.w);
                     for (int q = __float_as_int(h1.z); q < end; q++) {
                         const float4 q0 = __ldg(p.grid_table + 2 * q);
-                        tests++;
+                        if (kCount) tests++;
                         if (fabsf(x - q0.x) <= q0.y && fabsf(y - q0.z) <= q0.w) { best = t; win = q; break; }
                     }
                 }
@@ -294,6 +303,7 @@ struct GridWalk {
     // the other with 4.5 and 10 of 32 lanes (profiles/r1_bench_synth4000_ncu_summary.csv).  The walk ends
     // when the next cell starts beyond the best hit, where the ray leaves the grid, or where it leaves the
     // z range of the walls (t_exit replaces per-step bounds checks).
+    template <bool kCount>
     __device__ __forceinline__ void walk(const TraceParams &p, float ox, float oy, float oz, float dx, float dy,
                                          float dz, unsigned &tests)
     {
@@ -321,8 +331,8 @@ struct GridWalk {
         const float ax = x0 ? nanv : ix, ay = y0 ? nanv : iy;
         const float bx = -ox * ax, by = -oy * ay;
         // pending record: the head of the origin's cell
-        float4 q0 = __ldg(p.grid_table + 2 * ci);
-        const float4 h1 = __ldg(p.grid_table + 2 * ci + 1);
+        float4 q0, h1;
+        ldg256(p.grid_table + 2 * ci, q0, h1);
         float qc = h1.x;
         unsigned qtag = __float_as_uint(h1.y);
         int cur = ci, r = __float_as_int(h1.z), rend = __float_as_int(h1.w);
@@ -331,15 +341,16 @@ struct GridWalk {
         //   test the pending record (a dummy head has c = NaN and fails t < best); best / win by select
         //   adv  = the cell's list is exhausted -> step the DDA unless the next cell starts beyond
         //          min(best, t_exit), which ends the walk
-        //   fetch T[adv ? next cell's head : r] as the new pending record
+        //   fetch T[adv ? next cell's head : r] as the new pending record; its last two words are the
+        //   new (r, rend): every record carries the range of what follows it in its list
         // MISC (scenes with misc records only): such a record is skipped by the fast test and leaves the
         // loop with misc = its index.
-#define FMGI_WALK_LOOP(MISC_TEST, MISC_EXIT)                                                                         \
+#define FMGI_WALK_LOOP(MISC_TEST, MISC_EXIT, COUNT)                                                                       \
         asm volatile(                                                                                                \
             "{\n\t"                                                                                                  \
             ".reg .pred ky, ok, adv, cont, stepx, go, gx, gy, pm, real, more;\n\t"                                   \
             ".reg .f32 ak, bk, dh, oh, t, pi, pj, tn, lim, sa;\n\t"                                                  \
-            ".reg .b32 tb, bb, st, idx;\n\t"                                                                         \
+            ".reg .b32 tb, bb, st;\n\t"                                                                              \
             ".reg .b64 a;\n\t"                                                                                       \
             "mov.s32 %16, -1;\n\t"                                                                                   \
             "WALK:\n\t"                                                                                              \
@@ -363,8 +374,7 @@ struct GridWalk {
             MISC_TEST                                                                                                \
             "selp.f32 %0, t, %0, ok;\n\t"                                                                            \
             "selp.b32 %1, %14, %1, ok;\n\t"                                                                          \
-            "setp.eq.f32 real, %12, %12;\n\t"                                                                        \
-            "@real add.u32 %7, %7, 1;\n\t"                                                                           \
+            COUNT                                                                                                    \
             "setp.ge.s32 adv, %2, %3;\n\t"                                                                           \
             "min.f32 tn, %5, %6;\n\t"                                                                                \
             "min.f32 lim, %0, %30;\n\t"                                                                              \
@@ -380,14 +390,10 @@ struct GridWalk {
             "@go add.s32 %4, %4, st;\n\t"                                                                            \
             "@gx fma.rn.f32 %5, sa, %29, %5;\n\t"                                                                    \
             "@gy fma.rn.f32 %6, sa, %29, %6;\n\t"                                                                    \
-            "selp.b32 idx, %4, %2, go;\n\t"                                                                          \
-            "@!adv add.s32 %2, %2, 1;\n\t"                                                                           \
-            "@more mov.b32 %14, idx;\n\t"                                                                            \
-            "mul.wide.s32 a, idx, 32;\n\t"                                                                           \
+            "selp.b32 %14, %4, %2, go;\n\t"                                                                          \
+            "mul.wide.s32 a, %14, 32;\n\t"                                                                           \
             "add.s64 a, a, %18;\n\t"                                                                                 \
-            "@more ld.global.nc.v4.f32 {%8, %9, %10, %11}, [a];\n\t"                                                 \
-            "@more ld.global.nc.v2.b32 {%12, %13}, [a+16];\n\t"                                                      \
-            "@go ld.global.nc.v2.b32 {%2, %3}, [a+24];\n\t"                                                          \
+            "@more ld.global.nc.v8.b32 {%8, %9, %10, %11, %12, %13, %2, %3}, [a];\n\t"                               \
             "selp.u32 %15, 1, 0, more;\n\t"                                                                          \
             MISC_EXIT                                                                                                \
             "@more bra WALK;\n\t"                                                                                    \
@@ -397,16 +403,16 @@ struct GridWalk {
               "+f"(q0.y), "+f"(q0.z), "+f"(q0.w), "+f"(qc), "+r"(qtag), "+r"(cur), "=r"(more), "=r"(misc)            \
             : "r"(0), "l"(p.grid_table), "f"(ax), "f"(ay), "f"(bx), "f"(by), "f"(ox), "f"(oy), "f"(oz), "f"(dx),     \
               "f"(dy), "f"(dz), "f"(g.cell), "f"(t_exit), "r"(sx), "r"(sy))
+        // counting variant only (fmgi_options.count_tests): rectangle tests, dummy heads (c = NaN) excluded
+#define FMGI_WALK_COUNT "setp.eq.f32 real, %12, %12;\n\t@real add.u32 %7, %7, 1;\n\t"
+#define FMGI_WALK_MISC_TEST "and.b32 st, %13, 0x40000000;\n\tsetp.ne.u32 pm, st, 0;\n\tand.pred ok, ok, !pm;\n\t@pm mov.b32 %16, %14;\n\t"
         int more, misc;
         if (!p.grid_has_misc) {
-            FMGI_WALK_LOOP("", "");
+            if (kCount) FMGI_WALK_LOOP("", "", FMGI_WALK_COUNT); else FMGI_WALK_LOOP("", "", "");
         } else {
             do {
-                FMGI_WALK_LOOP("and.b32 st, %13, 0x40000000;\n\t"
-                               "setp.ne.u32 pm, st, 0;\n\t"
-                               "and.pred ok, ok, !pm;\n\t"
-                               "@pm mov.b32 %16, %14;\n\t",
-                               "@pm bra DONE;\n\t");
+                if (kCount) FMGI_WALK_LOOP(FMGI_WALK_MISC_TEST, "@pm bra DONE;\n\t", FMGI_WALK_COUNT);
+                else FMGI_WALK_LOOP(FMGI_WALK_MISC_TEST, "@pm bra DONE;\n\t", "");
                 if (misc >= 0) {
                     // The fast test skipped misc record `misc`; the next pending record is already loaded.
                     // The DDA decided with the old best: at worst it visits one cell more than needed.
@@ -417,6 +423,8 @@ struct GridWalk {
                 }
             } while (misc >= 0 && more);
         }
+#undef FMGI_WALK_COUNT
+#undef FMGI_WALK_MISC_TEST
 #undef FMGI_WALK_LOOP
     }
 
@@ -450,6 +458,7 @@ struct GridWalk {
     }
 };
 
+template <bool kCount>
 __device__ __forceinline__ int closest_hit_grid(const TraceParams &p, float ox, float oy, float oz,
                                                 float dx, float dy, float dz, float &t_out, unsigned &tests)
 {
@@ -457,8 +466,8 @@ __device__ __forceinline__ int closest_hit_grid(const TraceParams &p, float ox, 
     // the wall hit need a lookup
     GridWalk w;
     w.reset();
-    w.walk(p, ox, oy, oz, dx, dy, dz, tests);
-    w.planes(p, ox, oy, oz, dx, dy, dz, tests);
+    w.template walk<kCount>(p, ox, oy, oz, dx, dy, dz, tests);
+    w.template planes<kCount>(p, ox, oy, oz, dx, dy, dz, tests);
     return w.finish(p, ox, oy, oz, dx, dy, dz, t_out);
 }
 
@@ -466,13 +475,14 @@ __device__ __forceinline__ int closest_hit_grid(const TraceParams &p, float ox, 
 // of a flat's soup) are found by one cell lookup per z plane exactly as in the grid tier, which also
 // bounds `best` before the shared-memory scan of the vertical walls (x and y lists only).  Used when
 // every horizontal rectangle fits the plane table.
+template <bool kCount>
 __device__ __forceinline__ int closest_hit_soup_planes(const SoupTables &s, const TraceParams &p, float ox, float oy,
                                                        float oz, float dx, float dy, float dz, float &t_out,
                                                        unsigned &tests)
 {
     GridWalk w;
     w.reset();
-    w.planes(p, ox, oy, oz, dx, dy, dz, tests);
+    w.template planes<kCount>(p, ox, oy, oz, dx, dy, dz, tests);
     const float nanv = __int_as_float(0x7fc00000);
     float best = w.best;
     int code = -1;

@@ -48,7 +48,7 @@ class Options(C.Structure):
     _fields_ = [
         ("struct_size", C.c_uint32), ("max_depth", C.c_int32), ("seed", C.c_uint32), ("num_gpus", C.c_int32),
         ("shard", C.c_int32), ("num_shards", C.c_int32), ("tier", C.c_int32), ("deposit", C.c_int32),
-        ("device", C.c_int32), ("reserved", C.c_int32 * 7),
+        ("device", C.c_int32), ("count_tests", C.c_int32), ("reserved", C.c_int32 * 6),
     ]
 
 

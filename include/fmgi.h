@@ -86,7 +86,9 @@ typedef struct fmgi_options {
     int32_t  tier;            /* FMGI_TIER_* */
     int32_t  deposit;         /* FMGI_DEPOSIT_* */
     int32_t  device;          /* CUDA device ordinal for the fmgi_scene_* calls */
-    int32_t  reserved[7];
+    int32_t  count_tests;     /* != 0: also count the rectangle tests of the grid lookups (fmgi_stats.rect_tests);
+                                 costs two instructions per walk step, so off by default */
+    int32_t  reserved[6];
 } fmgi_options;
 
 typedef struct fmgi_stats {
@@ -94,7 +96,7 @@ typedef struct fmgi_stats {
     uint64_t rays;            /* closest-hit queries */
     uint64_t deposits;        /* texel deposits = photon-bounces (the BASELINE metric's unit) */
     uint64_t mirror_bounces;
-    uint64_t rect_tests;      /* rectangle tests executed (all lanes) */
+    uint64_t rect_tests;      /* rectangle tests executed (all lanes); grid lookups only with count_tests */
     uint64_t kernel_launches; /* our kernels launched */
     double   trace_ms;        /* device time of the trace kernels (CUDA events), max over GPUs */
     double   h2d_ms, d2h_ms;  /* upload / read-back, host clock */

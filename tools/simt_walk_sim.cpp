@@ -95,9 +95,8 @@ struct Sim {
             w.cells.push_back(r.y - r.x);
             for (int q = r.x; q < r.y; q++) {
                 const GridRec &rec = sc.grid_recs[q];
-                const int k = (rec.tag >> 28) & 3;
-                if (k >= 2) continue;      // parseLayout scenes have none in walk lists
-                const bool ky = k == 1;
+                if (rec.tag & kTagMisc) continue;      // parseLayout scenes have none in walk lists
+                const bool ky = (rec.tag & kTagAlongY) != 0;
                 const float t = (rec.c - (ky ? o[1] : o[0])) * (ky ? iy : ix);
                 const float pi = t * (ky ? d[0] : d[1]) + (ky ? o[0] : o[1]) - rec.mid_i;
                 const float pj = t * d[2] + o[2] - rec.mid_j;
@@ -108,7 +107,7 @@ struct Sim {
             if (tmx < tmy) { ci += sx; tmx += tdx; } else { ci += sy; tmy += tdy; }
         }
         w.t = best;
-        w.hit = win >= 0 ? (sc.grid_recs[win].tag & 0x0fffffff) : -1;
+        w.hit = win >= 0 ? (int)(sc.grid_recs[win].tag & kTagIdMask) : -1;
         return w.hit;
     }
 };
@@ -355,6 +354,98 @@ int main(int argc, char **argv)
                    s_lanes / rounds, iters / nrays, (rounds * cS + iters * cMm) / nrays);
         }
         (void)cF;
+    }
+    // ---- models Q / P: a warp walks 32 * K rays per round.  Q: every lane owns a private queue of K rays
+    //      (static); P: idle lanes take the next ray of the warp's shared pool (dynamic).  Idle lanes
+    //      switch to their next ray together, when at least `thr` lanes are idle (or nobody is walking).
+    {
+        // ray walk lengths of the scene, in emission order of a long run (recorded by a plain replay)
+        std::vector<int> lens;
+        {
+            rng_state = 777;
+            for (int wq = 0; wq < num_warps / 2; wq++) {
+                Lane L[32];
+                int budget[32];
+                for (int l = 0; l < 32; l++) budget[l] = photons_per_lane;
+                for (;;) {
+                    int alive = 0;
+                    for (int l = 0; l < 32; l++) {
+                        Lane &a = L[l];
+                        if (!a.alive && budget[l] > 0) {
+                            budget[l]--;
+                            a.alive = true; a.is_new = true; a.depth = 0;
+                            const double x = frand() * tot;
+                            a.emitter = std::min((int)(std::lower_bound(cdf.begin(), cdf.end(), x) - cdf.begin()), (int)cdf.size() - 1);
+                        }
+                        alive += a.alive;
+                    }
+                    if (!alive) break;
+                    for (int l = 0; l < 32; l++) {
+                        Lane &a = L[l];
+                        if (!a.alive) continue;
+                        if (a.is_new) {
+                            const EmitterRec &e = sim.sc.emitters[a.emitter];
+                            sample(e.n, e.u, e.v, e.is_window != 0, a.d);
+                            const float sx = frand(), sy = frand();
+                            for (int k = 0; k < 3; k++) a.p[k] = e.pos[k] + a.d[k] * 1e-5f + e.width[k] * sx + e.height[k] * sy;
+                            a.is_new = false;
+                        } else {
+                            const ShadeRect &sh = sim.sc.shade[a.hit];
+                            if (a.mirror) {
+                                const float k2 = 2.0f * (sh.n[0] * a.d[0] + sh.n[1] * a.d[1] + sh.n[2] * a.d[2]);
+                                for (int k = 0; k < 3; k++) a.d[k] -= k2 * sh.n[k];
+                            } else sample(sh.n, sh.u, sh.v, false, a.d);
+                            for (int k = 0; k < 3; k++) a.p[k] += a.d[k] * 1e-5f;
+                        }
+                        Walk w;
+                        sim.closest(a.p, a.d, w);
+                        int len = 0;
+                        for (int n : w.cells) len += std::max(n, 1);
+                        lens.push_back(len);
+                        if (w.hit < 0) { a.alive = false; continue; }
+                        a.hit = w.hit;
+                        for (int k = 0; k < 3; k++) a.p[k] += a.d[k] * w.t;
+                        a.mirror = a.p[2] < 0.0005f && frand() < 0.75f;
+                        if (++a.depth == max_depth) a.alive = false;
+                    }
+                }
+            }
+        }
+        { double m = 0; int mx = 0; for (int v : lens) { m += v; mx = std::max(mx, v); } printf("lens: n %zu mean %.2f max %d\n", lens.size(), m / lens.size(), mx); }
+        for (int dynamic = 0; dynamic < 2; dynamic++)
+            for (int K : {1, 2, 4, 8})
+                for (int thr : {1, 8, 16, 24}) {
+                    double iters = 0, switches = 0, sw_lanes = 0, nr = 0, act = 0;
+                    size_t pos = 0;
+                    while (pos + 32 * K <= lens.size()) {
+                        const int *pool = &lens[pos];
+                        pos += 32 * K;
+                        nr += 32 * K;
+                        int rem[32], next_own[32], pool_next = 0;
+                        for (int l = 0; l < 32; l++) { rem[l] = 0; next_own[l] = 0; }
+                        for (;;) {
+                            int idle_with_work = 0, walking = 0;
+                            for (int l = 0; l < 32; l++) {
+                                if (rem[l] > 0) walking++;
+                                else if (dynamic ? pool_next < 32 * K : next_own[l] < K) idle_with_work++;
+                            }
+                            if (!walking && !idle_with_work) break;
+                            if (idle_with_work && (idle_with_work >= thr || !walking)) {
+                                switches++;
+                                for (int l = 0; l < 32; l++)
+                                    if (rem[l] == 0) {
+                                        if (dynamic) { if (pool_next < 32 * K) { rem[l] = pool[pool_next++]; sw_lanes++; } }
+                                        else if (next_own[l] < K) { rem[l] = pool[next_own[l]++ * 32 + l]; sw_lanes++; }
+                                    }
+                                continue;
+                            }
+                            iters++;
+                            for (int l = 0; l < 32; l++) if (rem[l] > 0) { rem[l]--; act++; }
+                        }
+                    }
+                    printf("%s K=%d thr=%2d: warp iters/ray %.3f (lanes %.1f)  switch events/ray %.4f (lanes %.1f)\n", dynamic ? "P" : "Q", K, thr,
+                           iters / nr, act / iters, switches / nr, sw_lanes / switches);
+                }
     }
     return 0;
 }
