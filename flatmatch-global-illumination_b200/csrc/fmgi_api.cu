@@ -303,8 +303,10 @@ int fmgi_scene_create(fmgi_scene **out, const fmgi_rect *walls, int num_walls, c
     const int colliders = s->host.num_axis_rects + (int)s->host.general.size();
     int tier = o.tier;
     if (const char *v = getenv("FMGI_TIER")) tier = atoi(v);
+    // AUTO: the brute-force soup only for a handful of colliders (one bare room); measured on the
+    // 172-rectangle example.png scene the grid is 20 % faster than the soup + plane tables
     if (tier != FMGI_TIER_SOUP && tier != FMGI_TIER_GRID)
-        tier = (colliders <= 256 && soup_bytes <= (size_t)prop.sharedMemPerBlockOptin) ? FMGI_TIER_SOUP : FMGI_TIER_GRID;
+        tier = (colliders <= 64 && soup_bytes <= (size_t)prop.sharedMemPerBlockOptin) ? FMGI_TIER_SOUP : FMGI_TIER_GRID;
     if (tier == FMGI_TIER_SOUP && soup_bytes > (size_t)prop.sharedMemPerBlockOptin)
         return fail(FMGI_ERR_UNSUPPORTED, "rectangle soup does not fit in shared memory; use FMGI_TIER_GRID");
     s->tier = tier;

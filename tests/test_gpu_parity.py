@@ -668,8 +668,11 @@ def test_full_size_properties(dev_scene, scene):
     for k in ("photons", "rays", "deposits", "mirror_bounces"):
         assert sum(p[1][k] for p in parts) == sw[k]
     total = np.sum([p[0].astype(np.float64) for p in parts], axis=0)
-    assert np.allclose(total, whole, rtol=1e-4, atol=1.0)
-    assert abs(total[:, :3].sum() / whole[:, :3].sum(dtype=np.float64) - 1) < 1e-6
+    # The whole bake adds ~3e4 deposits of ~16 into each fp32 texel; once a texel passes 2^16 every add rounds
+    # by up to 2^-8 in the same direction, so the single sum drifts from the sum of eight 8x smaller sums by a
+    # few 1e-5 relative (measured 4.5e-5; the library re-zeroes its fp32 accumulator every 2^28 photons).
+    assert np.allclose(total, whole, rtol=1e-3, atol=1.0)
+    assert abs(total[:, :3].sum() / whole[:, :3].sum(dtype=np.float64) - 1) < 2e-4
     assert np.all(whole[:, 3] == 0) and np.all(whole[~scene.base_texel_mask()] == 0)
     # colour lanes: every deposit is (18 or 16, ., 18) x 0.9^k x tint -> R >= G >= B-ish ordering never inverts R < 0
     assert whole.min() >= 0
