@@ -400,6 +400,16 @@ def run_ours(args):
         if facts and facts.get("tier") == line["config"]["tier"]:
             line["roofline"]["traffic"] = facts.get("dram_bytes_per_launch")
             line["roofline"]["ncu"] = facts
+            if facts.get("warp_inst_per_ray"):
+                # the resource that actually binds this divergent traversal: instruction issue slots.
+                # warp instructions per ray come from the committed ncu capture of this kernel and scene,
+                # the ray rate is live; peak = one warp instruction per cycle and SM sub-partition.
+                issue_peak = sms * 4 * f_hz
+                issue = rays_per_s_kernel * facts["warp_inst_per_ray"]
+                line["roofline"]["issue"] = {
+                    "achieved": issue / 1e9, "peak": issue_peak / 1e9, "unit": "G warp-inst/s",
+                    "frac": issue / issue_peak, "warp_inst_per_ray": facts["warp_inst_per_ray"],
+                    "lanes_per_inst": facts.get("threads_per_instruction")}
         if world == 1 and args.workload.startswith("example") and not args.no_app:
             wall = reference_app_wall_time()
             if wall is not None:

@@ -32,10 +32,13 @@ KEEP = [
     "smsp__average_warps_issue_stalled_lg_throttle_per_issue_active.ratio",
     "smsp__average_warps_issue_stalled_mio_throttle_per_issue_active.ratio",
     "smsp__average_warps_issue_stalled_no_instruction_per_issue_active.ratio",
+    "l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed",
+    "l1tex__t_sector_pipe_lsu_mem_global_op_ld_hit_rate.pct", "l1tex__t_requests_pipe_lsu_mem_global_op_ld.sum",
+    "l1tex__t_output_wavefronts_pipe_lsu_mem_global_op_ld.sum", "smsp__warps_eligible.avg.per_cycle_active",
 ]
 
 
-def facts(rep, workload, tier, out_json, source):
+def facts(rep, workload, tier, out_json, source, rays=None):
     """Adds the per-launch counters bench.py quotes (DRAM traffic, issue-slot and pipe utilisation) to
     profiles/ncu_facts.json under `workload`."""
     import json
@@ -61,7 +64,13 @@ def facts(rep, workload, tier, out_json, source):
         "smem_wavefronts_pct": float(d["l1tex__data_pipe_lsu_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed"]),
         "threads_per_instruction": float(d["smsp__thread_inst_executed_per_inst_executed.ratio"]),
         "registers_per_thread": int(float(d["launch__registers_per_thread"])),
+        "l1_data_pipe_pct": float(d["l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed"]),
+        "l1_load_hit_pct": float(d["l1tex__t_sector_pipe_lsu_mem_global_op_ld_hit_rate.pct"]),
+        "warp_inst_per_launch": float(d["smsp__inst_executed.sum"]),
     }
+    if rays:       # rays traced by the captured launch (bench.py: rays_per_s x kernel_ms_per_step / passes)
+        entry["rays_per_launch"] = rays
+        entry["warp_inst_per_ray"] = entry["warp_inst_per_launch"] / rays
     allf = json.load(open(out_json)) if os.path.exists(out_json) else {}
     allf[workload] = entry
     json.dump(allf, open(out_json, "w"), indent=1, sort_keys=True)
@@ -69,8 +78,9 @@ def facts(rep, workload, tier, out_json, source):
 
 
 def main():
-    if sys.argv[1] == "--facts":            # --facts <rep> <workload> <tier> <source label>
-        return facts(sys.argv[2], sys.argv[3], sys.argv[4], "profiles/ncu_facts.json", sys.argv[5])
+    if sys.argv[1] == "--facts":            # --facts <rep> <workload> <tier> <source label> [rays in the launch]
+        return facts(sys.argv[2], sys.argv[3], sys.argv[4], "profiles/ncu_facts.json", sys.argv[5],
+                     float(sys.argv[6]) if len(sys.argv) > 6 else None)
     rep, out = sys.argv[1], sys.argv[2]
     launch = int(sys.argv[3]) if len(sys.argv) > 3 else 0
     txt = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True, check=True).stdout
