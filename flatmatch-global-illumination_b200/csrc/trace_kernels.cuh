@@ -376,11 +376,16 @@ struct GridWalk {
         float qc = h1.x;
         unsigned qtag = __float_as_uint(h1.y);
         int cur = ci, r = __float_as_int(h1.z), rend = __float_as_int(h1.w);
+        // One bound for hits and for the walk: every wall lies at least a cell inside the exit box and inside
+        // the z slab (with slack), so no hit has t >= t_exit, and "the next cell starts beyond the best hit"
+        // also covers "the ray has left the grid".  A walk that ends without a hit restores +inf below.
+        const float best_in = best;
+        best = fminf(best, t_exit);
         // Written in PTX so that it stays one predicated instruction stream: from the C form nvcc rebuilt
         // nested loops (inner loop over the records of a cell, reconvergence behind it).
         //   test the pending record (a dummy head has c = NaN and fails t < best); best / win by select
-        //   adv  = the cell's list is exhausted -> step the DDA unless the next cell starts beyond
-        //          min(best, t_exit), which ends the walk
+        //   adv  = the cell's list is exhausted -> step the DDA unless the next cell starts beyond best,
+        //          which ends the walk (best starts at t_exit: no wall lies beyond it)
         //   fetch T[adv ? next cell's head : r] as the new pending record; its last two words are the
         //   new (r, rend): every record carries the range of what follows it in its list
         // MISC (scenes with misc records only): such a record is skipped by the fast test and leaves the
@@ -417,8 +422,7 @@ struct GridWalk {
             COUNT                                                                                                    \
             "setp.ge.s32 adv, %2, %3;\n\t"                                                                           \
             "min.f32 tn, %5, %6;\n\t"                                                                                \
-            "min.f32 lim, %0, %30;\n\t"                                                                              \
-            "setp.lt.f32 cont, tn, lim;\n\t"                                                                         \
+            "setp.lt.f32 cont, tn, %0;\n\t"                                                                          \
             "setp.lt.f32 stepx, %5, %6;\n\t"                                                                         \
             "and.pred go, adv, cont;\n\t"                                                                            \
             "and.pred gx, go, stepx;\n\t"                                                                            \
@@ -465,6 +469,7 @@ struct GridWalk {
         }
 #undef FMGI_WALK_COUNT
 #undef FMGI_WALK_MISC_TEST
+        if (win < 0) best = best_in;
 #undef FMGI_WALK_LOOP
     }
 
