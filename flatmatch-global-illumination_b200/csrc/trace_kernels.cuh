@@ -266,13 +266,11 @@ struct GridWalk {
     // order.  Further planes take the loop.
     static constexpr int kFastPlanes = 3;
 
-    __device__ __forceinline__ bool plane_rest(const TraceParams &p, int head, float x, float y, float t, unsigned &tests,
-                                               bool count)
+    // the head's rectangle does not contain the crossing point: try the rest of the cell's list [q, end)
+    __device__ __forceinline__ bool plane_rest(const TraceParams &p, int q, int end, float x, float y, float t,
+                                               unsigned &tests, bool count)
     {
-        // the head's rectangle does not contain the crossing point: try the rest of the cell's list
-        const float4 h1 = __ldg(p.grid_table + 2 * head + 1);
-        const int end = __float_as_int(h1.w);
-        for (int q = __float_as_int(h1.z); q < end; q++) {
+        for (; q < end; q++) {
             const float4 q0 = __ldg(p.grid_table + 2 * q);
             if (count) tests++;
             if (fabsf(x - q0.x) <= q0.y && fabsf(y - q0.z) <= q0.w) { best = t; win = q; return true; }
@@ -291,7 +289,7 @@ struct GridWalk {
         const int base = down ? 0 : g.down_base;
         float tt[kFastPlanes], xx[kFastPlanes], yy[kFastPlanes];
         int hh[kFastPlanes];
-        float4 h0[kFastPlanes];
+        float4 h0[kFastPlanes], h1[kFastPlanes];
 #pragma unroll
         for (int i = 0; i < kFastPlanes; i++) {
             const float z = down ? g.plane_z[i] : g.plane_z[kMaxPlanesPerSign + i];
@@ -305,7 +303,8 @@ struct GridWalk {
 #pragma unroll
         for (int i = 0; i < kFastPlanes; i++) {
             h0[i] = make_float4(0.0f, -1.0f, 0.0f, -1.0f);
-            if (hh[i] >= 0) h0[i] = __ldg(p.grid_table + 2 * hh[i]);
+            h1[i] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+            if (hh[i] >= 0) ldg256(p.grid_table + 2 * hh[i], h0[i], h1[i]);
         }
 #pragma unroll
         for (int i = 0; i < kFastPlanes; i++) {
@@ -313,7 +312,7 @@ struct GridWalk {
             if (hh[i] >= 0 && (__float_as_uint(tt[i]) < __float_as_uint(best))) {
                 if (kCount) tests += h0[i].y >= 0.0f ? 1u : 0u;        // dummy heads (half width -1) are not tests
                 if (fabsf(xx[i] - h0[i].x) <= h0[i].y && fabsf(yy[i] - h0[i].z) <= h0[i].w) { best = tt[i]; win = hh[i]; }
-                else plane_rest(p, hh[i], xx[i], yy[i], tt[i], tests, kCount);
+                else plane_rest(p, __float_as_int(h1[i].z), __float_as_int(h1[i].w), xx[i], yy[i], tt[i], tests, kCount);
             }
         }
 #pragma unroll 1
@@ -326,10 +325,11 @@ struct GridWalk {
                             (unsigned)py < (unsigned)g.ny;
             if (go) {
                 const int head = base + pl * g.ncell + py * g.nx + px;
-                const float4 q0 = __ldg(p.grid_table + 2 * head);
+                float4 q0, q1;
+                ldg256(p.grid_table + 2 * head, q0, q1);
                 if (kCount) tests += q0.y >= 0.0f ? 1u : 0u;
                 if (fabsf(x - q0.x) <= q0.y && fabsf(y - q0.z) <= q0.w) { best = t; win = head; }
-                else plane_rest(p, head, x, y, t, tests, kCount);
+                else plane_rest(p, __float_as_int(q1.z), __float_as_int(q1.w), x, y, t, tests, kCount);
             }
         }
     }

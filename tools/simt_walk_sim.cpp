@@ -361,6 +361,7 @@ int main(int argc, char **argv)
     {
         // ray walk lengths of the scene, in emission order of a long run (recorded by a plain replay)
         std::vector<int> lens;
+        double miss_len = 0, miss_n = 0, hit_len = 0, hit_n = 0, miss_long = 0, hit_long = 0;
         {
             rng_state = 777;
             for (int wq = 0; wq < num_warps / 2; wq++) {
@@ -402,6 +403,7 @@ int main(int argc, char **argv)
                         int len = 0;
                         for (int n : w.cells) len += std::max(n, 1);
                         lens.push_back(len);
+                        if (w.hit < 0) { miss_len += len; miss_n++; if (len > 8) miss_long++; } else { hit_len += len; hit_n++; if (len > 8) hit_long++; }
                         if (w.hit < 0) { a.alive = false; continue; }
                         a.hit = w.hit;
                         for (int k = 0; k < 3; k++) a.p[k] += a.d[k] * w.t;
@@ -411,6 +413,7 @@ int main(int argc, char **argv)
                 }
             }
         }
+        printf("walk length: hits mean %.2f (n %.0f, >8: %.3f)  misses mean %.2f (n %.0f, >8: %.3f)\n", hit_len / hit_n, hit_n, hit_long / hit_n, miss_len / std::max(miss_n, 1.0), miss_n, miss_long / std::max(miss_n, 1.0));
         { double m = 0; int mx = 0; for (int v : lens) { m += v; mx = std::max(mx, v); } printf("lens: n %zu mean %.2f max %d\n", lens.size(), m / lens.size(), mx); }
         for (int dynamic = 0; dynamic < 2; dynamic++)
             for (int K : {1, 2, 4, 8})
