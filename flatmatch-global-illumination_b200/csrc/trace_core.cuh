@@ -1,5 +1,5 @@
-// The persistent photon-tracing kernel (soup tier: whole rectangle soup in shared memory; grid tier:
-// floor-plan grid walked from L2) plus the probe kernels that expose its device functions to the
+// The persistent photon-tracing kernel (grid tier: floor-plan grid walked from L1 / L2; soup tier: whole
+// rectangle soup in shared memory) plus the probe kernels that expose its device functions to the
 // parity tests.
 #pragma once
 #include "trace_kernels.cuh"

@@ -8,18 +8,19 @@
 //     dies (miss, or last allowed bounce) the warp's dead lanes are found with a ballot and
 //     refilled from the warp's chunk of the global photon index space, so the closest-hit loop
 //     always runs with full warps ("wavefront" compaction done in registers);
-//   * the rectangle soup lives in shared memory as per-axis lists of axis-parallel records; the
-//     loop trip count is warp uniform and the loads are broadcasts;
-//   * back-face culling (rectangle.c:70-72) halves the work instead of costing a test: the
-//     records of one normal axis are split by normal sign into two interleaved lists and every
-//     lane walks only the list its ray can face (two distinct, bank-disjoint addresses per warp);
+//   * scenes above 64 colliders (example.png included) find the closest hit through a floor-plan
+//     grid (GridWalk): a 2-D DDA through per-cell, per-sign-combination wall lists whose loop is 34
+//     instructions of straight-line predicated PTX - test the pending record, step, fetch with ONE
+//     256-bit load that also carries the continuation - then one head lookup per z plane crossed
+//     before the wall hit;
+//   * a bare room keeps the brute-force soup in shared memory: per-axis lists of axis-parallel
+//     records, warp-uniform trip count, broadcast loads; back-face culling (rectangle.c:70-72)
+//     halves the work instead of costing a test: the records of one normal axis are split by normal
+//     sign into two interleaved lists and every lane walks only the list its ray can face; its
+//     horizontal rectangles go through the grid's plane tables when they fit;
 //   * 0 <= t < best is one unsigned compare (negative and NaN floats are large unsigned
 //     integers); containment is |p - mid| <= half, which moves half of the compare work from the
 //     ALU pipe to the FMA pipe (the ALU pipe was the top pipe of the first version, see profiles/);
-//   * horizontal rectangles (a third of a flat) are not scanned at all when they fit the grid's
-//     plane tables: one cell lookup per z plane at the ray's crossing point (GridWalk::planes);
-//   * scenes beyond a few hundred rectangles use the floor-plan grid instead of the soup
-//     (GridWalk: plane lookups + a 2-D DDA through per-cell, per-sign-combination wall lists);
 //   * deposits are one 16-byte vector reduction (RED.E.ADD.F32x4) per bounce into the atlas,
 //     optionally warp-aggregated with __match_any_sync (measured: no gain, not the default);
 //   * per-photon Philox4x32-10 sub-streams (philox.cuh) replace the sequential libc stream.
