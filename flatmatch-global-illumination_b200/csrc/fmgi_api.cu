@@ -135,6 +135,7 @@ TraceParams base_params(const fmgi_scene *s)
     p.grid_table = reinterpret_cast<const float4 *>(s->d_grid_table);
     p.grid = s->host.grid;
     p.grid_has_misc = s->host.grid_misc != 0;
+    p.one = 1;
     p.shade = reinterpret_cast<const float4 *>(s->d_shade);
     p.emitters = reinterpret_cast<const float4 *>(s->d_emitters);
     p.num_emitters = (int)s->host.emitters.size();

@@ -69,6 +69,7 @@ struct TraceParams {
     int max_depth;
     uint32_t seed;
     int grid_has_misc;              // the walk lists hold misc records (scene_tables.h)
+    int one;                        // 1, opaque to the compiler: x * one + y keeps integer updates on the FMA pipe
 };
 
 // ---- closest hit against the shared-memory soup ----------------------------------------------
@@ -391,6 +392,47 @@ struct GridWalk {
         //   new (r, rend): every record carries the range of what follows it in its list
         // MISC (scenes with misc records only): such a record is skipped by the fast test and leaves the
         // loop with misc = its index.
+        // The ALU pipe (compares, selects, min/max, integer adds) and the FMA pipe each take one warp
+        // instruction every other cycle; the straightforward loop has 22 ALU-pipe instructions of 34 and is
+        // bound by that pipe, not by issue.  The balanced form moves seven of them to the FMA pipe: two of the
+        // four axis selects become a move plus a predicated add of -0 (x + -0 = x), best / win are updated by
+        // predicated moves, the cell index by two predicated integer adds, and the DDA increments read |1/d| of
+        // their own axis instead of a selected one.  (p.one = 1 from the constant bank keeps ptxas from folding
+        // x * 1 + y back into an ALU-pipe add or select.)
+#ifndef FMGI_WALK_BALANCED
+#define FMGI_WALK_BALANCED 1
+#endif
+#if FMGI_WALK_BALANCED
+#define FMGI_WALK_SEL_DO                                                                                             \
+            "add.rn.f32 dh, %27, 0f80000000;\n\t"                                                                    \
+            "@ky add.rn.f32 dh, %26, 0f80000000;\n\t"                                                                \
+            "add.rn.f32 oh, %24, 0f80000000;\n\t"                                                                    \
+            "@ky add.rn.f32 oh, %23, 0f80000000;\n\t"
+#define FMGI_WALK_UPDATE                                                                                             \
+            "@ok add.rn.f32 %0, t, 0f80000000;\n\t"                                                                  \
+            "@ok mad.lo.s32 %1, %14, %17, 0;\n\t"
+#define FMGI_WALK_STEP                                                                                               \
+            "@gx mad.lo.s32 %4, %31, %17, %4;\n\t"                                                                   \
+            "@gy mad.lo.s32 %4, %32, %17, %4;\n\t"                                                                   \
+            "abs.f32 sa, %19;\n\t"                                                                                   \
+            "@gx fma.rn.f32 %5, sa, %29, %5;\n\t"                                                                    \
+            "abs.f32 sa, %20;\n\t"                                                                                   \
+            "@gy fma.rn.f32 %6, sa, %29, %6;\n\t"
+#else
+#define FMGI_WALK_SEL_DO                                                                                             \
+            "selp.f32 dh, %26, %27, ky;\n\t"                                                                         \
+            "selp.f32 oh, %23, %24, ky;\n\t"
+#define FMGI_WALK_UPDATE                                                                                             \
+            "selp.f32 %0, t, %0, ok;\n\t"                                                                            \
+            "selp.b32 %1, %14, %1, ok;\n\t"
+#define FMGI_WALK_STEP                                                                                               \
+            "selp.b32 st, %31, %32, stepx;\n\t"                                                                      \
+            "selp.f32 sa, %19, %20, stepx;\n\t"                                                                      \
+            "abs.f32 sa, sa;\n\t"                                                                                    \
+            "@go add.s32 %4, %4, st;\n\t"                                                                            \
+            "@gx fma.rn.f32 %5, sa, %29, %5;\n\t"                                                                    \
+            "@gy fma.rn.f32 %6, sa, %29, %6;\n\t"
+#endif
 #define FMGI_WALK_LOOP(MISC_TEST, MISC_EXIT, COUNT)                                                                       \
         asm volatile(                                                                                                \
             "{\n\t"                                                                                                  \
@@ -403,8 +445,7 @@ struct GridWalk {
             "setp.lt.s32 ky, %13, 0;\n\t"                                                                            \
             "selp.f32 ak, %20, %19, ky;\n\t"                                                                         \
             "selp.f32 bk, %22, %21, ky;\n\t"                                                                         \
-            "selp.f32 dh, %26, %27, ky;\n\t"                                                                         \
-            "selp.f32 oh, %23, %24, ky;\n\t"                                                                         \
+            FMGI_WALK_SEL_DO                                                                                         \
             "fma.rn.f32 t, %12, ak, bk;\n\t"                                                                         \
             "fma.rn.f32 pi, t, dh, oh;\n\t"                                                                          \
             "fma.rn.f32 pj, t, %28, %25;\n\t"                                                                        \
@@ -418,8 +459,7 @@ struct GridWalk {
             "setp.le.and.f32 ok, pi, %9, ok;\n\t"                                                                    \
             "setp.le.and.f32 ok, pj, %11, ok;\n\t"                                                                   \
             MISC_TEST                                                                                                \
-            "selp.f32 %0, t, %0, ok;\n\t"                                                                            \
-            "selp.b32 %1, %14, %1, ok;\n\t"                                                                          \
+            FMGI_WALK_UPDATE                                                                                         \
             COUNT                                                                                                    \
             "setp.ge.s32 adv, %2, %3;\n\t"                                                                           \
             "min.f32 tn, %5, %6;\n\t"                                                                                \
@@ -429,12 +469,7 @@ struct GridWalk {
             "and.pred gx, go, stepx;\n\t"                                                                            \
             "and.pred gy, go, !stepx;\n\t"                                                                           \
             "or.pred more, cont, !adv;\n\t"                                                                          \
-            "selp.b32 st, %31, %32, stepx;\n\t"                                                                      \
-            "selp.f32 sa, %19, %20, stepx;\n\t"                                                                      \
-            "abs.f32 sa, sa;\n\t"                                                                                    \
-            "@go add.s32 %4, %4, st;\n\t"                                                                            \
-            "@gx fma.rn.f32 %5, sa, %29, %5;\n\t"                                                                    \
-            "@gy fma.rn.f32 %6, sa, %29, %6;\n\t"                                                                    \
+            FMGI_WALK_STEP                                                                                           \
             "selp.b32 %14, %4, %2, go;\n\t"                                                                          \
             "mul.wide.s32 a, %14, 32;\n\t"                                                                           \
             "add.s64 a, a, %18;\n\t"                                                                                 \
@@ -446,7 +481,7 @@ struct GridWalk {
             "}"                                                                                                      \
             : "+f"(best), "+r"(win), "+r"(r), "+r"(rend), "+r"(ci), "+f"(tmx), "+f"(tmy), "+r"(tests), "+f"(q0.x),   \
               "+f"(q0.y), "+f"(q0.z), "+f"(q0.w), "+f"(qc), "+r"(qtag), "+r"(cur), "=r"(more), "=r"(misc)            \
-            : "r"(0), "l"(p.grid_table), "f"(ax), "f"(ay), "f"(bx), "f"(by), "f"(ox), "f"(oy), "f"(oz), "f"(dx),     \
+            : "r"(p.one), "l"(p.grid_table), "f"(ax), "f"(ay), "f"(bx), "f"(by), "f"(ox), "f"(oy), "f"(oz), "f"(dx),     \
               "f"(dy), "f"(dz), "f"(g.cell), "f"(t_exit), "r"(sx), "r"(sy))
         // counting variant only (fmgi_options.count_tests): rectangle tests, dummy heads (c = NaN) excluded
 #define FMGI_WALK_COUNT "setp.eq.f32 real, %12, %12;\n\t@real add.u32 %7, %7, 1;\n\t"
@@ -470,6 +505,9 @@ struct GridWalk {
         }
 #undef FMGI_WALK_COUNT
 #undef FMGI_WALK_MISC_TEST
+#undef FMGI_WALK_SEL_DO
+#undef FMGI_WALK_UPDATE
+#undef FMGI_WALK_STEP
         if (win < 0) best = best_in;
 #undef FMGI_WALK_LOOP
     }

@@ -143,6 +143,22 @@ def test_budgets_and_counters_are_exact(any_tier_scene, oracle, scene):
     assert np.all(atlas[~scene.base_texel_mask()] == 0)      # mip slots are never written
 
 
+def test_rectangle_test_counter_is_opt_in_and_changes_nothing(dev_scene, dev_scene_grid):
+    """fmgi_options.count_tests selects the counting instantiation of the trace kernel (two more instructions per
+    walk step): same photons, rays, deposits and atlas; rect_tests only then.  The grid does a handful of tests
+    per ray where the brute-force scan of this scene did 67."""
+    spa = 40000
+    plain, sp = gpu_bake(dev_scene_grid, spa, max_depth=5, seed=21)
+    counted, sc = gpu_bake(dev_scene_grid, spa, max_depth=5, seed=21, count_tests=1)
+    for k in ("photons", "rays", "deposits", "mirror_bounces"):
+        assert sp[k] == sc[k]
+    assert sp["rect_tests"] == 0
+    assert 2.0 < sc["rect_tests"] / sc["rays"] < 10.0
+    assert np.allclose(plain, counted, rtol=1e-5, atol=1e-2)
+    auto, sa = gpu_bake(dev_scene, spa, max_depth=5, seed=21)          # AUTO picks the grid for 172 colliders
+    assert sa["tier"] == 2 and sa["rays"] == sp["rays"]
+
+
 def test_small_bake_matches_oracle_texel_by_texel(dev_scene, oracle, scene):
     """Same streams, small budget: atlases agree texel by texel except where a border path moved
     one deposit to the neighbouring texel; energy agrees to 1e-4."""
