@@ -43,6 +43,8 @@ struct Sim {
     HostScene sc;
     std::vector<fmgi_rect> walls, windows, lights;
 
+    // the kernel's order (GridWalk in csrc/trace_kernels.cuh): walls by the 2-D DDA, bounded by the grid box
+    // and the z range of the walls, then the z planes crossed before the wall hit, nearest first
     int closest(const float o[3], const float d[3], Walk &w) const
     {
         const GridDesc &g = sc.grid;
@@ -50,6 +52,43 @@ struct Sim {
         const int2 *ranges = reinterpret_cast<const int2 *>(sc.grid_ranges.data());
         float best = INFINITY;
         int win = -1;
+        const float ix = 1.0f / d[0], iy = 1.0f / d[1];
+        int cx = (int)floorf((o[0] - g.x0) * g.inv_cell), cy = (int)floorf((o[1] - g.y0) * g.inv_cell);
+        cx = std::min(std::max(cx, 0), g.nx - 1); cy = std::min(std::max(cy, 0), g.ny - 1);
+        float tmx = INFINITY, tmy = INFINITY, tdx = INFINITY, tdy = INFINITY, t_exit = INFINITY;
+        if (d[0] != 0) {
+            tmx = (g.x0 + (float)(cx + (d[0] > 0 ? 1 : 0)) * g.cell - o[0]) * ix;
+            tdx = g.cell * fabsf(ix);
+            t_exit = ((d[0] > 0 ? g.exit_hi_x : g.exit_lo_x) - o[0]) * ix;
+        }
+        if (d[1] != 0) {
+            tmy = (g.y0 + (float)(cy + (d[1] > 0 ? 1 : 0)) * g.cell - o[1]) * iy;
+            tdy = g.cell * fabsf(iy);
+            t_exit = fminf(t_exit, ((d[1] > 0 ? g.exit_hi_y : g.exit_lo_y) - o[1]) * iy);
+        }
+        if (d[2] != 0) t_exit = fminf(t_exit, ((d[2] < 0 ? g.wall_z_lo : g.wall_z_hi) - o[2]) / d[2] * 1.0001f);
+        const int sx = d[0] > 0 ? 1 : -1, sy = d[1] > 0 ? g.nx : -g.nx;
+        int ci = cy * g.nx + cx;
+        const int combo = (d[0] > 0 ? 1 : 0) + (d[1] > 0 ? 2 : 0);
+        const int2 *walk = ranges + (kWalkListBase + combo) * ncell;
+        best = fminf(best, t_exit);
+        for (;;) {
+            const int2 r = walk[ci];
+            w.cells.push_back(r.y - r.x);
+            for (int q = r.x; q < r.y; q++) {
+                const GridRec &rec = sc.grid_recs[q];
+                if (rec.tag & kTagMisc) continue;      // parseLayout scenes have none in walk lists
+                const bool ky = (rec.tag & kTagAlongY) != 0;
+                const float t = (rec.c - (ky ? o[1] : o[0])) * (ky ? iy : ix);
+                const float pi = t * (ky ? d[0] : d[1]) + (ky ? o[0] : o[1]) - rec.mid_i;
+                const float pj = t * d[2] + o[2] - rec.mid_j;
+                if (t >= 0 && t < best && fabsf(pi) <= rec.half_i && fabsf(pj) <= rec.half_j) { best = t; win = q; }
+            }
+            const float t_next = fminf(tmx, tmy);
+            if (!(t_next < best)) break;
+            if (tmx < tmy) { ci += sx; tmx += tdx; } else { ci += sy; tmy += tdy; }
+        }
+        if (win < 0) best = INFINITY;
         if (d[2] != 0.0f) {
             const float iz = 1.0f / d[2];
             const int first = d[2] < 0 ? 0 : kMaxPlanesPerSign;
@@ -71,40 +110,6 @@ struct Sim {
                 }
                 w.plane_cands.push_back(c);
             }
-        }
-        const float ix = 1.0f / d[0], iy = 1.0f / d[1];
-        int cx = (int)floorf((o[0] - g.x0) * g.inv_cell), cy = (int)floorf((o[1] - g.y0) * g.inv_cell);
-        cx = std::min(std::max(cx, 0), g.nx - 1); cy = std::min(std::max(cy, 0), g.ny - 1);
-        float tmx = INFINITY, tmy = INFINITY, tdx = INFINITY, tdy = INFINITY, t_exit = INFINITY;
-        if (d[0] != 0) {
-            tmx = (g.x0 + (float)(cx + (d[0] > 0 ? 1 : 0)) * g.cell - o[0]) * ix;
-            tdx = g.cell * fabsf(ix);
-            t_exit = (g.x0 + (d[0] > 0 ? (float)(g.nx - 1) : 1.0f) * g.cell - o[0]) * ix;
-        }
-        if (d[1] != 0) {
-            tmy = (g.y0 + (float)(cy + (d[1] > 0 ? 1 : 0)) * g.cell - o[1]) * iy;
-            tdy = g.cell * fabsf(iy);
-            t_exit = fminf(t_exit, (g.y0 + (d[1] > 0 ? (float)(g.ny - 1) : 1.0f) * g.cell - o[1]) * iy);
-        }
-        const int sx = d[0] > 0 ? 1 : -1, sy = d[1] > 0 ? g.nx : -g.nx;
-        int ci = cy * g.nx + cx;
-        const int combo = (d[0] > 0 ? 1 : 0) + (d[1] > 0 ? 2 : 0);
-        const int2 *walk = ranges + (kWalkListBase + combo) * ncell;
-        for (;;) {
-            const int2 r = walk[ci];
-            w.cells.push_back(r.y - r.x);
-            for (int q = r.x; q < r.y; q++) {
-                const GridRec &rec = sc.grid_recs[q];
-                if (rec.tag & kTagMisc) continue;      // parseLayout scenes have none in walk lists
-                const bool ky = (rec.tag & kTagAlongY) != 0;
-                const float t = (rec.c - (ky ? o[1] : o[0])) * (ky ? iy : ix);
-                const float pi = t * (ky ? d[0] : d[1]) + (ky ? o[0] : o[1]) - rec.mid_i;
-                const float pj = t * d[2] + o[2] - rec.mid_j;
-                if (t >= 0 && t < best && fabsf(pi) <= rec.half_i && fabsf(pj) <= rec.half_j) { best = t; win = q; }
-            }
-            const float t_next = fminf(tmx, tmy);
-            if (!(t_next < fminf(best, t_exit))) break;
-            if (tmx < tmy) { ci += sx; tmx += tdx; } else { ci += sy; tmy += tdy; }
         }
         w.t = best;
         w.hit = win >= 0 ? (int)(sc.grid_recs[win].tag & kTagIdMask) : -1;
@@ -269,7 +274,7 @@ int main(int argc, char **argv)
     }
     printf("rays %.0f  tests/ray %.2f  cells/ray %.2f (empty %.2f)  alive lanes/outer %.1f\n", rays, tests / rays,
            cells_visited / rays, empty_cells / rays, lanes_alive / outer);
-    printf("planes: head iters/ray %.3f (lanes %.1f)  cand iters/ray %.3f (lanes %.1f)\n", pl_head_iters * 32 / rays / 32 * 1.0,
+    printf("planes: head iters/ray %.3f (lanes %.1f)  cand iters/ray %.3f (lanes %.1f)\n", pl_head_iters / rays,
            pl_head_lanes / pl_head_iters, pl_cand_iters / rays, pl_cand_lanes / pl_cand_iters);
     printf("V0 current : warp iters/outer %.2f  test iters %.2f (lanes %.1f)  adv iters %.2f (lanes %.1f)\n", v0_iters / outer,
            v0_test_iters / outer, v0_test_lanes / v0_test_iters, v0_adv_iters / outer, v0_adv_lanes / v0_adv_iters);
