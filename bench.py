@@ -410,6 +410,20 @@ def run_ours(args):
                     "achieved": issue / 1e9, "peak": issue_peak / 1e9, "unit": "G warp-inst/s",
                     "frac": issue / issue_peak, "warp_inst_per_ray": facts["warp_inst_per_ray"],
                     "lanes_per_inst": facts.get("threads_per_instruction")}
+        # the deposit instruction's own rate, measured in this run - at uniform-random texels
+        # of an atlas-sized scratch buffer (HBM-bound once the atlas exceeds L2) and of an L2-resident one (what
+        # a bake reaches when its deposits are local: photons are handed out emitter by emitter)
+        try:
+            dep_rate = (deposits_all / world) / (args.steps * kms * 1e-3)
+            peak_atlas = fmgi.deposit_peak(num_texels, 300_000_000, device=local)
+            peak_l2 = fmgi.deposit_peak(min(num_texels, 1 << 20), 300_000_000, device=local)
+            line["roofline"]["deposit"] = {
+                "achieved": dep_rate, "peak": peak_l2, "frac": dep_rate / peak_l2,
+                "peak_uniform_over_atlas": peak_atlas, "unit": "deposits/s per GPU (RED.E.ADD.F32x4)",
+                "note": "peak = bare deposit instruction at uniform-random texels of an L2-resident footprint; "
+                        "peak_uniform_over_atlas = the same over a scratch buffer of the atlas size"}
+        except Exception as e:                       # a probe must never cost the bench line
+            line["roofline"]["deposit"] = {"error": str(e)}
         if world == 1 and args.workload.startswith("example") and not args.no_app:
             wall = reference_app_wall_time()
             if wall is not None:

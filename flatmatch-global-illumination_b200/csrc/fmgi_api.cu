@@ -937,6 +937,39 @@ int fmgi_probe_philox(const uint32_t ctr[4], const uint32_t key[2], uint32_t out
     return FMGI_OK;
 }
 
+int fmgi_probe_deposit_peak(uint64_t num_texels, uint64_t num_deposits, int device, double *deposits_per_s)
+{
+    if (!deposits_per_s || num_texels == 0 || num_texels > 0xffffffffull || num_deposits == 0)
+        return fail(FMGI_ERR_ARG, "bad argument");
+    int ndev = 0;
+    FMGI_CUDA(cudaGetDeviceCount(&ndev));
+    if (device < 0 || device >= ndev) return fail(FMGI_ERR_ARG, "device ordinal out of range");
+    DeviceGuard guard(device);
+    int sms = 0;
+    FMGI_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
+    DevBuf<float4> atlas;
+    FMGI_CUDA(atlas.alloc((size_t)num_texels));
+    FMGI_CUDA(cudaMemset(atlas, 0, (size_t)num_texels * sizeof(float4)));
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    FMGI_CUDA(cudaEventCreate(&e0));
+    cudaError_t err = cudaEventCreate(&e1);
+    float ms = 0;
+    if (err == cudaSuccess) {
+        k_probe_red_peak<<<sms * 8, 256>>>(atlas, (uint32_t)num_texels, num_deposits / 4 + 1, 1u);      // warm-up
+        cudaEventRecord(e0);
+        k_probe_red_peak<<<sms * 8, 256>>>(atlas, (uint32_t)num_texels, num_deposits, 2u);
+        cudaEventRecord(e1);
+        err = cudaEventSynchronize(e1);
+        if (err == cudaSuccess) err = cudaGetLastError();
+        if (err == cudaSuccess) err = cudaEventElapsedTime(&ms, e0, e1);
+    }
+    cudaEventDestroy(e0);
+    if (e1) cudaEventDestroy(e1);
+    if (err != cudaSuccess) return fail(FMGI_ERR_CUDA, std::string("deposit peak probe: ") + cudaGetErrorString(err));
+    *deposits_per_s = ms > 0 ? (double)num_deposits / (ms * 1e-3) : 0.0;
+    return FMGI_OK;
+}
+
 int fmgi_probe_sample_dirs(const float normal[3], int sky, uint32_t seed, int n, float *dirs_out)
 {
     if (!normal || !dirs_out || n < 0) return fail(FMGI_ERR_ARG, "bad argument");

@@ -241,6 +241,21 @@ __global__ void k_probe_sample_dirs(float4 n, float4 u, float4 v, int sky, uint3
     }
 }
 
+// Deposit roofline probe: the trace kernel's deposit instruction - one RED.E.ADD.F32x4 per
+// bounce - at uniform-random texels of an atlas-sized footprint, with nothing else in the loop but a 32-bit
+// mix that picks the texel.  Its rate is the "A_peak" the bench line compares the bake's deposit rate with.
+__global__ void __launch_bounds__(256) k_probe_red_peak(float4 *__restrict__ atlas, uint32_t num_texels,
+                                                        unsigned long long num_deposits, uint32_t seed)
+{
+    const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+    for (unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; i < num_deposits; i += stride) {
+        uint32_t h = (uint32_t)i * 0x9E3779B1u + seed;           // lowbias32-style mix: distinct per deposit
+        h ^= h >> 16; h *= 0x21F0AAADu; h ^= h >> 15; h *= 0x735A2D97u; h ^= h >> 15;
+        const uint32_t idx = (uint32_t)(((unsigned long long)h * num_texels) >> 32);
+        atomicAdd(atlas + idx, make_float4(16.2f, 16.2f, 16.2f, 0.0f));
+    }
+}
+
 // ---- ambient occlusion ------------------------------------------------------------------
 //
 // performAmbientOcclusionNative (photonmap.c:436-491) on the closest-hit code of the photon tracer: one

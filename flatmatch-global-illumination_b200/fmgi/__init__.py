@@ -71,7 +71,7 @@ EXPORTS = [
     "fmgi_ambient_occlusion", "fmgi_scene_ambient_occlusion", "fmgi_geosphere",
     "fmgi_bake", "fmgi_scene_create", "fmgi_scene_destroy", "fmgi_scene_trace", "fmgi_scene_sync",
     "fmgi_scene_photon_count", "fmgi_probe_closest_hit", "fmgi_probe_tile_ids", "fmgi_probe_philox",
-    "fmgi_probe_sample_dirs", "fmgi_probe_paths",
+    "fmgi_probe_sample_dirs", "fmgi_probe_paths", "fmgi_probe_deposit_peak",
 ]
 
 _lib = None
@@ -110,6 +110,7 @@ def lib() -> C.CDLL:
     L.fmgi_ambient_occlusion.argtypes = [C.POINTER(Geometry), C.POINTER(Options)]
     L.fmgi_geosphere.argtypes = [C.c_int, C.c_void_p, C.c_int]
     L.fmgi_scene_ambient_occlusion.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+    L.fmgi_probe_deposit_peak.argtypes = [C.c_uint64, C.c_uint64, C.c_int, C.POINTER(C.c_double)]
     L.fmgi_probe_closest_hit.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
     L.fmgi_probe_tile_ids.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
     L.fmgi_probe_philox.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
@@ -283,6 +284,14 @@ def philox(ctr, key) -> np.ndarray:
     out = np.empty(4, dtype=np.uint32)
     _check(lib().fmgi_probe_philox(c.ctypes.data, k.ctypes.data, out.ctypes.data))
     return out
+
+
+def deposit_peak(num_texels: int, num_deposits: int = 400_000_000, device: int = 0) -> float:
+    """Deposits per second of the bare deposit instruction at uniform-random texels (fmgi_probe_deposit_peak)."""
+    out = C.c_double(0.0)
+    _check(lib().fmgi_probe_deposit_peak(C.c_uint64(int(num_texels)), C.c_uint64(int(num_deposits)), int(device),
+                                         C.byref(out)))
+    return out.value
 
 
 def sample_dirs(normal, sky: bool, seed: int, n: int) -> np.ndarray:

@@ -180,6 +180,10 @@ int fmgi_probe_tile_ids(fmgi_scene *scene, const int32_t *rect_index, const floa
                         int num_points, int32_t *tile_ids);
 /* Philox4x32-10 block on the device. */
 int fmgi_probe_philox(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]);
+/* Deposit roofline: rate of the trace kernel's deposit instruction (one 16-byte vector
+ * reduction, RED.E.ADD.F32x4) at uniform-random texels of a scratch atlas of num_texels float4, nothing else
+ * in the loop.  Deposits per second, device-timed. */
+int fmgi_probe_deposit_peak(uint64_t num_texels, uint64_t num_deposits, int device, double *deposits_per_s);
 /* n directions around `normal` from the device sampler (sky != 0: window fold). */
 int fmgi_probe_sample_dirs(const float normal[3], int sky, uint32_t seed, int n, float *dirs_out);
 /* Per-photon paths: atlas index deposited at bounce b of photons [first, first+count) of

@@ -159,6 +159,16 @@ def test_rectangle_test_counter_is_opt_in_and_changes_nothing(dev_scene, dev_sce
     assert sa["tier"] == 2 and sa["rays"] == sp["rays"]
 
 
+def test_deposit_peak_probe(fmgi, scene):
+    """fmgi_probe_deposit_peak (the deposit roofline of SURVEY.md 8d-ii): the bare RED.E.ADD.F32x4 at uniform-random
+    texels.  An L2-resident footprint sustains an order of magnitude more than the bake deposits (measured
+    1.9e11/s on a B200); a footprint far beyond L2 is bound by random 32-byte sector traffic (2.6e10/s at 457 MB)."""
+    small = fmgi.deposit_peak(scene.num_texels, 100_000_000)
+    large = fmgi.deposit_peak(28_591_084, 100_000_000)
+    assert small > 2e10 and large > 2e9
+    assert large < small
+
+
 def test_small_bake_matches_oracle_texel_by_texel(dev_scene, oracle, scene):
     """Same streams, small budget: atlases agree texel by texel except where a border path moved
     one deposit to the neighbouring texel; energy agrees to 1e-4."""
