@@ -2,7 +2,9 @@
 // point (global_illumination_cl.h:10), the options/counters extension and the parity probes.
 // Replaces the OpenCL host code of global_illumination_cl.c:148-321.
 #include <cuda_runtime.h>
+#include <unistd.h>
 
+#include <algorithm>
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
@@ -37,6 +39,31 @@ int fail(int code, const std::string &msg)
         if (err__ != cudaSuccess)                                                                   \
             return fail(FMGI_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(err__));      \
     } while (0)
+
+// Wall time since the process was started, from /proc/self/stat (field 22, clock ticks since boot) and
+// /proc/uptime; 10 ms resolution.  Only for the FMGI_STATS=2 breakdown line.
+double ms_since_process_start()
+{
+    FILE *f = fopen("/proc/self/stat", "r");
+    if (!f) return 0.0;
+    char buf[2048];
+    const size_t n = fread(buf, 1, sizeof buf - 1, f);
+    fclose(f);
+    buf[n] = 0;
+    const char *p = strrchr(buf, ')');            // the command name may contain spaces
+    if (!p) return 0.0;
+    unsigned long long start = 0;
+    int field = 2;
+    for (p++; *p && field < 22; p++)
+        if (*p == ' ' && ++field == 22) sscanf(p + 1, "%llu", &start);
+    double up = 0.0;
+    f = fopen("/proc/uptime", "r");
+    if (!f) return 0.0;
+    if (fscanf(f, "%lf", &up) != 1) up = 0.0;
+    fclose(f);
+    const double hz = (double)sysconf(_SC_CLK_TCK);
+    return up > 0.0 && hz > 0.0 ? (up - (double)start / hz) * 1e3 : 0.0;
+}
 
 double now_ms()
 {
@@ -88,9 +115,24 @@ cudaError_t upload(T **dst, const std::vector<T> &src)
 
 }  // namespace
 
+// Host-side precompute of one scene (scene_prep.cpp): built once per bake, uploaded to every GPU that takes part.
+struct HostBuild {
+    HostScene scene;
+    std::vector<float> wall_wh;                 // the walls' width and height vectors (6 floats per wall)
+    std::vector<float> wall_area;               // |width| * |height| per wall, float (rectangle.c:194-197)
+    std::vector<int> wall_floor;                // rectangle.c:317
+    int tier = FMGI_TIER_SOUP;
+    int kernel_tier = FMGI_TIER_SOUP;           // tier, or kTierSoupPlanes (soup + the grid's plane tables)
+    size_t smem_bytes = 0;
+    uint64_t tests_per_ray = 0;
+    double prepare_ms = 0, grid_ms = 0;         // host clock: rectangle tables, floor-plan grid
+};
+
 struct fmgi_scene {
     int device = 0;
-    HostScene host;
+    std::shared_ptr<HostBuild> build;           // host-side tables, shared by the per-GPU scenes of one bake
+    HostScene &host;
+    explicit fmgi_scene(std::shared_ptr<HostBuild> b) : build(std::move(b)), host(build->scene) {}
     // device tables
     AxisPairBlock *d_axis = nullptr;
     GeneralRect *d_general = nullptr;
@@ -104,14 +146,18 @@ struct fmgi_scene {
     TileWall *h_tile_walls = nullptr;           // pinned staging for it
     float *d_ao = nullptr;                      // ambient occlusion: widths, heights (3 floats per wall), then float4 directions
     AoWall *d_ao_walls = nullptr;
-    std::vector<float> wall_wh;                 // the walls' width and height vectors (6 floats per wall)
-    std::vector<float> wall_area;               // |width| * |height| per wall, float (rectangle.c:194-197)
-    std::vector<int> wall_floor;                // rectangle.c:317
     unsigned long long *d_counters = nullptr;   // 4 counters + work counter
     unsigned long long *h_jobs = nullptr;       // pinned staging
     unsigned long long *h_counters = nullptr;   // pinned
     cudaEvent_t ev_start = nullptr, ev_stop = nullptr;
     cudaStream_t last_stream = nullptr;
+    std::vector<cudaStream_t> streams;          // every stream work of this scene was enqueued on
+    void note_stream(cudaStream_t st)
+    {
+        last_stream = st;
+        for (cudaStream_t t : streams) if (t == st) return;
+        streams.push_back(st);
+    }
     bool traced = false;
     int num_sms = 0, clock_khz = 0, blocks_per_sm = 0;
     size_t smem_bytes = 0;
@@ -148,14 +194,14 @@ TraceParams base_params(const fmgi_scene *s)
 }
 
 // Job tables, per accumulation pass: chunk_begin[E + 1] (prefix of the emitters' chunk counts; a chunk is
-// kChunkPhotons consecutive photon indices of ONE emitter, the unit a warp claims), photon_first[E],
+// `chunk` consecutive photon indices of ONE emitter, the unit a warp claims), photon_first[E],
 // photon_count[E].
 inline size_t job_table_words(size_t E) { return 3 * E + 2; }
 
 // Fills the pinned job tables for (spa, shard): emitter e's N photons (photonmap.c:414-418) are split
 // into num_shards contiguous index ranges.  Returns the shard's photon total; *chunks its chunk total.
 unsigned long long fill_jobs(const fmgi_scene *s, int spa, const fmgi_options &o, unsigned long long *jobs,
-                             unsigned long long *chunks = nullptr)
+                             unsigned long long *chunks = nullptr, int chunk = kChunkPhotons)
 {
     const int E = (int)s->host.emitters.size();
     unsigned long long total = 0, total_chunks = 0;
@@ -167,7 +213,7 @@ unsigned long long fill_jobs(const fmgi_scene *s, int spa, const fmgi_options &o
         jobs[E + 1 + e] = first;
         jobs[2 * E + 1 + e] = last - first;
         total += last - first;
-        total_chunks += (last - first + kChunkPhotons - 1) / kChunkPhotons;
+        total_chunks += (last - first + chunk - 1) / chunk;
     }
     jobs[E] = total_chunks;
     if (chunks) *chunks = total_chunks;
@@ -218,121 +264,104 @@ cudaError_t launch_trace(fmgi_scene *s, const TraceParams &p, int deposit, bool 
     });
 }
 
-}  // namespace
 
-extern "C" {
-
-void fmgi_default_options(fmgi_options *opt)
+// device attributes do not change; cudaDevAttrClockRate in particular is slow to query (and
+// cudaGetDeviceProperties costs about a millisecond per call)
+struct DevAttr { int valid, sms, smem_optin, clock_khz; };
+int device_attrs(int device, DevAttr &out)
 {
-    if (!opt) return;
-    memset(opt, 0, sizeof *opt);
-    opt->struct_size = sizeof *opt;
-    opt->max_depth = 8;          // photonmap.c:173
-    opt->seed = 1;
-    opt->num_gpus = 1;
-    opt->num_shards = 1;
-    opt->tier = FMGI_TIER_AUTO;
-    opt->deposit = FMGI_DEPOSIT_VEC4;
+    static DevAttr cache[64];
+    static std::mutex mu;
+    std::lock_guard<std::mutex> lock(mu);
+    DevAttr &a = cache[device & 63];
+    if (!a.valid) {
+        FMGI_CUDA(cudaDeviceGetAttribute(&a.sms, cudaDevAttrMultiProcessorCount, device));
+        FMGI_CUDA(cudaDeviceGetAttribute(&a.smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
+        FMGI_CUDA(cudaDeviceGetAttribute(&a.clock_khz, cudaDevAttrClockRate, device));
+        a.valid = 1;
+    }
+    out = a;
+    return FMGI_OK;
 }
 
-const char *fmgi_last_error(void) { return g_last_error.c_str(); }
-const char *fmgi_version(void) { return "fmgi-b200 0.1 (sm_100a)"; }
-
-void fmgi_release_cache(void) { MemPool::get().release(); }
-
-int fmgi_device_count(void)
+// Host half of fmgi_scene_create: rectangle tables, tier choice, floor-plan grid.  No device work, so one
+// build serves every GPU of a multi-GPU bake.
+int build_host(std::shared_ptr<HostBuild> &out, const fmgi_rect *walls, int num_walls, const fmgi_rect *windows,
+               int num_windows, const fmgi_rect *lights, int num_lights, int num_texels, const fmgi_options &o)
 {
-    int n = 0;
-    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
-    return n;
-}
-
-int fmgi_scene_create(fmgi_scene **out, const fmgi_rect *walls, int num_walls, const fmgi_rect *windows,
-                      int num_windows, const fmgi_rect *lights, int num_lights, int num_texels,
-                      const fmgi_options *opt)
-{
-    if (!out) return fail(FMGI_ERR_ARG, "out is NULL");
-    *out = nullptr;
     if ((num_walls && !walls) || (num_windows && !windows) || (num_lights && !lights))
         return fail(FMGI_ERR_ARG, "NULL rectangle table with non-zero count");
-    const fmgi_options o = resolve(opt);
     int ndev = 0;
     FMGI_CUDA(cudaGetDeviceCount(&ndev));
     if (o.device < 0 || o.device >= ndev) return fail(FMGI_ERR_ARG, "device ordinal out of range");
+    DevAttr attr;
+    if (int rc = device_attrs(o.device, attr)) return rc;
 
-    // a scene that fails half-way gives its device blocks back through fmgi_scene_destroy
-    std::unique_ptr<fmgi_scene, void (*)(fmgi_scene *)> s(new fmgi_scene, fmgi_scene_destroy);
-    s->device = o.device;
-    const char *why = prepare_scene(s->host, walls, num_walls, windows, num_windows, lights, num_lights, num_texels);
+    auto b = std::make_shared<HostBuild>();
+    const double t0 = now_ms();
+    const char *why = prepare_scene(b->scene, walls, num_walls, windows, num_windows, lights, num_lights, num_texels);
     if (why[0]) return fail(FMGI_ERR_ARG, why);
-
-    s->wall_area.resize(num_walls);
-    s->wall_floor.resize(num_walls);
+    b->wall_area.resize(num_walls);
+    b->wall_floor.resize(num_walls);
+    b->wall_wh.reserve((size_t)6 * num_walls);
     for (int i = 0; i < num_walls; i++) {
-        const ShadeRect &sh = s->host.shade[i];
-        s->wall_area[i] = sh.wlen * sh.hlen;                                            // getArea, rectangle.c:194-197
-        s->wall_floor[i] = walls[i].pos[2] == 0 && walls[i].width[2] == 0 && walls[i].height[2] == 0;
-        for (int c = 0; c < 3; c++) {
-            s->wall_wh.push_back(walls[i].width[c]);
-        }
-        for (int c = 0; c < 3; c++) {
-            s->wall_wh.push_back(walls[i].height[c]);
-        }
+        const ShadeRect &sh = b->scene.shade[i];
+        b->wall_area[i] = sh.wlen * sh.hlen;                                            // getArea, rectangle.c:194-197
+        b->wall_floor[i] = walls[i].pos[2] == 0 && walls[i].width[2] == 0 && walls[i].height[2] == 0;
+        for (int c = 0; c < 3; c++) b->wall_wh.push_back(walls[i].width[c]);
+        for (int c = 0; c < 3; c++) b->wall_wh.push_back(walls[i].height[c]);
     }
-    DeviceGuard guard(o.device);
-    // cudaGetDeviceProperties costs about a millisecond per call: query the three attributes we need
-    struct { size_t sharedMemPerBlockOptin; } prop;
-    {
-        // device attributes do not change; cudaDevAttrClockRate in particular is slow to query
-        struct Attr { int valid, sms, smem_optin, clock_khz; };
-        static Attr cache[64];
-        static std::mutex mu;
-        std::lock_guard<std::mutex> lock(mu);
-        Attr &a = cache[o.device & 63];
-        if (!a.valid) {
-            FMGI_CUDA(cudaDeviceGetAttribute(&a.sms, cudaDevAttrMultiProcessorCount, o.device));
-            FMGI_CUDA(cudaDeviceGetAttribute(&a.smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, o.device));
-            FMGI_CUDA(cudaDeviceGetAttribute(&a.clock_khz, cudaDevAttrClockRate, o.device));
-            a.valid = 1;
-        }
-        s->num_sms = a.sms; s->clock_khz = a.clock_khz;
-        prop.sharedMemPerBlockOptin = (size_t)a.smem_optin;
-    }
+    b->prepare_ms = now_ms() - t0;
 
     // tier: brute force over the shared-memory soup for small scenes, floor-plan grid otherwise
-    const size_t soup_bytes = s->host.axis.size() * sizeof(AxisPairBlock) + s->host.general.size() * sizeof(GeneralRect);
-    const int colliders = s->host.num_axis_rects + (int)s->host.general.size();
+    HostScene &hs = b->scene;
+    const size_t soup_bytes = hs.axis.size() * sizeof(AxisPairBlock) + hs.general.size() * sizeof(GeneralRect);
+    const int colliders = hs.num_axis_rects + (int)hs.general.size();
     int tier = o.tier;
     if (const char *v = getenv("FMGI_TIER")) tier = atoi(v);
     // AUTO: the brute-force soup only for a handful of colliders (one bare room); measured on the
     // 172-rectangle example.png scene the grid is 20 % faster than the soup + plane tables
     if (tier != FMGI_TIER_SOUP && tier != FMGI_TIER_GRID)
-        tier = (colliders <= 64 && soup_bytes <= (size_t)prop.sharedMemPerBlockOptin) ? FMGI_TIER_SOUP : FMGI_TIER_GRID;
-    if (tier == FMGI_TIER_SOUP && soup_bytes > (size_t)prop.sharedMemPerBlockOptin)
+        tier = (colliders <= 64 && soup_bytes <= (size_t)attr.smem_optin) ? FMGI_TIER_SOUP : FMGI_TIER_GRID;
+    if (tier == FMGI_TIER_SOUP && soup_bytes > (size_t)attr.smem_optin)
         return fail(FMGI_ERR_UNSUPPORTED, "rectangle soup does not fit in shared memory; use FMGI_TIER_GRID");
-    s->tier = tier;
-    s->kernel_tier = tier;
+    b->tier = tier;
+    b->kernel_tier = tier;
     float cell = 0.0f;
     if (const char *v = getenv("FMGI_GRID_CELL")) cell = (float)atof(v);
-    build_grid(s->host, walls, num_walls, windows, num_windows, lights, num_lights, cell);
+    const double t1 = now_ms();
+    build_grid(hs, walls, num_walls, windows, num_windows, lights, num_lights, cell);
+    b->grid_ms = now_ms() - t1;
     if (tier == FMGI_TIER_SOUP) {
-        s->smem_bytes = soup_bytes;
+        b->smem_bytes = soup_bytes;
         // each lane walks one of the two blocks of every pair: two rectangle tests per pair
-        s->tests_per_ray = s->host.axis.size() + s->host.general.size();
+        b->tests_per_ray = hs.axis.size() + hs.general.size();
         // horizontal rectangles through the plane tables when all of them fit (and there are any)
-        bool planes = s->host.grid_overflow_horizontal == 0 && s->host.pair_begin[3] > s->host.pair_begin[2];
+        bool planes = hs.grid_overflow_horizontal == 0 && hs.pair_begin[3] > hs.pair_begin[2];
         if (const char *v = getenv("FMGI_SOUP_PLANES")) planes = planes && atoi(v) != 0;       // tuning knob
         if (planes) {
-            s->kernel_tier = kTierSoupPlanes;
-            s->tests_per_ray = 2 * (size_t)s->host.pair_begin[2] + s->host.general.size();   // x and y lists only
+            b->kernel_tier = kTierSoupPlanes;
+            b->tests_per_ray = 2 * (size_t)hs.pair_begin[2] + hs.general.size();   // x and y lists only
         }
-    } else {
-        s->smem_bytes = 0;
     }
-    if (s->kernel_tier != FMGI_TIER_SOUP) {
-        FMGI_CUDA(upload(&s->d_grid_table, s->host.grid_table));
-    }
+    out = b;
+    return FMGI_OK;
+}
 
+// Device half: uploads the tables of a host build to o.device.
+int scene_from_build(fmgi_scene **out, std::shared_ptr<HostBuild> b, const fmgi_options &o)
+{
+    *out = nullptr;
+    DevAttr attr;
+    if (int rc = device_attrs(o.device, attr)) return rc;
+    // a scene that fails half-way gives its device blocks back through fmgi_scene_destroy
+    std::unique_ptr<fmgi_scene, void (*)(fmgi_scene *)> s(new fmgi_scene(b), fmgi_scene_destroy);
+    s->device = o.device;
+    s->num_sms = attr.sms; s->clock_khz = attr.clock_khz;
+    s->tier = b->tier; s->kernel_tier = b->kernel_tier;
+    s->smem_bytes = b->smem_bytes; s->tests_per_ray = b->tests_per_ray;
+    DeviceGuard guard(o.device);
+    if (s->kernel_tier != FMGI_TIER_SOUP) FMGI_CUDA(upload(&s->d_grid_table, s->host.grid_table));
     FMGI_CUDA(upload(&s->d_axis, s->host.axis));
     FMGI_CUDA(upload(&s->d_general, s->host.general));
     FMGI_CUDA(upload(&s->d_shade, s->host.shade));
@@ -363,12 +392,58 @@ int fmgi_scene_create(fmgi_scene **out, const fmgi_rect *walls, int num_walls, c
     return FMGI_OK;
 }
 
+}  // namespace
+
+extern "C" {
+
+void fmgi_default_options(fmgi_options *opt)
+{
+    if (!opt) return;
+    memset(opt, 0, sizeof *opt);
+    opt->struct_size = sizeof *opt;
+    opt->max_depth = 8;          // photonmap.c:173
+    opt->seed = 1;
+    opt->num_gpus = 1;
+    opt->num_shards = 1;
+    opt->tier = FMGI_TIER_AUTO;
+    opt->deposit = FMGI_DEPOSIT_VEC4;
+}
+
+const char *fmgi_last_error(void) { return g_last_error.c_str(); }
+#ifndef FMGI_SRC_HASH
+#define FMGI_SRC_HASH "unknown"
+#endif
+const char *fmgi_version(void) { return "fmgi-b200 0.2 (sm_100a) src " FMGI_SRC_HASH; }
+const char *fmgi_source_hash(void) { return FMGI_SRC_HASH; }
+
+void fmgi_release_cache(void) { MemPool::get().release(); }
+
+int fmgi_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+int fmgi_scene_create(fmgi_scene **out, const fmgi_rect *walls, int num_walls, const fmgi_rect *windows,
+                      int num_windows, const fmgi_rect *lights, int num_lights, int num_texels,
+                      const fmgi_options *opt)
+{
+    if (!out) return fail(FMGI_ERR_ARG, "out is NULL");
+    *out = nullptr;
+    const fmgi_options o = resolve(opt);
+    std::shared_ptr<HostBuild> b;
+    const int rc = build_host(b, walls, num_walls, windows, num_windows, lights, num_lights, num_texels, o);
+    if (rc) return rc;
+    return scene_from_build(out, b, o);
+}
+
 void fmgi_scene_destroy(fmgi_scene *s)
 {
     if (!s) return;
     DeviceGuard guard(s->device);
     if (s->traced) cudaEventSynchronize(s->ev_stop);      // blocks go back to the pool: nothing may still use them
-    if (s->last_stream || s->traced) cudaStreamSynchronize(s->last_stream);
+    for (cudaStream_t st : s->streams) cudaStreamSynchronize(st);
     MemPool &pool = MemPool::get();
     pool.free(s->d_axis); pool.free(s->d_general); pool.free(s->d_shade); pool.free(s->d_emitters);
     pool.free(s->d_grid_table);
@@ -426,12 +501,20 @@ int fmgi_scene_trace(fmgi_scene *s, void *atlas_dev, int spa, const fmgi_options
     if (passes > 1 && !s->d_scratch)
         FMGI_CUDA(pool.alloc((void **)&s->d_scratch, atlas_bytes ? atlas_bytes : 16, false));
 
+    // Chunk size: kChunkPhotons for big bakes; a small bake is cut finer so that every resident warp of every SM
+    // gets a few chunks (a 1e6-photon shard in 256-photon chunks is 3906 chunks for 4736 resident warps, each
+    // grinding its chunk serially: the kernel then takes 0.23 ms for 0.03 ms of work).
+    const unsigned long long wave = (unsigned long long)s->num_sms * s->blocks_per_sm;
+    const unsigned long long per_pass = total_all / (unsigned long long)passes;
+    int chunk = kChunkPhotons;
+    while (chunk > kMinChunkPhotons && per_pass / chunk < 4 * wave * (kTraceThreads / 32)) chunk >>= 1;
+    if (const char *v = getenv("FMGI_CHUNK")) { const int c = atoi(v); if (c >= 1 && c <= 65536) chunk = c; }   // tuning knob
     fmgi_options op = o;
     op.num_shards = o.num_shards * passes;
     std::vector<unsigned long long> totals(passes), chunks(passes);
     for (int c = 0; c < passes; c++) {
         op.shard = o.shard * passes + c;
-        totals[c] = fill_jobs(s, spa, op, s->h_jobs + c * table_words, &chunks[c]);
+        totals[c] = fill_jobs(s, spa, op, s->h_jobs + c * table_words, &chunks[c], chunk);
     }
     FMGI_CUDA(cudaMemcpyAsync(s->d_jobs, s->h_jobs, passes * table_words * sizeof(unsigned long long),
                               cudaMemcpyHostToDevice, st));
@@ -445,6 +528,7 @@ int fmgi_scene_trace(fmgi_scene *s, void *atlas_dev, int spa, const fmgi_options
         p.photon_first = p.job_begin + (E + 1);
         p.photon_count = p.job_begin + (2 * E + 1);
         p.total_jobs = chunks[c];
+        p.chunk = chunk;
         p.atlas = reinterpret_cast<float4 *>(passes > 1 ? (void *)s->d_scratch : atlas_dev);
         p.max_depth = o.max_depth;
         p.seed = o.seed;
@@ -454,7 +538,6 @@ int fmgi_scene_trace(fmgi_scene *s, void *atlas_dev, int spa, const fmgi_options
         }
         // persistent grid: one wave of resident CTAs, never more warps than chunks of work
         unsigned long long want = (chunks[c] * 32 + kTraceThreads - 1) / kTraceThreads;
-        const unsigned long long wave = (unsigned long long)s->num_sms * s->blocks_per_sm;
         const int blocks = (int)(want < wave ? (want ? want : 1) : wave);
         FMGI_CUDA(launch_trace(s, p, o.deposit, false, blocks, st, count_tests));
         if (passes > 1 && s->host.num_texels > 0) {
@@ -467,7 +550,7 @@ int fmgi_scene_trace(fmgi_scene *s, void *atlas_dev, int spa, const fmgi_options
     FMGI_CUDA(cudaEventRecord(s->ev_stop, st));
     FMGI_CUDA(cudaMemcpyAsync(s->h_counters, s->d_counters, 8 * sizeof(unsigned long long),
                               cudaMemcpyDeviceToHost, st));
-    s->last_stream = st;
+    s->note_stream(st);
     s->traced = true;
     return FMGI_OK;
 }
@@ -504,8 +587,74 @@ int fmgi_scene_sync(fmgi_scene *s, fmgi_stats *stats)
 
 namespace {
 
+// ---- process-wide per-GPU runtime: streams, events and peer mappings are created once ---------------------
+//
+// performGlobalIlluminationCl is a one-shot call, but a process that bakes more than once (a harness, a
+// service) must not pay stream / event creation and cudaDeviceEnablePeerAccess on every call; the primary
+// contexts themselves persist for the life of the process anyway.
+struct GpuRuntime {
+    struct Dev {
+        bool ready = false;
+        cudaStream_t trace = nullptr, copy = nullptr;
+        cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};   // upload 0/1, fold 2/3, read-back 4/5
+    };
+    std::mutex mu;
+    Dev dev[64];
+    signed char peer[64][64];      // 0 unknown, 1 enabled (row device maps column device's memory), -1 unavailable
+    GpuRuntime() { memset(peer, 0, sizeof peer); }
+    static GpuRuntime &get() { static GpuRuntime r; return r; }
+
+    // current device must be d
+    cudaError_t ensure(int d)
+    {
+        Dev &v = dev[d & 63];
+        if (v.ready) return cudaSuccess;
+        cudaError_t e = cudaStreamCreateWithFlags(&v.trace, cudaStreamNonBlocking);
+        if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&v.copy, cudaStreamNonBlocking);
+        for (int i = 0; i < 6 && e == cudaSuccess; i++) e = cudaEventCreate(&v.ev[i]);
+        if (e == cudaSuccess) v.ready = true;
+        return e;
+    }
+    // current device must be a; true when a can read b's memory directly
+    bool map_peer(int a, int b)
+    {
+        if (a == b) return true;
+        std::lock_guard<std::mutex> lock(mu);
+        signed char &st = peer[a & 63][b & 63];
+        if (st == 0) {
+            int can = 0;
+            cudaDeviceCanAccessPeer(&can, a, b);
+            if (can) {
+                const cudaError_t pe = cudaDeviceEnablePeerAccess(b, 0);
+                if (pe != cudaSuccess && pe != cudaErrorPeerAccessAlreadyEnabled) can = 0;
+                cudaGetLastError();
+            }
+            st = can ? 1 : -1;
+        }
+        return st == 1;
+    }
+};
+
+template <typename Fn>
+void parallel_for(int n, Fn fn)
+{
+    if (n == 1) { fn(0); return; }
+    std::vector<std::thread> th;
+    for (int g = 0; g < n; g++) th.emplace_back(fn, g);
+    for (auto &t : th) t.join();
+}
+
 // Host-buffer bake.  tiles_out == NULL: geo->texels receives the float atlas (fmgi_bake); otherwise the
 // atlas is tone-mapped on GPU 0 and only the packed RGB tiles come back (fmgi_bake_tiles).
+//
+// Shape (G GPUs, one host thread each):
+//   1. every GPU traces its photon shard into its own ZEROED device atlas; at the same time GPU g uploads
+//      slice g of the caller's atlas (texels [lo_g, hi_g)) on a second stream, so the upload hides behind
+//      the trace (global_illumination_cl.c:295 initialises the device buffer from the host array);
+//   2. reduce-scatter over peer memory: GPU g sums slice g of ALL atlases, reading the other GPUs' copies
+//      through NVLink peer mappings, plus the uploaded host slice (k_fold_slice) - every GPU pulls
+//      (G-1)/G of one atlas at the same time instead of GPU 0 pulling G-1 atlases;
+//   3. every GPU writes its slice straight back into the caller's atlas over its own PCIe link.
 int bake_impl(struct Geometry *geo_, int spa, const fmgi_options *opt, fmgi_stats *stats, uint8_t *tiles_out,
               int tint_extra)
 {
@@ -517,132 +666,170 @@ int bake_impl(struct Geometry *geo_, int spa, const fmgi_options *opt, fmgi_stat
     int ndev = 0;
     FMGI_CUDA(cudaGetDeviceCount(&ndev));
     if (ndev < 1) return fail(FMGI_ERR_CUDA, "no CUDA device");
-    const int G = o.num_gpus > ndev ? ndev : o.num_gpus;
-    const size_t atlas_bytes = (size_t)geo->numTexels * sizeof(float4);
+    if (o.device < 0 || o.device >= ndev) return fail(FMGI_ERR_ARG, "device ordinal out of range");
+    const int G = std::min(std::min(o.num_gpus, ndev), kMaxFoldPeers + 1);
+    const size_t num_texels = (size_t)geo->numTexels;
+    // the caller's current device is restored on every exit path (the workers and the fold switch devices)
+    DeviceGuard entry_guard(o.device);
+
+    std::shared_ptr<HostBuild> build;
+    const double tb0 = now_ms();
+    if (int rc = build_host(build, geo->walls, geo->numWalls, geo->windows, geo->numWindows, geo->lights, geo->numLights,
+                            geo->numTexels, o))
+        return rc;
+    const double build_ms = now_ms() - tb0;
 
     struct PerGpu {
+        int device = 0;
         fmgi_scene *scene = nullptr;
-        float4 *atlas = nullptr;
-        cudaStream_t stream = nullptr;
+        float4 *atlas = nullptr;      // this GPU's deposits (whole atlas)
+        float4 *init = nullptr;       // the caller's values of this GPU's slice
+        float4 *staged = nullptr;     // peers' slices copied over when no peer mapping exists
+        size_t lo = 0, hi = 0;        // slice [lo, hi) in texels
         fmgi_stats st;
         int rc = FMGI_OK;
         std::string err;
-        double h2d_ms = 0, create_ms = 0, sync_ms = 0;
+        double init_ms = 0, create_ms = 0, sync_ms = 0;
+        float h2d_ms = 0, fold_ms = 0, d2h_ms = 0;
     };
     std::vector<PerGpu> gpus(G);
+    GpuRuntime &rt = GpuRuntime::get();
+    for (int g = 0; g < G; g++) {
+        gpus[g].device = (o.device + g) % ndev;          // G <= ndev: distinct GPUs, starting at the caller's
+        // slices in units of 64 texels (1 KiB)
+        const size_t units = (num_texels + 63) / 64;
+        gpus[g].lo = std::min(num_texels, units * g / G * 64);
+        gpus[g].hi = std::min(num_texels, units * (g + 1) / G * 64);
+    }
+    memset(&gpus[0].st, 0, sizeof(fmgi_stats));
 
-    auto worker = [&](int g) {
+    // ---- phase 1: upload + trace ---------------------------------------------------------------------------
+    parallel_for(G, [&](int g) {
         PerGpu &me = gpus[g];
         auto bail = [&](int rc) { me.rc = rc; me.err = g_last_error; };
         fmgi_options og = o;
-        og.device = o.device + g < ndev ? o.device + g : g;
+        og.device = me.device;
         // the caller's shard is subdivided over this call's GPUs
         og.num_shards = o.num_shards * G;
         og.shard = o.shard * G + g;
-        if (cudaSetDevice(og.device) != cudaSuccess) return bail(fail(FMGI_ERR_CUDA, "cudaSetDevice failed"));
+        const double ti0 = now_ms();
+        if (cudaSetDevice(me.device) != cudaSuccess || rt.ensure(me.device) != cudaSuccess)
+            return bail(fail(FMGI_ERR_CUDA, "cudaSetDevice / stream creation failed"));
+        me.init_ms = now_ms() - ti0;                      // context creation on the first call of the process
+        GpuRuntime::Dev &dv = rt.dev[me.device & 63];
         const double tc0 = now_ms();
-        int rc = fmgi_scene_create(&me.scene, geo->walls, geo->numWalls, geo->windows, geo->numWindows, geo->lights,
-                                   geo->numLights, geo->numTexels, &og);
+        int rc = scene_from_build(&me.scene, build, og);
         if (rc) return bail(rc);
         me.create_ms = now_ms() - tc0;
-        cudaSetDevice(og.device);
-        if (cudaStreamCreateWithFlags(&me.stream, cudaStreamNonBlocking) != cudaSuccess ||
-            MemPool::get().alloc((void **)&me.atlas, atlas_bytes ? atlas_bytes : 16, false) != cudaSuccess)
+        cudaSetDevice(me.device);
+        const size_t slice = me.hi - me.lo;
+        MemPool &pool = MemPool::get();
+        if (pool.alloc((void **)&me.atlas, std::max<size_t>(num_texels, 1) * sizeof(float4), false) != cudaSuccess ||
+            pool.alloc((void **)&me.init, std::max<size_t>(slice, 1) * sizeof(float4), false) != cudaSuccess)
             return bail(fail(FMGI_ERR_CUDA, "atlas allocation failed"));
-        const double t0 = now_ms();
-        cudaError_t e;
-        // GPU 0 starts from the caller's atlas (CL_MEM_COPY_HOST_PTR, global_illumination_cl.c:295)
-        if (g == 0) e = cudaMemcpyAsync(me.atlas, geo->texels, atlas_bytes, cudaMemcpyHostToDevice, me.stream);
-        else e = cudaMemsetAsync(me.atlas, 0, atlas_bytes, me.stream);
-        if (e == cudaSuccess) e = cudaStreamSynchronize(me.stream);
-        if (e != cudaSuccess) return bail(fail(FMGI_ERR_CUDA, std::string("atlas upload: ") + cudaGetErrorString(e)));
-        me.h2d_ms = now_ms() - t0;
+        cudaError_t e = cudaMemsetAsync(me.atlas, 0, num_texels * sizeof(float4), dv.trace);
+        if (e != cudaSuccess) return bail(fail(FMGI_ERR_CUDA, std::string("atlas clear: ") + cudaGetErrorString(e)));
+        // the trace is enqueued FIRST: an upload from pageable memory (what main.c hands us, parseLayout.c:526)
+        // blocks the host thread while the driver stages it, and then runs under the kernel instead of before it
         const double ts0 = now_ms();
-        rc = fmgi_scene_trace(me.scene, me.atlas, spa, &og, me.stream);
+        rc = fmgi_scene_trace(me.scene, me.atlas, spa, &og, dv.trace);
         if (rc) return bail(rc);
+        cudaSetDevice(me.device);
+        // the caller's atlas (CL_MEM_COPY_HOST_PTR, global_illumination_cl.c:295) rides on the copy stream
+        e = cudaEventRecord(dv.ev[0], dv.copy);
+        if (e == cudaSuccess && slice)
+            e = cudaMemcpyAsync(me.init, geo->texels + 4 * me.lo, slice * sizeof(float4), cudaMemcpyHostToDevice, dv.copy);
+        if (e == cudaSuccess) e = cudaEventRecord(dv.ev[1], dv.copy);
+        if (e != cudaSuccess) return bail(fail(FMGI_ERR_CUDA, std::string("atlas upload: ") + cudaGetErrorString(e)));
         rc = fmgi_scene_sync(me.scene, &me.st);
         if (rc) return bail(rc);
         me.sync_ms = now_ms() - ts0;
-    };
-
-    if (G == 1) worker(0);
-    else {
-        std::vector<std::thread> th;
-        for (int g = 0; g < G; g++) th.emplace_back(worker, g);
-        for (auto &t : th) t.join();
-    }
+        cudaSetDevice(me.device);
+        e = cudaStreamSynchronize(dv.copy);
+        if (e == cudaSuccess) cudaEventElapsedTime(&me.h2d_ms, dv.ev[0], dv.ev[1]);
+        if (e != cudaSuccess) return bail(fail(FMGI_ERR_CUDA, std::string("atlas upload: ") + cudaGetErrorString(e)));
+    });
 
     int rc = FMGI_OK;
     for (int g = 0; g < G; g++)
         if (gpus[g].rc) { rc = gpus[g].rc; g_last_error = gpus[g].err; }
 
-    double reduce_ms = 0, d2h_ms = 0;
-    const int dev0 = gpus[0].scene ? gpus[0].scene->device : 0;
+    // ---- phase 2: reduce-scatter fold over peer memory, then every GPU returns its slice -------------------------
+    const double tf0 = now_ms();
     if (rc == FMGI_OK) {
-        cudaSetDevice(dev0);
-        cudaError_t e = cudaSuccess;
-        if (G > 1) {
-            // fold the peers' atlases into GPU 0's, reading them over NVLink peer mappings
-            const double t0 = now_ms();
-            std::vector<const float4 *> peers;
-            std::vector<float4 *> staged;
-            for (int g = 1; g < G && e == cudaSuccess; g++) {
-                int can = 0;
-                cudaDeviceCanAccessPeer(&can, dev0, gpus[g].scene->device);
-                if (can) {
-                    cudaError_t pe = cudaDeviceEnablePeerAccess(gpus[g].scene->device, 0);
-                    if (pe != cudaSuccess && pe != cudaErrorPeerAccessAlreadyEnabled) can = 0;
-                    cudaGetLastError();
-                }
-                if (can) peers.push_back(gpus[g].atlas);
-                else {
-                    float4 *tmp = nullptr;
-                    e = MemPool::get().alloc((void **)&tmp, atlas_bytes ? atlas_bytes : 16, false);
+        parallel_for(G, [&](int g) {
+            PerGpu &me = gpus[g];
+            auto bail = [&](cudaError_t e, const char *what) {
+                me.rc = fail(FMGI_ERR_CUDA, std::string(what) + ": " + cudaGetErrorString(e)); me.err = g_last_error;
+            };
+            cudaSetDevice(me.device);
+            GpuRuntime::Dev &dv = rt.dev[me.device & 63];
+            MemPool &pool = MemPool::get();
+            const size_t slice = me.hi - me.lo;
+            cudaError_t e = cudaEventRecord(dv.ev[2], dv.trace);
+            if (slice) {
+                std::vector<const float4 *> peers;
+                size_t staged_at = 0;
+                for (int q = 0; q < G && e == cudaSuccess; q++) {
+                    if (q == g) continue;
+                    if (rt.map_peer(me.device, gpus[q].device)) { peers.push_back(gpus[q].atlas + me.lo); continue; }
+                    // no peer mapping: copy the peer's slice over
+                    if (!me.staged) e = pool.alloc((void **)&me.staged, (size_t)(G - 1) * slice * sizeof(float4), false);
                     if (e == cudaSuccess)
-                        e = cudaMemcpyPeer(tmp, dev0, gpus[g].atlas, gpus[g].scene->device, atlas_bytes);
-                    staged.push_back(tmp);
-                    peers.push_back(tmp);
+                        e = cudaMemcpyPeerAsync(me.staged + staged_at, me.device, gpus[q].atlas + me.lo, gpus[q].device,
+                                                slice * sizeof(float4), dv.trace);
+                    peers.push_back(me.staged + staged_at);
+                    staged_at += slice;
+                }
+                if (e == cudaSuccess) {
+                    const int blocks = me.scene->num_sms * 8;
+                    PeerList pl;
+                    for (size_t q = 0; q < peers.size(); q++) pl.p[q] = peers[q];
+                    k_fold_slice<<<blocks, 256, 0, dv.trace>>>(me.atlas + me.lo, me.init, pl, (int)peers.size(), slice);
+                    me.scene->launches++;
+                    e = cudaGetLastError();
                 }
             }
-            const float4 **d_peers = nullptr;
-            if (e == cudaSuccess) e = MemPool::get().alloc((void **)&d_peers, peers.size() * sizeof(float4 *), false);
-            if (e == cudaSuccess)
-                e = cudaMemcpy(d_peers, peers.data(), peers.size() * sizeof(float4 *), cudaMemcpyHostToDevice);
-            if (e == cudaSuccess && geo->numTexels > 0) {
-                const int blocks = gpus[0].scene->num_sms * 8;
-                k_fold_peers<<<blocks, 256, 0, gpus[0].stream>>>(gpus[0].atlas, d_peers, (int)peers.size(),
-                                                               (size_t)geo->numTexels);
-                gpus[0].scene->launches++;
-                e = cudaGetLastError();
-                if (e == cudaSuccess) e = cudaStreamSynchronize(gpus[0].stream);
-            }
-            MemPool::get().free(d_peers);
-            for (float4 *t : staged) MemPool::get().free(t);
-            reduce_ms = now_ms() - t0;
+            if (e == cudaSuccess) e = cudaEventRecord(dv.ev[3], dv.trace);
+            if (e == cudaSuccess) e = cudaEventRecord(dv.ev[4], dv.trace);
+            if (e == cudaSuccess && !tiles_out && slice)
+                e = cudaMemcpyAsync(geo->texels + 4 * me.lo, me.atlas + me.lo, slice * sizeof(float4),
+                                    cudaMemcpyDeviceToHost, dv.trace);
+            if (e == cudaSuccess) e = cudaEventRecord(dv.ev[5], dv.trace);
+            if (e == cudaSuccess) e = cudaStreamSynchronize(dv.trace);
+            if (e != cudaSuccess) return bail(e, "atlas fold / read-back");
+            cudaEventElapsedTime(&me.fold_ms, dv.ev[2], dv.ev[3]);
+            cudaEventElapsedTime(&me.d2h_ms, dv.ev[4], dv.ev[5]);
+        });
+        for (int g = 0; g < G; g++)
+            if (gpus[g].rc) { rc = gpus[g].rc; g_last_error = gpus[g].err; }
+    }
+    const double fold_host_ms = now_ms() - tf0;
+
+    double tiles_ms = 0;
+    if (rc == FMGI_OK && tiles_out) {
+        // gather the folded slices on GPU 0, then normalise + tone-map + pack there: 3 bytes per texel come back
+        const double t0 = now_ms();
+        PerGpu &g0 = gpus[0];
+        cudaSetDevice(g0.device);
+        GpuRuntime::Dev &dv = rt.dev[g0.device & 63];
+        cudaError_t e = cudaSuccess;
+        for (int q = 1; q < G && e == cudaSuccess; q++)
+            if (gpus[q].hi > gpus[q].lo)
+                e = cudaMemcpyPeerAsync(g0.atlas + gpus[q].lo, g0.device, gpus[q].atlas + gpus[q].lo, gpus[q].device,
+                                        (gpus[q].hi - gpus[q].lo) * sizeof(float4), dv.trace);
+        const uint64_t tile_bytes = fmgi_tile_bytes(geo->walls, geo->numWalls);
+        unsigned char *d_rgb = nullptr;
+        if (e == cudaSuccess) e = MemPool::get().alloc((void **)&d_rgb, tile_bytes ? tile_bytes : 16, false);
+        if (e == cudaSuccess) {
+            if (fmgi_scene_tonemap(g0.scene, g0.atlas, spa, tint_extra, d_rgb, dv.trace) != FMGI_OK) e = cudaErrorUnknown;
+            cudaSetDevice(g0.device);
         }
-        if (e == cudaSuccess && !tiles_out) {
-            const double t0 = now_ms();
-            e = cudaMemcpyAsync(geo->texels, gpus[0].atlas, atlas_bytes, cudaMemcpyDeviceToHost, gpus[0].stream);
-            if (e == cudaSuccess) e = cudaStreamSynchronize(gpus[0].stream);
-            d2h_ms = now_ms() - t0;
-        }
-        if (e == cudaSuccess && tiles_out) {
-            // normalise + tone-map + pack on the device, read back 3 bytes per texel
-            const double t0 = now_ms();
-            const uint64_t tile_bytes = fmgi_tile_bytes(geo->walls, geo->numWalls);
-            unsigned char *d_rgb = nullptr;
-            e = MemPool::get().alloc((void **)&d_rgb, tile_bytes ? tile_bytes : 16, false);
-            if (e == cudaSuccess) {
-                if (fmgi_scene_tonemap(gpus[0].scene, gpus[0].atlas, spa, tint_extra, d_rgb, gpus[0].stream) != FMGI_OK)
-                    e = cudaErrorUnknown;
-                cudaSetDevice(dev0);
-            }
-            if (e == cudaSuccess) e = cudaMemcpyAsync(tiles_out, d_rgb, tile_bytes, cudaMemcpyDeviceToHost, gpus[0].stream);
-            if (e == cudaSuccess) e = cudaStreamSynchronize(gpus[0].stream);
-            MemPool::get().free(d_rgb);
-            d2h_ms = now_ms() - t0;
-        }
-        if (e != cudaSuccess) rc = fail(FMGI_ERR_CUDA, std::string("atlas fold/read-back: ") + cudaGetErrorString(e));
+        if (e == cudaSuccess) e = cudaMemcpyAsync(tiles_out, d_rgb, tile_bytes, cudaMemcpyDeviceToHost, dv.trace);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(dv.trace);
+        MemPool::get().free(d_rgb);
+        if (e != cudaSuccess) rc = fail(FMGI_ERR_CUDA, std::string("tile tone-map / read-back: ") + cudaGetErrorString(e));
+        tiles_ms = now_ms() - t0;
     }
 
     if (stats) {
@@ -652,28 +839,43 @@ int bake_impl(struct Geometry *geo_, int spa, const fmgi_options *opt, fmgi_stat
             stats->photons += s.photons; stats->rays += s.rays; stats->deposits += s.deposits;
             stats->mirror_bounces += s.mirror_bounces; stats->rect_tests += s.rect_tests;
             if (gpus[g].scene) stats->kernel_launches += gpus[g].scene->launches;
-            if (s.trace_ms > stats->trace_ms) stats->trace_ms = s.trace_ms;
-            if (gpus[g].h2d_ms > stats->h2d_ms) stats->h2d_ms = gpus[g].h2d_ms;
+            stats->trace_ms = std::max(stats->trace_ms, s.trace_ms);
+            stats->h2d_ms = std::max(stats->h2d_ms, (double)gpus[g].h2d_ms);
+            stats->reduce_ms = std::max(stats->reduce_ms, (double)gpus[g].fold_ms);
+            stats->d2h_ms = std::max(stats->d2h_ms, (double)gpus[g].d2h_ms);
+            stats->init_ms = std::max(stats->init_ms, gpus[g].init_ms);
+            stats->upload_ms = std::max(stats->upload_ms, gpus[g].create_ms);
         }
-        stats->reduce_ms = reduce_ms;
-        stats->d2h_ms = d2h_ms;
+        if (tiles_out) stats->d2h_ms = tiles_ms;
+        stats->prepare_ms = build->prepare_ms;
+        stats->grid_build_ms = build->grid_ms;
         stats->num_gpus = G;
         stats->tier = gpus[0].st.tier;
         stats->num_sms = gpus[0].st.num_sms;
         stats->sm_clock_khz = gpus[0].st.sm_clock_khz;
     }
     for (int g = 0; g < G; g++) {
-        if (gpus[g].scene) cudaSetDevice(gpus[g].scene->device);
-        if (gpus[g].stream) cudaStreamSynchronize(gpus[g].stream);
-        fmgi_scene_destroy(gpus[g].scene);
-        if (gpus[g].atlas) MemPool::get().free(gpus[g].atlas);
-        if (gpus[g].stream) cudaStreamDestroy(gpus[g].stream);
+        PerGpu &me = gpus[g];
+        cudaSetDevice(me.device);
+        if (rt.dev[me.device & 63].ready) {
+            cudaStreamSynchronize(rt.dev[me.device & 63].trace);
+            cudaStreamSynchronize(rt.dev[me.device & 63].copy);
+        }
+        fmgi_scene_destroy(me.scene);
+        MemPool &pool = MemPool::get();
+        pool.free(me.atlas); pool.free(me.init); pool.free(me.staged);
     }
+    // atlas-sized blocks do not outlive the call (no state survives but small cached tables)
+    size_t keep_mb = 256;
+    if (const char *v = getenv("FMGI_CACHE_MB")) keep_mb = (size_t)strtoull(v, nullptr, 0);
+    MemPool::get().trim(keep_mb << 20);
     if (stats) stats->total_ms = now_ms() - t_begin;
     if (getenv("FMGI_DEBUG_TIMING"))
-        fprintf(stderr, "[fmgi] bake: total %.3f ms (scene %.3f, h2d %.3f, trace+sync host %.3f [device %.3f], fold %.3f, "
-                        "d2h %.3f)\n", now_ms() - t_begin, gpus[0].create_ms, gpus[0].h2d_ms, gpus[0].sync_ms,
-                gpus[0].st.trace_ms, reduce_ms, d2h_ms);
+        fprintf(stderr, "[fmgi] bake: total %.3f ms (host tables %.3f [grid %.3f], context/streams %.3f, table upload %.3f, "
+                        "atlas h2d %.3f (overlapped), trace+sync host %.3f [device %.3f], fold %.3f + d2h %.3f [host %.3f], "
+                        "tiles %.3f)\n",
+                now_ms() - t_begin, build_ms, build->grid_ms, gpus[0].init_ms, gpus[0].create_ms, gpus[0].h2d_ms,
+                gpus[0].sync_ms, gpus[0].st.trace_ms, gpus[0].fold_ms, gpus[0].d2h_ms, fold_host_ms, tiles_ms);
     return rc;
 }
 
@@ -712,13 +914,20 @@ void performGlobalIlluminationCl(struct Geometry *geo, int numSamplesPerArea)
     printf("[INF] photon-mapped %llu photons / %llu bounces on %d GPU(s): trace %.1f ms (%.3g bounces/s), total %.1f ms\n",
            (unsigned long long)st.photons, (unsigned long long)st.deposits, st.num_gpus, st.trace_ms,
            st.trace_ms > 0 ? st.deposits / (st.trace_ms * 1e-3) : 0.0, st.total_ms);
-    if (const char *v = getenv("FMGI_STATS"))
-        if (atoi(v))
-            printf("[INF] rays %llu, mirror bounces %llu, rectangle tests %llu, h2d %.2f ms, d2h %.2f ms, fold %.2f ms, "
-                   "launches %llu\n",
-                   (unsigned long long)st.rays, (unsigned long long)st.mirror_bounces,
-                   (unsigned long long)st.rect_tests, st.h2d_ms, st.d2h_ms, st.reduce_ms,
-                   (unsigned long long)st.kernel_launches);
+    int verbose = 0;
+    if (const char *v = getenv("FMGI_STATS")) verbose = atoi(v);
+    if (verbose)
+        printf("[INF] rays %llu, mirror bounces %llu, rectangle tests %llu, h2d %.2f ms, d2h %.2f ms, fold %.2f ms, "
+               "launches %llu\n",
+               (unsigned long long)st.rays, (unsigned long long)st.mirror_bounces,
+               (unsigned long long)st.rect_tests, st.h2d_ms, st.d2h_ms, st.reduce_ms,
+               (unsigned long long)st.kernel_launches);
+    if (verbose >= 2)
+        // where the call's time went; before_call = process start -> this call (loader, parseLayout), from /proc
+        printf("[INF] fmgi breakdown: before_call %.1f ms, init %.1f ms, tables %.2f ms, upload %.2f ms, trace %.2f ms, "
+               "fold %.2f ms, d2h %.2f ms, call %.1f ms\n",
+               ms_since_process_start() - st.total_ms, st.init_ms, st.prepare_ms + st.grid_build_ms, st.upload_ms,
+               st.trace_ms, st.reduce_ms, st.d2h_ms, st.total_ms);
 }
 
 // ---- tile post-processing ----------------------------------------------------------------
@@ -750,9 +959,9 @@ int fmgi_scene_tonemap(fmgi_scene *s, const void *atlas_dev, int spa, int tint_e
         TileWall &t = s->h_tile_walls[i];
         t.base = sh.base;
         t.first = (int32_t)pixels;
-        const float tiles_per_sample = tiles / (s->wall_area[i] * spa);            // main.c:73 (int / (float * int))
+        const float tiles_per_sample = tiles / (s->build->wall_area[i] * spa);            // main.c:73 (int / (float * int))
         t.scale = (float)(0.35 * tiles_per_sample);                                // main.c:77: double product, float arg
-        t.is_floor = s->wall_floor[i];
+        t.is_floor = s->build->wall_floor[i];
         pixels += tiles;
     }
     if (pixels > 0x7fffffffLL) return fail(FMGI_ERR_UNSUPPORTED, "more than 2^31 tile pixels");
@@ -763,6 +972,7 @@ int fmgi_scene_tonemap(fmgi_scene *s, const void *atlas_dev, int spa, int tint_e
     k_tonemap<<<(int)blocks, 256, 0, st>>>(reinterpret_cast<const float4 *>(atlas_dev), s->d_tile_walls, W, pixels,
                                          tint_extra, reinterpret_cast<unsigned char *>(rgb_dev));
     s->launches++;
+    s->note_stream(st);
     FMGI_CUDA(cudaGetLastError());
     return FMGI_OK;
 }
@@ -798,8 +1008,8 @@ int fmgi_scene_ambient_occlusion(fmgi_scene *s, void *atlas_dev, void *cuda_stre
     const int num_dirs = (int)dirs.size() / 3;
     std::vector<float> blob;                                   // widths | heights | float4 directions
     blob.reserve((size_t)6 * W + 4 * num_dirs + 4);
-    for (int i = 0; i < W; i++) for (int c = 0; c < 3; c++) blob.push_back(s->wall_wh[6 * i + c]);
-    for (int i = 0; i < W; i++) for (int c = 0; c < 3; c++) blob.push_back(s->wall_wh[6 * i + 3 + c]);
+    for (int i = 0; i < W; i++) for (int c = 0; c < 3; c++) blob.push_back(s->build->wall_wh[6 * i + c]);
+    for (int i = 0; i < W; i++) for (int c = 0; c < 3; c++) blob.push_back(s->build->wall_wh[6 * i + 3 + c]);
     while (blob.size() % 4) blob.push_back(0.0f);
     const size_t dirs_at = blob.size();
     for (int k = 0; k < num_dirs; k++) {
@@ -833,7 +1043,7 @@ int fmgi_scene_ambient_occlusion(fmgi_scene *s, void *atlas_dev, void *cuda_stre
     if (s->kernel_tier == kTierSoupPlanes) FMGI_CUDA(go(k_ambient_occlusion<kTierSoupPlanes>));
     else if (s->kernel_tier == FMGI_TIER_SOUP) FMGI_CUDA(go(k_ambient_occlusion<FMGI_TIER_SOUP>));
     else FMGI_CUDA(go(k_ambient_occlusion<FMGI_TIER_GRID>));
-    s->last_stream = st;
+    s->note_stream(st);
     return FMGI_OK;
 }
 
@@ -1001,7 +1211,7 @@ int fmgi_probe_paths(fmgi_scene *s, int emitter_index, int max_depth, uint32_t s
         s->h_jobs[e] = total;
         s->h_jobs[E + 1 + e] = e == emitter_index ? first : 0;
         s->h_jobs[2 * E + 1 + e] = e == emitter_index ? (unsigned long long)count : 0;
-        if (e == emitter_index) total += ((unsigned long long)count + kChunkPhotons - 1) / kChunkPhotons;
+        if (e == emitter_index) total += ((unsigned long long)count + kMinChunkPhotons - 1) / kMinChunkPhotons;
     }
     s->h_jobs[E] = total;
     FMGI_CUDA(cudaMemcpy(s->d_jobs, s->h_jobs, job_table_words(E) * sizeof(unsigned long long), cudaMemcpyHostToDevice));
@@ -1012,6 +1222,7 @@ int fmgi_probe_paths(fmgi_scene *s, int emitter_index, int max_depth, uint32_t s
     FMGI_CUDA(cudaMemset(d_path, 0xff, pb));
     TraceParams p = base_params(s);
     p.total_jobs = total;
+    p.chunk = kMinChunkPhotons;
     p.max_depth = max_depth;
     p.seed = seed;
     p.path_out = d_path;

@@ -83,6 +83,43 @@ public:
         if (prev >= 0) cudaSetDevice(prev);
     }
 
+    // Releases cached (not live) blocks, largest first, until at most `keep_bytes` stay cached.  Called at
+    // the end of every host-buffer entry point so that atlas-sized blocks do not outlive the call
+    // (FMGI_CACHE_MB, default 256: small tables and staging buffers stay, a 1.8 GB atlas does not).
+    void trim(size_t keep_bytes)
+    {
+        std::vector<Block> victims;
+        {
+            std::lock_guard<std::mutex> lock(mu_);
+            size_t cached = 0;
+            for (const Block &b : free_) cached += b.bytes;
+            while (cached > keep_bytes && !free_.empty()) {
+                size_t big = 0;
+                for (size_t i = 1; i < free_.size(); i++)
+                    if (free_[i].bytes > free_[big].bytes) big = i;
+                cached -= free_[big].bytes;
+                victims.push_back(free_[big]);
+                free_.erase(free_.begin() + big);
+            }
+        }
+        if (victims.empty()) return;
+        int prev = -1;
+        cudaGetDevice(&prev);
+        for (const Block &b : victims) {
+            if (b.pinned) cudaFreeHost(b.ptr);
+            else { cudaSetDevice(b.device); cudaFree(b.ptr); }
+        }
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+
+    size_t cached_bytes()
+    {
+        std::lock_guard<std::mutex> lock(mu_);
+        size_t cached = 0;
+        for (const Block &b : free_) cached += b.bytes;
+        return cached;
+    }
+
 private:
     struct Block { void *ptr; size_t bytes; int device; bool pinned; };
     static size_t round_up(size_t b)

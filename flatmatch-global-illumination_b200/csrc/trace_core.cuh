@@ -75,10 +75,10 @@ __global__ void __launch_bounds__(kTraceThreads, kMinBlocks) k_trace(const Trace
                     k = __shfl_sync(kFullMask, k, 0);
                     if (k >= p.total_jobs) { exhausted = true; break; }
                     w_emitter = find_emitter(p.job_begin, p.num_emitters, k);
-                    const unsigned long long first = (k - __ldg(p.job_begin + w_emitter)) * kChunkPhotons;
+                    const unsigned long long first = (k - __ldg(p.job_begin + w_emitter)) * (unsigned)p.chunk;
                     const unsigned long long left = __ldg(p.photon_count + w_emitter) - first;
                     w_base = __ldg(p.photon_first + w_emitter) + first;
-                    w_cnt = left < (unsigned long long)kChunkPhotons ? (int)left : kChunkPhotons;
+                    w_cnt = left < (unsigned long long)p.chunk ? (int)left : p.chunk;
                     w_pos = 0;
                 }
                 const int avail = w_cnt - w_pos;
@@ -388,16 +388,24 @@ __global__ void k_accumulate(float4 *__restrict__ atlas, const float4 *__restric
     }
 }
 
-// atlas0 += sum of the peers' atlases, read straight over NVLink peer mappings (multi-GPU fold).
-__global__ void k_fold_peers(float4 *__restrict__ dst, const float4 *const *__restrict__ peers, int num_peers, size_t n)
+// Multi-GPU fold, reduce-scatter shaped: this GPU owns one slice of the atlas and sums that slice of every GPU's
+// deposits - its own (`own`, in/out) and the peers', read straight over NVLink peer mappings - on top of the
+// caller's values of the slice (`init`, all four lanes: lane 3 and the mip slots pass through untouched).
+constexpr int kMaxFoldPeers = 31;
+struct PeerList { const float4 *p[kMaxFoldPeers]; };
+
+__global__ void k_fold_slice(float4 *__restrict__ own, const float4 *__restrict__ init, const PeerList peers, int num_peers,
+                             size_t n)
 {
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
-        float4 a = dst[i];
+        float4 r = init[i];
+        const float4 a = own[i];
+        r.x += a.x; r.y += a.y; r.z += a.z;
         for (int g = 0; g < num_peers; g++) {
-            const float4 b = peers[g][i];
-            a.x += b.x; a.y += b.y; a.z += b.z;
+            const float4 b = peers.p[g][i];
+            r.x += b.x; r.y += b.y; r.z += b.z;
         }
-        dst[i] = a;
+        own[i] = r;
     }
 }
 

@@ -34,7 +34,8 @@
 namespace fmgi {
 
 constexpr int kTraceThreads = 256;
-constexpr int kChunkPhotons = 256;          // photon indices a warp claims per global atomic
+constexpr int kChunkPhotons = 256;          // photon indices a warp claims per global atomic (big bakes)
+constexpr int kMinChunkPhotons = 32;        // ... small bakes use smaller chunks so that every SM gets work
 constexpr unsigned kFullMask = 0xffffffffu;
 // internal kernel variant: soup tier whose horizontal rectangles go through the grid's plane tables
 constexpr int kTierSoupPlanes = 3;
@@ -53,13 +54,14 @@ struct TraceParams {
     const float4 *emitters;      // 6 float4 per emitter
     const float *ao_width;       // ambient occlusion only: the walls' width / height vectors (3 floats each)
     const float *ao_height;
-    // this shard's photon index space in chunks of kChunkPhotons photons of ONE emitter (the unit a warp
+    // this shard's photon index space in chunks of `chunk` photons of ONE emitter (the unit a warp
     // claims): chunks [job_begin[e], job_begin[e+1]) belong to emitter e; chunk j of emitter e covers
-    // photon indices photon_first[e] + [j * kChunkPhotons, min((j + 1) * kChunkPhotons, photon_count[e]))
+    // photon indices photon_first[e] + [j * chunk, min((j + 1) * chunk, photon_count[e]))
     const unsigned long long *job_begin;
     const unsigned long long *photon_first;
     const unsigned long long *photon_count;
     int num_emitters;
+    int chunk;                       // photons per chunk: kMinChunkPhotons .. kChunkPhotons
     unsigned long long total_jobs;   // chunks
     unsigned long long *work_counter;
     // output
@@ -363,8 +365,12 @@ struct GridWalk {
         const float ex = ((xp ? g.exit_hi_x : g.exit_lo_x) - ox) * ix, ey = ((yp ? g.exit_hi_y : g.exit_lo_y) - oy) * iy;
         // no wall beyond the z range of the walls (with a little slack for the approximate reciprocal)
         const float ez = ((dz < 0.0f ? g.wall_z_lo : g.wall_z_hi) - oz) * iz * 1.0001f;
-        tmx = x0 ? inf : tmx; tmy = y0 ? inf : tmy;
-        const float t_exit = fminf(fminf(x0 ? inf : ex, y0 ? inf : ey), dz == 0.0f ? inf : ez);
+        // A ray that starts outside the exit box or the z slab and moves away from it has a negative t_exit
+        // (a huge number for the unsigned "0 <= t < best" compare): clamped to 0 nothing passes the test, and
+        // with the DDA times clamped alike "the next cell starts beyond best" ends the walk after the first head
+        // instead of stepping off the grid.
+        tmx = x0 ? inf : fmaxf(tmx, 0.0f); tmy = y0 ? inf : fmaxf(tmy, 0.0f);
+        const float t_exit = fmaxf(fminf(fminf(x0 ? inf : ex, y0 ? inf : ey), dz == 0.0f ? inf : ez), 0.0f);
         const int sx = xp ? 1 : -1, sy = yp ? g.nx : -g.nx;
         // current cell as an index into T: the head of the walk list of the ray's sign combination
         int ci = g.walk_base + ((xp ? 1 : 0) + (yp ? 2 : 0)) * g.ncell + cy * g.nx + cx;

@@ -59,6 +59,7 @@ class Stats(C.Structure):
         ("trace_ms", C.c_double), ("h2d_ms", C.c_double), ("d2h_ms", C.c_double), ("reduce_ms", C.c_double),
         ("total_ms", C.c_double),
         ("num_gpus", C.c_int32), ("tier", C.c_int32), ("num_sms", C.c_int32), ("sm_clock_khz", C.c_int32),
+        ("init_ms", C.c_double), ("prepare_ms", C.c_double), ("grid_build_ms", C.c_double), ("upload_ms", C.c_double),
     ]
 
     def as_dict(self):
@@ -66,7 +67,8 @@ class Stats(C.Structure):
 
 
 EXPORTS = [
-    "performGlobalIlluminationCl", "fmgi_default_options", "fmgi_last_error", "fmgi_version", "fmgi_device_count",
+    "performGlobalIlluminationCl", "fmgi_default_options", "fmgi_last_error", "fmgi_version", "fmgi_source_hash",
+    "fmgi_device_count",
     "fmgi_release_cache", "fmgi_tile_bytes", "fmgi_scene_tonemap", "fmgi_bake_tiles",
     "fmgi_ambient_occlusion", "fmgi_scene_ambient_occlusion", "fmgi_geosphere",
     "fmgi_bake", "fmgi_scene_create", "fmgi_scene_destroy", "fmgi_scene_trace", "fmgi_scene_sync",
@@ -91,6 +93,7 @@ def lib() -> C.CDLL:
     L = C.CDLL(str(LIB_PATH))
     L.fmgi_last_error.restype = C.c_char_p
     L.fmgi_version.restype = C.c_char_p
+    L.fmgi_source_hash.restype = C.c_char_p
     L.fmgi_default_options.argtypes = [C.POINTER(Options)]
     L.performGlobalIlluminationCl.restype = None
     L.performGlobalIlluminationCl.argtypes = [C.POINTER(Geometry), C.c_int]

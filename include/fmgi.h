@@ -99,18 +99,26 @@ typedef struct fmgi_stats {
     uint64_t rect_tests;      /* rectangle tests executed (all lanes); grid lookups only with count_tests */
     uint64_t kernel_launches; /* our kernels launched */
     double   trace_ms;        /* device time of the trace kernels (CUDA events), max over GPUs */
-    double   h2d_ms, d2h_ms;  /* upload / read-back, host clock */
-    double   reduce_ms;       /* multi-GPU atlas fold */
+    double   h2d_ms, d2h_ms;  /* atlas upload (runs under the trace) / read-back, CUDA events, max over GPUs */
+    double   reduce_ms;       /* atlas fold: reduce-scatter over peer memory + the caller's values (CUDA events) */
     double   total_ms;        /* whole call, host clock */
     int32_t  num_gpus;
     int32_t  tier;
     int32_t  num_sms;
     int32_t  sm_clock_khz;    /* cudaDevAttrClockRate */
+    /* host-buffer entry points only (fmgi_bake, fmgi_bake_tiles), host clock, max over GPUs */
+    double   init_ms;         /* cudaSetDevice + stream/event creation: the CUDA context on the first call of a process */
+    double   prepare_ms;      /* rectangle tables (scene_prep.cpp) */
+    double   grid_build_ms;   /* floor-plan grid (build_grid) */
+    double   upload_ms;       /* table upload + kernel attribute queries per GPU */
 } fmgi_stats;
 
 void        fmgi_default_options(fmgi_options *opt);
 const char *fmgi_last_error(void);
 const char *fmgi_version(void);
+/* sha256 prefix of the sources the library was built from (Makefile); profiles/ncu_facts.json carries the hash of the
+ * build its ncu counters were captured on, and bench.py marks them stale when the two differ. */
+const char *fmgi_source_hash(void);
 int         fmgi_device_count(void);
 /* The library keeps freed device / pinned blocks in a process-wide cache so that repeated bakes do
  * not pay cudaMalloc/cudaFree again; this returns the cached blocks to the driver. */

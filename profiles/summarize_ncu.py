@@ -53,8 +53,16 @@ def facts(rep, workload, tier, out_json, source, rays=None):
         scale = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}[u[k]]
         return float(d[k]) * scale
 
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "flatmatch-global-illumination_b200"))
+    import fmgi
+
     entry = {
         "kernel": d["Kernel Name"], "tier": tier, "source": source,
+        # the build the capture belongs to: must be run right after the capture, on the same tree
+        "src_hash": fmgi.lib().fmgi_source_hash().decode(),
+        "pipe_fmaheavy_pct": float(d.get("sm__inst_executed_pipe_fmaheavy.avg.pct_of_peak_sustained_active", "nan")),
+        "pipe_xu_pct": float(d.get("sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active", "nan")),
+        "warps_eligible_per_cycle": float(d.get("smsp__warps_eligible.avg.per_cycle_active", "nan")),
         "duration_ms": float(d["gpu__time_duration.sum"]) * {"ms": 1, "us": 1e-3, "s": 1e3, "ns": 1e-6}[u["gpu__time_duration.sum"]],
         "dram_bytes_per_launch": bytes_of("dram__bytes_read.sum") + bytes_of("dram__bytes_write.sum"),
         "issue_active_pct": float(d["smsp__issue_active.avg.pct_of_peak_sustained_active"]),

@@ -77,6 +77,57 @@ def dev_scene_grid(fmgi, scene):
 
 
 @pytest.fixture(scope="session")
+def dev_scene_soup(fmgi, scene):
+    """The same flat through the brute-force soup tier (explicit: AUTO picks the grid above 64 colliders);
+    its horizontal rectangles go through the grid's plane tables (kernel variant soup + planes)."""
+    s = fmgi.DeviceScene(scene.walls, scene.windows, scene.lights, scene.num_texels, tier=fmgi.TIER_SOUP)
+    yield s
+    s.close()
+
+
+@pytest.fixture(scope="session")
+def dev_scene_soup_plain(fmgi, scene):
+    """Soup tier with the plane tables switched off: every collider in the shared-memory scan."""
+    import os
+
+    os.environ["FMGI_SOUP_PLANES"] = "0"
+    try:
+        s = fmgi.DeviceScene(scene.walls, scene.windows, scene.lights, scene.num_texels, tier=fmgi.TIER_SOUP)
+    finally:
+        del os.environ["FMGI_SOUP_PLANES"]
+    yield s
+    s.close()
+
+
+_RECORD = {}
+
+
+@pytest.fixture(scope="session")
+def record():
+    """Measured parity figures (mismatch counts, identical-path shares, radiance statistics) are collected here and
+    written to gpurun_out/parity_r2.json at the end of the session; the committed copy is profiles/parity_r2.json."""
+    def put(name, **values):
+        _RECORD.setdefault(name, {}).update({k: (float(v) if isinstance(v, (np.floating, float)) else
+                                                 int(v) if isinstance(v, (np.integer, int)) else v)
+                                             for k, v in values.items()})
+    return put
+
+
+def pytest_sessionfinish(session, exitstatus):
+    if not _RECORD:
+        return
+    out = ROOT / "gpurun_out"
+    try:
+        out.mkdir(exist_ok=True)
+        path = out / "parity_r2.json"
+        old = json.loads(path.read_text()) if path.exists() else {}
+        old.update(_RECORD)
+        path.write_text(json.dumps(old, indent=1, sort_keys=True) + "\n")
+    except OSError:
+        pass
+
+
+@pytest.fixture(scope="session")
 def synth800():
     import refbind
 
@@ -88,6 +139,24 @@ def synth4000():
     import refbind
 
     return refbind.Scene.load(GOLDEN / "synth4000_scene.npz")
+
+
+def outside_rays(scene, n, seed):
+    """Rays whose origins lie OUTSIDE the walls' bounding box in x, y or z (up to 8 m away, a few much
+    farther), with uniform directions: towards the flat, past it and away from it."""
+    rng = np.random.default_rng(seed)
+    w = scene.walls
+    corners = np.concatenate([w["pos"][:, :3], w["pos"][:, :3] + w["width"][:, :3] + w["height"][:, :3]])
+    lo, hi = corners.min(axis=0), corners.max(axis=0)
+    o = rng.uniform(lo - 8, hi + 8, size=(n, 3))
+    axis = rng.integers(0, 3, n)
+    side = rng.integers(0, 2, n)
+    dist = rng.uniform(1e-4, 8, n)
+    dist[: n // 50] = rng.uniform(100, 1e5, n // 50)          # far away: the walk must not step off the grid
+    o[np.arange(n), axis] = np.where(side == 1, hi[axis] + dist, lo[axis] - dist)
+    d = rng.normal(size=(n, 3))
+    d /= np.linalg.norm(d, axis=1, keepdims=True)
+    return o.astype(np.float32), d.astype(np.float32)
 
 
 def random_rays(scene, n, seed):

@@ -12,7 +12,7 @@ import ctypes
 import numpy as np
 import pytest
 
-from conftest import GOLDEN, random_rays
+from conftest import GOLDEN, outside_rays, random_rays
 
 pytestmark = pytest.mark.gpu
 
@@ -52,24 +52,73 @@ def test_philox_on_device(fmgi, oracle):
         assert np.array_equal(fmgi.philox(ctr, key), oracle.philox(ctr, key))
 
 
-@pytest.fixture(params=["soup", "grid"])
-def any_tier_scene(request, dev_scene, dev_scene_grid):
-    return dev_scene if request.param == "soup" else dev_scene_grid
+@pytest.fixture(params=["soup_planes", "soup", "grid"])
+def any_tier_scene(request, dev_scene_soup, dev_scene_soup_plain, dev_scene_grid):
+    """The three closest-hit kernels on the same flat: brute-force soup with the horizontal rectangles in the
+    plane tables, plain brute-force soup, floor-plan grid (what AUTO picks for this scene)."""
+    s = {"soup_planes": dev_scene_soup, "soup": dev_scene_soup_plain, "grid": dev_scene_grid}[request.param]
+    s.tier_name = request.param
+    return s
 
 
-def test_closest_hit_matches_oracle(any_tier_scene, oracle, scene):
+def test_tier_fixtures_run_the_kernels_they_name(dev_scene, dev_scene_soup, dev_scene_soup_plain, dev_scene_grid):
+    spa = 2000
+    assert gpu_bake(dev_scene_soup, spa, count_tests=1)[1]["tier"] == 1
+    assert gpu_bake(dev_scene_soup_plain, spa)[1]["tier"] == 1
+    assert gpu_bake(dev_scene_grid, spa)[1]["tier"] == 2
+    assert gpu_bake(dev_scene, spa)[1]["tier"] == 2           # AUTO: 172 colliders > 64
+    # rectangle tests per ray tell the kernels apart: plain soup scans every pair block of the ray's sign
+    # (94 tests), soup + planes only the x / y lists plus the counted plane lookups, the grid a handful
+    t_plain = gpu_bake(dev_scene_soup_plain, spa, count_tests=1)[1]
+    t_planes = gpu_bake(dev_scene_soup, spa, count_tests=1)[1]
+    t_grid = gpu_bake(dev_scene_grid, spa, count_tests=1)[1]
+    per_ray = [t["rect_tests"] / t["rays"] for t in (t_plain, t_planes, t_grid)]
+    assert per_ray[0] > per_ray[1] > 20 > per_ray[2] > 2, per_ray
+
+
+def test_closest_hit_matches_oracle(any_tier_scene, oracle, scene, record):
     """>= 1e6 rays: same wall index as the reference's linear scan with intersects()
-    (rectangle.c:67, photonmap.cl:194-206); distance within 1e-4 relative."""
+    (rectangle.c:67, photonmap.cl:194-206); distance within 1e-4 relative (expect
+    < 1e-6 index mismatches, ties excepted)."""
     o, d = random_rays(scene, 1_000_000, 11)
     gi, gt = any_tier_scene.closest_hit(o, d)
     ci, ct = oracle.closest_hit(scene.walls, o, d, oracle.ACCEL_LINEAR)
     mism = gi != ci
-    assert mism.mean() < 5e-6, f"{mism.sum()} index mismatches"
     both = (gi >= 0) & ~mism
-    assert both.mean() > 0.5
     rel = np.abs(gt[both] - ct[both]) / np.maximum(ct[both], 1e-4)
+    record(f"closest_hit_example_{any_tier_scene.tier_name}", rays=len(o), index_mismatches=int(mism.sum()),
+           max_rel_distance_error=float(rel.max()), hit_share=float(both.mean()))
+    assert mism.sum() <= 2, f"{mism.sum()} index mismatches in 1e6 rays"
+    assert both.mean() > 0.5
     assert rel.max() < 1e-4
     assert np.all(np.isinf(gt[gi < 0]))
+
+
+@pytest.mark.parametrize("which", ["example", "synth800"])
+def test_closest_hit_from_outside_the_bounding_box(any_tier_scene, fmgi, oracle, scene, synth800, record, which):
+    """Origins outside the walls' bounding box in x, y or z - an emitter above the wall z range, a probe ray from
+    the garden: rays that enter the flat find the reference's hit, rays that start outside and move away hit
+    nothing, and the grid walk ends at once instead of stepping off its table (t_exit clamped to 0)."""
+    if which == "example":
+        sc, dev = scene, any_tier_scene
+    else:
+        if any_tier_scene.tier_name != "grid":
+            pytest.skip("synth800 runs once, through the grid")
+        sc, dev = synth800, fmgi.DeviceScene(synth800.walls, synth800.windows, synth800.lights, synth800.num_texels)
+    o, d = outside_rays(sc, 400_000, 31)
+    gi, gt = dev.closest_hit(o, d)
+    ci, ct = oracle.closest_hit(sc.walls, o, d, oracle.ACCEL_LINEAR)
+    mism = gi != ci
+    both = (gi >= 0) & ~mism
+    rel = np.abs(gt[both] - ct[both]) / np.maximum(ct[both], 1e-4)
+    record(f"closest_hit_outside_{which}_{any_tier_scene.tier_name}", rays=len(o), index_mismatches=int(mism.sum()),
+           max_rel_distance_error=float(rel.max()), hit_share=float(both.mean()))
+    assert mism.sum() <= 2, f"{mism.sum()} index mismatches"
+    assert 0.02 < both.mean() < 0.9                 # some rays enter the flat, many miss it
+    assert rel.max() < 1e-4
+    assert np.all(np.isinf(gt[gi < 0]))
+    if which != "example":
+        dev.close()
 
 
 def test_texel_index_is_bit_exact(dev_scene, oracle, scene):
@@ -111,7 +160,7 @@ def test_sampler_moments_and_sky_fold(fmgi):
         assert abs((d.astype(np.float64) @ np.array(normal) / np.linalg.norm(normal)).mean() - 2 / 3) < 2e-3
 
 
-def test_photon_paths_match_oracle(any_tier_scene, oracle, scene):
+def test_photon_paths_match_oracle(any_tier_scene, oracle, scene, record):
     dev_scene = any_tier_scene
     """Same Philox sub-streams -> the same sequence of deposited texels, photon by photon.  The
     oracle evaluates sqrt/sin/cos in double like the reference, the kernel in float with SFU
@@ -121,6 +170,8 @@ def test_photon_paths_match_oracle(any_tier_scene, oracle, scene):
         got = dev_scene.paths(e, depth, seed, 5, count)
         want = oracle.trace_paths(scene, e, depth, seed, 5, count)
         same = np.all(got == want, axis=1)
+        record(f"paths_example_{dev_scene.tier_name}_emitter{e}", photons=count, depth=depth,
+               identical_paths=float(same.mean()), identical_first_bounce=float((got[:, 0] == want[:, 0]).mean()))
         assert same.mean() > 0.995, f"emitter {e}: {same.mean():.5f} identical paths"
         # first bounce depends only on emission: stricter
         assert (got[:, 0] == want[:, 0]).mean() > 0.9995
@@ -192,8 +243,10 @@ def parity_stats(lum_gpu, lum_ref, floor_frac=0.05):
     return s, sp, lit.mean()
 
 
-@pytest.mark.parametrize("depth,photons", [(8, 1.0e9), (3, 1.0e9)])
-def test_radiance_parity_with_native_reference(dev_scene, scene, depth, photons):
+@pytest.mark.parametrize("depth,photons,tier", [(8, 1.0e9, "grid"), (3, 1.0e9, "grid"), (8, 1.0e9, "soup_planes"),
+                                                 (3, 1.0e9, "soup")])
+def test_radiance_parity_with_native_reference(dev_scene_grid, dev_scene_soup, dev_scene_soup_plain, scene, record,
+                                               depth, photons, tier):
     """BASELINE.json: per-texel relative RMS < 2 % after the reference's normalisation and total
     deposited energy within 0.1 %, against performPhotonMappingNative (photonmap.c:408) at the
     same depth.  The reference side is the committed fixture (6.15e8 photons over 8 seeded
@@ -204,6 +257,7 @@ def test_radiance_parity_with_native_reference(dev_scene, scene, depth, photons)
     lum_ref = 0.5 * (lum_a + lum_b)
     area = sum(scene.photon_counts(1_000_000)) / 1e6
     spa = int(photons / area)
+    dev_scene = {"grid": dev_scene_grid, "soup_planes": dev_scene_soup, "soup": dev_scene_soup_plain}[tier]
     atlas, st = gpu_bake(dev_scene, spa, max_depth=depth, seed=2024)
     mask = scene.base_texel_mask()
     lum_gpu = ((atlas[:, :3].astype(np.float64) @ LUMA) * scene.normalisation(spa))[mask]
@@ -213,16 +267,17 @@ def test_radiance_parity_with_native_reference(dev_scene, scene, depth, photons)
     s, sp, lit = parity_stats(lum_gpu, lum_ref)
     print(f"depth {depth}: S={s:.4%} S'={sp:.4%} (lit share {lit:.3f}); reference half-vs-half "
           f"S={s_ab:.4%} S'={sp_ab:.4%}; gpu photons {st['photons']:.3e}")
+    e_ref = 0.5 * (z["rgb_total_a"] / float(z["spa_a"]) + z["rgb_total_b"] / float(z["spa_b"]))
+    e_gpu = atlas[:, :3].sum(axis=0, dtype=np.float64) / spa
+    rel = np.abs(e_gpu / e_ref - 1)
+    print(f"energy per unit density rel. diff {rel}")
+    record(f"radiance_example_depth{depth}_{tier}", gpu_photons=int(st["photons"]), S=float(s), S_per_texel=float(sp),
+           reference_half_vs_half_S_per_texel=float(sp_ab), energy_rel_diff=[float(x) for x in e_gpu / e_ref - 1])
     assert sp < 0.02, f"per-texel relative RMS {sp:.4%}"
     assert s < 0.02
     # a systematic error would not shrink with photon count: GPU-vs-reference must not exceed the
     # reference's own half-vs-half scatter (each half has half the reference's photons)
     assert sp < sp_ab * 1.05
-
-    e_ref = 0.5 * (z["rgb_total_a"] / float(z["spa_a"]) + z["rgb_total_b"] / float(z["spa_b"]))
-    e_gpu = atlas[:, :3].sum(axis=0, dtype=np.float64) / spa
-    rel = np.abs(e_gpu / e_ref - 1)
-    print(f"energy per unit density rel. diff {rel}")
     assert np.all(rel < 1e-3)
 
 
@@ -358,6 +413,25 @@ def test_in_library_multi_gpu_bake(fmgi, scene):
         for k in ("photons", "rays", "deposits", "mirror_bounces"):
             assert stg[k] == st1[k], (g, k)
         assert np.allclose(texg, tex1, rtol=1e-5, atol=5e-2)
+    # the caller's current device survives the call, whichever device the bake starts on, and a bake that
+    # starts on GPU 1 uses distinct GPUs (1, 2, ... wrapping to 0), adds onto the caller's values and leaves
+    # lane 3 / the mip slots alone
+    import torch
+
+    torch.cuda.set_device(n - 1)
+    rng = np.random.default_rng(3)
+    texd = fmgi.aligned_texels(scene.num_texels)
+    texd[...] = rng.random(texd.shape, dtype=np.float32)
+    before = texd.copy()
+    std = fmgi.bake(fmgi.make_geometry(scene.walls, scene.windows, scene.lights, texd), spa, max_depth=depth, seed=5,
+                    num_gpus=2, device=1)
+    assert torch.cuda.current_device() == n - 1
+    torch.cuda.set_device(0)
+    assert std["num_gpus"] == 2 and std["deposits"] == st1["deposits"]
+    assert np.allclose(texd[:, :3] - before[:, :3], tex1[:, :3], rtol=1e-4, atol=5e-2)
+    assert np.array_equal(texd[:, 3], before[:, 3])
+    mask = scene.base_texel_mask()
+    assert np.array_equal(texd[~mask], before[~mask])
 
 
 # ---- grid tier on the synthetic multi-room layouts (BASELINE.json configs[2]) -------------------------------
