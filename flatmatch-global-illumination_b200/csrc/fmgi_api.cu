@@ -689,7 +689,7 @@ int bake_impl(struct Geometry *geo_, int spa, const fmgi_options *opt, fmgi_stat
         fmgi_stats st;
         int rc = FMGI_OK;
         std::string err;
-        double init_ms = 0, create_ms = 0, sync_ms = 0;
+        double init_ms = 0, create_ms = 0, sync_ms = 0, alloc_ms = 0;
         float h2d_ms = 0, fold_ms = 0, d2h_ms = 0;
     };
     std::vector<PerGpu> gpus(G);
@@ -724,9 +724,11 @@ int bake_impl(struct Geometry *geo_, int spa, const fmgi_options *opt, fmgi_stat
         cudaSetDevice(me.device);
         const size_t slice = me.hi - me.lo;
         MemPool &pool = MemPool::get();
+        const double ta0 = now_ms();
         if (pool.alloc((void **)&me.atlas, std::max<size_t>(num_texels, 1) * sizeof(float4), false) != cudaSuccess ||
             pool.alloc((void **)&me.init, std::max<size_t>(slice, 1) * sizeof(float4), false) != cudaSuccess)
             return bail(fail(FMGI_ERR_CUDA, "atlas allocation failed"));
+        me.alloc_ms = now_ms() - ta0;
         cudaError_t e = cudaMemsetAsync(me.atlas, 0, num_texels * sizeof(float4), dv.trace);
         if (e != cudaSuccess) return bail(fail(FMGI_ERR_CUDA, std::string("atlas clear: ") + cudaGetErrorString(e)));
         // the trace is enqueued FIRST: an upload from pageable memory (what main.c hands us, parseLayout.c:526)
@@ -868,14 +870,17 @@ int bake_impl(struct Geometry *geo_, int spa, const fmgi_options *opt, fmgi_stat
     // atlas-sized blocks do not outlive the call (no state survives but small cached tables)
     size_t keep_mb = 256;
     if (const char *v = getenv("FMGI_CACHE_MB")) keep_mb = (size_t)strtoull(v, nullptr, 0);
+    const double tt0 = now_ms();
     MemPool::get().trim(keep_mb << 20);
+    const double trim_ms = now_ms() - tt0;
     if (stats) stats->total_ms = now_ms() - t_begin;
     if (getenv("FMGI_DEBUG_TIMING"))
         fprintf(stderr, "[fmgi] bake: total %.3f ms (host tables %.3f [grid %.3f], context/streams %.3f, table upload %.3f, "
                         "atlas h2d %.3f (overlapped), trace+sync host %.3f [device %.3f], fold %.3f + d2h %.3f [host %.3f], "
-                        "tiles %.3f)\n",
+                        "tiles %.3f, atlas alloc %.3f, cache trim %.3f)\n",
                 now_ms() - t_begin, build_ms, build->grid_ms, gpus[0].init_ms, gpus[0].create_ms, gpus[0].h2d_ms,
-                gpus[0].sync_ms, gpus[0].st.trace_ms, gpus[0].fold_ms, gpus[0].d2h_ms, fold_host_ms, tiles_ms);
+                gpus[0].sync_ms, gpus[0].st.trace_ms, gpus[0].fold_ms, gpus[0].d2h_ms, fold_host_ms, tiles_ms,
+                gpus[0].alloc_ms, trim_ms);
     return rc;
 }
 

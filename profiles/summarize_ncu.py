@@ -60,7 +60,7 @@ def facts(rep, workload, tier, out_json, source, rays=None):
         "kernel": d["Kernel Name"], "tier": tier, "source": source,
         # the build the capture belongs to: must be run right after the capture, on the same tree
         "src_hash": fmgi.lib().fmgi_source_hash().decode(),
-        "pipe_fmaheavy_pct": float(d.get("sm__inst_executed_pipe_fmaheavy.avg.pct_of_peak_sustained_active", "nan")),
+        "pipe_fmaheavy_pct": (float(d["sm__inst_executed_pipe_fmaheavy.avg.pct_of_peak_sustained_active"]) if "sm__inst_executed_pipe_fmaheavy.avg.pct_of_peak_sustained_active" in d else None),
         "pipe_xu_pct": float(d.get("sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active", "nan")),
         "warps_eligible_per_cycle": float(d.get("smsp__warps_eligible.avg.per_cycle_active", "nan")),
         "duration_ms": float(d["gpu__time_duration.sum"]) * {"ms": 1, "us": 1e-3, "s": 1e3, "ns": 1e-6}[u["gpu__time_duration.sum"]],

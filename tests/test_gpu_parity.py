@@ -25,6 +25,16 @@ def device_atlas(num_texels):
     return torch.zeros((num_texels, 4), dtype=torch.float32, device="cuda")
 
 
+def split_mismatches(gi, gt, ci, ct):
+    """Index mismatches are of two kinds: TIES - both sides hit, at the same distance (two rectangles share the
+    edge or overlap where the ray lands; the reference's strict `<` keeps the lowest index, photonmap.cl:199, the
+    grid keeps whichever it met first) - and real disagreements (a ray grazing a rectangle edge that one side's
+    rounding counts as inside and the other's as outside)."""
+    mism = gi != ci
+    tie = mism & (gi >= 0) & (ci >= 0) & (np.abs(gt - ct) <= 1e-5 * np.maximum(ct, 1e-4))
+    return int(tie.sum()), int((mism & ~tie).sum())
+
+
 def gpu_bake(dev_scene, spa, **opts):
     import torch
 
@@ -86,9 +96,11 @@ def test_closest_hit_matches_oracle(any_tier_scene, oracle, scene, record):
     mism = gi != ci
     both = (gi >= 0) & ~mism
     rel = np.abs(gt[both] - ct[both]) / np.maximum(ct[both], 1e-4)
+    ties, real = split_mismatches(gi, gt, ci, ct)
     record(f"closest_hit_example_{any_tier_scene.tier_name}", rays=len(o), index_mismatches=int(mism.sum()),
-           max_rel_distance_error=float(rel.max()), hit_share=float(both.mean()))
-    assert mism.sum() <= 2, f"{mism.sum()} index mismatches in 1e6 rays"
+           ties=ties, edge_grazing=real, max_rel_distance_error=float(rel.max()), hit_share=float(both.mean()))
+    # measured on a B200 (profiles/parity_r2.json): 0-3 mismatches per 1e6 rays, all of them ties
+    assert real <= 1 and ties <= 5, f"{real} edge-grazing disagreements, {ties} ties in 1e6 rays"
     assert both.mean() > 0.5
     assert rel.max() < 1e-4
     assert np.all(np.isinf(gt[gi < 0]))
@@ -111,9 +123,10 @@ def test_closest_hit_from_outside_the_bounding_box(any_tier_scene, fmgi, oracle,
     mism = gi != ci
     both = (gi >= 0) & ~mism
     rel = np.abs(gt[both] - ct[both]) / np.maximum(ct[both], 1e-4)
+    ties, real = split_mismatches(gi, gt, ci, ct)
     record(f"closest_hit_outside_{which}_{any_tier_scene.tier_name}", rays=len(o), index_mismatches=int(mism.sum()),
-           max_rel_distance_error=float(rel.max()), hit_share=float(both.mean()))
-    assert mism.sum() <= 2, f"{mism.sum()} index mismatches"
+           ties=ties, edge_grazing=real, max_rel_distance_error=float(rel.max()), hit_share=float(both.mean()))
+    assert real <= 1 and ties <= 5, f"{real} edge-grazing disagreements, {ties} ties"
     assert 0.02 < both.mean() < 0.9                 # some rays enter the flat, many miss it
     assert rel.max() < 1e-4
     assert np.all(np.isinf(gt[gi < 0]))
