@@ -25,14 +25,32 @@ def device_atlas(num_texels):
     return torch.zeros((num_texels, 4), dtype=torch.float32, device="cuda")
 
 
-def split_mismatches(gi, gt, ci, ct):
-    """Index mismatches are of two kinds: TIES - both sides hit, at the same distance (two rectangles share the
-    edge or overlap where the ray lands; the reference's strict `<` keeps the lowest index, photonmap.cl:199, the
-    grid keeps whichever it met first) - and real disagreements (a ray grazing a rectangle edge that one side's
-    rounding counts as inside and the other's as outside)."""
-    mism = gi != ci
-    tie = mism & (gi >= 0) & (ci >= 0) & (np.abs(gt - ct) <= 1e-5 * np.maximum(ct, 1e-4))
-    return int(tie.sum()), int((mism & ~tie).sum())
+def edge_distance(walls, idx, p):
+    """Distance (m) of point p from the nearest edge of walls[idx], measured in the rectangle's own (u, v) frame."""
+    w = walls[idx]
+    wd, ht = w["width"][:3].astype(np.float64), w["height"][:3].astype(np.float64)
+    e = p - w["pos"][:3].astype(np.float64)
+    lw, lh = np.linalg.norm(wd), np.linalg.norm(ht)
+    u, v = e @ wd / lw, e @ ht / lh
+    return min(abs(u), abs(lw - u), abs(v), abs(lh - v))
+
+
+def split_mismatches(walls, o, d, gi, gt, ci, ct, eps=2e-5):
+    """Closest-hit index mismatches are legitimate only where the ray passes through a rectangle EDGE: one side's
+    rounding counts the point as inside (edges are inclusive, rectangle.c:93), the other's as outside, or two
+    rectangles share the edge and tie (the reference's strict `<` keeps the lowest index, photonmap.cl:199).
+    Returns (mismatches at an edge, mismatches anywhere else): the second number must be zero."""
+    at_edge = elsewhere = 0
+    for r in np.nonzero(gi != ci)[0]:
+        near = []
+        for idx, t in ((gi[r], gt[r]), (ci[r], ct[r])):
+            if idx >= 0:
+                near.append(edge_distance(walls, idx, o[r].astype(np.float64) + float(t) * d[r].astype(np.float64)))
+        if near and min(near) < eps:
+            at_edge += 1
+        else:
+            elsewhere += 1
+    return at_edge, elsewhere
 
 
 def gpu_bake(dev_scene, spa, **opts):
@@ -96,11 +114,13 @@ def test_closest_hit_matches_oracle(any_tier_scene, oracle, scene, record):
     mism = gi != ci
     both = (gi >= 0) & ~mism
     rel = np.abs(gt[both] - ct[both]) / np.maximum(ct[both], 1e-4)
-    ties, real = split_mismatches(gi, gt, ci, ct)
+    at_edge, elsewhere = split_mismatches(scene.walls, o, d, gi, gt, ci, ct)
     record(f"closest_hit_example_{any_tier_scene.tier_name}", rays=len(o), index_mismatches=int(mism.sum()),
-           ties=ties, edge_grazing=real, max_rel_distance_error=float(rel.max()), hit_share=float(both.mean()))
-    # measured on a B200 (profiles/parity_r2.json): 0-3 mismatches per 1e6 rays, all of them ties
-    assert real <= 1 and ties <= 5, f"{real} edge-grazing disagreements, {ties} ties in 1e6 rays"
+           at_rectangle_edge=at_edge, elsewhere=elsewhere, max_rel_distance_error=float(rel.max()),
+           hit_share=float(both.mean()))
+    # measured on a B200 (profiles/parity_r2.json): 0-3 mismatches per 1e6 rays, every one of them a ray through
+    # a rectangle edge (half of these rays start ON a wall, so edges are met far more often than by chance)
+    assert elsewhere == 0 and at_edge <= 8, f"{elsewhere} mismatches away from any edge, {at_edge} at edges"
     assert both.mean() > 0.5
     assert rel.max() < 1e-4
     assert np.all(np.isinf(gt[gi < 0]))
@@ -123,10 +143,11 @@ def test_closest_hit_from_outside_the_bounding_box(any_tier_scene, fmgi, oracle,
     mism = gi != ci
     both = (gi >= 0) & ~mism
     rel = np.abs(gt[both] - ct[both]) / np.maximum(ct[both], 1e-4)
-    ties, real = split_mismatches(gi, gt, ci, ct)
+    at_edge, elsewhere = split_mismatches(sc.walls, o, d, gi, gt, ci, ct)
     record(f"closest_hit_outside_{which}_{any_tier_scene.tier_name}", rays=len(o), index_mismatches=int(mism.sum()),
-           ties=ties, edge_grazing=real, max_rel_distance_error=float(rel.max()), hit_share=float(both.mean()))
-    assert real <= 1 and ties <= 5, f"{real} edge-grazing disagreements, {ties} ties"
+           at_rectangle_edge=at_edge, elsewhere=elsewhere, max_rel_distance_error=float(rel.max()),
+           hit_share=float(both.mean()))
+    assert elsewhere == 0 and at_edge <= 4, f"{elsewhere} mismatches away from any edge, {at_edge} at edges"
     assert 0.02 < both.mean() < 0.9                 # some rays enter the flat, many miss it
     assert rel.max() < 1e-4
     assert np.all(np.isinf(gt[gi < 0]))
