@@ -17,6 +17,7 @@
 
 #include "mem_pool.h"
 #include "trace_core.cuh"
+#include "trace_pool.cuh"
 
 using namespace fmgi;
 
@@ -166,6 +167,9 @@ struct fmgi_scene {
     uint64_t launches = 0;
     uint64_t tests_per_ray = 0;
     int min_blocks = 4;                         // resident CTAs per SM the trace kernel is compiled for
+    int pool_k = 0;                             // pooled kernel (trace_pool.cuh): rays per lane, 0 = not usable for this scene
+    int pool_blocks_per_sm = 0;
+    bool pooled_last = false;                   // the last trace ran the pooled kernel
 };
 
 namespace {
@@ -248,6 +252,17 @@ cudaError_t with_trace_kernel(int tier, int deposit, bool probe, int min_blocks,
     if (min_blocks == 3) { FMGI_PICK_DEPOSIT(FMGI_TIER_SOUP, 3) }
     FMGI_PICK_DEPOSIT(FMGI_TIER_SOUP, 4)
 #undef FMGI_PICK_DEPOSIT
+}
+
+// The pooled kernel (trace_pool.cuh) for K rays per lane.
+template <typename Fn>
+cudaError_t with_pool_kernel(int k, Fn fn)
+{
+    switch (k) {
+        case 2: return fn(k_trace_pool<2, FMGI_DEPOSIT_VEC4, 8>, 2);
+        case 3: return fn(k_trace_pool<3, FMGI_DEPOSIT_VEC4, 7>, 3);
+        default: return fn(k_trace_pool<4, FMGI_DEPOSIT_VEC4, 5>, 4);
+    }
 }
 
 cudaError_t launch_trace(fmgi_scene *s, const TraceParams &p, int deposit, bool probe, int blocks, cudaStream_t st,
@@ -388,6 +403,25 @@ int scene_from_build(fmgi_scene **out, std::shared_ptr<HostBuild> b, const fmgi_
         return e;
     }));
     if (s->blocks_per_sm < 1) return fail(FMGI_ERR_CUDA, "trace kernel does not fit on an SM");
+    // pooled kernel: grid tier without misc records (those leave the PTX walk loop for a slow path)
+    // opt-in (FMGI_POOL_K = 2..4 rays per lane): measured on example.png the pool needs 0.28 warp iterations of the walk
+    // loop per ray instead of 0.52, but its switch code and the shared memory it takes from L1 still cost more
+    int pool_k = 0;
+    if (const char *v = getenv("FMGI_POOL_K")) pool_k = atoi(v);
+    if (s->kernel_tier == FMGI_TIER_GRID && s->host.grid_misc == 0 && pool_k >= 2 &&
+        (int)s->host.emitters.size() < kPoolMaxEmitters) {
+        pool_k = pool_k > 4 ? 4 : pool_k;
+        FMGI_CUDA(with_pool_kernel(pool_k, [&](auto kernel, int k) {
+            const size_t smem = (size_t)(kPoolThreads / 32) * 32 * k * kPoolSlotBytes;
+            cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e == cudaSuccess)
+                e = cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+            if (e == cudaSuccess)
+                e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&sp->pool_blocks_per_sm, kernel, kPoolThreads, smem);
+            return e;
+        }));
+        if (s->pool_blocks_per_sm >= 1) s->pool_k = pool_k;
+    }
     *out = s.release();
     return FMGI_OK;
 }
@@ -536,10 +570,31 @@ int fmgi_scene_trace(fmgi_scene *s, void *atlas_dev, int spa, const fmgi_options
             FMGI_CUDA(cudaMemsetAsync(s->d_scratch, 0, atlas_bytes, st));
             FMGI_CUDA(cudaMemsetAsync(s->d_counters + 4, 0, sizeof(unsigned long long), st));   // work counter
         }
-        // persistent grid: one wave of resident CTAs, never more warps than chunks of work
-        unsigned long long want = (chunks[c] * 32 + kTraceThreads - 1) / kTraceThreads;
-        const int blocks = (int)(want < wave ? (want ? want : 1) : wave);
-        FMGI_CUDA(launch_trace(s, p, o.deposit, false, blocks, st, count_tests));
+        // Pooled kernel (trace_pool.cuh) when the pass keeps every resident warp's pool busy for a while and the
+        // photon ids fit its packed word; k_trace otherwise (small bakes, soup tiers, misc records, counting).
+        const unsigned long long pool_warps = (unsigned long long)s->num_sms * s->pool_blocks_per_sm * (kPoolThreads / 32);
+        bool pooled = s->pool_k > 0 && !count_tests && o.deposit == FMGI_DEPOSIT_VEC4 && o.max_depth <= kPoolMaxDepth &&
+                      totals[c] >= 8ull * pool_warps * 32 * s->pool_k;
+        for (int e = 0; pooled && e < E; e++) {
+            const unsigned long long *job = s->h_jobs + c * table_words;
+            pooled = job[E + 1 + e] + job[2 * E + 1 + e] < kPoolMaxPhotonIndex;
+        }
+        if (const char *v = getenv("FMGI_POOL")) pooled = pooled && atoi(v) != 0;       // tuning / test knob
+        if (pooled) {
+            FMGI_CUDA(with_pool_kernel(s->pool_k, [&](auto kernel, int k) {
+                const size_t smem = (size_t)(kPoolThreads / 32) * 32 * k * kPoolSlotBytes;
+                const int blocks = s->num_sms * s->pool_blocks_per_sm;
+                kernel<<<blocks, kPoolThreads, smem, st>>>(p);
+                s->launches++;
+                return cudaGetLastError();
+            }));
+        } else {
+            // persistent grid: one wave of resident CTAs, never more warps than chunks of work
+            unsigned long long want = (chunks[c] * 32 + kTraceThreads - 1) / kTraceThreads;
+            const int blocks = (int)(want < wave ? (want ? want : 1) : wave);
+            FMGI_CUDA(launch_trace(s, p, o.deposit, false, blocks, st, count_tests));
+        }
+        s->pooled_last = pooled;
         if (passes > 1 && s->host.num_texels > 0) {
             k_accumulate<<<s->num_sms * 8, 256, 0, st>>>(reinterpret_cast<float4 *>(atlas_dev), s->d_scratch,
                                                          (size_t)s->host.num_texels);
@@ -574,6 +629,7 @@ int fmgi_scene_sync(fmgi_scene *s, fmgi_stats *stats)
             stats->trace_ms = ms;
         }
         stats->num_gpus = 1;
+        stats->pool_rays = s->pooled_last ? s->pool_k : 0;
         stats->tier = s->tier;
         stats->num_sms = s->num_sms;
         stats->sm_clock_khz = s->clock_khz;
@@ -664,13 +720,17 @@ int bake_impl(struct Geometry *geo_, int spa, const fmgi_options *opt, fmgi_stat
     const double t_begin = now_ms();
     fmgi_options o = resolve(opt);
     int ndev = 0;
-    FMGI_CUDA(cudaGetDeviceCount(&ndev));
+    FMGI_CUDA(cudaGetDeviceCount(&ndev));               // the first CUDA call of a process initialises the driver
+    const double driver_ms = now_ms() - t_begin;
     if (ndev < 1) return fail(FMGI_ERR_CUDA, "no CUDA device");
     if (o.device < 0 || o.device >= ndev) return fail(FMGI_ERR_ARG, "device ordinal out of range");
     const int G = std::min(std::min(o.num_gpus, ndev), kMaxFoldPeers + 1);
     const size_t num_texels = (size_t)geo->numTexels;
     // the caller's current device is restored on every exit path (the workers and the fold switch devices)
+    const double tg0 = now_ms();
     DeviceGuard entry_guard(o.device);
+    cudaFree(nullptr);                                  // primary context of the first GPU (first call of a process)
+    const double context_ms = now_ms() - tg0;
 
     std::shared_ptr<HostBuild> build;
     const double tb0 = now_ms();
@@ -845,13 +905,14 @@ int bake_impl(struct Geometry *geo_, int spa, const fmgi_options *opt, fmgi_stat
             stats->h2d_ms = std::max(stats->h2d_ms, (double)gpus[g].h2d_ms);
             stats->reduce_ms = std::max(stats->reduce_ms, (double)gpus[g].fold_ms);
             stats->d2h_ms = std::max(stats->d2h_ms, (double)gpus[g].d2h_ms);
-            stats->init_ms = std::max(stats->init_ms, gpus[g].init_ms);
+            stats->init_ms = std::max(stats->init_ms, driver_ms + context_ms + gpus[g].init_ms);
             stats->upload_ms = std::max(stats->upload_ms, gpus[g].create_ms);
         }
         if (tiles_out) stats->d2h_ms = tiles_ms;
         stats->prepare_ms = build->prepare_ms;
         stats->grid_build_ms = build->grid_ms;
         stats->num_gpus = G;
+        stats->pool_rays = gpus[0].st.pool_rays;
         stats->tier = gpus[0].st.tier;
         stats->num_sms = gpus[0].st.num_sms;
         stats->sm_clock_khz = gpus[0].st.sm_clock_khz;
@@ -877,10 +938,10 @@ int bake_impl(struct Geometry *geo_, int spa, const fmgi_options *opt, fmgi_stat
     if (getenv("FMGI_DEBUG_TIMING"))
         fprintf(stderr, "[fmgi] bake: total %.3f ms (host tables %.3f [grid %.3f], context/streams %.3f, table upload %.3f, "
                         "atlas h2d %.3f (overlapped), trace+sync host %.3f [device %.3f], fold %.3f + d2h %.3f [host %.3f], "
-                        "tiles %.3f, atlas alloc %.3f, cache trim %.3f)\n",
+                        "tiles %.3f, atlas alloc %.3f, cache trim %.3f, driver init %.3f, context %.3f)\n",
                 now_ms() - t_begin, build_ms, build->grid_ms, gpus[0].init_ms, gpus[0].create_ms, gpus[0].h2d_ms,
                 gpus[0].sync_ms, gpus[0].st.trace_ms, gpus[0].fold_ms, gpus[0].d2h_ms, fold_host_ms, tiles_ms,
-                gpus[0].alloc_ms, trim_ms);
+                gpus[0].alloc_ms, trim_ms, driver_ms, context_ms);
     return rc;
 }
 

@@ -60,6 +60,7 @@ class Stats(C.Structure):
         ("total_ms", C.c_double),
         ("num_gpus", C.c_int32), ("tier", C.c_int32), ("num_sms", C.c_int32), ("sm_clock_khz", C.c_int32),
         ("init_ms", C.c_double), ("prepare_ms", C.c_double), ("grid_build_ms", C.c_double), ("upload_ms", C.c_double),
+        ("pool_rays", C.c_int32), ("reserved0", C.c_int32),
     ]
 
     def as_dict(self):

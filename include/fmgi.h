@@ -111,6 +111,8 @@ typedef struct fmgi_stats {
     double   prepare_ms;      /* rectangle tables (scene_prep.cpp) */
     double   grid_build_ms;   /* floor-plan grid (build_grid) */
     double   upload_ms;       /* table upload + kernel attribute queries per GPU */
+    int32_t  pool_rays;       /* 0: k_trace ran; K > 0: the pooled kernel (trace_pool.cuh) with K rays per lane */
+    int32_t  reserved0;
 } fmgi_stats;
 
 void        fmgi_default_options(fmgi_options *opt);

@@ -515,6 +515,43 @@ def test_synth4000_grid_tier(fmgi, oracle, synth4000):
     s.close()
 
 
+@pytest.mark.parametrize("k", [2, 3, 4])
+def test_pooled_kernel_matches_k_trace(fmgi, scene, synth800, monkeypatch, k):
+    """trace_pool.cuh (opt-in, FMGI_POOL_K rays per lane): the same photon streams walked from a per-warp pool in
+    shared memory - identical counters, atlas equal up to the order of the float atomics, on example.png and on
+    the ceiling-lit synth800 layout."""
+    for sc, spa, depth in ((scene, 400_000, 8), (synth800, 150_000, 4)):
+        monkeypatch.setenv("FMGI_POOL_K", "0")
+        classic = fmgi.DeviceScene(sc.walls, sc.windows, sc.lights, sc.num_texels, tier=fmgi.TIER_GRID)
+        monkeypatch.setenv("FMGI_POOL_K", str(k))
+        pooled = fmgi.DeviceScene(sc.walls, sc.windows, sc.lights, sc.num_texels, tier=fmgi.TIER_GRID)
+        a, sa = gpu_bake(classic, spa, max_depth=depth, seed=31)
+        b, sb = gpu_bake(pooled, spa, max_depth=depth, seed=31)
+        assert sa["pool_rays"] == 0 and sb["pool_rays"] == k
+        for key in ("photons", "rays", "deposits", "mirror_bounces"):
+            assert sa[key] == sb[key], key
+        assert np.allclose(a, b, rtol=1e-4, atol=0.5)
+        assert abs(b[:, :3].sum(dtype=np.float64) / a[:, :3].sum(dtype=np.float64) - 1) < 1e-6
+        # a bake too small to keep the pools busy falls back to k_trace
+        _, ss = gpu_bake(pooled, 1000, max_depth=depth, seed=31)
+        assert ss["pool_rays"] == 0
+        classic.close(); pooled.close()
+
+
+def test_chunk_size_does_not_change_the_sample_set(dev_scene, monkeypatch):
+    """Small bakes are handed out in smaller photon chunks (32..256 per warp claim) so that every SM gets work;
+    the chunk size only changes who traces which photon."""
+    spa, depth = 3000, 6                                    # 46k photons: chunks of 32
+    ref, sr = gpu_bake(dev_scene, spa, max_depth=depth, seed=8)
+    for chunk in ("1", "7", "256", "4096"):
+        monkeypatch.setenv("FMGI_CHUNK", chunk)
+        got, sg = gpu_bake(dev_scene, spa, max_depth=depth, seed=8)
+        for key in ("photons", "rays", "deposits", "mirror_bounces"):
+            assert sr[key] == sg[key], (chunk, key)
+        assert np.allclose(got, ref, rtol=1e-5, atol=1e-2)
+    monkeypatch.delenv("FMGI_CHUNK")
+
+
 def test_accumulation_passes_keep_the_sample_set(dev_scene, monkeypatch):
     """Big bakes are traced in several fp32 accumulation passes (finer shards into a scratch atlas
     that is folded into the caller's atlas): same photons, same counters, same sums."""
