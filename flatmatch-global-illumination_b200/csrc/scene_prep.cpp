@@ -356,6 +356,12 @@ void build_grid(HostScene &out, const fmgi_rect *walls, int num_walls, const fmg
     const int num_used = g.planes_up + g.planes_down + 4;
     g.down_base = g.planes_up * ncell;
     g.walk_base = (g.planes_up + g.planes_down) * ncell;
+    for (int dir = 0; dir < 2; dir++)
+        for (int i = 0; i < 4; i++) {
+            const int count = dir == 0 ? g.planes_up : g.planes_down;
+            g.fast_z[dir][i] = i < count ? g.plane_z[(dir == 0 ? 0 : kMaxPlanesPerSign) + i] : std::nanf("");
+            g.fast_base[dir][i] = (dir == 0 ? 0 : g.down_base) + (i < count ? i : 0) * ncell;
+        }
     auto used_list = [&](int u) {      // compact list number -> CSR list number
         if (u < g.planes_up) return u;
         if (u < g.planes_up + g.planes_down) return kMaxPlanesPerSign + (u - g.planes_up);

@@ -120,6 +120,11 @@ struct GridDesc {
     float wall_z_lo, wall_z_hi;                         // z range of everything in the walk lists
     int32_t down_base;      // T index of the first head of the first plane with normal -z (planes_up * ncell)
     int32_t walk_base;      // T index of the first head of walk list 0 ((planes_up + planes_down) * ncell)
+    // The first three planes a ray travelling down (index 0: faces normals +z) / up (index 1) can meet, nearest
+    // first, as the plane lookup reads them with one indexed constant load each: plane coordinates (NaN in an
+    // unused slot: its ray parameter is NaN and fails every compare) and T indices of their first heads.
+    float fast_z[2][4];
+    int32_t fast_base[2][4];
 };
 
 struct HostScene {

@@ -65,35 +65,49 @@ __global__ void __launch_bounds__(kTraceThreads, kMinBlocks) k_trace(const Trace
 
     for (;;) {
         // ---- A. refill dead lanes from the warp's chunk of the photon index space ---------------
+        // Fast path: the chunk still holds a photon for every dead lane - one ballot, lane l takes the
+        // popc(dead lanes below l)-th of them.  Otherwise (chunk boundary, about once per chunk) the loop
+        // below hands out what is left, claims the next chunk and goes on.
         is_new = false;
-        if (!exhausted) {
-            unsigned dead = __ballot_sync(kFullMask, !alive);
-            while (dead) {
-                if (w_pos == w_cnt) {
-                    unsigned long long k = 0;
-                    if (lane == 0) k = atomicAdd(p.work_counter, 1ull);
-                    k = __shfl_sync(kFullMask, k, 0);
-                    if (k >= p.total_jobs) { exhausted = true; break; }
-                    w_emitter = find_emitter(p.job_begin, p.num_emitters, k);
-                    const unsigned long long first = (k - __ldg(p.job_begin + w_emitter)) * (unsigned)p.chunk;
-                    const unsigned long long left = __ldg(p.photon_count + w_emitter) - first;
-                    w_base = __ldg(p.photon_first + w_emitter) + first;
-                    w_cnt = left < (unsigned long long)p.chunk ? (int)left : p.chunk;
-                    w_pos = 0;
-                }
-                const int avail = w_cnt - w_pos;
-                const int rank = __popc(dead & lt_mask);
-                if (!alive && rank < avail) {
-                    photon = w_base + (unsigned)(w_pos + rank);
+        unsigned dead = __ballot_sync(kFullMask, !alive);
+        if (dead != 0u && !exhausted) {
+            if (w_cnt - w_pos >= __popc(dead)) {
+                if (!alive) {
+                    photon = w_base + (unsigned)(w_pos + __popc(dead & lt_mask));
                     emitter = w_emitter;
                     alive = true; is_new = true; mirror = false; depth = 0;
                     n_photons++;
                 }
-                w_pos += min(__popc(dead), avail);
-                dead = __ballot_sync(kFullMask, !alive);
+                w_pos += __popc(dead);
+                dead = 0u;
+            } else {
+                while (dead) {
+                    if (w_pos == w_cnt) {
+                        unsigned long long k = 0;
+                        if (lane == 0) k = atomicAdd(p.work_counter, 1ull);
+                        k = __shfl_sync(kFullMask, k, 0);
+                        if (k >= p.total_jobs) { exhausted = true; break; }
+                        w_emitter = find_emitter(p.job_begin, p.num_emitters, k);
+                        const unsigned long long first = (k - __ldg(p.job_begin + w_emitter)) * (unsigned)p.chunk;
+                        const unsigned long long left = __ldg(p.photon_count + w_emitter) - first;
+                        w_base = __ldg(p.photon_first + w_emitter) + first;
+                        w_cnt = left < (unsigned long long)p.chunk ? (int)left : p.chunk;
+                        w_pos = 0;
+                    }
+                    const int avail = w_cnt - w_pos;
+                    const int rank = __popc(dead & lt_mask);
+                    if (!alive && rank < avail) {
+                        photon = w_base + (unsigned)(w_pos + rank);
+                        emitter = w_emitter;
+                        alive = true; is_new = true; mirror = false; depth = 0;
+                        n_photons++;
+                    }
+                    w_pos += min(__popc(dead), avail);
+                    dead = __ballot_sync(kFullMask, !alive);
+                }
             }
         }
-        if (__ballot_sync(kFullMask, alive) == 0u) break;
+        if (dead == kFullMask) break;
 
         bool dep = false;
         int idx = 0;

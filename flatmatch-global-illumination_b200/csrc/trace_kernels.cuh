@@ -282,52 +282,73 @@ struct GridWalk {
         return false;
     }
 
+    // The lookup is written as ONE predicated instruction stream for the first three planes of the ray's direction:
+    // ray parameters, crossing points, cells and head indices of all three, their head loads back to back
+    // (independent, so the latencies overlap), then the containment tests in plane order with best / win updated
+    // by select.  The first version branched per plane (head test, "rest of the list" loop, break out), which cost
+    // 7.5 warp instructions per ray at 19 of 32 lanes - a fifth of the kernel (profiles/r2a_example_sections.txt).
+    // What is left to a branch is the rest of a cell's list when the head's rectangle does not contain the crossing
+    // point (a cell that straddles two rooms: one ray in five on example.png): ONE loop serves all three planes.
     template <bool kCount>
     __device__ __forceinline__ void planes(const TraceParams &p, float ox, float oy, float oz, float dx, float dy,
                                            float dz, unsigned &tests)
     {
         const GridDesc &g = p.grid;
-        const bool down = dz < 0.0f;                                   // d.z < 0 faces normals +z
+        const int dir = dz < 0.0f ? 0 : 1;                             // d.z < 0 faces normals +z
         const float iz = rcp_fast(dz);                                 // d.z == 0: t = +-inf or NaN, never < best
-        const int count = down ? g.planes_up : g.planes_down;
-        const int base = down ? 0 : g.down_base;
+        const float4 fz = *reinterpret_cast<const float4 *>(g.fast_z[dir]);
+        const int4 fb = *reinterpret_cast<const int4 *>(g.fast_base[dir]);
+        const float zz[kFastPlanes] = {fz.x, fz.y, fz.z};
+        const int bb[kFastPlanes] = {fb.x, fb.y, fb.z};
         float tt[kFastPlanes], xx[kFastPlanes], yy[kFastPlanes];
         int hh[kFastPlanes];
+        bool go[kFastPlanes];
         float4 h0[kFastPlanes], h1[kFastPlanes];
 #pragma unroll
         for (int i = 0; i < kFastPlanes; i++) {
-            const float z = down ? g.plane_z[i] : g.plane_z[kMaxPlanesPerSign + i];
-            tt[i] = (z - oz) * iz;
+            tt[i] = (zz[i] - oz) * iz;
             xx[i] = fmaf(tt[i], dx, ox); yy[i] = fmaf(tt[i], dy, oy);
             const int px = __float2int_rd(fmaf(xx[i], g.inv_cell, g.bx)), py = __float2int_rd(fmaf(yy[i], g.inv_cell, g.by));
-            const bool go = i < count && (__float_as_uint(tt[i]) < __float_as_uint(best)) && (unsigned)px < (unsigned)g.nx &&
-                            (unsigned)py < (unsigned)g.ny;
-            hh[i] = go ? base + i * g.ncell + py * g.nx + px : -1;
+            go[i] = (__float_as_uint(tt[i]) < __float_as_uint(best)) && (unsigned)px < (unsigned)g.nx &&
+                    (unsigned)py < (unsigned)g.ny;
+            hh[i] = bb[i] + py * g.nx + px;
         }
 #pragma unroll
         for (int i = 0; i < kFastPlanes; i++) {
             h0[i] = make_float4(0.0f, -1.0f, 0.0f, -1.0f);
             h1[i] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-            if (hh[i] >= 0) ldg256(p.grid_table + 2 * hh[i], h0[i], h1[i]);
+            if (go[i]) ldg256(p.grid_table + 2 * hh[i], h0[i], h1[i]);
         }
+        unsigned need = 0;
 #pragma unroll
         for (int i = 0; i < kFastPlanes; i++) {
             // a hit on a nearer plane makes the farther ones moot (tt[i] >= best)
-            if (hh[i] >= 0 && (__float_as_uint(tt[i]) < __float_as_uint(best))) {
-                if (kCount) tests += h0[i].y >= 0.0f ? 1u : 0u;        // dummy heads (half width -1) are not tests
-                if (fabsf(xx[i] - h0[i].x) <= h0[i].y && fabsf(yy[i] - h0[i].z) <= h0[i].w) { best = tt[i]; win = hh[i]; }
-                else plane_rest(p, __float_as_int(h1[i].z), __float_as_int(h1[i].w), xx[i], yy[i], tt[i], tests, kCount);
-            }
+            const bool live = go[i] && (__float_as_uint(tt[i]) < __float_as_uint(best));
+            const bool in = live && fabsf(xx[i] - h0[i].x) <= h0[i].y && fabsf(yy[i] - h0[i].z) <= h0[i].w;
+            if (kCount) tests += live && h0[i].y >= 0.0f ? 1u : 0u;    // dummy heads (half width -1) are not tests
+            best = in ? tt[i] : best;
+            win = in ? hh[i] : win;
+            need |= (live && !in && __float_as_int(h1[i].z) < __float_as_int(h1[i].w)) ? (1u << i) : 0u;
         }
+        const unsigned act = __activemask();
+        if (__any_sync(act, need != 0u)) {
+#pragma unroll
+            for (int i = 0; i < kFastPlanes; i++)
+                if ((need >> i & 1u) && (__float_as_uint(tt[i]) < __float_as_uint(best)))
+                    plane_rest(p, __float_as_int(h1[i].z), __float_as_int(h1[i].w), xx[i], yy[i], tt[i], tests, kCount);
+        }
+        const bool down = dir == 0;
+        const int count = down ? g.planes_up : g.planes_down;
+        const int base = down ? 0 : g.down_base;
 #pragma unroll 1
         for (int pl = kFastPlanes; pl < g.planes_max; pl++) {
             const float z = down ? g.plane_z[pl] : g.plane_z[kMaxPlanesPerSign + pl];
             const float t = (z - oz) * iz;
             const float x = fmaf(t, dx, ox), y = fmaf(t, dy, oy);
             const int px = __float2int_rd(fmaf(x, g.inv_cell, g.bx)), py = __float2int_rd(fmaf(y, g.inv_cell, g.by));
-            const bool go = pl < count && (__float_as_uint(t) < __float_as_uint(best)) && (unsigned)px < (unsigned)g.nx &&
-                            (unsigned)py < (unsigned)g.ny;
-            if (go) {
+            const bool go2 = pl < count && (__float_as_uint(t) < __float_as_uint(best)) && (unsigned)px < (unsigned)g.nx &&
+                             (unsigned)py < (unsigned)g.ny;
+            if (go2) {
                 const int head = base + pl * g.ncell + py * g.nx + px;
                 float4 q0, q1;
                 ldg256(p.grid_table + 2 * head, q0, q1);
