@@ -197,6 +197,12 @@ TraceParams base_params(const fmgi_scene *s)
     return p;
 }
 
+void set_seed(TraceParams &p, uint32_t seed)
+{
+    p.seed = seed;
+    for (int r = 0; r < 10; r++) p.philox_keys[r] = seed + (uint32_t)r * kPhiloxW;     // Philox2x32 round keys
+}
+
 // Job tables, per accumulation pass: chunk_begin[E + 1] (prefix of the emitters' chunk counts; a chunk is
 // `chunk` consecutive photon indices of ONE emitter, the unit a warp claims), photon_first[E],
 // photon_count[E].
@@ -451,6 +457,7 @@ const char *fmgi_version(void) { return "fmgi-b200 0.2 (sm_100a) src " FMGI_SRC_
 const char *fmgi_source_hash(void) { return FMGI_SRC_HASH; }
 
 void fmgi_release_cache(void) { MemPool::get().release(); }
+uint64_t fmgi_cached_bytes(void) { return MemPool::get().cached_bytes(); }
 
 int fmgi_device_count(void)
 {
@@ -518,6 +525,12 @@ int fmgi_scene_trace(fmgi_scene *s, void *atlas_dev, int spa, const fmgi_options
     // shard of the photon index space, so the sample set does not change.
     std::vector<unsigned long long> whole(table_words);
     const unsigned long long total_all = fill_jobs(s, spa, o, whole.data());
+    // limits of the packed Philox counter word (philox.cuh)
+    if (o.max_depth > kPhiloxMaxDepth) return fail(FMGI_ERR_UNSUPPORTED, "more than 15 bounces per photon");
+    if (E >= kPhiloxMaxEmitters) return fail(FMGI_ERR_UNSUPPORTED, "more than 2^20 emitters");
+    for (int e = 0; e < E; e++)
+        if (whole[E + 1 + e] + whole[2 * E + 1 + e] > kPhiloxMaxPhotons)
+            return fail(FMGI_ERR_UNSUPPORTED, "more than 2^40 photons from one emitter");
     int passes = (int)((total_all + kAccumPhotons - 1) / kAccumPhotons);
     if (const char *v = getenv("FMGI_ACCUM_PASSES")) passes = atoi(v);     // tuning / test knob
     if (passes < 1) passes = 1;
@@ -565,7 +578,7 @@ int fmgi_scene_trace(fmgi_scene *s, void *atlas_dev, int spa, const fmgi_options
         p.chunk = chunk;
         p.atlas = reinterpret_cast<float4 *>(passes > 1 ? (void *)s->d_scratch : atlas_dev);
         p.max_depth = o.max_depth;
-        p.seed = o.seed;
+        set_seed(p, o.seed);
         if (passes > 1) {
             FMGI_CUDA(cudaMemsetAsync(s->d_scratch, 0, atlas_bytes, st));
             FMGI_CUDA(cudaMemsetAsync(s->d_counters + 4, 0, sizeof(unsigned long long), st));   // work counter
@@ -712,7 +725,7 @@ void parallel_for(int n, Fn fn)
 //      (G-1)/G of one atlas at the same time instead of GPU 0 pulling G-1 atlases;
 //   3. every GPU writes its slice straight back into the caller's atlas over its own PCIe link.
 int bake_impl(struct Geometry *geo_, int spa, const fmgi_options *opt, fmgi_stats *stats, uint8_t *tiles_out,
-              int tint_extra)
+              int tint_extra, bool one_shot = false)
 {
     fmgi_geometry *geo = reinterpret_cast<fmgi_geometry *>(geo_);
     if (!geo) return fail(FMGI_ERR_ARG, "geo is NULL");
@@ -928,8 +941,13 @@ int bake_impl(struct Geometry *geo_, int spa, const fmgi_options *opt, fmgi_stat
         MemPool &pool = MemPool::get();
         pool.free(me.atlas); pool.free(me.init); pool.free(me.staged);
     }
-    // atlas-sized blocks do not outlive the call (no state survives but small cached tables)
-    size_t keep_mb = 256;
+    // The reference entry point is one-shot (global_illumination_cl.c:315-320 releases everything): atlas-sized
+    // blocks do not outlive it, only small tables and staging buffers stay cached (256 MB at most).  fmgi_bake /
+    // fmgi_bake_tiles are called repeatedly by harnesses: they keep up to FMGI_CACHE_MB (default 8 GB, about three
+    // atlases of the largest size the reference allows) so that a bake does not pay cudaMalloc / cudaFree of
+    // gigabyte blocks every call - measured up to 0.7 s per call when the driver has to unmap them;
+    // fmgi_release_cache() returns everything.
+    size_t keep_mb = one_shot ? 256 : 8192;
     if (const char *v = getenv("FMGI_CACHE_MB")) keep_mb = (size_t)strtoull(v, nullptr, 0);
     const double tt0 = now_ms();
     MemPool::get().trim(keep_mb << 20);
@@ -972,7 +990,7 @@ void performGlobalIlluminationCl(struct Geometry *geo, int numSamplesPerArea)
     if (const char *v = getenv("FMGI_GPUS")) o.num_gpus = atoi(v);
     if (const char *v = getenv("FMGI_DEPOSIT")) o.deposit = atoi(v);
     fmgi_stats st;
-    const int rc = fmgi_bake(geo, numSamplesPerArea, &o, &st);
+    const int rc = bake_impl(geo, numSamplesPerArea, &o, &st, nullptr, 0, true);
     if (rc != FMGI_OK) {
         printf("[Err] photon mapping on the GPU failed: %s\n", fmgi_last_error());
         exit(1);
@@ -1213,6 +1231,17 @@ int fmgi_probe_philox(const uint32_t ctr[4], const uint32_t key[2], uint32_t out
     return FMGI_OK;
 }
 
+int fmgi_probe_philox2x32(const uint32_t ctr[2], uint32_t key, uint32_t out[2])
+{
+    if (!ctr || !out) return fail(FMGI_ERR_ARG, "bad argument");
+    DevBuf<uint32_t> d;
+    FMGI_CUDA(d.alloc(2));
+    k_probe_philox2<<<1, 1>>>(ctr[0], ctr[1], key, d);
+    FMGI_CUDA(cudaGetLastError());
+    FMGI_CUDA(cudaMemcpy(out, d, 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+    return FMGI_OK;
+}
+
 int fmgi_probe_deposit_peak(uint64_t num_texels, uint64_t num_deposits, int device, double *deposits_per_s)
 {
     if (!deposits_per_s || num_texels == 0 || num_texels > 0xffffffffull || num_deposits == 0)
@@ -1265,7 +1294,7 @@ int fmgi_probe_sample_dirs(const float normal[3], int sky, uint32_t seed, int n,
 int fmgi_probe_paths(fmgi_scene *s, int emitter_index, int max_depth, uint32_t seed, uint64_t first, int count,
                      int32_t *texel_out)
 {
-    if (!s || !texel_out || count < 0 || max_depth < 1) return fail(FMGI_ERR_ARG, "bad argument");
+    if (!s || !texel_out || count < 0 || max_depth < 1 || max_depth > kPhiloxMaxDepth) return fail(FMGI_ERR_ARG, "bad argument");
     const int E = (int)s->host.emitters.size();
     if (emitter_index < 0 || emitter_index >= E) return fail(FMGI_ERR_ARG, "emitter index out of range");
     if (count == 0) return FMGI_OK;
@@ -1290,7 +1319,7 @@ int fmgi_probe_paths(fmgi_scene *s, int emitter_index, int max_depth, uint32_t s
     p.total_jobs = total;
     p.chunk = kMinChunkPhotons;
     p.max_depth = max_depth;
-    p.seed = seed;
+    set_seed(p, seed);
     p.path_out = d_path;
     int blocks = (count + kTraceThreads - 1) / kTraceThreads;
     if (blocks > s->num_sms) blocks = s->num_sms;

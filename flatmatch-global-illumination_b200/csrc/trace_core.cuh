@@ -112,15 +112,12 @@ __global__ void __launch_bounds__(kTraceThreads, kMinBlocks) k_trace(const Trace
         bool dep = false;
         int idx = 0;
         if (alive) {
-            // ---- P. one Philox block per event: emission (event 0) or the bounce just done --------
-            const Philox4 w = philox4x32_10((uint32_t)photon, (uint32_t)(photon >> 32), (uint32_t)depth, 0u,
-                                            p.seed, (uint32_t)emitter);
+            // ---- P. one Philox2x32 block per event: emission direction (event 0) or the bounce just done ----
+            const uint32_t idw = philox_event_word((uint32_t)(photon >> 32), (uint32_t)emitter, 0u);
+            const Philox2 w = philox2x32_10((uint32_t)photon, idw | ((uint32_t)depth << 28), p.philox_keys);
             // ---- S. new direction: emission and re-emission share the sampler ------------------------
-            // emission (photonmap.c:169-185) draws dx, dy from words 0, 1 and the direction from words 2, 3;
-            // a bounce (photonmap.c:228-233) draws its direction from words 0, 1
             const float4 *frame = is_new ? p.emitters + 6 * emitter : p.shade + 6 * hit_id;
             const float4 fn = ldg4(frame + 3);
-            const uint32_t wa = is_new ? w.w2 : w.w0, wb = is_new ? w.w3 : w.w1;
             float4 e0 = make_float4(px, py, pz, 0.0f);
             if (is_new) {
                 e0 = ldg4(frame);
@@ -133,15 +130,16 @@ __global__ void __launch_bounds__(kTraceThreads, kMinBlocks) k_trace(const Trace
             } else {                                            // photonmap.c:179-181, :233
                 float4 fu, fv;
                 ldg256(frame + 4, fu, fv);
-                sample_hemisphere(u24(wa), u24(wb), is_new && __float_as_int(e0.w) != 0, fn, fu, fv, dx, dy, dz);
+                sample_hemisphere(u24(w.w0), u24(w.w1), is_new && __float_as_int(e0.w) != 0, fn, fu, fv, dx, dy, dz);
             }
-            roulette = r16(wa, wb);
+            roulette = r16(w.w0, w.w1);
             px = __fadd_rn(e0.x, __fmul_rn(dx, 1E-5f));         // photonmap.c:183, :254
             py = __fadd_rn(e0.y, __fmul_rn(dy, 1E-5f));
             pz = __fadd_rn(e0.z, __fmul_rn(dz, 1E-5f));
-            if (is_new) {                                       // photonmap.c:184-185
+            if (is_new) {                                       // photonmap.c:175-176, :184-185
+                const Philox2 wp = philox2x32_10((uint32_t)photon, idw | (kEventEmitPosition << 28), p.philox_keys);
                 const float4 e1 = ldg4(frame + 1), e2 = ldg4(frame + 2);
-                const float sx = u24(w.w0), sy = u24(w.w1);
+                const float sx = u24(wp.w0), sy = u24(wp.w1);
                 px = __fadd_rn(__fadd_rn(px, __fmul_rn(e1.x, sx)), __fmul_rn(e2.x, sy));
                 py = __fadd_rn(__fadd_rn(py, __fmul_rn(e1.y, sx)), __fmul_rn(e2.y, sy));
                 pz = __fadd_rn(__fadd_rn(pz, __fmul_rn(e1.z, sx)), __fmul_rn(e2.z, sy));
@@ -244,13 +242,23 @@ __global__ void k_probe_philox(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c
     out[0] = w.w0; out[1] = w.w1; out[2] = w.w2; out[3] = w.w3;
 }
 
-// Directions as the emission event draws them: photon i of a one-emitter scene, words w2/w3.
+__global__ void k_probe_philox2(uint32_t c0, uint32_t c1, uint32_t key, uint32_t *out)
+{
+    uint32_t keys[10];
+    for (int r = 0; r < 10; r++) keys[r] = key + (uint32_t)r * kPhiloxW;
+    const Philox2 w = philox2x32_10(c0, c1, keys);
+    out[0] = w.w0; out[1] = w.w1;
+}
+
+// Directions as the emission event draws them: photon i of emitter 0, event 0.
 __global__ void k_probe_sample_dirs(float4 n, float4 u, float4 v, int sky, uint32_t seed, int count, float *out)
 {
+    uint32_t keys[10];
+    for (int r = 0; r < 10; r++) keys[r] = seed + (uint32_t)r * kPhiloxW;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < count; i += gridDim.x * blockDim.x) {
-        const Philox4 w = philox4x32_10((uint32_t)i, 0u, 0u, 0u, seed, 0u);
+        const Philox2 w = philox2x32_10((uint32_t)i, 0u, keys);
         float dx, dy, dz;
-        sample_hemisphere(u24(w.w2), u24(w.w3), sky != 0, n, u, v, dx, dy, dz);
+        sample_hemisphere(u24(w.w0), u24(w.w1), sky != 0, n, u, v, dx, dy, dz);
         out[3 * i] = dx; out[3 * i + 1] = dy; out[3 * i + 2] = dz;
     }
 }

@@ -23,7 +23,7 @@
 //     ALU pipe to the FMA pipe (the ALU pipe was the top pipe of the first version, see profiles/);
 //   * deposits are one 16-byte vector reduction (RED.E.ADD.F32x4) per bounce into the atlas,
 //     optionally warp-aggregated with __match_any_sync (measured: no gain, not the default);
-//   * per-photon Philox4x32-10 sub-streams (philox.cuh) replace the sequential libc stream.
+//   * per-photon Philox2x32-10 sub-streams (philox.cuh) replace the sequential libc stream.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -70,6 +70,7 @@ struct TraceParams {
     int32_t *path_out;              // probe builds only
     int max_depth;
     uint32_t seed;
+    uint32_t philox_keys[10];       // seed + r * W: the Philox2x32 round keys of this bake (philox.cuh)
     int grid_has_misc;              // the walk lists hold misc records (scene_tables.h)
     int one;                        // 1, opaque to the compiler: x * one + y keeps integer updates on the FMA pipe
 };

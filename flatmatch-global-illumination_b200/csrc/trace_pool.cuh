@@ -24,10 +24,10 @@ constexpr int kPoolThreads = 128;           // 4 warps per CTA: 40 KB of shared 
 constexpr int kPoolSlotBytes = 80;          // five float4 per slot
 constexpr int kSwitchLanes = 8;             // idle lanes that trigger a switch while the pool has rays
 
-// limits of the packed photon id word (photon index bits 32..39 | emitter << 8 | bounce << 28)
-constexpr unsigned long long kPoolMaxPhotonIndex = 1ull << 40;
-constexpr int kPoolMaxEmitters = 1 << 20;
-constexpr int kPoolMaxDepth = 15;
+// the slot's packed photon id word is the Philox counter word (philox.cuh): same limits
+constexpr unsigned long long kPoolMaxPhotonIndex = kPhiloxMaxPhotons;
+constexpr int kPoolMaxEmitters = kPhiloxMaxEmitters;
+constexpr int kPoolMaxDepth = kPhiloxMaxDepth;
 
 // Walk set-up of one ray: what GridWalk::walk computes before its loop (same expressions).
 struct WalkStart {
@@ -276,10 +276,10 @@ __global__ void __launch_bounds__(kPoolThreads, kMinBlocks) k_trace_pool(const T
             float4 na = make_float4(0.0f, 0.0f, 0.0f, 0.0f), nb = make_float4(0.0f, 0.0f, 1.0f, 0.0f);
             float4 nc = make_float4(0.0f, __int_as_float(p.grid.walk_base), nanv, nanv);          // the null walk
             if (alive) {
-                const Philox4 w = philox4x32_10(photon_lo, photon_hi, (uint32_t)depth, 0u, p.seed, (uint32_t)emitter);
+                const uint32_t idw0 = philox_event_word(photon_hi, (uint32_t)emitter, 0u);
+                const Philox2 w = philox2x32_10(photon_lo, idw0 | ((uint32_t)depth << 28), p.philox_keys);
                 const float4 *frame = is_new ? p.emitters + 6 * emitter : p.shade + 6 * hit_id;
                 const float4 fn = ldg4(frame + 3);
-                const uint32_t wu = is_new ? w.w2 : w.w0, wv = is_new ? w.w3 : w.w1;
                 float4 e0 = make_float4(px, py, pz, 0.0f);
                 if (is_new) {
                     e0 = ldg4(frame);
@@ -292,15 +292,16 @@ __global__ void __launch_bounds__(kPoolThreads, kMinBlocks) k_trace_pool(const T
                 } else {                                            // photonmap.c:179-181, :233
                     float4 fu, fv;
                     ldg256(frame + 4, fu, fv);
-                    sample_hemisphere(u24(wu), u24(wv), is_new && __float_as_int(e0.w) != 0, fn, fu, fv, dx, dy, dz);
+                    sample_hemisphere(u24(w.w0), u24(w.w1), is_new && __float_as_int(e0.w) != 0, fn, fu, fv, dx, dy, dz);
                 }
-                roulette = r16(wu, wv);
+                roulette = r16(w.w0, w.w1);
                 px = __fadd_rn(e0.x, __fmul_rn(dx, 1E-5f));         // photonmap.c:183, :254
                 py = __fadd_rn(e0.y, __fmul_rn(dy, 1E-5f));
                 pz = __fadd_rn(e0.z, __fmul_rn(dz, 1E-5f));
-                if (is_new) {                                       // photonmap.c:184-185
+                if (is_new) {                                       // photonmap.c:175-176, :184-185
+                    const Philox2 wp = philox2x32_10(photon_lo, idw0 | (kEventEmitPosition << 28), p.philox_keys);
                     const float4 e1 = ldg4(frame + 1), e2 = ldg4(frame + 2);
-                    const float ux = u24(w.w0), uy = u24(w.w1);
+                    const float ux = u24(wp.w0), uy = u24(wp.w1);
                     px = __fadd_rn(__fadd_rn(px, __fmul_rn(e1.x, ux)), __fmul_rn(e2.x, uy));
                     py = __fadd_rn(__fadd_rn(py, __fmul_rn(e1.y, ux)), __fmul_rn(e2.y, uy));
                     pz = __fadd_rn(__fadd_rn(pz, __fmul_rn(e1.z, ux)), __fmul_rn(e2.z, uy));

@@ -70,11 +70,11 @@ class Stats(C.Structure):
 EXPORTS = [
     "performGlobalIlluminationCl", "fmgi_default_options", "fmgi_last_error", "fmgi_version", "fmgi_source_hash",
     "fmgi_device_count",
-    "fmgi_release_cache", "fmgi_tile_bytes", "fmgi_scene_tonemap", "fmgi_bake_tiles",
+    "fmgi_release_cache", "fmgi_cached_bytes", "fmgi_tile_bytes", "fmgi_scene_tonemap", "fmgi_bake_tiles",
     "fmgi_ambient_occlusion", "fmgi_scene_ambient_occlusion", "fmgi_geosphere",
     "fmgi_bake", "fmgi_scene_create", "fmgi_scene_destroy", "fmgi_scene_trace", "fmgi_scene_sync",
     "fmgi_scene_photon_count", "fmgi_probe_closest_hit", "fmgi_probe_tile_ids", "fmgi_probe_philox",
-    "fmgi_probe_sample_dirs", "fmgi_probe_paths", "fmgi_probe_deposit_peak",
+    "fmgi_probe_sample_dirs", "fmgi_probe_paths", "fmgi_probe_deposit_peak", "fmgi_probe_philox2x32",
 ]
 
 _lib = None
@@ -95,6 +95,7 @@ def lib() -> C.CDLL:
     L.fmgi_last_error.restype = C.c_char_p
     L.fmgi_version.restype = C.c_char_p
     L.fmgi_source_hash.restype = C.c_char_p
+    L.fmgi_cached_bytes.restype = C.c_uint64
     L.fmgi_default_options.argtypes = [C.POINTER(Options)]
     L.performGlobalIlluminationCl.restype = None
     L.performGlobalIlluminationCl.argtypes = [C.POINTER(Geometry), C.c_int]
@@ -118,6 +119,7 @@ def lib() -> C.CDLL:
     L.fmgi_probe_closest_hit.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
     L.fmgi_probe_tile_ids.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
     L.fmgi_probe_philox.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+    L.fmgi_probe_philox2x32.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p]
     L.fmgi_probe_sample_dirs.argtypes = [C.c_void_p, C.c_int, C.c_uint32, C.c_int, C.c_void_p]
     L.fmgi_probe_paths.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_uint32, C.c_uint64, C.c_int, C.c_void_p]
     _lib = L
@@ -287,6 +289,13 @@ def philox(ctr, key) -> np.ndarray:
     k = np.asarray(key, dtype=np.uint32)
     out = np.empty(4, dtype=np.uint32)
     _check(lib().fmgi_probe_philox(c.ctypes.data, k.ctypes.data, out.ctypes.data))
+    return out
+
+
+def philox2x32(ctr, key: int) -> np.ndarray:
+    c = np.asarray(ctr, dtype=np.uint32)
+    out = np.empty(2, dtype=np.uint32)
+    _check(lib().fmgi_probe_philox2x32(c.ctypes.data, int(key) & 0xFFFFFFFF, out.ctypes.data))
     return out
 
 

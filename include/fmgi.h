@@ -78,8 +78,8 @@ enum { FMGI_TIER_AUTO = 0, FMGI_TIER_SOUP = 1, FMGI_TIER_GRID = 2 };
 
 typedef struct fmgi_options {
     uint32_t struct_size;     /* = sizeof(fmgi_options); lets the struct grow */
-    int32_t  max_depth;       /* bounces per photon; reference = 8 (photonmap.c:173) */
-    uint32_t seed;            /* Philox key word 0 */
+    int32_t  max_depth;       /* bounces per photon, 1..15; reference = 8 (photonmap.c:173) */
+    uint32_t seed;            /* Philox key */
     int32_t  num_gpus;        /* fmgi_bake only: GPUs to shard photons over (0 = 1) */
     int32_t  shard;           /* this caller's shard of every emitter's photon range ... */
     int32_t  num_shards;      /* ... out of num_shards (0/1 = everything) */
@@ -123,8 +123,11 @@ const char *fmgi_version(void);
 const char *fmgi_source_hash(void);
 int         fmgi_device_count(void);
 /* The library keeps freed device / pinned blocks in a process-wide cache so that repeated bakes do
- * not pay cudaMalloc/cudaFree again; this returns the cached blocks to the driver. */
+ * not pay cudaMalloc/cudaFree again: at most 256 MB after performGlobalIlluminationCl (atlas-sized blocks are
+ * released before it returns), at most FMGI_CACHE_MB (default 8192) after fmgi_bake / fmgi_bake_tiles.
+ * fmgi_release_cache() returns the cached blocks to the driver; fmgi_cached_bytes() reports them. */
 void        fmgi_release_cache(void);
+uint64_t    fmgi_cached_bytes(void);
 
 /* Host-buffer bake with options: what performGlobalIlluminationCl wraps. */
 int fmgi_bake(struct Geometry *geo, int numSamplesPerArea, const fmgi_options *opt, fmgi_stats *stats);
@@ -188,8 +191,11 @@ int fmgi_probe_closest_hit(fmgi_scene *scene, const float *origins, const float 
 /* getTileIdAt (rectangle.c:205) for points on walls[rect_index[i]]. */
 int fmgi_probe_tile_ids(fmgi_scene *scene, const int32_t *rect_index, const float *points,
                         int num_points, int32_t *tile_ids);
-/* Philox4x32-10 block on the device. */
+/* Philox4x32-10 block on the device (known-answer probe; the tracer itself draws Philox2x32-10 blocks). */
 int fmgi_probe_philox(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]);
+/* Philox2x32-10 block on the device: the tracer's generator (csrc/philox.cuh: key = seed, counter =
+ * {photon lo, photon hi | emitter << 8 | event << 28}). */
+int fmgi_probe_philox2x32(const uint32_t ctr[2], uint32_t key, uint32_t out[2]);
 /* Deposit roofline: rate of the trace kernel's deposit instruction (one 16-byte vector
  * reduction, RED.E.ADD.F32x4) at uniform-random texels of a scratch atlas of num_texels float4, nothing else
  * in the loop.  Deposits per second, device-timed. */

@@ -113,14 +113,27 @@ void orc_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t ou
     out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
 }
 
+/* Philox2x32-10 (same paper; M = D256D193, W = 9E3779B9): the generator the CUDA tracer draws from. */
+void orc_philox2x32_10(const uint32_t ctr[2], uint32_t key, uint32_t out[2])
+{
+    uint32_t c0 = ctr[0], c1 = ctr[1];
+    for (int r = 0; r < 10; r++) {
+        uint64_t p0 = (uint64_t)0xD256D193u * c0;
+        uint32_t n0 = (uint32_t)(p0 >> 32) ^ key ^ c1;
+        c1 = (uint32_t)p0; c0 = n0;
+        key += 0x9E3779B9u;
+    }
+    out[0] = c0; out[1] = c1;
+}
+
 /* ------------------------------------------------------------------------------------------
  * Random source.  LIBC: rand()/(double)RAND_MAX in call order (photonmap.c:175-176,228;
  * vector3_cl.c:107-108,131-132).
- * PHILOX (the CUDA path's stream, see DESIGN.md "Random stream"): one block per event,
- *   key = {seed, emitter}, counter = {photon lo, photon hi, event, 0};
+ * PHILOX (the CUDA path's stream, see DESIGN.md "Random stream"): one Philox2x32-10 block per event,
+ *   key = seed, counter = {photon lo, photon hi (8 bits) | emitter << 8 | event << 28};
  *   u24(w) = (w >> 8) * 2^-24;  r16(a, b) = (((a & 255) << 8) | (b & 255)) * 2^-16;
- *   event 0 (emission):  dx = u24(w0), dy = u24(w1), xi1 = u24(w2), xi2 = u24(w3),
- *                        roulette of bounce 1 = r16(w2, w3);
+ *   event 15 (emission position): dx = u24(w0), dy = u24(w1);
+ *   event 0 (emission direction): xi1 = u24(w0), xi2 = u24(w1), roulette of bounce 1 = r16(w0, w1);
  *   event b (after bounce b): xi1 = u24(w0), xi2 = u24(w1), roulette of bounce b+1 = r16(w0, w1).
  * The roulette draw of a bounce is therefore known before the bounce happens, which lets the
  * kernel finish a photon's last deposit without another generator call.
@@ -137,11 +150,11 @@ typedef struct {
 static void rng_event(rng_t *g, uint32_t event)
 {
     if (g->mode == ORC_RNG_PHILOX) {
-        uint32_t ctr[4] = {g->photon_lo, g->photon_hi, event, 0};
-        orc_philox4x32_10(ctr, g->key, g->block);
-        uint32_t a = event == 0 ? g->block[2] : g->block[0];
-        uint32_t b = event == 0 ? g->block[3] : g->block[1];
-        g->roulette_next = (double)((float)(((a & 255u) << 8) | (b & 255u)) * (1.0f / 65536.0f));
+        uint32_t ctr[2] = {g->photon_lo, g->photon_hi | (g->key[1] << 8) | (event << 28)};   /* key[1] = emitter */
+        orc_philox2x32_10(ctr, g->key[0], g->block);
+        uint32_t a = g->block[0], b = g->block[1];
+        if (event != 15)
+            g->roulette_next = (double)((float)(((a & 255u) << 8) | (b & 255u)) * (1.0f / 65536.0f));
     }
 }
 
@@ -361,10 +374,11 @@ static void trace_photon(const scene_t *s, const orc_rect *src, int is_window, r
                          int max_depth, float *texels, orc_stats *st, int32_t *path)
 {
     v3 colour = is_window ? V(18, 18, 18) : V(16, 16, 18);           /* photonmap.c:169-171 */
-    rng_event(g, 0);
+    rng_event(g, 15);                                                /* PHILOX: emission position block */
     float dx = rng_u01(g, 0);                                        /* :175 */
     float dy = rng_u01(g, 1);                                        /* :176 */
-    v3 dir = sample_hemisphere(g, ld(src->n), is_window, 2);         /* :179-181 */
+    rng_event(g, 0);                                                 /* PHILOX: emission direction block */
+    v3 dir = sample_hemisphere(g, ld(src->n), is_window, 0);         /* :179-181 */
     v3 pos = vadd4(ld(src->pos), vmul(dir, 1E-5f),                   /* :183-185 */
                    vmul(ld(src->width), dx), vmul(ld(src->height), dy));
     st->photons++;

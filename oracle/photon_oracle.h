@@ -46,6 +46,7 @@ uint64_t orc_photon_budget(const orc_rect *emitter, int samples_per_area);
 
 /* Philox4x32-10 (Salmon et al., SC'11; Random123 v1.14 constants). */
 void orc_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]);
+void orc_philox2x32_10(const uint32_t ctr[2], uint32_t key, uint32_t out[2]);
 
 /* Whole bake, same emitter order and budgets as performPhotonMappingNative (photonmap.c:408-434).
  * texels: numTexels x float4, accumulated in place.

@@ -367,6 +367,8 @@ class OracleLib:
         L.orc_photon_budget.argtypes = [C.c_void_p, C.c_int]
         L.orc_philox4x32_10.restype = None
         L.orc_philox4x32_10.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        L.orc_philox2x32_10.restype = None
+        L.orc_philox2x32_10.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p]
         L.orc_ambient_occlusion.restype = None
         L.orc_ambient_occlusion.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int]
         L.orc_tonemap_tiles.restype = None
@@ -430,4 +432,10 @@ class OracleLib:
         k = np.asarray(key, dtype=np.uint32)
         out = np.empty(4, dtype=np.uint32)
         self.lib.orc_philox4x32_10(c.ctypes.data, k.ctypes.data, out.ctypes.data)
+        return out
+
+    def philox2x32(self, ctr, key: int):
+        c = np.asarray(ctr, dtype=np.uint32)
+        out = np.empty(2, dtype=np.uint32)
+        self.lib.orc_philox2x32_10(c.ctypes.data, int(key) & 0xFFFFFFFF, out.ctypes.data)
         return out

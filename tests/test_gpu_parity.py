@@ -78,6 +78,14 @@ def test_philox_on_device(fmgi, oracle):
     for _ in range(20):
         ctr, key = rng.integers(0, 2**32, 4, dtype=np.uint64), rng.integers(0, 2**32, 2, dtype=np.uint64)
         assert np.array_equal(fmgi.philox(ctr, key), oracle.philox(ctr, key))
+    # the tracer's own generator: Philox2x32-10 (Random123 known answers, then random blocks vs the oracle)
+    from test_oracle import PHILOX2X32_KATS
+
+    for ctr, key, want in PHILOX2X32_KATS:
+        assert fmgi.philox2x32(ctr, key).tolist() == want
+    for _ in range(20):
+        ctr, key = rng.integers(0, 2**32, 2, dtype=np.uint64), int(rng.integers(0, 2**32))
+        assert np.array_equal(fmgi.philox2x32(ctr, key), oracle.philox2x32(ctr, key))
 
 
 @pytest.fixture(params=["soup_planes", "soup", "grid"])
@@ -550,6 +558,88 @@ def test_chunk_size_does_not_change_the_sample_set(dev_scene, monkeypatch):
             assert sr[key] == sg[key], (chunk, key)
         assert np.allclose(got, ref, rtol=1e-5, atol=1e-2)
     monkeypatch.delenv("FMGI_CHUNK")
+
+
+def wall_mean_luminance(atlas_dev, walls, spa):
+    """Per-wall mean of the NORMALISED luminance (main.c:68-79 scaling, rectangle.c:277 weights) of a RAW device
+    atlas, computed on the device: mean over the wall's base texels of lum * 0.35 * tiles / (area * spa)."""
+    import torch
+
+    lum = (atlas_dev[:, :3].double() @ torch.tensor(LUMA, dtype=torch.float64, device=atlas_dev.device))
+    csum = torch.cat([torch.zeros(1, dtype=torch.float64, device=lum.device), torch.cumsum(lum, 0)])
+    base = torch.tensor(walls["lightmapSetup"][:, 0].astype(np.int64), device=lum.device)
+    tiles = torch.tensor((walls["lightmapSetup"][:, 1].astype(np.int64) * walls["lightmapSetup"][:, 2]), device=lum.device)
+    sums = (csum[base + tiles] - csum[base]).cpu().numpy()
+    tiles = tiles.cpu().numpy().astype(np.float64)
+    area = (np.linalg.norm(walls["width"][:, :3].astype(np.float64), axis=1) *
+            np.linalg.norm(walls["height"][:, :3].astype(np.float64), axis=1))
+    return sums / tiles * 0.35 * tiles / (area * spa), tiles
+
+
+@pytest.mark.parametrize("tile_size", [200, 800])
+def test_radiance_parity_synth4000(fmgi, synth4000, record, tile_size):
+    """BASELINE.json configs[2] and [3] against the compiled reference: the 21.5k-rectangle layout, 1e9 photons x 4
+    bounces, per-wall mean of the normalised luminance and total energy vs 5.45e8 photons of
+    performPhotonMappingNative at depth 4 (fixture: oracle/make_golden.py atlas --fixture synth4000 --depth 4, two
+    independent halves).  tile_size 800 is the hi-res layout (fmgi.layout.retile, 1.83 GB atlas): the normalised
+    radiance of a wall must not depend on its texel density, so the same fixture serves."""
+    import torch
+    from fmgi import layout
+
+    sc = synth4000
+    z = np.load(GOLDEN / "synth4000_native_depth4.npz")
+    depth = int(z["depth"])
+    assert depth == 4
+    walls, num_texels = (sc.walls, sc.num_texels) if tile_size == 200 else layout.retile(sc.walls, float(tile_size))
+    s = fmgi.DeviceScene(walls, sc.windows, sc.lights, num_texels)
+    area = sum(sc.photon_counts(1_000_000)) / 1e6
+    spa = int(1.0e9 / area)
+    atlas = device_atlas(num_texels)
+    s.trace(atlas.data_ptr(), spa, stream=torch.cuda.current_stream().cuda_stream, max_depth=depth, seed=4000)
+    st = s.sync()
+    assert st["tier"] == fmgi.TIER_GRID and abs(st["photons"] - 1e9) < 1e6
+    wall_gpu, _ = wall_mean_luminance(atlas, s.walls, spa)
+    e_gpu = atlas[:, :3].sum(dim=0, dtype=torch.float64).cpu().numpy() / spa
+    if tile_size == 200:                        # the strided per-texel sample of the fixture
+        mask = torch.tensor(sc.base_texel_mask(), device="cuda")
+        lum_all = (atlas[:, :3].double() @ torch.tensor(LUMA, dtype=torch.float64, device="cuda"))
+        norm = torch.tensor(sc.normalisation(spa), device="cuda")
+        lum_gpu = (lum_all * norm)[mask][:: int(z["stride"])].cpu().numpy()
+    del atlas
+    s.close()
+
+    wall_a, wall_b = z["wall_lum_a"], z["wall_lum_b"]
+    wall_ref = 0.5 * (wall_a + wall_b)
+    ref_tiles = (sc.walls["lightmapSetup"][:, 1].astype(np.int64) * sc.walls["lightmapSetup"][:, 2])
+    bright = wall_ref > 0.05 * wall_ref.mean()
+    big = bright & (ref_tiles >= 1024)          # walls of >= 5 m^2: 8121 of 21552, where the noise is small
+    rel = (wall_gpu - wall_ref) / wall_ref
+    rel_ab = (wall_a - wall_b) / wall_ref
+    rms = lambda v: float(np.sqrt(np.mean(v ** 2)))
+    wrms = lambda v, w: float(np.sqrt(np.sum(w * v ** 2) / np.sum(w)))
+    e_ref = 0.5 * (z["rgb_total_a"] / float(z["spa_a"]) + z["rgb_total_b"] / float(z["spa_b"]))
+    figures = dict(gpu_photons=int(st["photons"]), walls=int(bright.sum()), big_walls=int(big.sum()),
+                   big_wall_rel_rms=rms(rel[big]), big_wall_rel_rms_reference_halves=rms(rel_ab[big]),
+                   area_weighted_rel_rms=wrms(rel[bright], ref_tiles[bright]),
+                   area_weighted_rel_rms_reference_halves=wrms(rel_ab[bright], ref_tiles[bright]),
+                   all_wall_rel_rms=rms(rel[bright]), all_wall_rel_rms_reference_halves=rms(rel_ab[bright]),
+                   mean_bias=float(np.average(rel[bright], weights=ref_tiles[bright])),
+                   energy_rel_diff=[float(x) for x in e_gpu / e_ref - 1])
+    if tile_size == 200:
+        lum_a, lum_b = z["lum_a"].astype(np.float64), z["lum_b"].astype(np.float64)
+        s_ab, sp_ab, _ = parity_stats(lum_a, lum_b)
+        s_g, sp_g, _ = parity_stats(lum_gpu, 0.5 * (lum_a + lum_b))
+        figures.update(S_per_texel=float(sp_g), S_per_texel_reference_halves=float(sp_ab))
+        # ~80 deposits per texel on the reference side: per texel this is a noise check only
+        assert sp_g < 1.05 * sp_ab
+    print(f"synth4000 tile_size {tile_size}: {figures}")
+    record(f"radiance_synth4000_depth4_tile{tile_size}", **figures)
+    # per-wall bars (VERDICT r1): rel. RMS < 1 % where the reference's own noise allows it, energy within 0.1 %
+    assert figures["big_wall_rel_rms"] < 0.01 and figures["area_weighted_rel_rms"] < 0.01
+    assert figures["big_wall_rel_rms"] < 1.2 * figures["big_wall_rel_rms_reference_halves"]
+    assert figures["all_wall_rel_rms"] < 1.2 * figures["all_wall_rel_rms_reference_halves"]
+    assert abs(figures["mean_bias"]) < 1e-3
+    assert np.all(np.abs(e_gpu / e_ref - 1) < 1e-3)
 
 
 def test_accumulation_passes_keep_the_sample_set(dev_scene, monkeypatch):

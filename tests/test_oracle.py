@@ -82,6 +82,16 @@ def test_philox_known_answers(oracle):
     ]
     for ctr, key, want in kats:
         assert oracle.philox(ctr, key).tolist() == want
+    # ... and for philox2x32-10, the generator the CUDA tracer draws from (csrc/philox.cuh)
+    for ctr, key, want in PHILOX2X32_KATS:
+        assert oracle.philox2x32(ctr, key).tolist() == want
+
+
+PHILOX2X32_KATS = [
+    ([0, 0], 0, [0xFF1DAE59, 0x6CD10DF2]),
+    ([0xFFFFFFFF, 0xFFFFFFFF], 0xFFFFFFFF, [0x2C3F628B, 0xAB4FD7AD]),
+    ([0x243F6A88, 0x85A308D3], 0x13198A2E, [0xDD7CE038, 0xF62A4C12]),
+]
 
 
 def test_philox_mode_statistics_match_libc_mode(oracle, scene):
