@@ -279,8 +279,12 @@ class Harness:
         if not torch.cuda.is_available():
             raise SystemExit("bench.py: no CUDA device (the product path has no CPU fallback)")
         torch.cuda.set_device(self.local)
+        self.cpu_group = None
         if self.world > 1:
             dist.init_process_group("nccl", device_id=torch.device("cuda", self.local))
+            # host-side barrier for the phases in which rank 0 drives every GPU itself: a NCCL barrier would leave
+            # a spinning kernel on the other ranks' GPUs, and two processes on one GPU are time-sliced
+            self.cpu_group = dist.new_group(backend="gloo")
         self.flush = torch.empty(192 * 1024 * 1024 // 4, dtype=torch.float32, device="cuda")   # > 126 MB L2
         self.stream = torch.cuda.current_stream()
 
@@ -288,6 +292,12 @@ class Harness:
         if self.world > 1:
             self.dist.barrier()
         self.torch.cuda.synchronize()
+
+    def barrier_idle(self):
+        """Barrier that leaves the GPUs idle while waiting (gloo)."""
+        self.torch.cuda.synchronize()
+        if self.world > 1:
+            self.dist.barrier(group=self.cpu_group)
 
     def close(self):
         if self.world > 1:
@@ -375,7 +385,7 @@ def measure(h, workload, steps, warmup, e2e_steps, photons=0.0, total_photons=0.
     # link - what the reference-facing entry point does with FMGI_GPUS=N.  The other ranks wait at the barrier.
     e2e = None
     if e2e_steps > 0:
-        h.barrier()
+        h.barrier_idle()
         if rank == 0:
             tex = torch.zeros((num_texels, 4), dtype=torch.float32).pin_memory().numpy()    # pinned host atlas
             geo = fmgi.make_geometry(walls, windows, lights, tex)
@@ -402,7 +412,7 @@ def measure(h, workload, steps, warmup, e2e_steps, photons=0.0, total_photons=0.
                                     "fold": mean("reduce_ms"), "atlas_d2h": mean("d2h_ms"), "total": mean("total_ms")},
                    "first_call_ms": first["total_ms"], "first_call_init_ms": first["init_ms"]}
             del tex, geo
-        h.barrier()
+        h.barrier_idle()
 
     if rank != 0:
         return None

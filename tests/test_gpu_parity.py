@@ -439,8 +439,9 @@ def test_general_rectangles(fmgi, oracle, scene, tier):
 
 
 def test_in_library_multi_gpu_bake(fmgi, scene):
-    """fmgi_bake with num_gpus > 1: one host thread per GPU, disjoint photon ranges, peer atlases
-    folded into GPU 0 by a kernel reading them over NVLink peer mappings."""
+    """fmgi_bake with num_gpus > 1: one host thread per GPU, disjoint photon ranges; GPU g folds slice g of every
+    GPU's atlas (reading the peers' copies over NVLink peer mappings) onto the caller's values of that slice and
+    writes it back over its own PCIe link."""
     n = fmgi.lib().fmgi_device_count()
     if n < 2:
         pytest.skip("needs at least 2 GPUs")
@@ -454,7 +455,8 @@ def test_in_library_multi_gpu_bake(fmgi, scene):
         assert stg["num_gpus"] == g
         for k in ("photons", "rays", "deposits", "mirror_bounces"):
             assert stg[k] == st1[k], (g, k)
-        assert np.allclose(texg, tex1, rtol=1e-5, atol=5e-2)
+        # fp32 sums in another order: the hottest texel (2.2e4, ~1400 deposits) moves by 1.4e-5 relative
+        assert np.allclose(texg, tex1, rtol=5e-5, atol=5e-2)
     # the caller's current device survives the call, whichever device the bake starts on, and a bake that
     # starts on GPU 1 uses distinct GPUs (1, 2, ... wrapping to 0), adds onto the caller's values and leaves
     # lane 3 / the mip slots alone
