@@ -83,23 +83,29 @@ public:
         if (prev >= 0) cudaSetDevice(prev);
     }
 
-    // Releases cached (not live) blocks, largest first, until at most `keep_bytes` stay cached.  Called at
-    // the end of every host-buffer entry point so that atlas-sized blocks do not outlive the call
-    // (FMGI_CACHE_MB, default 256: small tables and staging buffers stay, a 1.8 GB atlas does not).
+    // Releases cached (not live) blocks, largest first, until at most `keep_bytes` stay cached PER DEVICE (pinned
+    // host blocks count as one more "device").  Called at the end of every host-buffer entry point:
+    // performGlobalIlluminationCl keeps 256 MB (small tables and staging buffers stay, a 1.8 GB atlas does not),
+    // fmgi_bake keeps FMGI_CACHE_MB (default 8 GB) because cudaFree of gigabyte blocks was measured at up to 0.5 s.
     void trim(size_t keep_bytes)
     {
         std::vector<Block> victims;
         {
             std::lock_guard<std::mutex> lock(mu_);
-            size_t cached = 0;
-            for (const Block &b : free_) cached += b.bytes;
-            while (cached > keep_bytes && !free_.empty()) {
-                size_t big = 0;
-                for (size_t i = 1; i < free_.size(); i++)
-                    if (free_[i].bytes > free_[big].bytes) big = i;
-                cached -= free_[big].bytes;
-                victims.push_back(free_[big]);
-                free_.erase(free_.begin() + big);
+            std::map<int, size_t> cached;             // device (-1: pinned) -> cached bytes
+            for (const Block &b : free_) cached[b.pinned ? -1 : b.device] += b.bytes;
+            for (auto &kv : cached) {
+                while (kv.second > keep_bytes) {
+                    size_t big = (size_t)-1;
+                    for (size_t i = 0; i < free_.size(); i++)
+                        if ((free_[i].pinned ? -1 : free_[i].device) == kv.first &&
+                            (big == (size_t)-1 || free_[i].bytes > free_[big].bytes))
+                            big = i;
+                    if (big == (size_t)-1) break;
+                    kv.second -= free_[big].bytes;
+                    victims.push_back(free_[big]);
+                    free_.erase(free_.begin() + big);
+                }
             }
         }
         if (victims.empty()) return;
