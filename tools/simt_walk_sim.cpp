@@ -168,7 +168,7 @@ int main(int argc, char **argv)
     double v2_iters = 0, v2_lanes = 0;                              // merged, two tests per iteration
     double pl_head_iters = 0, pl_cand_iters = 0, pl_head_lanes = 0, pl_cand_lanes = 0;
     double outer = 0, lanes_alive = 0;
-    std::vector<double> hist(64, 0.0);
+    std::vector<double> hist(64, 0.0), hist_max(64, 0.0);
 
     for (int wq = 0; wq < num_warps; wq++) {
         Lane L[32];
@@ -257,6 +257,7 @@ int main(int argc, char **argv)
                     if (a) { v0_adv_iters++; v0_adv_lanes += a; }
                 }
                 v1_iters += max1; v2_iters += max2;
+                hist_max[std::min(max1, 63)]++;
                 for (int l = 0; l < 32; l++) { v1_lanes += len1[l]; v2_lanes += len2[l]; }
             }
             // ---- shade --------------------------------------------------------------------------
@@ -288,6 +289,12 @@ int main(int argc, char **argv)
     double hs = 0; for (double h : hist) hs += h;
     for (int i = 0; i < 24; i++) printf(" %d:%.3f", i, hist[i] / hs);
     printf("\n");
+    // the same per warp: steps of the warp's longest walk = iterations the whole warp spends in the walk loop
+    printf("warp-max histogram:");
+    double hm = 0, mean_max = 0; for (double h : hist_max) hm += h;
+    for (int i = 0; i < 64; i++) mean_max += i * hist_max[i] / hm;
+    for (int i = 0; i < 40; i++) printf(" %d:%.3f", i, hist_max[i] / hm);
+    printf("\nmean steps per ray %.2f, mean of the warp maximum %.2f\n", v1_lanes / rays, mean_max);
     // ---- model R: walk capped at M iterations per round; unfinished lanes keep walking next round and
     //      skip the shade/emit phase ("if-if" scheduling).  Model P: per-warp pool of 32*K rays, lanes
     //      fetch the next ray when at least `thr` lanes are idle.
