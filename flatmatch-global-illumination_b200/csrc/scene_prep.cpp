@@ -171,10 +171,22 @@ const char *prepare_scene(HostScene &out, const fmgi_rect *walls, int num_walls,
 void build_grid(HostScene &out, const fmgi_rect *walls, int num_walls, const fmgi_rect *windows, int num_windows,
                 const fmgi_rect *lights, int num_lights, float cell_hint)
 {
+    std::vector<GridItem> items;
+    grid_classify(out, walls, num_walls, windows, num_windows, lights, num_lights, cell_hint, items);
+    grid_assemble_host(out, items);
+}
+
+// First half of build_grid: the grid's geometry and plane tables (GridDesc) and, per collider, which list(s) it goes
+// to, the cells it covers and its record.  O(number of rectangles); the per-cell work is grid_assemble_host / the
+// device assembler (grid_build.cuh).
+void grid_classify(HostScene &out, const fmgi_rect *walls, int num_walls, const fmgi_rect *windows, int num_windows,
+                   const fmgi_rect *lights, int num_lights, float cell_hint, std::vector<GridItem> &items)
+{
     GridDesc &g = out.grid;
     g = GridDesc();
     out.grid_ranges.clear();
     out.grid_recs.clear();
+    out.grid_table.clear();
     out.grid_overflow_horizontal = 0;
     out.grid_misc = 0;
 
@@ -205,8 +217,9 @@ void build_grid(HostScene &out, const fmgi_rect *walls, int num_walls, const fmg
     const int ncell = g.nx * g.ny;
 
     // classify: which list does each wall go to, and with which record
-    struct Item { int list; int axis, neg; int cx0, cx1, cy0, cy1; GridRec rec; };
-    std::vector<Item> items;
+    typedef GridItem Item;
+    items.clear();
+    items.reserve((size_t)num_walls);
     std::vector<float> up, down;
     const float eps = 1e-3f * cell;
     int general_index = 0;
@@ -298,6 +311,26 @@ void build_grid(HostScene &out, const fmgi_rect *walls, int num_walls, const fmg
     g.bx = -g.x0 * g.inv_cell; g.by = -g.y0 * g.inv_cell;
     g.exit_lo_x = g.x0 + g.cell; g.exit_hi_x = g.x0 + (float)(g.nx - 1) * g.cell;
     g.exit_lo_y = g.y0 + g.cell; g.exit_hi_y = g.y0 + (float)(g.ny - 1) * g.cell;
+    // list bases of T and the fast plane tables
+    g.down_base = g.planes_up * ncell;
+    g.walk_base = (g.planes_up + g.planes_down) * ncell;
+    for (int dir = 0; dir < 2; dir++)
+        for (int i = 0; i < 4; i++) {
+            const int count = dir == 0 ? g.planes_up : g.planes_down;
+            g.fast_z[dir][i] = i < count ? g.plane_z[(dir == 0 ? 0 : kMaxPlanesPerSign) + i] : std::nanf("");
+            g.fast_base[dir][i] = (dir == 0 ? 0 : g.down_base) + (i < count ? i : 0) * ncell;
+        }
+}
+
+// Second half of build_grid on the host: bins the items into per-(list, cell) lists and lays out T.
+void grid_assemble_host(HostScene &out, const std::vector<GridItem> &items)
+{
+    typedef GridItem Item;
+    GridDesc &g = out.grid;
+    const int ncell = g.ncell;
+    const float cell = g.cell;
+    out.grid_ranges.clear();
+    out.grid_recs.clear();
 
     // lists are numbered: [0, 8) planes +z, [8, 16) planes -z, 16 + combo = walk lists, where
     // combo = (d.x > 0) + 2 * (d.y > 0) is the sign combination of the rays that walk the list
@@ -354,14 +387,6 @@ void build_grid(HostScene &out, const fmgi_rect *walls, int num_walls, const fmg
 
     // T: heads (first record inline + continuation range), then the remaining records
     const int num_used = g.planes_up + g.planes_down + 4;
-    g.down_base = g.planes_up * ncell;
-    g.walk_base = (g.planes_up + g.planes_down) * ncell;
-    for (int dir = 0; dir < 2; dir++)
-        for (int i = 0; i < 4; i++) {
-            const int count = dir == 0 ? g.planes_up : g.planes_down;
-            g.fast_z[dir][i] = i < count ? g.plane_z[(dir == 0 ? 0 : kMaxPlanesPerSign) + i] : std::nanf("");
-            g.fast_base[dir][i] = (dir == 0 ? 0 : g.down_base) + (i < count ? i : 0) * ncell;
-        }
     auto used_list = [&](int u) {      // compact list number -> CSR list number
         if (u < g.planes_up) return u;
         if (u < g.planes_up + g.planes_down) return kMaxPlanesPerSign + (u - g.planes_up);

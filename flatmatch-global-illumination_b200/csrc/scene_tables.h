@@ -153,12 +153,29 @@ const char *prepare_scene(HostScene &out, const fmgi_rect *walls, int num_walls,
                           const fmgi_rect *windows, int num_windows,
                           const fmgi_rect *lights, int num_lights, int num_texels);
 
+// One collider as build_grid bins it: list < 0: the walk lists its rays can face (axis 0 / 1: the two sign
+// combinations that face normal sign `neg`; axis 2 or 3: all four), else the plane list; cells [cx0, cx1] x [cy0, cy1].
+struct GridItem {
+    int32_t list;
+    int32_t axis, neg;
+    int32_t cx0, cx1, cy0, cy1;
+    int32_t pad;
+    GridRec rec;
+};
+static_assert(sizeof(GridItem) == 64, "GridItem is 64 bytes");
+
 // Builds the floor-plan grid of the grid tier.  cell_hint <= 0 picks the cell edge from the scene
 // (about two colliders per cell).  Needs the wall table again because HostScene keeps only
 // derived records.
 void build_grid(HostScene &scene, const fmgi_rect *walls, int num_walls,
                 const fmgi_rect *windows, int num_windows, const fmgi_rect *lights, int num_lights,
                 float cell_hint);
+
+// The two halves of build_grid (scene_prep.cpp): per-collider classification + GridDesc, and the per-cell assembly
+// of T, which also exists as device kernels (grid_build.cuh) for large scenes.
+void grid_classify(HostScene &scene, const fmgi_rect *walls, int num_walls, const fmgi_rect *windows, int num_windows,
+                   const fmgi_rect *lights, int num_lights, float cell_hint, std::vector<GridItem> &items);
+void grid_assemble_host(HostScene &scene, const std::vector<GridItem> &items);
 
 // Geodesic half-sphere direction set (xyz triples); iterations = 4 is the reference's geoSphere4.
 std::vector<float> geosphere_directions(int iterations);

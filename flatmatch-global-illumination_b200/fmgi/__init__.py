@@ -75,6 +75,7 @@ EXPORTS = [
     "fmgi_bake", "fmgi_scene_create", "fmgi_scene_destroy", "fmgi_scene_trace", "fmgi_scene_sync",
     "fmgi_scene_photon_count", "fmgi_probe_closest_hit", "fmgi_probe_tile_ids", "fmgi_probe_philox",
     "fmgi_probe_sample_dirs", "fmgi_probe_paths", "fmgi_probe_deposit_peak", "fmgi_probe_philox2x32",
+    "fmgi_probe_grid_table",
 ]
 
 _lib = None
@@ -120,6 +121,8 @@ def lib() -> C.CDLL:
     L.fmgi_probe_tile_ids.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
     L.fmgi_probe_philox.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
     L.fmgi_probe_philox2x32.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p]
+    L.fmgi_probe_grid_table.restype = C.c_int64
+    L.fmgi_probe_grid_table.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64]
     L.fmgi_probe_sample_dirs.argtypes = [C.c_void_p, C.c_int, C.c_uint32, C.c_int, C.c_void_p]
     L.fmgi_probe_paths.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_uint32, C.c_uint64, C.c_int, C.c_void_p]
     _lib = L
@@ -260,6 +263,15 @@ class DeviceScene:
 
     def tile_bytes(self) -> int:
         return int(lib().fmgi_tile_bytes(self.walls.ctypes.data, len(self.walls)))
+
+    def grid_table(self) -> np.ndarray:
+        """The device's floor-plan grid table T as (records, 8) uint32 words."""
+        n = int(lib().fmgi_probe_grid_table(self._h, None, 0))
+        if n < 0:
+            raise FmgiError(lib().fmgi_last_error().decode())
+        out = np.zeros((max(n, 1), 8), dtype=np.uint32)
+        lib().fmgi_probe_grid_table(self._h, out.ctypes.data, n)
+        return out[:n]
 
     # -- parity probes ---------------------------------------------------------------------------
     def closest_hit(self, origins, dirs):

@@ -109,7 +109,7 @@ typedef struct fmgi_stats {
     /* host-buffer entry points only (fmgi_bake, fmgi_bake_tiles), host clock, max over GPUs */
     double   init_ms;         /* cudaSetDevice + stream/event creation: the CUDA context on the first call of a process */
     double   prepare_ms;      /* rectangle tables (scene_prep.cpp) */
-    double   grid_build_ms;   /* floor-plan grid (build_grid) */
+    double   grid_build_ms;   /* floor-plan grid: host classification + per-cell assembly (host, or device for >= 2048 colliders) */
     double   upload_ms;       /* table upload + kernel attribute queries per GPU */
     int32_t  pool_rays;       /* 0: k_trace ran; K > 0: the pooled kernel (trace_pool.cuh) with K rays per lane */
     int32_t  reserved0;
@@ -191,6 +191,11 @@ int fmgi_probe_closest_hit(fmgi_scene *scene, const float *origins, const float 
 /* getTileIdAt (rectangle.c:205) for points on walls[rect_index[i]]. */
 int fmgi_probe_tile_ids(fmgi_scene *scene, const int32_t *rect_index, const float *points,
                         int num_points, int32_t *tile_ids);
+/* The floor-plan grid table T the trace kernels walk (32-byte records, csrc/scene_tables.h), as it sits on the device:
+ * copies up to max_records records to records_out (may be NULL) and returns the table's record count, -1 on error.
+ * Scenes of 2048 colliders and more assemble T on the GPU (csrc/grid_build.cuh; FMGI_GRID_BUILD=host|device
+ * overrides); the probe lets a test compare the two builders bit for bit. */
+int64_t fmgi_probe_grid_table(fmgi_scene *scene, void *records_out, uint64_t max_records);
 /* Philox4x32-10 block on the device (known-answer probe; the tracer itself draws Philox2x32-10 blocks). */
 int fmgi_probe_philox(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]);
 /* Philox2x32-10 block on the device: the tracer's generator (csrc/philox.cuh: key = seed, counter =

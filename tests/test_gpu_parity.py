@@ -548,6 +548,35 @@ def test_pooled_kernel_matches_k_trace(fmgi, scene, synth800, monkeypatch, k):
         classic.close(); pooled.close()
 
 
+def test_device_grid_table_equals_host(fmgi, scene, synth800, synth4000, monkeypatch):
+    """csrc/grid_build.cuh assembles the floor-plan grid table on the GPU for scenes of 2048 colliders and more
+    (count / scan / scatter / per-list ordering / layout).  It must be the table scene_prep.cpp builds on the
+    host, bit for bit: flats, the 21.5k-rectangle layout, a staircase with more z planes than the plane table
+    (misc records in the walk lists) and a random soup with arbitrarily oriented rectangles."""
+    import refbind
+
+    cases = [("example", scene), ("synth800", synth800), ("synth4000", synth4000)]
+    w, wi, li, n = staircase_scene(fmgi)
+    cases.append(("staircase", refbind.Scene(w, wi, li, n)))
+    w, wi, li, n = random_scene(fmgi, 5)
+    cases.append(("random", refbind.Scene(w, wi, li, n)))
+    for name, sc in cases:
+        tables = {}
+        for how in ("host", "device"):
+            monkeypatch.setenv("FMGI_GRID_BUILD", how)
+            s = fmgi.DeviceScene(sc.walls, sc.windows, sc.lights, sc.num_texels, tier=fmgi.TIER_GRID)
+            tables[how] = s.grid_table()
+            s.close()
+        assert tables["host"].shape == tables["device"].shape, name
+        assert len(tables["host"]) > 100 and np.array_equal(tables["host"], tables["device"]), name
+    monkeypatch.delenv("FMGI_GRID_BUILD")
+    # the default picks the device builder for the big layout and reports its time
+    s = fmgi.DeviceScene(synth4000.walls, synth4000.windows, synth4000.lights, synth4000.num_texels)
+    _, st = gpu_bake(s, 10, max_depth=2)
+    assert 0 < st["grid_build_ms"] < 50
+    s.close()
+
+
 def test_chunk_size_does_not_change_the_sample_set(dev_scene, monkeypatch):
     """Small bakes are handed out in smaller photon chunks (32..256 per warp claim) so that every SM gets work;
     the chunk size only changes who traces which photon."""
