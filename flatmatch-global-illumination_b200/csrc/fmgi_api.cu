@@ -199,6 +199,12 @@ TraceParams base_params(const fmgi_scene *s)
     p.photon_count = s->d_jobs + (2 * p.num_emitters + 1);
     p.work_counter = s->d_counters + 4;
     p.counters = s->d_counters;
+    p.grid_records = (unsigned)s->grid_records;
+    p.num_walls = (unsigned)s->host.num_walls;
+    p.num_texels = (unsigned)s->host.num_texels;
+#ifdef FMGI_CHECKED
+    if (getenv("FMGI_CHECK_SELFTEST")) p.num_texels /= 2;      // makes the checks fire: half of the deposits are "outside"
+#endif
     return p;
 }
 
@@ -669,6 +675,14 @@ int fmgi_scene_sync(fmgi_scene *s, fmgi_stats *stats)
         stats->prepare_ms = s->build->prepare_ms;
         stats->grid_build_ms = s->build->grid_ms + s->grid_device_ms;
         stats->pool_rays = s->pooled_last ? s->pool_k : 0;
+#ifdef FMGI_CHECKED
+        stats->bounds_violations = (int32_t)std::min<unsigned long long>(s->h_counters[6], 0x7fffffffull);
+        if (s->h_counters[6])
+            fprintf(stderr, "[fmgi] bounds-checked build: %llu index violations, first at site %llu\n", s->h_counters[6],
+                    s->h_counters[7]);
+#else
+        stats->bounds_violations = -1;
+#endif
         stats->tier = s->tier;
         stats->num_sms = s->num_sms;
         stats->sm_clock_khz = s->clock_khz;
@@ -954,6 +968,8 @@ int bake_impl(struct Geometry *geo_, int spa, const fmgi_options *opt, fmgi_stat
             if (gpus[g].scene) stats->grid_build_ms = std::max(stats->grid_build_ms, build->grid_ms + gpus[g].scene->grid_device_ms);
         stats->num_gpus = G;
         stats->pool_rays = gpus[0].st.pool_rays;
+        stats->bounds_violations = gpus[0].st.bounds_violations < 0 ? -1 : 0;
+        for (int g = 0; g < G && stats->bounds_violations >= 0; g++) stats->bounds_violations += gpus[g].st.bounds_violations;
         stats->tier = gpus[0].st.tier;
         stats->num_sms = gpus[0].st.num_sms;
         stats->sm_clock_khz = gpus[0].st.sm_clock_khz;

@@ -116,6 +116,9 @@ __global__ void __launch_bounds__(kTraceThreads, kMinBlocks) k_trace(const Trace
             const uint32_t idw = philox_event_word((uint32_t)(photon >> 32), (uint32_t)emitter, 0u);
             const Philox2 w = philox2x32_10((uint32_t)photon, idw | ((uint32_t)depth << 28), p.philox_keys);
             // ---- S. new direction: emission and re-emission share the sampler ------------------------
+            if (!FMGI_CHECK(p, is_new ? (unsigned)emitter < (unsigned)p.num_emitters : (unsigned)hit_id < p.num_walls, 7)) {
+                emitter = 0; hit_id = 0;
+            }
             const float4 *frame = is_new ? p.emitters + 6 * emitter : p.shade + 6 * hit_id;
             const float4 fn = ldg4(frame + 3);
             float4 e0 = make_float4(px, py, pz, 0.0f);
@@ -153,7 +156,7 @@ __global__ void __launch_bounds__(kTraceThreads, kMinBlocks) k_trace(const Trace
             n_rays++;
 
             // ---- D. bounce: texel, roulette, attenuation (photonmap.c:200-247) ------------------------
-            if (hit_id < 0) {
+            if (hit_id < 0 || !FMGI_CHECK(p, (unsigned)hit_id < p.num_walls, 8)) {
                 alive = false;                                   // photonmap.c:200-201: photon leaves the flat
             } else {
                 px = __fadd_rn(px, __fmul_rn(dx, t));            // photonmap.c:208
@@ -173,7 +176,7 @@ __global__ void __launch_bounds__(kTraceThreads, kMinBlocks) k_trace(const Trace
                 } else {
                     n_mirror++;
                 }
-                dep = true;
+                dep = FMGI_CHECK(p, (unsigned)idx < p.num_texels, 9);
                 if (kProbe) p.path_out[(photon - __ldg(p.photon_first + emitter)) * p.max_depth + depth] = idx;
                 depth++;
                 n_deposits++;
@@ -342,7 +345,7 @@ __global__ void __launch_bounds__(kTraceThreads) k_ambient_occlusion(const Trace
             fac_sum = __fadd_rn(fac_sum, d.z);
         }
         const float v = (float)((double)dist_sum / ((double)fac_sum * 1.5));              // photonmap.c:473
-        p.atlas[w.base + j] = make_float4(v, v, v, 0.0f);
+        if (FMGI_CHECK(p, (unsigned)(w.base + j) < p.num_texels, 10)) p.atlas[w.base + j] = make_float4(v, v, v, 0.0f);
     }
 }
 

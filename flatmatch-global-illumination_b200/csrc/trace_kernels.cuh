@@ -73,7 +73,31 @@ struct TraceParams {
     uint32_t philox_keys[10];       // seed + r * W: the Philox2x32 round keys of this bake (philox.cuh)
     int grid_has_misc;              // the walk lists hold misc records (scene_tables.h)
     int one;                        // 1, opaque to the compiler: x * one + y keeps integer updates on the FMA pipe
+    // table sizes: read only by the bounds-checked build (FMGI_CHECKED, lib/libfmgi_cuda_checked.so)
+    unsigned grid_records, num_walls, num_texels;
 };
+
+// ---- bounds-checked build ----------------------------------------------------------------------------------------
+// compute-sanitizer is not available on the GPU pool, so the library can be built with -DFMGI_CHECKED: every
+// data-dependent index - grid table records, shading / emitter records, atlas texels - is then compared with its
+// table size before it is used; a violation is counted (counters[6], first site code in counters[7]), the access
+// is skipped, and fmgi_stats.bounds_violations reports the count (the Python mirror raises on any).  The GPU test
+// suite and profiles/sanitize_small.py run against that library as the memcheck stand-in (tools/gpu_checked.sh).
+#ifdef FMGI_CHECKED
+__device__ __noinline__ void fmgi_report(const TraceParams &p, int code)
+{
+    atomicAdd(p.counters + 6, 1ull);
+    atomicCAS(p.counters + 7, 0ull, (unsigned long long)code);
+}
+__device__ __forceinline__ bool fmgi_check(const TraceParams &p, bool ok, int code)
+{
+    if (!ok) fmgi_report(p, code);
+    return ok;
+}
+#define FMGI_CHECK(p, cond, code) fmgi_check((p), (cond), (code))
+#else
+#define FMGI_CHECK(p, cond, code) (true)
+#endif
 
 // ---- closest hit against the shared-memory soup ----------------------------------------------
 
@@ -276,6 +300,7 @@ struct GridWalk {
                                                unsigned &tests, bool count)
     {
         for (; q < end; q++) {
+            if (!FMGI_CHECK(p, (unsigned)q < p.grid_records, 2)) break;
             const float4 q0 = __ldg(p.grid_table + 2 * q);
             if (count) tests++;
             if (fabsf(x - q0.x) <= q0.y && fabsf(y - q0.z) <= q0.w) { best = t; win = q; return true; }
@@ -313,6 +338,7 @@ struct GridWalk {
             go[i] = (__float_as_uint(tt[i]) < __float_as_uint(best)) && (unsigned)px < (unsigned)g.nx &&
                     (unsigned)py < (unsigned)g.ny;
             hh[i] = bb[i] + py * g.nx + px;
+            go[i] = go[i] && FMGI_CHECK(p, (unsigned)hh[i] < p.grid_records, 1);
         }
 #pragma unroll
         for (int i = 0; i < kFastPlanes; i++) {
@@ -349,7 +375,7 @@ struct GridWalk {
             const int px = __float2int_rd(fmaf(x, g.inv_cell, g.bx)), py = __float2int_rd(fmaf(y, g.inv_cell, g.by));
             const bool go2 = pl < count && (__float_as_uint(t) < __float_as_uint(best)) && (unsigned)px < (unsigned)g.nx &&
                              (unsigned)py < (unsigned)g.ny;
-            if (go2) {
+            if (go2 && FMGI_CHECK(p, (unsigned)(base + pl * g.ncell + py * g.nx + px) < p.grid_records, 3)) {
                 const int head = base + pl * g.ncell + py * g.nx + px;
                 float4 q0, q1;
                 ldg256(p.grid_table + 2 * head, q0, q1);
@@ -401,6 +427,7 @@ struct GridWalk {
         const float ax = x0 ? nanv : ix, ay = y0 ? nanv : iy;
         const float bx = -ox * ax, by = -oy * ay;
         // pending record: the head of the origin's cell
+        if (!FMGI_CHECK(p, (unsigned)ci < p.grid_records, 4)) ci = g.walk_base;
         float4 q0, h1;
         ldg256(p.grid_table + 2 * ci, q0, h1);
         float qc = h1.x;
@@ -461,10 +488,25 @@ struct GridWalk {
             "@gx fma.rn.f32 %5, sa, %29, %5;\n\t"                                                                    \
             "@gy fma.rn.f32 %6, sa, %29, %6;\n\t"
 #endif
+        // bounds-checked build: the index of a record that is about to be LOADED (`more`; the index left behind by a
+        // walk's last iteration may be the end of T) and lies outside T is replaced by 0, flagged in the misc register
+        // (-2) and ends the lane's walk
+#ifdef FMGI_CHECKED
+#define FMGI_WALK_BOUNDS                                                                                             \
+            "setp.ge.u32 oob, %14, %33;\n\t"                                                                         \
+            "and.pred oob, oob, more;\n\t"                                                                           \
+            "@oob mov.b32 %14, 0;\n\t"                                                                               \
+            "@oob mov.b32 %16, -2;\n\t"                                                                              \
+            "and.pred more, more, !oob;\n\t"
+#define FMGI_WALK_BOUNDS_OPERAND , "r"(p.grid_records)
+#else
+#define FMGI_WALK_BOUNDS
+#define FMGI_WALK_BOUNDS_OPERAND
+#endif
 #define FMGI_WALK_LOOP(MISC_TEST, MISC_EXIT, COUNT)                                                                       \
         asm volatile(                                                                                                \
             "{\n\t"                                                                                                  \
-            ".reg .pred ky, ok, adv, cont, stepx, go, gx, gy, pm, real, more;\n\t"                                   \
+            ".reg .pred ky, ok, adv, cont, stepx, go, gx, gy, pm, real, more, oob;\n\t"                              \
             ".reg .f32 ak, bk, dh, oh, t, pi, pj, tn, lim, sa;\n\t"                                                  \
             ".reg .b32 tb, bb, st;\n\t"                                                                              \
             ".reg .b64 a;\n\t"                                                                                       \
@@ -499,6 +541,7 @@ struct GridWalk {
             "or.pred more, cont, !adv;\n\t"                                                                          \
             FMGI_WALK_STEP                                                                                           \
             "selp.b32 %14, %4, %2, go;\n\t"                                                                          \
+            FMGI_WALK_BOUNDS                                                                                         \
             "mul.wide.s32 a, %14, 32;\n\t"                                                                           \
             "add.s64 a, a, %18;\n\t"                                                                                 \
             "@more ld.global.nc.v8.b32 {%8, %9, %10, %11, %12, %13, %2, %3}, [a];\n\t"                               \
@@ -510,7 +553,7 @@ struct GridWalk {
             : "+f"(best), "+r"(win), "+r"(r), "+r"(rend), "+r"(ci), "+f"(tmx), "+f"(tmy), "+r"(tests), "+f"(q0.x),   \
               "+f"(q0.y), "+f"(q0.z), "+f"(q0.w), "+f"(qc), "+r"(qtag), "+r"(cur), "=r"(more), "=r"(misc)            \
             : "r"(p.one), "l"(p.grid_table), "f"(ax), "f"(ay), "f"(bx), "f"(by), "f"(ox), "f"(oy), "f"(oz), "f"(dx),     \
-              "f"(dy), "f"(dz), "f"(g.cell), "f"(t_exit), "r"(sx), "r"(sy))
+              "f"(dy), "f"(dz), "f"(g.cell), "f"(t_exit), "r"(sx), "r"(sy) FMGI_WALK_BOUNDS_OPERAND)
         // counting variant only (fmgi_options.count_tests): rectangle tests, dummy heads (c = NaN) excluded
 #define FMGI_WALK_COUNT "setp.eq.f32 real, %12, %12;\n\t@real add.u32 %7, %7, 1;\n\t"
 #define FMGI_WALK_MISC_TEST "and.b32 st, %13, 0x40000000;\n\tsetp.ne.u32 pm, st, 0;\n\tand.pred ok, ok, !pm;\n\t@pm mov.b32 %16, %14;\n\t"
@@ -531,6 +574,11 @@ struct GridWalk {
                 }
             } while (misc >= 0 && more);
         }
+#ifdef FMGI_CHECKED
+        if (misc == -2) fmgi_report(p, 5);
+#endif
+#undef FMGI_WALK_BOUNDS
+#undef FMGI_WALK_BOUNDS_OPERAND
 #undef FMGI_WALK_COUNT
 #undef FMGI_WALK_MISC_TEST
 #undef FMGI_WALK_SEL_DO
@@ -546,7 +594,7 @@ struct GridWalk {
     {
         int id = -1;
         t_out = best;
-        if (win >= 0) {
+        if (win >= 0 && FMGI_CHECK(p, (unsigned)win < p.grid_records, 6)) {
             const float2 q1 = ldg2(p.grid_table + 2 * win + 1);
             const unsigned tag = __float_as_uint(q1.y);
             if ((tag & (kTagMisc | kTagHorizontal)) == (kTagMisc | kTagHorizontal)) {

@@ -88,7 +88,9 @@ __device__ __forceinline__ void walk_pool(const TraceParams &p, float4 *wa, floa
             const int rank = __popc(idle & lt_mask);
             if (!more && rank < avail) {
                 slot = next + rank;
-                const float4 a = wa[slot], b = wb[slot], c = wc[slot];
+                const float4 a = wa[slot], b = wb[slot];
+                float4 c = wc[slot];
+                if (!FMGI_CHECK(p, (unsigned)__float_as_int(c.y) < p.grid_records, 11)) c.y = __int_as_float(g.walk_base);
                 ox = a.x; oy = a.y; oz = a.z; tmx = a.w;
                 dx = b.x; dy = b.y; dz = b.z; tmy = b.w;
                 best = c.x; ci = __float_as_int(c.y); ax = c.z; ay = c.w;
@@ -215,7 +217,7 @@ __global__ void __launch_bounds__(kPoolThreads, kMinBlocks) k_trace_pool(const T
                 float t;
                 hit_id = w.finish(p, px, py, pz, dx, dy, dz, t);
                 n_rays++;
-                if (hit_id < 0) {
+                if (hit_id < 0 || !FMGI_CHECK(p, (unsigned)hit_id < p.num_walls, 8)) {
                     alive = false;                                   // photonmap.c:200-201: photon leaves the flat
                 } else {
                     px = __fadd_rn(px, __fmul_rn(dx, t));            // photonmap.c:208
@@ -233,7 +235,7 @@ __global__ void __launch_bounds__(kPoolThreads, kMinBlocks) k_trace_pool(const T
                     } else {
                         n_mirror++;
                     }
-                    dep = true;
+                    dep = FMGI_CHECK(p, (unsigned)idx < p.num_texels, 9);
                     depth++;
                     n_deposits++;
                     if (depth == p.max_depth) alive = false;         // photonmap.c:187

@@ -11,12 +11,14 @@ Names follow the reference: ``Geometry`` (geometry.h:7-15), ``Rectangle`` record
 from __future__ import annotations
 
 import ctypes as C
+import os
 from pathlib import Path
 
 import numpy as np
 
 _PKG = Path(__file__).resolve().parent.parent
-LIB_PATH = _PKG / "lib" / "libfmgi_cuda.so"
+# FMGI_LIB selects another build of the library, e.g. lib/libfmgi_cuda_checked.so (bounds-checked kernels)
+LIB_PATH = Path(os.environ.get("FMGI_LIB") or (_PKG / "lib" / "libfmgi_cuda.so"))
 
 # rectangle.h:19-26 — 80 bytes, 16-byte aligned
 RECT_DTYPE = np.dtype(
@@ -60,11 +62,14 @@ class Stats(C.Structure):
         ("total_ms", C.c_double),
         ("num_gpus", C.c_int32), ("tier", C.c_int32), ("num_sms", C.c_int32), ("sm_clock_khz", C.c_int32),
         ("init_ms", C.c_double), ("prepare_ms", C.c_double), ("grid_build_ms", C.c_double), ("upload_ms", C.c_double),
-        ("pool_rays", C.c_int32), ("reserved0", C.c_int32),
+        ("pool_rays", C.c_int32), ("bounds_violations", C.c_int32),
     ]
 
     def as_dict(self):
-        return {n: getattr(self, n) for n, _ in self._fields_}
+        d = {n: getattr(self, n) for n, _ in self._fields_}
+        if d["bounds_violations"] > 0:
+            raise FmgiError(f"bounds-checked build: {d['bounds_violations']} index violations")
+        return d
 
 
 EXPORTS = [

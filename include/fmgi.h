@@ -112,7 +112,8 @@ typedef struct fmgi_stats {
     double   grid_build_ms;   /* floor-plan grid: host classification + per-cell assembly (host, or device for >= 2048 colliders) */
     double   upload_ms;       /* table upload + kernel attribute queries per GPU */
     int32_t  pool_rays;       /* 0: k_trace ran; K > 0: the pooled kernel (trace_pool.cuh) with K rays per lane */
-    int32_t  reserved0;
+    int32_t  bounds_violations; /* -1: regular build; >= 0: lib/libfmgi_cuda_checked.so (-DFMGI_CHECKED) - data-dependent
+                                 indices (grid records, shading records, texels) found outside their tables */
 } fmgi_stats;
 
 void        fmgi_default_options(fmgi_options *opt);

@@ -577,6 +577,24 @@ def test_device_grid_table_equals_host(fmgi, scene, synth800, synth4000, monkeyp
     s.close()
 
 
+def test_bounds_checked_build_reports_violations(fmgi, scene, monkeypatch):
+    """lib/libfmgi_cuda_checked.so (-DFMGI_CHECKED, the stand-in for compute-sanitizer memcheck, which is closed on the
+    GPU pool): run the suite with FMGI_LIB pointing at it and every data-dependent index is compared with its table
+    size.  This test checks the checker: with FMGI_CHECK_SELFTEST the atlas is declared half its size, so deposits
+    into the upper half must be counted and refused; the regular build reports -1 (no checks compiled in)."""
+    s = fmgi.DeviceScene(scene.walls, scene.windows, scene.lights, scene.num_texels)
+    _, st = gpu_bake(s, 2000)
+    if st["bounds_violations"] < 0:
+        s.close()
+        pytest.skip("regular build: bounds checks are compiled out (run with FMGI_LIB=.../libfmgi_cuda_checked.so)")
+    assert st["bounds_violations"] == 0
+    monkeypatch.setenv("FMGI_CHECK_SELFTEST", "1")
+    with pytest.raises(fmgi.FmgiError, match="index violations"):
+        gpu_bake(s, 2000)
+    monkeypatch.delenv("FMGI_CHECK_SELFTEST")
+    s.close()
+
+
 def test_chunk_size_does_not_change_the_sample_set(dev_scene, monkeypatch):
     """Small bakes are handed out in smaller photon chunks (32..256 per warp claim) so that every SM gets work;
     the chunk size only changes who traces which photon."""
