@@ -254,6 +254,9 @@ def reference_app_wall_time():
             if best is None or dt < best:
                 best, out = dt, r.stdout
         res = {"wall_s": best}
+        m2 = re.search(rb"\[INF\] fmgi exit_begin ([0-9.]+) ms", out)
+        if m2:
+            res["exit_begin_ms"] = float(m2.group(1))
         m = re.search(rb"\[INF\] fmgi breakdown: (.*)", out)
         if m:
             for part in m.group(1).decode().split(","):

@@ -1050,6 +1050,10 @@ void performGlobalIlluminationCl(struct Geometry *geo, int numSamplesPerArea)
                (unsigned long long)st.rays, (unsigned long long)st.mirror_bounces,
                (unsigned long long)st.rect_tests, st.h2d_ms, st.d2h_ms, st.reduce_ms,
                (unsigned long long)st.kernel_launches);
+    if (verbose >= 2) {
+        // when the caller's own exit begins (tiles written, geometry freed): what follows is process teardown
+        atexit([] { printf("[INF] fmgi exit_begin %.1f ms\n", ms_since_process_start()); fflush(stdout); });
+    }
     if (verbose >= 2)
         // where the call's time went; before_call = process start -> this call (loader, parseLayout), from /proc
         printf("[INF] fmgi breakdown: before_call %.1f ms, init %.1f ms, tables %.2f ms, upload %.2f ms, trace %.2f ms, "
