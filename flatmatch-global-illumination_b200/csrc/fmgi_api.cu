@@ -578,13 +578,16 @@ int fmgi_scene_trace(fmgi_scene *s, void *atlas_dev, int spa, const fmgi_options
     if (passes > 1 && !s->d_scratch)
         FMGI_CUDA(pool.alloc((void **)&s->d_scratch, atlas_bytes ? atlas_bytes : 16, false));
 
-    // Chunk size: kChunkPhotons for big bakes; a small bake is cut finer so that every resident warp of every SM
-    // gets a few chunks (a 1e6-photon shard in 256-photon chunks is 3906 chunks for 4736 resident warps, each
-    // grinding its chunk serially: the kernel then takes 0.23 ms for 0.03 ms of work).
+    // Chunk size: kChunkPhotons for big bakes; a smaller bake is cut finer, down to 32 photons, so that every
+    // resident warp gets at least 32 chunks: the last chunk of a warp is a serial tail (256 photons on 32 lanes are
+    // 8 photons x 5 rays per lane) that the other warps cannot help with.  Measured on example.png, 8 bounces:
+    // 1.25e7 photons 2.80 ms with 256-photon chunks, 2.71 ms with 64; 1.25e6 photons 0.44 vs 0.33 ms (32); at 1e8
+    // photons the big chunk wins by 0.7 % (fewer claims).  Round 1 used 256 always and sized the grid by the
+    // chunk count: a 1.25e5-photon shard then ran 61 CTAs with one serial chunk per warp (0.23 ms, now 0.07).
     const unsigned long long wave = (unsigned long long)s->num_sms * s->blocks_per_sm;
     const unsigned long long per_pass = total_all / (unsigned long long)passes;
     int chunk = kChunkPhotons;
-    while (chunk > kMinChunkPhotons && per_pass / chunk < 4 * wave * (kTraceThreads / 32)) chunk >>= 1;
+    while (chunk > kMinChunkPhotons && per_pass / chunk < 32 * wave * (kTraceThreads / 32)) chunk >>= 1;
     if (const char *v = getenv("FMGI_CHUNK")) { const int c = atoi(v); if (c >= 1 && c <= 65536) chunk = c; }   // tuning knob
     fmgi_options op = o;
     op.num_shards = o.num_shards * passes;
