@@ -450,8 +450,12 @@ int scene_from_build(fmgi_scene **out, std::shared_ptr<HostBuild> b, const fmgi_
         FMGI_CUDA(with_pool_kernel(pool_k, [&](auto kernel, int k) {
             const size_t smem = (size_t)(kPoolThreads / 32) * 32 * k * kPoolSlotBytes;
             cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-            if (e == cudaSuccess)
-                e = cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+            // shared-memory carve-out: just what the resident CTAs need (FMGI_POOL_CARVEOUT = percent overrides) - the
+            // rest of the 256 KB stays L1 for the grid table
+            int carve = -1;
+            if (const char *v = getenv("FMGI_POOL_CARVEOUT")) carve = atoi(v);
+            if (e == cudaSuccess && carve >= 0)
+                e = cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
             if (e == cudaSuccess)
                 e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&sp->pool_blocks_per_sm, kernel, kPoolThreads, smem);
             return e;
