@@ -19,6 +19,7 @@
 #include "grid_build.cuh"
 #include "trace_core.cuh"
 #include "trace_pool.cuh"
+#include "tile_kernels.cuh"
 
 using namespace fmgi;
 
@@ -148,6 +149,7 @@ struct fmgi_scene {
     float4 *d_scratch = nullptr;                // per-pass fp32 atlas when a bake needs several passes
     TileWall *d_tile_walls = nullptr;           // tone-map wall table (fmgi_scene_tonemap)
     TileWall *h_tile_walls = nullptr;           // pinned staging for it
+    PngWall *d_png_walls = nullptr, *h_png_walls = nullptr;   // PNG layout of the tiles (fmgi_scene_tiles_png)
     float *d_ao = nullptr;                      // ambient occlusion: widths, heights (3 floats per wall), then float4 directions
     AoWall *d_ao_walls = nullptr;
     unsigned long long *d_counters = nullptr;   // 4 counters + work counter
@@ -524,6 +526,7 @@ void fmgi_scene_destroy(fmgi_scene *s)
     pool.free(s->d_grid_table);
     pool.free(s->d_jobs); pool.free(s->d_counters); pool.free(s->d_scratch);
     pool.free(s->d_tile_walls); pool.free(s->h_tile_walls);
+    pool.free(s->d_png_walls); pool.free(s->h_png_walls);
     pool.free(s->d_ao); pool.free(s->d_ao_walls);
     pool.free(s->h_jobs); pool.free(s->h_counters);
     if (s->ev_start) cudaEventDestroy(s->ev_start);
@@ -703,6 +706,8 @@ int fmgi_scene_sync(fmgi_scene *s, fmgi_stats *stats)
 
 namespace {
 
+int tonemap_impl(fmgi_scene *s, const void *atlas_dev, int spa, int tint_extra, void *out_dev, cudaStream_t st, bool png);
+
 // ---- process-wide per-GPU runtime: streams, events and peer mappings are created once ---------------------
 //
 // performGlobalIlluminationCl is a one-shot call, but a process that bakes more than once (a harness, a
@@ -772,7 +777,7 @@ void parallel_for(int n, Fn fn)
 //      (G-1)/G of one atlas at the same time instead of GPU 0 pulling G-1 atlases;
 //   3. every GPU writes its slice straight back into the caller's atlas over its own PCIe link.
 int bake_impl(struct Geometry *geo_, int spa, const fmgi_options *opt, fmgi_stats *stats, uint8_t *tiles_out,
-              int tint_extra, bool one_shot = false)
+              int tint_extra, bool one_shot = false, bool tiles_png = false)
 {
     fmgi_geometry *geo = reinterpret_cast<fmgi_geometry *>(geo_);
     if (!geo) return fail(FMGI_ERR_ARG, "geo is NULL");
@@ -940,11 +945,12 @@ int bake_impl(struct Geometry *geo_, int spa, const fmgi_options *opt, fmgi_stat
             if (gpus[q].hi > gpus[q].lo)
                 e = cudaMemcpyPeerAsync(g0.atlas + gpus[q].lo, g0.device, gpus[q].atlas + gpus[q].lo, gpus[q].device,
                                         (gpus[q].hi - gpus[q].lo) * sizeof(float4), dv.trace);
-        const uint64_t tile_bytes = fmgi_tile_bytes(geo->walls, geo->numWalls);
+        const uint64_t tile_bytes = tiles_png ? fmgi_tile_png_bytes(geo->walls, geo->numWalls, nullptr)
+                                              : fmgi_tile_bytes(geo->walls, geo->numWalls);
         unsigned char *d_rgb = nullptr;
         if (e == cudaSuccess) e = MemPool::get().alloc((void **)&d_rgb, tile_bytes ? tile_bytes : 16, false);
         if (e == cudaSuccess) {
-            if (fmgi_scene_tonemap(g0.scene, g0.atlas, spa, tint_extra, d_rgb, dv.trace) != FMGI_OK) e = cudaErrorUnknown;
+            if (tonemap_impl(g0.scene, g0.atlas, spa, tint_extra, d_rgb, dv.trace, tiles_png) != FMGI_OK) e = cudaErrorUnknown;
             cudaSetDevice(g0.device);
         }
         if (e == cudaSuccess) e = cudaMemcpyAsync(tiles_out, d_rgb, tile_bytes, cudaMemcpyDeviceToHost, dv.trace);
@@ -1030,6 +1036,13 @@ int fmgi_bake_tiles(struct Geometry *geo, int spa, const fmgi_options *opt, int 
     return bake_impl(geo, spa, opt, stats, rgb_out, tint_extra);
 }
 
+int fmgi_bake_tiles_png(struct Geometry *geo, int spa, const fmgi_options *opt, int tint_extra, uint8_t *png_out,
+                        fmgi_stats *stats)
+{
+    if (!png_out) return fail(FMGI_ERR_ARG, "png_out is NULL");
+    return bake_impl(geo, spa, opt, stats, png_out, tint_extra, false, true);
+}
+
 // ---- the reference boundary (global_illumination_cl.h:10) -------------------------------------------------
 
 void performGlobalIlluminationCl(struct Geometry *geo, int numSamplesPerArea)
@@ -1078,23 +1091,30 @@ uint64_t fmgi_tile_bytes(const fmgi_rect *walls, int num_walls)
     return n;
 }
 
-int fmgi_scene_tonemap(fmgi_scene *s, const void *atlas_dev, int spa, int tint_extra, void *rgb_dev, void *cuda_stream)
+} // extern "C"
+
+namespace {
+
+// Device tone-map of every wall's base level: packed RGB (png == false) or complete PNG files (png == true).
+int tonemap_impl(fmgi_scene *s, const void *atlas_dev, int spa, int tint_extra, void *out_dev, cudaStream_t st, bool png)
 {
-    if (!s || !atlas_dev || !rgb_dev) return fail(FMGI_ERR_ARG, "scene, atlas or output is NULL");
+    if (!s || !atlas_dev || !out_dev) return fail(FMGI_ERR_ARG, "scene, atlas or output is NULL");
     DeviceGuard guard(s->device);
-    cudaStream_t st = (cudaStream_t)cuda_stream;
     const int W = s->host.num_walls;
     MemPool &pool = MemPool::get();
     if (!s->d_tile_walls) {
         FMGI_CUDA(pool.alloc((void **)&s->d_tile_walls, (W ? W : 1) * sizeof(TileWall), false));
         FMGI_CUDA(pool.alloc((void **)&s->h_tile_walls, (W ? W : 1) * sizeof(TileWall), true));
+        FMGI_CUDA(pool.alloc((void **)&s->d_png_walls, (W ? W : 1) * sizeof(PngWall), false));
+        FMGI_CUDA(pool.alloc((void **)&s->h_png_walls, (W ? W : 1) * sizeof(PngWall), true));
     } else {
         FMGI_CUDA(cudaStreamSynchronize(st));                     // pinned staging is reused
     }
-    long long pixels = 0;
+    long long pixels = 0, file_off = 0;
     for (int i = 0; i < W; i++) {
         const ShadeRect &sh = s->host.shade[i];
-        const int tiles = (sh.tiles & 0xffff) * (sh.tiles >> 16);
+        const int tw = sh.tiles & 0xffff, th = sh.tiles >> 16;
+        const int tiles = tw * th;
         TileWall &t = s->h_tile_walls[i];
         t.base = sh.base;
         t.first = (int32_t)pixels;
@@ -1102,18 +1122,54 @@ int fmgi_scene_tonemap(fmgi_scene *s, const void *atlas_dev, int spa, int tint_e
         t.scale = (float)(0.35 * tiles_per_sample);                                // main.c:77: double product, float arg
         t.is_floor = s->build->wall_floor[i];
         pixels += tiles;
+        PngWall &pw = s->h_png_walls[i];
+        pw.file_off = file_off; pw.width = tw; pw.height = th;
+        file_off += (long long)png_file_bytes(tw, th);
     }
     if (pixels > 0x7fffffffLL) return fail(FMGI_ERR_UNSUPPORTED, "more than 2^31 tile pixels");
     if (pixels == 0) return FMGI_OK;
     FMGI_CUDA(cudaMemcpyAsync(s->d_tile_walls, s->h_tile_walls, W * sizeof(TileWall), cudaMemcpyHostToDevice, st));
     long long blocks = (pixels + 255) / 256;
     if (blocks > (long long)s->num_sms * 16) blocks = (long long)s->num_sms * 16;
-    k_tonemap<<<(int)blocks, 256, 0, st>>>(reinterpret_cast<const float4 *>(atlas_dev), s->d_tile_walls, W, pixels,
-                                         tint_extra, reinterpret_cast<unsigned char *>(rgb_dev));
-    s->launches++;
+    if (!png) {
+        k_tonemap<false><<<(int)blocks, 256, 0, st>>>(reinterpret_cast<const float4 *>(atlas_dev), s->d_tile_walls, W, pixels,
+                                                    tint_extra, reinterpret_cast<unsigned char *>(out_dev), nullptr);
+        s->launches++;
+    } else {
+        FMGI_CUDA(cudaMemcpyAsync(s->d_png_walls, s->h_png_walls, W * sizeof(PngWall), cudaMemcpyHostToDevice, st));
+        k_tonemap<true><<<(int)blocks, 256, 0, st>>>(reinterpret_cast<const float4 *>(atlas_dev), s->d_tile_walls, W, pixels,
+                                                   tint_extra, reinterpret_cast<unsigned char *>(out_dev), s->d_png_walls);
+        k_png_finish<<<(W + 255) / 256, 256, 0, st>>>(s->d_png_walls, W, reinterpret_cast<unsigned char *>(out_dev));
+        s->launches += 2;
+    }
     s->note_stream(st);
     FMGI_CUDA(cudaGetLastError());
     return FMGI_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int fmgi_scene_tonemap(fmgi_scene *s, const void *atlas_dev, int spa, int tint_extra, void *rgb_dev, void *cuda_stream)
+{
+    return tonemap_impl(s, atlas_dev, spa, tint_extra, rgb_dev, (cudaStream_t)cuda_stream, false);
+}
+
+uint64_t fmgi_tile_png_bytes(const fmgi_rect *walls, int num_walls, uint64_t *offsets_out)
+{
+    uint64_t n = 0;
+    for (int i = 0; walls && i < num_walls; i++) {
+        if (offsets_out) offsets_out[i] = n;
+        n += png_file_bytes(walls[i].lightmap[1], walls[i].lightmap[2]);
+    }
+    if (offsets_out && walls) offsets_out[num_walls] = n;
+    return n;
+}
+
+int fmgi_scene_tiles_png(fmgi_scene *s, const void *atlas_dev, int spa, int tint_extra, void *png_dev, void *cuda_stream)
+{
+    return tonemap_impl(s, atlas_dev, spa, tint_extra, png_dev, (cudaStream_t)cuda_stream, true);
 }
 
 // ---- ambient occlusion --------------------------------------------------------------------

@@ -349,59 +349,6 @@ __global__ void __launch_bounds__(kTraceThreads) k_ambient_occlusion(const Trace
     }
 }
 
-// ---- tile post-processing ---------------------------------------------------------------
-//
-// Device version of what the caller does to the lightmap before it becomes tiles/tile_N.png:
-// main.c:68-79 (texel *= 0.35 * tiles / (area * samplesPerArea)) and saveAs_core (rectangle.c:293-336:
-// tone-map 1 - exp(-2 L) at constant chroma, x255, clamp, floor tint).  One thread per base-level
-// texel; every implicit promotion of the reference is kept (double luminance sum and exp, float
-// ratio, uint8 x double floor tint) with explicitly rounded operations so that nothing is contracted.
-struct TileWall {
-    int32_t base;        // atlas index of the wall's base level
-    int32_t first;       // index of its first texel in the packed RGB output
-    float scale;         // (float)(0.35 * tilesPerSample), main.c:73-77
-    int32_t is_floor;    // rectangle.c:317
-};
-
-__device__ __forceinline__ unsigned char tile_clamp(float d)          // rectangle.c:287-292
-{
-    if (d < 0.0f) d = 0.0f;
-    if (d > 255.0f) d = 255.0f;
-    return (unsigned char)__float2uint_rz(d);                          // NaN (black texel, 0/0) -> 0
-}
-
-__global__ void k_tonemap(const float4 *__restrict__ atlas, const TileWall *__restrict__ walls, int num_walls,
-                          long long num_pixels, int tint_extra, unsigned char *__restrict__ rgb)
-{
-    for (long long g = blockIdx.x * (long long)blockDim.x + threadIdx.x; g < num_pixels;
-         g += (long long)gridDim.x * blockDim.x) {
-        int lo = 0, hi = num_walls - 1;                                // wall whose pixel range holds g
-        while (lo < hi) {
-            const int mid = (lo + hi + 1) >> 1;
-            if ((long long)walls[mid].first <= g) lo = mid; else hi = mid - 1;
-        }
-        const TileWall w = walls[lo];
-        const float4 t = atlas[w.base + (int)(g - w.first)];
-        float r = __fmul_rn(t.x, w.scale), gg = __fmul_rn(t.y, w.scale), b = __fmul_rn(t.z, w.scale);
-        const float lum = (float)__dadd_rn(__dadd_rn(__dmul_rn(0.2126, (double)r), __dmul_rn(0.7152, (double)gg)),
-                                           __dmul_rn(0.0722, (double)b));                  // rectangle.c:277
-        const float perceptive = (float)__dsub_rn(1.0, exp((double)__fmul_rn(-2.0f, lum)));   // rectangle.c:269
-        const float q = __fdiv_rn(perceptive, lum);
-        r = __fmul_rn(r, q); gg = __fmul_rn(gg, q); b = __fmul_rn(b, q);
-        unsigned char d0 = tile_clamp(__fmul_rn(r, 255.0f)), d1 = tile_clamp(__fmul_rn(gg, 255.0f)),
-                      d2 = tile_clamp(__fmul_rn(b, 255.0f));
-        if (w.is_floor) {                                              // rectangle.c:317-334
-            d1 = (unsigned char)__double2uint_rz(__dmul_rn((double)d1, 0.95));
-            d2 = (unsigned char)__double2uint_rz(__dmul_rn((double)d2, 0.9));
-            if (tint_extra) {
-                d1 = (unsigned char)__float2uint_rz(__fmul_rn((float)d1, 0.95f));
-                d2 = (unsigned char)__float2uint_rz(__fmul_rn((float)d2, 0.9f));
-            }
-        }
-        rgb[3 * g] = d0; rgb[3 * g + 1] = d1; rgb[3 * g + 2] = d2;
-    }
-}
-
 // atlas += scratch (colour lanes only): folds one fp32 accumulation pass into the caller's atlas.
 __global__ void k_accumulate(float4 *__restrict__ atlas, const float4 *__restrict__ scratch, size_t n)
 {

@@ -80,7 +80,7 @@ EXPORTS = [
     "fmgi_bake", "fmgi_scene_create", "fmgi_scene_destroy", "fmgi_scene_trace", "fmgi_scene_sync",
     "fmgi_scene_photon_count", "fmgi_probe_closest_hit", "fmgi_probe_tile_ids", "fmgi_probe_philox",
     "fmgi_probe_sample_dirs", "fmgi_probe_paths", "fmgi_probe_deposit_peak", "fmgi_probe_philox2x32",
-    "fmgi_probe_grid_table",
+    "fmgi_probe_grid_table", "fmgi_tile_png_bytes", "fmgi_scene_tiles_png", "fmgi_bake_tiles_png",
 ]
 
 _lib = None
@@ -118,6 +118,10 @@ def lib() -> C.CDLL:
     L.fmgi_tile_bytes.argtypes = [C.c_void_p, C.c_int]
     L.fmgi_scene_tonemap.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
     L.fmgi_bake_tiles.argtypes = [C.POINTER(Geometry), C.c_int, C.POINTER(Options), C.c_int, C.c_void_p, C.POINTER(Stats)]
+    L.fmgi_bake_tiles_png.argtypes = [C.POINTER(Geometry), C.c_int, C.POINTER(Options), C.c_int, C.c_void_p, C.POINTER(Stats)]
+    L.fmgi_tile_png_bytes.restype = C.c_uint64
+    L.fmgi_tile_png_bytes.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+    L.fmgi_scene_tiles_png.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
     L.fmgi_ambient_occlusion.argtypes = [C.POINTER(Geometry), C.POINTER(Options)]
     L.fmgi_geosphere.argtypes = [C.c_int, C.c_void_p, C.c_int]
     L.fmgi_scene_ambient_occlusion.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
@@ -208,6 +212,25 @@ def bake_tiles(geo: Geometry, walls: np.ndarray, num_samples_per_area: int, tint
     return out[:n], st.as_dict()
 
 
+def tile_png_layout(walls: np.ndarray):
+    """(total bytes, offsets[num_walls + 1]) of the PNG files fmgi_bake_tiles_png / fmgi_scene_tiles_png produce."""
+    off = np.zeros(len(walls) + 1, dtype=np.uint64)
+    n = int(lib().fmgi_tile_png_bytes(walls.ctypes.data, len(walls), off.ctypes.data))
+    return n, off
+
+
+def bake_tiles_png(geo: Geometry, walls: np.ndarray, num_samples_per_area: int, tint_extra: int = 0, **opts):
+    """fmgi_bake_tiles_png: bake, tone-map and assemble one PNG file per wall on the device.
+    Returns (buffer, offsets, counters); wall i's file is buffer[offsets[i]:offsets[i + 1]]."""
+    o = options(**opts)
+    st = Stats()
+    n, off = tile_png_layout(walls)
+    out = np.zeros(max(n, 1), dtype=np.uint8)
+    _check(lib().fmgi_bake_tiles_png(C.byref(geo), int(num_samples_per_area), C.byref(o), int(tint_extra),
+                                     out.ctypes.data, C.byref(st)))
+    return out[:n], off, st.as_dict()
+
+
 def geosphere(iterations: int = 4) -> np.ndarray:
     n = lib().fmgi_geosphere(int(iterations), None, 0)
     out = np.zeros((n, 3), dtype=np.float32)
@@ -265,6 +288,11 @@ class DeviceScene:
         """fmgi_scene_tonemap: RAW device atlas -> packed RGB tiles on the device."""
         _check(lib().fmgi_scene_tonemap(self._h, C.c_void_p(atlas_ptr), int(spa), int(tint_extra),
                                         C.c_void_p(rgb_ptr), C.c_void_p(stream)))
+
+    def tiles_png(self, atlas_ptr: int, spa: int, png_ptr: int, tint_extra: int = 0, stream: int = 0) -> None:
+        """fmgi_scene_tiles_png: RAW device atlas -> one complete PNG file per wall, on the device."""
+        _check(lib().fmgi_scene_tiles_png(self._h, C.c_void_p(atlas_ptr), int(spa), int(tint_extra),
+                                          C.c_void_p(png_ptr), C.c_void_p(stream)))
 
     def tile_bytes(self) -> int:
         return int(lib().fmgi_tile_bytes(self.walls.ctypes.data, len(self.walls)))

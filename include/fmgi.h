@@ -171,6 +171,17 @@ int fmgi_scene_tonemap(fmgi_scene *scene, const void *atlas_dev, int numSamplesP
 int fmgi_bake_tiles(struct Geometry *geo, int numSamplesPerArea, const fmgi_options *opt, int tintExtra,
                     uint8_t *rgb_out, fmgi_stats *stats);
 
+/* The same tiles as complete PNG FILES assembled on the device (rectangle.c:338-346 saveAs + png_helper.c:255
+ * write_png_file): 8-bit RGB, filter 0, zlib stream of stored blocks (no compression, so the layout is known in
+ * advance), Adler-32 and CRC-32 computed on the GPU.  Wall i's file is bytes [offsets[i], offsets[i + 1]) of the
+ * output; fmgi_tile_png_bytes returns the total and fills offsets_out (num_walls + 1 entries, may be NULL).  A decoder
+ * reads the pixels write_png_file would have written. */
+uint64_t fmgi_tile_png_bytes(const fmgi_rect *walls, int num_walls, uint64_t *offsets_out);
+int fmgi_scene_tiles_png(fmgi_scene *scene, const void *atlas_dev, int numSamplesPerArea, int tintExtra,
+                         void *png_dev, void *cuda_stream);
+int fmgi_bake_tiles_png(struct Geometry *geo, int numSamplesPerArea, const fmgi_options *opt, int tintExtra,
+                        uint8_t *png_out, fmgi_stats *stats);
+
 /* ---- extension: ambient occlusion on the device ---------------------------- */
 
 /* performAmbientOcclusionNative (global_illumination_native.h:16, photonmap.c:436-491) on the closest-hit

@@ -793,6 +793,67 @@ def test_device_tonemap_is_byte_exact(fmgi, dev_scene, oracle, scene, tint):
     assert (got > 0).mean() > 0.9
 
 
+def test_device_png_tiles_decode_to_the_packed_tiles(fmgi, dev_scene, scene, synth800):
+    """fmgi_scene_tiles_png: every wall's tile as a complete PNG file assembled on the GPU (stored-block zlib stream,
+    Adler-32 and CRC-32 computed on the device).  PIL - which checks both checksums - must decode each file to exactly
+    the RGB bytes fmgi_scene_tonemap packs, i.e. to what the reference's saveAs hands to write_png_file
+    (rectangle.c:338-346); a tile taller than one stored block (65535 raw bytes) is part of the case."""
+    import io
+
+    import torch
+    from PIL import Image
+
+    from fmgi import layout
+
+    big_walls, big_texels = layout.retile(synth800.walls, 3000.0)       # some tiles above 65535 raw bytes
+    big = fmgi.DeviceScene(big_walls, synth800.windows, synth800.lights, big_texels)
+    for s, spa, tint in ((dev_scene, 30000, 0), (dev_scene, 30000, 1), (big, 3000, 0)):
+        atlas = device_atlas(s.num_texels)
+        stream = torch.cuda.current_stream().cuda_stream
+        s.trace(atlas.data_ptr(), spa, stream=stream, max_depth=8, seed=3)
+        s.sync()
+        rgb = torch.zeros(s.tile_bytes(), dtype=torch.uint8, device="cuda")
+        s.tonemap(atlas.data_ptr(), spa, rgb.data_ptr(), tint_extra=tint, stream=stream)
+        total, off = fmgi.tile_png_layout(s.walls)
+        png = torch.zeros(total, dtype=torch.uint8, device="cuda")
+        s.tiles_png(atlas.data_ptr(), spa, png.data_ptr(), tint_extra=tint, stream=stream)
+        torch.cuda.synchronize()
+        want, files = rgb.cpu().numpy(), png.cpu().numpy()
+        at, raw_max = 0, 0
+        for i, w in enumerate(s.walls):
+            tw, th = int(w["lightmapSetup"][1]), int(w["lightmapSetup"][2])
+            raw_max = max(raw_max, th * (3 * tw + 1))
+            img = Image.open(io.BytesIO(files[int(off[i]): int(off[i + 1])].tobytes()))
+            img.load()
+            assert img.size == (tw, th) and img.mode == "RGB", i
+            assert np.array_equal(np.asarray(img).reshape(-1), want[at: at + 3 * tw * th]), i
+            at += 3 * tw * th
+        assert at == want.size
+        if s is big:
+            assert raw_max > 65535
+    big.close()
+
+
+def test_bake_tiles_png_through_the_host_call(fmgi, scene):
+    import io
+
+    from PIL import Image
+
+    spa = 20000
+    tex = fmgi.aligned_texels(scene.num_texels)
+    geo = fmgi.make_geometry(scene.walls, scene.windows, scene.lights, tex)
+    files, off, st = fmgi.bake_tiles_png(geo, scene.walls, spa, tint_extra=0, seed=6, max_depth=8)
+    rgb, _ = fmgi.bake_tiles(geo, scene.walls, spa, tint_extra=0, seed=6, max_depth=8)
+    assert st["deposits"] > 0 and not tex.any()                     # the float atlas is not written back
+    at = 0
+    for i, w in enumerate(scene.walls):
+        tw, th = int(w["lightmapSetup"][1]), int(w["lightmapSetup"][2])
+        img = np.asarray(Image.open(io.BytesIO(files[int(off[i]): int(off[i + 1])].tobytes()))).reshape(-1)
+        d = np.abs(img.astype(np.int32) - rgb[at: at + 3 * tw * th].astype(np.int32))
+        assert d.max() <= 1                                          # two bakes: float atomics order differs
+        at += 3 * tw * th
+
+
 def test_bake_tiles_returns_packed_tiles_only(fmgi, oracle, scene):
     spa = 20000
     tex = fmgi.aligned_texels(scene.num_texels)
