@@ -811,7 +811,7 @@ int bake_impl(struct Geometry *geo_, int spa, const fmgi_options *opt, fmgi_stat
         float4 *init = nullptr;       // the caller's values of this GPU's slice
         float4 *staged = nullptr;     // peers' slices copied over when no peer mapping exists
         size_t lo = 0, hi = 0;        // slice [lo, hi) in texels
-        fmgi_stats st;
+        fmgi_stats st = {};
         int rc = FMGI_OK;
         std::string err;
         double init_ms = 0, create_ms = 0, sync_ms = 0, alloc_ms = 0;
@@ -826,7 +826,6 @@ int bake_impl(struct Geometry *geo_, int spa, const fmgi_options *opt, fmgi_stat
         gpus[g].lo = std::min(num_texels, units * g / G * 64);
         gpus[g].hi = std::min(num_texels, units * (g + 1) / G * 64);
     }
-    memset(&gpus[0].st, 0, sizeof(fmgi_stats));
 
     // ---- phase 1: upload + trace ---------------------------------------------------------------------------
     parallel_for(G, [&](int g) {
@@ -1264,6 +1263,11 @@ int fmgi_ambient_occlusion(struct Geometry *geo_, const fmgi_options *opt)
     }
     MemPool::get().free(atlas);
     fmgi_scene_destroy(scene);
+    {
+        size_t keep_mb = 8192;                     // as fmgi_bake: bounded cache per device
+        if (const char *v = getenv("FMGI_CACHE_MB")) keep_mb = (size_t)strtoull(v, nullptr, 0);
+        MemPool::get().trim(keep_mb << 20);
+    }
     if (rc == FMGI_OK && e != cudaSuccess) rc = fail(FMGI_ERR_CUDA, std::string("ambient occlusion: ") + cudaGetErrorString(e));
     return rc;
 }
