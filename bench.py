@@ -434,7 +434,7 @@ def measure(h, workload, steps, warmup, e2e_steps, photons=0.0, total_photons=0.
                    "photons_per_gpu_per_step": photons_all / world / steps, "depth": depth,
                    "samples_per_area_per_gpu": spa_gpu, "parallelism": f"photon-range shards x{world}",
                    "atlas_bytes": 16 * num_texels, "texels_per_m2": tile_size or 200,
-                   "tier": ["auto", "soup", "grid"][st["tier"]],
+                   "tier": {0: "auto", 1: "soup", 2: "grid", 4: "rooms"}[st["tier"]],
                    "l2": "flushed between steps (192 MiB fill)",
                    "deposit": ["vec4", "scalar", "warp_agg"][args.deposit]},
         "rays_per_s": rays_all / (ms * 1e-3), "photons_per_s": photons_all / (ms * 1e-3),

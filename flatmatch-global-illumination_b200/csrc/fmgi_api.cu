@@ -17,6 +17,7 @@
 
 #include "mem_pool.h"
 #include "grid_build.cuh"
+#include "room_tables.h"
 #include "trace_core.cuh"
 #include "trace_pool.cuh"
 #include "tile_kernels.cuh"
@@ -129,6 +130,8 @@ struct HostBuild {
     size_t smem_bytes = 0;
     uint64_t tests_per_ray = 0;
     double prepare_ms = 0, grid_ms = 0;         // host clock: rectangle tables, floor-plan grid
+    RoomScene rooms;                            // room tier: box decomposition (rooms_build.cpp)
+    double rooms_ms = 0;
     std::vector<GridItem> grid_items;           // classified colliders, kept when T is assembled on the device
     bool device_grid = false;                   // T is assembled per GPU by grid_build.cuh instead of on the host
 };
@@ -144,6 +147,10 @@ struct fmgi_scene {
     ShadeRect *d_shade = nullptr;
     EmitterRec *d_emitters = nullptr;
     GridRec *d_grid_table = nullptr;            // grid tier / plane tables
+    RoomLeaf *d_room_leaves = nullptr;          // room tier
+    RoomEntry *d_room_entries = nullptr;
+    RoomNode *d_room_nodes = nullptr;
+    int32_t *d_room_start_range = nullptr, *d_room_start_leaves = nullptr;
     unsigned long long *d_jobs = nullptr;       // per accumulation pass: chunk_begin[E+1], photon_first[E], photon_count[E]
     size_t job_tables = 0;                      // passes the job-table buffers have room for
     float4 *d_scratch = nullptr;                // per-pass fp32 atlas when a bake needs several passes
@@ -201,6 +208,15 @@ TraceParams base_params(const fmgi_scene *s)
     p.photon_count = s->d_jobs + (2 * p.num_emitters + 1);
     p.work_counter = s->d_counters + 4;
     p.counters = s->d_counters;
+    p.room_leaves = reinterpret_cast<const float4 *>(s->d_room_leaves);
+    p.room_entries = reinterpret_cast<const float4 *>(s->d_room_entries);
+    p.room_nodes = reinterpret_cast<const float4 *>(s->d_room_nodes);
+    p.room_start_range = s->d_room_start_range;
+    p.room_start_leaves = s->d_room_start_leaves;
+    for (int k = 0; k < 3; k++) { p.room_lo[k] = s->build->rooms.root_lo[k]; p.room_hi[k] = s->build->rooms.root_hi[k]; }
+    p.room_num_leaves = (unsigned)s->build->rooms.leaves.size();
+    p.room_num_entries = (unsigned)s->build->rooms.entries.size();
+    p.room_num_nodes = (unsigned)s->build->rooms.nodes.size();
     p.grid_records = (unsigned)s->grid_records;
     p.num_walls = (unsigned)s->host.num_walls;
     p.num_texels = (unsigned)s->host.num_texels;
@@ -248,6 +264,7 @@ template <typename Fn>
 cudaError_t with_trace_kernel(int tier, int deposit, bool probe, int min_blocks, bool count, Fn fn)
 {
     if (count && !probe) {      // counting variant: one instantiation per tier
+        if (tier == kTierRooms) return fn(k_trace<kTierRooms, FMGI_DEPOSIT_VEC4, false, 4, true>);
         if (tier == FMGI_TIER_GRID) return fn(k_trace<FMGI_TIER_GRID, FMGI_DEPOSIT_VEC4, false, 4, true>);
         if (tier == kTierSoupPlanes) return fn(k_trace<kTierSoupPlanes, FMGI_DEPOSIT_VEC4, false, 4, true>);
     }
@@ -256,6 +273,10 @@ cudaError_t with_trace_kernel(int tier, int deposit, bool probe, int min_blocks,
         case FMGI_DEPOSIT_SCALAR: return fn(k_trace<T, FMGI_DEPOSIT_SCALAR, false, B>);          \
         case FMGI_DEPOSIT_WARP_AGG: return fn(k_trace<T, FMGI_DEPOSIT_WARP_AGG, false, B>);      \
         default: return fn(k_trace<T, FMGI_DEPOSIT_VEC4, false, B>);                             \
+    }
+    if (tier == kTierRooms) {
+        if (probe) return fn(k_trace<kTierRooms, FMGI_DEPOSIT_VEC4, true, 3>);
+        FMGI_PICK_DEPOSIT(kTierRooms, 4)
     }
     if (tier == FMGI_TIER_GRID) {
         if (probe) return fn(k_trace<FMGI_TIER_GRID, FMGI_DEPOSIT_VEC4, true, 3>);
@@ -353,12 +374,23 @@ int build_host(std::shared_ptr<HostBuild> &out, const fmgi_rect *walls, int num_
     const int colliders = hs.num_axis_rects + (int)hs.general.size();
     int tier = o.tier;
     if (const char *v = getenv("FMGI_TIER")) tier = atoi(v);
-    // AUTO: the brute-force soup only for a handful of colliders (one bare room); measured on the
-    // 172-rectangle example.png scene the grid is 20 % faster than the soup + plane tables
-    if (tier != FMGI_TIER_SOUP && tier != FMGI_TIER_GRID)
-        tier = (colliders <= 64 && soup_bytes <= (size_t)attr.smem_optin) ? FMGI_TIER_SOUP : FMGI_TIER_GRID;
-    if (tier == FMGI_TIER_SOUP && soup_bytes > (size_t)attr.smem_optin)
-        return fail(FMGI_ERR_UNSUPPORTED, "rectangle soup does not fit in shared memory; use FMGI_TIER_GRID");
+    // AUTO: the brute-force soup only for a handful of colliders (one bare room); everything else walks the box
+    // decomposition of the room tier when every collider is axis parallel (all parseLayout output is), else the
+    // floor-plan grid (measured on the 172-rectangle example.png scene the grid is 20 % faster than the soup + plane
+    // tables, and the room tier 2x faster than the grid)
+    const bool want_rooms = tier == FMGI_TIER_ROOMS;
+    if (tier != FMGI_TIER_SOUP && tier != FMGI_TIER_GRID && tier != FMGI_TIER_ROOMS)
+        tier = (colliders <= 64 && soup_bytes <= (size_t)attr.smem_optin) ? FMGI_TIER_SOUP : FMGI_TIER_ROOMS;
+    if (tier == FMGI_TIER_ROOMS) {
+        const double tr0 = now_ms();
+        const char *refused = build_rooms(b->rooms, walls, num_walls, windows, num_windows, lights, num_lights);
+        b->rooms_ms = now_ms() - tr0;
+        if (refused[0]) {
+            if (want_rooms) return fail(FMGI_ERR_UNSUPPORTED, std::string("room tier: ") + refused);
+            b->rooms = RoomScene();
+            tier = FMGI_TIER_GRID;
+        }
+    }
     b->tier = tier;
     b->kernel_tier = tier;
     float cell = 0.0f;
@@ -367,15 +399,17 @@ int build_host(std::shared_ptr<HostBuild> &out, const fmgi_rect *walls, int num_
     // runs on the device for scenes of a few thousand colliders and more (grid_build.cuh) - 11 ms on the host for
     // 21.5k rectangles, a fraction of a millisecond on the GPU.  FMGI_GRID_BUILD=host|device overrides.
     const double t1 = now_ms();
-    grid_classify(hs, walls, num_walls, windows, num_windows, lights, num_lights, cell, b->grid_items);
-    b->device_grid = num_walls >= 2048;
-    if (const char *v = getenv("FMGI_GRID_BUILD")) b->device_grid = v[0] == 'd';
-    if (!b->device_grid) {
-        grid_assemble_host(hs, b->grid_items);
-        b->grid_items.clear();
-        b->grid_items.shrink_to_fit();
+    if (tier != FMGI_TIER_ROOMS) {
+        grid_classify(hs, walls, num_walls, windows, num_windows, lights, num_lights, cell, b->grid_items);
+        b->device_grid = num_walls >= 2048;
+        if (const char *v = getenv("FMGI_GRID_BUILD")) b->device_grid = v[0] == 'd';
+        if (!b->device_grid) {
+            grid_assemble_host(hs, b->grid_items);
+            b->grid_items.clear();
+            b->grid_items.shrink_to_fit();
+        }
     }
-    b->grid_ms = now_ms() - t1;
+    b->grid_ms = now_ms() - t1 + b->rooms_ms;
     if (tier == FMGI_TIER_SOUP) {
         b->smem_bytes = soup_bytes;
         // each lane walks one of the two blocks of every pair: two rectangle tests per pair
@@ -405,7 +439,13 @@ int scene_from_build(fmgi_scene **out, std::shared_ptr<HostBuild> b, const fmgi_
     s->tier = b->tier; s->kernel_tier = b->kernel_tier;
     s->smem_bytes = b->smem_bytes; s->tests_per_ray = b->tests_per_ray;
     DeviceGuard guard(o.device);
-    if (s->kernel_tier != FMGI_TIER_SOUP) {
+    if (s->kernel_tier == kTierRooms) {
+        FMGI_CUDA(upload(&s->d_room_leaves, b->rooms.leaves));
+        FMGI_CUDA(upload(&s->d_room_entries, b->rooms.entries));
+        FMGI_CUDA(upload(&s->d_room_nodes, b->rooms.nodes));
+        FMGI_CUDA(upload(&s->d_room_start_range, b->rooms.start_range));
+        FMGI_CUDA(upload(&s->d_room_start_leaves, b->rooms.start_leaves));
+    } else if (s->kernel_tier != FMGI_TIER_SOUP) {
         if (b->device_grid) {
             const double tg0 = now_ms();
             FMGI_CUDA(grid_assemble_device(s->host.grid, b->grid_items, &s->d_grid_table, &s->grid_records, nullptr));
@@ -524,6 +564,8 @@ void fmgi_scene_destroy(fmgi_scene *s)
     MemPool &pool = MemPool::get();
     pool.free(s->d_axis); pool.free(s->d_general); pool.free(s->d_shade); pool.free(s->d_emitters);
     pool.free(s->d_grid_table);
+    pool.free(s->d_room_leaves); pool.free(s->d_room_entries); pool.free(s->d_room_nodes);
+    pool.free(s->d_room_start_range); pool.free(s->d_room_start_leaves);
     pool.free(s->d_jobs); pool.free(s->d_counters); pool.free(s->d_scratch);
     pool.free(s->d_tile_walls); pool.free(s->h_tile_walls);
     pool.free(s->d_png_walls); pool.free(s->h_png_walls);
@@ -1234,7 +1276,8 @@ int fmgi_scene_ambient_occlusion(fmgi_scene *s, void *atlas_dev, void *cuda_stre
         s->launches++;
         return cudaGetLastError();
     };
-    if (s->kernel_tier == kTierSoupPlanes) FMGI_CUDA(go(k_ambient_occlusion<kTierSoupPlanes>));
+    if (s->kernel_tier == kTierRooms) FMGI_CUDA(go(k_ambient_occlusion<kTierRooms>));
+    else if (s->kernel_tier == kTierSoupPlanes) FMGI_CUDA(go(k_ambient_occlusion<kTierSoupPlanes>));
     else if (s->kernel_tier == FMGI_TIER_SOUP) FMGI_CUDA(go(k_ambient_occlusion<FMGI_TIER_SOUP>));
     else FMGI_CUDA(go(k_ambient_occlusion<FMGI_TIER_GRID>));
     s->note_stream(st);
@@ -1292,7 +1335,9 @@ int fmgi_probe_closest_hit(fmgi_scene *s, const float *origins, const float *dir
     const TraceParams p = base_params(s);
     int blocks = (n + 255) / 256;
     if (blocks > s->num_sms * 4) blocks = s->num_sms * 4;
-    if (s->kernel_tier == kTierSoupPlanes) {
+    if (s->kernel_tier == kTierRooms) {
+        k_probe_closest_hit<kTierRooms><<<blocks, 256>>>(p, d_o, d_d, n, d_i, d_t);
+    } else if (s->kernel_tier == kTierSoupPlanes) {
         if (s->smem_bytes > 48 * 1024)
             FMGI_CUDA(cudaFuncSetAttribute(k_probe_closest_hit<kTierSoupPlanes>,
                                            cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->smem_bytes));

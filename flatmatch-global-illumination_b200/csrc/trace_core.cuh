@@ -8,6 +8,29 @@ namespace fmgi {
 
 __device__ __forceinline__ float4 ldg4(const float4 *p) { return __ldg(p); }
 
+// Room tier for a ray that may start anywhere (probes, ambient occlusion): a ray from outside the root box enters
+// it where the slab test says (or misses it), then the first box is located by tree descent.
+__device__ __forceinline__ int closest_hit_rooms_from_anywhere(const TraceParams &p, float ox, float oy, float oz, float dx,
+                                                               float dy, float dz, float &t_out)
+{
+    const float inf = __int_as_float(0x7f800000);
+    t_out = inf;
+    float t0 = 0.0f, t1 = inf;
+    const float o[3] = {ox, oy, oz}, d[3] = {dx, dy, dz};
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+        if (d[k] == 0.0f) {
+            if (o[k] < p.room_lo[k] || o[k] > p.room_hi[k]) return -1;
+        } else {
+            const float ta = (p.room_lo[k] - o[k]) / d[k], tb = (p.room_hi[k] - o[k]) / d[k];
+            t0 = fmaxf(t0, fminf(ta, tb)); t1 = fminf(t1, fmaxf(ta, tb));
+        }
+    }
+    if (!(t0 <= t1)) return -1;                                // the ray misses the scene's box
+    int leaf = rooms_locate(p, fmaf(t0, dx, ox), fmaf(t0, dy, oy), fmaf(t0, dz, oz), dx, dy, dz);
+    return closest_hit_rooms(p, leaf, ox, oy, oz, dx, dy, dz, t_out);
+}
+
 // Binary search: largest e with job_begin[e] <= job (job < total_jobs).
 __device__ __forceinline__ int find_emitter(const unsigned long long *__restrict__ job_begin, int num_emitters,
                                             unsigned long long job)
@@ -46,7 +69,7 @@ __global__ void __launch_bounds__(kTraceThreads, kMinBlocks) k_trace(const Trace
 {
     extern __shared__ float4 smem[];
     SoupTables soup;
-    if (kTier != FMGI_TIER_GRID) soup = stage_soup(p, smem);
+    if (kTier != FMGI_TIER_GRID && kTier != kTierRooms) soup = stage_soup(p, smem);
 
     const int lane = threadIdx.x & 31;
     const unsigned lt_mask = (1u << lane) - 1u;
@@ -55,7 +78,7 @@ __global__ void __launch_bounds__(kTraceThreads, kMinBlocks) k_trace(const Trace
     bool alive = false, is_new = false, mirror = false;
     float px = 0, py = 0, pz = 0, dx = 0, dy = 0, dz = 1;
     float cr = 0, cg = 0, cb = 0, roulette = 0;
-    int depth = 0, emitter = 0, hit_id = 0;
+    int depth = 0, emitter = 0, hit_id = 0, leaf = 0;            // leaf: the photon's box (room tier)
     unsigned long long photon = 0;
     // the warp's chunk (warp uniform): photon indices w_base + [w_pos, w_cnt) of emitter w_emitter
     unsigned long long w_base = 0;
@@ -152,6 +175,10 @@ __global__ void __launch_bounds__(kTraceThreads, kMinBlocks) k_trace(const Trace
             float t;
             if (kTier == FMGI_TIER_SOUP) hit_id = closest_hit_soup(soup, px, py, pz, dx, dy, dz, t);
             else if (kTier == kTierSoupPlanes) hit_id = closest_hit_soup_planes<kCount>(soup, p, px, py, pz, dx, dy, dz, t, n_tests);
+            else if (kTier == kTierRooms) {
+                if (is_new) leaf = rooms_start(p, emitter, px, py, pz, dx, dy, dz);
+                hit_id = closest_hit_rooms<kCount>(p, leaf, px, py, pz, dx, dy, dz, t, &n_tests);
+            }
             else hit_id = closest_hit_grid<kCount>(p, px, py, pz, dx, dy, dz, t, n_tests);
             n_rays++;
 
@@ -214,13 +241,14 @@ __global__ void k_probe_closest_hit(const TraceParams p, const float *__restrict
 {
     extern __shared__ float4 smem[];
     SoupTables soup;
-    if (kTier != FMGI_TIER_GRID) soup = stage_soup(p, smem);
+    if (kTier != FMGI_TIER_GRID && kTier != kTierRooms) soup = stage_soup(p, smem);
     unsigned tests = 0;
     for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < num_rays; r += gridDim.x * blockDim.x) {
         float t;
         const float ox = origins[3 * r], oy = origins[3 * r + 1], oz = origins[3 * r + 2];
         const float dx = dirs[3 * r], dy = dirs[3 * r + 1], dz = dirs[3 * r + 2];
-        const int id = kTier == FMGI_TIER_SOUP ? closest_hit_soup(soup, ox, oy, oz, dx, dy, dz, t)
+        const int id = kTier == kTierRooms ? closest_hit_rooms_from_anywhere(p, ox, oy, oz, dx, dy, dz, t)
+                     : kTier == FMGI_TIER_SOUP ? closest_hit_soup(soup, ox, oy, oz, dx, dy, dz, t)
                      : kTier == kTierSoupPlanes ? closest_hit_soup_planes<false>(soup, p, ox, oy, oz, dx, dy, dz, t, tests)
                                                 : closest_hit_grid<false>(p, ox, oy, oz, dx, dy, dz, t, tests);
         hit_index[r] = id;
@@ -301,7 +329,7 @@ __global__ void __launch_bounds__(kTraceThreads) k_ambient_occlusion(const Trace
 {
     extern __shared__ float4 smem[];
     SoupTables soup;
-    if (kTier != FMGI_TIER_GRID) soup = stage_soup(p, smem);
+    if (kTier != FMGI_TIER_GRID && kTier != kTierRooms) soup = stage_soup(p, smem);
     unsigned tests = 0;
     for (long long g = blockIdx.x * (long long)blockDim.x + threadIdx.x; g < num_pixels;
          g += (long long)gridDim.x * blockDim.x) {
@@ -337,7 +365,8 @@ __global__ void __launch_bounds__(kTraceThreads) k_ambient_occlusion(const Trace
             const float ox = __fadd_rn(cx, __fmul_rn(dx, 1E-5f)), oy = __fadd_rn(cy, __fmul_rn(dy, 1E-5f)),
                         oz = __fadd_rn(cz, __fmul_rn(dz, 1E-5f));                         // photonmap.c:457
             float t;
-            const int id = kTier == FMGI_TIER_SOUP ? closest_hit_soup(soup, ox, oy, oz, dx, dy, dz, t)
+            const int id = kTier == kTierRooms ? closest_hit_rooms_from_anywhere(p, ox, oy, oz, dx, dy, dz, t)
+                         : kTier == FMGI_TIER_SOUP ? closest_hit_soup(soup, ox, oy, oz, dx, dy, dz, t)
                          : kTier == kTierSoupPlanes ? closest_hit_soup_planes<false>(soup, p, ox, oy, oz, dx, dy, dz, t, tests)
                                                     : closest_hit_grid<false>(p, ox, oy, oz, dx, dy, dz, t, tests);
             if (id < 0) t = 10.0f;                                                       // photonmap.c:462-466

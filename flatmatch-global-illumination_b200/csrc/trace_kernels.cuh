@@ -39,6 +39,8 @@ constexpr int kMinChunkPhotons = 32;        // ... small bakes use smaller chunk
 constexpr unsigned kFullMask = 0xffffffffu;
 // internal kernel variant: soup tier whose horizontal rectangles go through the grid's plane tables
 constexpr int kTierSoupPlanes = 3;
+// room tier (room_tables.h): FMGI_TIER_ROOMS
+constexpr int kTierRooms = FMGI_TIER_ROOMS;
 
 struct TraceParams {
     // closest-hit tables (global memory; staged into shared memory by the soup kernel)
@@ -73,8 +75,15 @@ struct TraceParams {
     uint32_t philox_keys[10];       // seed + r * W: the Philox2x32 round keys of this bake (philox.cuh)
     int grid_has_misc;              // the walk lists hold misc records (scene_tables.h)
     int one;                        // 1, opaque to the compiler: x * one + y keeps integer updates on the FMA pipe
+    // room tier (room_tables.h): leaf boxes (4 float4 each), face entries (2 float4 each), kd-tree nodes (1 float4 each)
+    const float4 *room_leaves;
+    const float4 *room_entries;
+    const float4 *room_nodes;
+    const int *room_start_range;    // per emitter: [2e], [2e + 1]: its candidate first leaves in room_start_leaves
+    const int *room_start_leaves;
+    float room_lo[3], room_hi[3];   // the root box
     // table sizes: read only by the bounds-checked build (FMGI_CHECKED, lib/libfmgi_cuda_checked.so)
-    unsigned grid_records, num_walls, num_texels;
+    unsigned grid_records, num_walls, num_texels, room_num_leaves, room_num_entries, room_num_nodes;
 };
 
 // ---- bounds-checked build ----------------------------------------------------------------------------------------
@@ -659,6 +668,103 @@ __device__ __forceinline__ int closest_hit_soup_planes(const SoupTables &s, cons
     const float2 q1 = ldg2(p.grid_table + 2 * w.win + 1);
     t_out = __fdiv_rn(__fsub_rn(q1.x, oz), dz);
     return (int)(__float_as_uint(q1.y) & kTagIdMask);
+}
+
+// ---- closest hit through the box decomposition (room tier, room_tables.h) -----------------------------------------
+
+// Leaf a ray that starts at (x, y, z) and travels along d is in: kd-tree descent; a point exactly on a split plane
+// belongs to the side the ray travels towards.  The point is clamped into the root box first.
+__device__ __forceinline__ int rooms_locate(const TraceParams &p, float x, float y, float z, float dx, float dy, float dz)
+{
+    x = fminf(fmaxf(x, p.room_lo[0]), p.room_hi[0]);
+    y = fminf(fmaxf(y, p.room_lo[1]), p.room_hi[1]);
+    z = fminf(fmaxf(z, p.room_lo[2]), p.room_hi[2]);
+    int n = 0;
+    for (int guard = 0; guard < 256; guard++) {
+        if (!FMGI_CHECK(p, (unsigned)n < p.room_num_nodes, 20)) return 0;
+        const float4 nd = __ldg(p.room_nodes + n);
+        const int axis = __float_as_int(nd.y);
+        if (axis < 0) return __float_as_int(nd.z);
+        const float c = axis == 0 ? x : (axis == 1 ? y : z);
+        const float dc = axis == 0 ? dx : (axis == 1 ? dy : dz);
+        const bool right = c > nd.x || (c == nd.x && dc > 0.0f);
+        n = right ? __float_as_int(nd.w) : __float_as_int(nd.z);
+    }
+    return 0;
+}
+
+// First box of a photon emitted by `emitter`: one of the (one or two) boxes the emitter rectangle touches - the one
+// that contains the start point - else the tree descent.
+__device__ __forceinline__ int rooms_start(const TraceParams &p, int emitter, float x, float y, float z, float dx, float dy,
+                                           float dz)
+{
+    const int b = __ldg(p.room_start_range + 2 * emitter), e = __ldg(p.room_start_range + 2 * emitter + 1);
+    for (int q = b; q < e; q++) {
+        const int leaf = __ldg(p.room_start_leaves + q);
+        float4 b0, b1;
+        ldg256(p.room_leaves + 4 * leaf, b0, b1);
+        if (x >= b0.x && x <= b0.w && y >= b0.y && y <= b1.x && z >= b0.z && z <= b1.y) return leaf;
+    }
+    return rooms_locate(p, x, y, z, dx, dy, dz);
+}
+
+// The ray leaves its box through the nearest of the three faces it travels towards; the face's entries - first the
+// colliders that face into the box, in wall-index order, then the boxes behind the face - say what is at the exit
+// point: a hit (the closest one: nothing lies inside a box), the next box, or nothing (the ray leaves the scene).
+// `leaf` is the box the ray starts in and, on return, the box the hit was found in: a bounce starts there.
+// A collider whose plane lies BEHIND the origin (negative ray parameter: an origin that rounding put a few ulps
+// beyond a wall) is not a hit (rectangle.c:76 rejects t < 0): the ray goes on into the box behind it.
+template <bool kCount = false>
+__device__ __forceinline__ int closest_hit_rooms(const TraceParams &p, int &leaf, float ox, float oy, float oz, float dx,
+                                                 float dy, float dz, float &t_out, unsigned *tests = nullptr)
+{
+    const float inf = __int_as_float(0x7f800000);
+    const float ix = rcp_fast(dx), iy = rcp_fast(dy), iz = rcp_fast(dz);
+    const bool xp = dx > 0.0f, yp = dy > 0.0f, zp = dz > 0.0f;
+    t_out = inf;
+    int cur = leaf;
+#pragma unroll 1
+    for (int guard = 0; guard < 4096; guard++) {
+        if (!FMGI_CHECK(p, (unsigned)cur < p.room_num_leaves, 21)) return -1;
+        const float4 *L = p.room_leaves + 4 * cur;
+        float4 b0, b1;                                   // {lo.x, lo.y, lo.z, hi.x}, {hi.y, hi.z, -, -}
+        ldg256(L, b0, b1);
+        float tx = ((xp ? b0.w : b0.x) - ox) * ix, ty = ((yp ? b1.x : b0.y) - oy) * iy, tz = ((zp ? b1.y : b0.z) - oz) * iz;
+        tx = dx == 0.0f ? inf : tx; ty = dy == 0.0f ? inf : ty; tz = dz == 0.0f ? inf : tz;
+        // nearest face; the two in-plane coordinates of the exit point, in ascending axis order
+        const bool ax_y = ty < tx, ax_z = tz < fminf(tx, ty);
+        const float t = fminf(fminf(tx, ty), tz);
+        const int a = ax_z ? 2 : (ax_y ? 1 : 0);
+        const float hx = fmaf(t, dx, ox), hy = fmaf(t, dy, oy), hz = fmaf(t, dz, oz);
+        const float pu = a == 0 ? hy : hx, pv = a == 2 ? hy : hz;
+        const int f = 2 * a + ((a == 0 ? xp : (a == 1 ? yp : zp)) ? 1 : 0);
+        const int *fb = reinterpret_cast<const int *>(L + 2) + f;
+        int q = __ldg(fb);
+        const int qe = __ldg(fb + 1);
+        int next = -1;
+        for (; q < qe; q++) {
+            if (!FMGI_CHECK(p, (unsigned)q < p.room_num_entries, 22)) break;
+            float4 e0, e1;                               // {u_lo, u_hi, v_lo, v_hi}, {target, c, -, -}
+            ldg256(p.room_entries + 2 * q, e0, e1);
+            if (kCount) (*tests)++;
+            if (pu >= e0.x && pu <= e0.y && pv >= e0.z && pv <= e0.w) {
+                const int target = __float_as_int(e1.x);
+                if (target >= 0) {
+                    if (t < 0.0f) continue;              // the plane lies behind the origin
+                    // the distance with the reference's formula for an axis-parallel normal, IEEE division
+                    const float oa = a == 0 ? ox : (a == 1 ? oy : oz), da = a == 0 ? dx : (a == 1 ? dy : dz);
+                    t_out = __fdiv_rn(__fsub_rn(e1.y, oa), da);
+                    leaf = cur;
+                    return target;
+                }
+                next = ~target;
+                break;
+            }
+        }
+        if (next < 0) return -1;                         // nothing behind this part of the face: the ray leaves the scene
+        cur = next;
+    }
+    return -1;
 }
 
 // ---- texel index: rectangle.c:205-230, same operations in the same order, no contraction ----------

@@ -31,7 +31,7 @@ RECT_DTYPE = np.dtype(
 )
 
 DEPOSIT_VEC4, DEPOSIT_SCALAR, DEPOSIT_WARP_AGG = 0, 1, 2
-TIER_AUTO, TIER_SOUP, TIER_GRID = 0, 1, 2
+TIER_AUTO, TIER_SOUP, TIER_GRID, TIER_ROOMS = 0, 1, 2, 4
 
 
 class Geometry(C.Structure):

@@ -74,7 +74,7 @@ typedef enum fmgi_status {
 } fmgi_status;
 
 enum { FMGI_DEPOSIT_VEC4 = 0, FMGI_DEPOSIT_SCALAR = 1, FMGI_DEPOSIT_WARP_AGG = 2 };
-enum { FMGI_TIER_AUTO = 0, FMGI_TIER_SOUP = 1, FMGI_TIER_GRID = 2 };
+enum { FMGI_TIER_AUTO = 0, FMGI_TIER_SOUP = 1, FMGI_TIER_GRID = 2, FMGI_TIER_ROOMS = 4 };
 
 typedef struct fmgi_options {
     uint32_t struct_size;     /* = sizeof(fmgi_options); lets the struct grow */

@@ -77,6 +77,14 @@ def dev_scene_grid(fmgi, scene):
 
 
 @pytest.fixture(scope="session")
+def dev_scene_rooms(fmgi, scene):
+    """The same flat through the room tier (box decomposition; what AUTO picks for axis-parallel scenes)."""
+    s = fmgi.DeviceScene(scene.walls, scene.windows, scene.lights, scene.num_texels, tier=fmgi.TIER_ROOMS)
+    yield s
+    s.close()
+
+
+@pytest.fixture(scope="session")
 def dev_scene_soup(fmgi, scene):
     """The same flat through the brute-force soup tier (explicit: AUTO picks the grid above 64 colliders);
     its horizontal rectangles go through the grid's plane tables (kernel variant soup + planes)."""

@@ -1,0 +1,125 @@
+// TEST INFRASTRUCTURE (CPU): checks the room tier's box decomposition (csrc/rooms_build.cpp) without a GPU: a host
+// replay of the device traversal against a brute-force scan with the reference's intersects() semantics
+// (rectangle.c:67-95) on random rays, plus the structure's statistics (leaves, entries, steps and entry tests per ray).
+//
+// usage: rooms_check scene.bin num_rays
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+
+#include "../../flatmatch-global-illumination_b200/csrc/room_tables.h"
+
+using namespace fmgi;
+
+static uint64_t rng_state = 0x1234567ull;
+static inline double urand()
+{
+    rng_state += 0x9E3779B97F4A7C15ull;
+    uint64_t z = rng_state;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    z ^= z >> 31;
+    return (double)(z >> 11) * (1.0 / 9007199254740992.0);
+}
+
+// rectangle.c:67-95 in float, the reference's operation order
+static float intersects(const fmgi_rect &r, const float o[3], const float d[3], float closest)
+{
+    const float denom = r.n[0] * d[0] + r.n[1] * d[1] + r.n[2] * d[2];
+    if (denom >= 0) return -1;
+    const float fac = (r.n[0] * (r.pos[0] - o[0]) + r.n[1] * (r.pos[1] - o[1]) + r.n[2] * (r.pos[2] - o[2])) / denom;
+    if (fac < 0) return -1;
+    if (!(fac < closest)) return -1;
+    const float p[3] = {o[0] + d[0] * fac - r.pos[0], o[1] + d[1] * fac - r.pos[1], o[2] + d[2] * fac - r.pos[2]};
+    const float wl = sqrtf(r.width[0] * r.width[0] + r.width[1] * r.width[1] + r.width[2] * r.width[2]);
+    const float hl = sqrtf(r.height[0] * r.height[0] + r.height[1] * r.height[1] + r.height[2] * r.height[2]);
+    if (!(wl > 0) || !(hl > 0)) return -1;
+    const float iw = 1.0f / wl, ih = 1.0f / hl;
+    const float u = (r.width[0] * iw) * p[0] + (r.width[1] * iw) * p[1] + (r.width[2] * iw) * p[2];
+    const float v = (r.height[0] * ih) * p[0] + (r.height[1] * ih) * p[1] + (r.height[2] * ih) * p[2];
+    if (u < 0 || v < 0 || u > wl || v > hl) return -1;
+    return fac;
+}
+
+int main(int argc, char **argv)
+{
+    if (argc < 3) { fprintf(stderr, "usage: %s scene.bin num_rays\n", argv[0]); return 2; }
+    FILE *f = fopen(argv[1], "rb");
+    if (!f) { perror("scene"); return 2; }
+    int32_t cnt[3];
+    if (fread(cnt, 4, 3, f) != 3) return 2;
+    std::vector<fmgi_rect> walls(cnt[0]), windows(cnt[1]), lights(cnt[2]);
+    if (fread(walls.data(), sizeof(fmgi_rect), cnt[0], f) != (size_t)cnt[0]) return 2;
+    if (fread(windows.data(), sizeof(fmgi_rect), cnt[1], f) != (size_t)cnt[1]) return 2;
+    if (fread(lights.data(), sizeof(fmgi_rect), cnt[2], f) != (size_t)cnt[2]) return 2;
+    fclose(f);
+    const int num_rays = atoi(argv[2]);
+    RoomScene rs;
+    const char *why = build_rooms(rs, walls.data(), cnt[0], windows.data(), cnt[1], lights.data(), cnt[2]);
+    if (why[0]) { printf("refused: %s\n", why); return 3; }
+    size_t wall_entries = 0;
+    for (const RoomEntry &e : rs.entries) wall_entries += e.target >= 0;
+    printf("rooms: %zu leaves, %zu entries (%zu colliders, %zu portals), depth %d, build %.1f ms\n", rs.leaves.size(),
+           rs.entries.size(), wall_entries, rs.entries.size() - wall_entries, rs.max_depth, rs.build_ms);
+
+    // rays as the path produces them: half start inside the bounding box, half on a wall (offset 1e-5 along the ray)
+    float lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
+    for (const fmgi_rect &r : walls)
+        for (int c = 0; c < 4; c++)
+            for (int k = 0; k < 3; k++) {
+                const float x = r.pos[k] + (c & 1 ? r.width[k] : 0.0f) + (c & 2 ? r.height[k] : 0.0f);
+                lo[k] = fminf(lo[k], x); hi[k] = fmaxf(hi[k], x);
+            }
+    long steps = 0, tests = 0, mism = 0, mism_edge = 0, hits = 0, max_steps = 0;
+    std::vector<long> hist(32, 0);
+    for (int i = 0; i < num_rays; i++) {
+        float o[3], d[3];
+        double n2 = 0;
+        for (int k = 0; k < 3; k++) { d[k] = (float)(urand() * 2 - 1); n2 += (double)d[k] * d[k]; }
+        if (n2 < 1e-4 || n2 > 1) { i--; continue; }
+        for (int k = 0; k < 3; k++) d[k] = (float)(d[k] / sqrt(n2));
+        if (i & 1) {
+            const fmgi_rect &r = walls[(size_t)(urand() * walls.size()) % walls.size()];
+            const float a = (float)urand(), b = (float)urand();
+            float dn = 0;
+            for (int k = 0; k < 3; k++) dn += d[k] * r.n[k];
+            if (dn < 0) for (int k = 0; k < 3; k++) d[k] -= 2 * dn * r.n[k];
+            for (int k = 0; k < 3; k++) o[k] = r.pos[k] + a * r.width[k] + b * r.height[k] + d[k] * 1e-5f;
+        } else {
+            for (int k = 0; k < 3; k++) o[k] = (float)(lo[k] + urand() * (hi[k] - lo[k]));
+        }
+        // brute force: strict "<", lowest index wins ties
+        float best = INFINITY;
+        int want = -1;
+        for (size_t w = 0; w < walls.size(); w++) {
+            const float t = intersects(walls[w], o, d, best);
+            if (t >= 0) { best = t; want = (int)w; }
+        }
+        float t;
+        int leaf_out;
+        long s0 = steps;
+        const int leaf = rooms_locate(rs, o, d);
+        const int got = leaf < 0 ? -1 : rooms_closest_hit(rs, leaf, o, d, t, leaf_out, steps, tests);
+        const long st = steps - s0;
+        max_steps = std::max(max_steps, st);
+        hist[std::min<long>(st, 31)]++;
+        hits += got >= 0;
+        if (got != want) {
+            mism++;
+            if (mism <= 5)
+                printf("mismatch ray %d: got %d want %d (t %.7g vs %.7g) o=(%.6f %.6f %.6f) d=(%.6f %.6f %.6f)\n", i, got, want,
+                       got >= 0 ? t : -1.0f, best, o[0], o[1], o[2], d[0], d[1], d[2]);
+        } else if (got >= 0 && fabsf(t - best) > 1e-4f * fmaxf(best, 1e-3f)) {
+            mism_edge++;
+        }
+    }
+    printf("rays %d: hits %.3f, steps/ray %.3f (max %ld), entry tests/ray %.3f, index mismatches %ld, distance mismatches %ld\n",
+           num_rays, (double)hits / num_rays, (double)steps / num_rays, max_steps, (double)tests / num_rays, mism, mism_edge);
+    printf("steps histogram:");
+    for (int i = 0; i < 16; i++) printf(" %d:%.3f", i, (double)hist[i] / num_rays);
+    printf("\n");
+    return mism > num_rays / 20000 + 2 || mism_edge ? 1 : 0;
+}

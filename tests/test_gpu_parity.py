@@ -88,21 +88,29 @@ def test_philox_on_device(fmgi, oracle):
         assert np.array_equal(fmgi.philox2x32(ctr, key), oracle.philox2x32(ctr, key))
 
 
-@pytest.fixture(params=["soup_planes", "soup", "grid"])
-def any_tier_scene(request, dev_scene_soup, dev_scene_soup_plain, dev_scene_grid):
-    """The three closest-hit kernels on the same flat: brute-force soup with the horizontal rectangles in the
-    plane tables, plain brute-force soup, floor-plan grid (what AUTO picks for this scene)."""
-    s = {"soup_planes": dev_scene_soup, "soup": dev_scene_soup_plain, "grid": dev_scene_grid}[request.param]
+TIERS = {"soup": 1, "grid": 2, "rooms": 4}          # fmgi.TIER_*
+
+
+@pytest.fixture(params=["soup_planes", "soup", "grid", "rooms"])
+def any_tier_scene(request, dev_scene_soup, dev_scene_soup_plain, dev_scene_grid, dev_scene_rooms):
+    """The four closest-hit kernels on the same flat: brute-force soup with the horizontal rectangles in the
+    plane tables, plain brute-force soup, floor-plan grid, box decomposition (room tier: what AUTO picks here)."""
+    s = {"soup_planes": dev_scene_soup, "soup": dev_scene_soup_plain, "grid": dev_scene_grid,
+         "rooms": dev_scene_rooms}[request.param]
     s.tier_name = request.param
     return s
 
 
-def test_tier_fixtures_run_the_kernels_they_name(dev_scene, dev_scene_soup, dev_scene_soup_plain, dev_scene_grid):
+def test_tier_fixtures_run_the_kernels_they_name(dev_scene, dev_scene_soup, dev_scene_soup_plain, dev_scene_grid,
+                                                 dev_scene_rooms):
     spa = 2000
     assert gpu_bake(dev_scene_soup, spa, count_tests=1)[1]["tier"] == 1
     assert gpu_bake(dev_scene_soup_plain, spa)[1]["tier"] == 1
     assert gpu_bake(dev_scene_grid, spa)[1]["tier"] == 2
-    assert gpu_bake(dev_scene, spa)[1]["tier"] == 2           # AUTO: 172 colliders > 64
+    assert gpu_bake(dev_scene_rooms, spa)[1]["tier"] == 4
+    assert gpu_bake(dev_scene, spa)[1]["tier"] == 4           # AUTO: 172 axis-parallel colliders > 64 -> room tier
+    t_rooms = gpu_bake(dev_scene_rooms, spa, count_tests=1)[1]
+    assert 1.0 < t_rooms["rect_tests"] / t_rooms["rays"] < 6.0     # face entries looked at per ray
     # rectangle tests per ray tell the kernels apart: plain soup scans every pair block of the ray's sign
     # (94 tests), soup + planes only the x / y lists plus the counted plane lookups, the grid a handful
     t_plain = gpu_bake(dev_scene_soup_plain, spa, count_tests=1)[1]
@@ -142,9 +150,10 @@ def test_closest_hit_from_outside_the_bounding_box(any_tier_scene, fmgi, oracle,
     if which == "example":
         sc, dev = scene, any_tier_scene
     else:
-        if any_tier_scene.tier_name != "grid":
-            pytest.skip("synth800 runs once, through the grid")
-        sc, dev = synth800, fmgi.DeviceScene(synth800.walls, synth800.windows, synth800.lights, synth800.num_texels)
+        if any_tier_scene.tier_name not in ("grid", "rooms"):
+            pytest.skip("synth800 runs through the grid and the room tier")
+        sc, dev = synth800, fmgi.DeviceScene(synth800.walls, synth800.windows, synth800.lights, synth800.num_texels,
+                                             tier=TIERS[any_tier_scene.tier_name])
     o, d = outside_rays(sc, 400_000, 31)
     gi, gt = dev.closest_hit(o, d)
     ci, ct = oracle.closest_hit(sc.walls, o, d, oracle.ACCEL_LINEAR)
@@ -248,8 +257,8 @@ def test_rectangle_test_counter_is_opt_in_and_changes_nothing(dev_scene, dev_sce
     assert sp["rect_tests"] == 0
     assert 2.0 < sc["rect_tests"] / sc["rays"] < 10.0
     assert np.allclose(plain, counted, rtol=1e-5, atol=1e-2)
-    auto, sa = gpu_bake(dev_scene, spa, max_depth=5, seed=21)          # AUTO picks the grid for 172 colliders
-    assert sa["tier"] == 2 and sa["rays"] == sp["rays"]
+    auto, sa = gpu_bake(dev_scene, spa, max_depth=5, seed=21)          # AUTO picks the room tier for this flat
+    assert sa["tier"] == 4 and sa["rays"] == sp["rays"]
 
 
 def test_deposit_peak_probe(fmgi, scene):
@@ -285,10 +294,10 @@ def parity_stats(lum_gpu, lum_ref, floor_frac=0.05):
     return s, sp, lit.mean()
 
 
-@pytest.mark.parametrize("depth,photons,tier", [(8, 1.0e9, "grid"), (3, 1.0e9, "grid"), (8, 1.0e9, "soup_planes"),
-                                                 (3, 1.0e9, "soup")])
-def test_radiance_parity_with_native_reference(dev_scene_grid, dev_scene_soup, dev_scene_soup_plain, scene, record,
-                                               depth, photons, tier):
+@pytest.mark.parametrize("depth,photons,tier", [(8, 1.0e9, "rooms"), (3, 1.0e9, "rooms"), (8, 1.0e9, "grid"),
+                                                 (3, 1.0e9, "grid"), (8, 1.0e9, "soup_planes"), (3, 1.0e9, "soup")])
+def test_radiance_parity_with_native_reference(dev_scene_rooms, dev_scene_grid, dev_scene_soup, dev_scene_soup_plain, scene,
+                                               record, depth, photons, tier):
     """BASELINE.json: per-texel relative RMS < 2 % after the reference's normalisation and total
     deposited energy within 0.1 %, against performPhotonMappingNative (photonmap.c:408) at the
     same depth.  The reference side is the committed fixture (6.15e8 photons over 8 seeded
@@ -299,7 +308,8 @@ def test_radiance_parity_with_native_reference(dev_scene_grid, dev_scene_soup, d
     lum_ref = 0.5 * (lum_a + lum_b)
     area = sum(scene.photon_counts(1_000_000)) / 1e6
     spa = int(photons / area)
-    dev_scene = {"grid": dev_scene_grid, "soup_planes": dev_scene_soup, "soup": dev_scene_soup_plain}[tier]
+    dev_scene = {"rooms": dev_scene_rooms, "grid": dev_scene_grid, "soup_planes": dev_scene_soup,
+                 "soup": dev_scene_soup_plain}[tier]
     atlas, st = gpu_bake(dev_scene, spa, max_depth=depth, seed=2024)
     mask = scene.base_texel_mask()
     lum_gpu = ((atlas[:, :3].astype(np.float64) @ LUMA) * scene.normalisation(spa))[mask]
@@ -421,6 +431,12 @@ def test_general_rectangles(fmgi, oracle, scene, tier):
 
     walls, windows, lights = rotated_scene(scene)
     rs = refbind.Scene(walls, windows, lights, scene.num_texels)
+    # the room tier needs axis-parallel colliders: asked for explicitly it refuses, AUTO falls back to the grid
+    with pytest.raises(fmgi.FmgiError, match="room tier"):
+        fmgi.DeviceScene(rs.walls, rs.windows, rs.lights, rs.num_texels, tier=fmgi.TIER_ROOMS)
+    auto = fmgi.DeviceScene(rs.walls, rs.windows, rs.lights, rs.num_texels)
+    assert gpu_bake(auto, 500)[1]["tier"] == fmgi.TIER_GRID
+    auto.close()
     s = fmgi.DeviceScene(rs.walls, rs.windows, rs.lights, rs.num_texels,
                          tier=fmgi.TIER_SOUP if tier == "soup" else fmgi.TIER_GRID)
     o, d = random_rays(rs, 200_000, 4)
@@ -481,11 +497,10 @@ def test_in_library_multi_gpu_bake(fmgi, scene):
 # ---- grid tier on the synthetic multi-room layouts (BASELINE.json configs[2]) -------------------------------
 
 
-@pytest.mark.parametrize("tier", ["soup", "grid"])
+@pytest.mark.parametrize("tier", ["soup", "grid", "rooms"])
 def test_synth800_closest_hit_and_bake(fmgi, oracle, synth800, tier):
     sc = synth800
-    s = fmgi.DeviceScene(sc.walls, sc.windows, sc.lights, sc.num_texels,
-                         tier=fmgi.TIER_SOUP if tier == "soup" else fmgi.TIER_GRID)
+    s = fmgi.DeviceScene(sc.walls, sc.windows, sc.lights, sc.num_texels, tier=TIERS[tier])
     o, d = random_rays(sc, 300_000, 21)
     gi, gt = s.closest_hit(o, d)
     ci, ct = oracle.closest_hit(sc.walls, o, d, oracle.ACCEL_LINEAR)
@@ -517,7 +532,7 @@ def test_synth4000_grid_tier(fmgi, oracle, synth4000):
     assert np.max(np.abs(gt[both] - ct[both]) / np.maximum(ct[both], 1e-4)) < 1e-4
     spa, depth = 25, 4                         # the oracle's linear scan costs 21.5k tests per ray
     atlas, st = gpu_bake(s, spa, max_depth=depth, seed=3)
-    assert st["tier"] == fmgi.TIER_GRID
+    assert st["tier"] == fmgi.TIER_ROOMS
     assert st["photons"] == sum(sc.photon_counts(spa))
     want, so = oracle.bake(sc, spa, depth, oracle.ACCEL_LINEAR, oracle.RNG_PHILOX, 3)
     assert abs(st["deposits"] - so["deposits"]) <= 1e-3 * so["deposits"] + 2
@@ -646,7 +661,7 @@ def test_radiance_parity_synth4000(fmgi, synth4000, record, tile_size):
     atlas = device_atlas(num_texels)
     s.trace(atlas.data_ptr(), spa, stream=torch.cuda.current_stream().cuda_stream, max_depth=depth, seed=4000)
     st = s.sync()
-    assert st["tier"] == fmgi.TIER_GRID and abs(st["photons"] - 1e9) < 1e6
+    assert st["tier"] == fmgi.TIER_ROOMS and abs(st["photons"] - 1e9) < 1e6
     wall_gpu, _ = wall_mean_luminance(atlas, s.walls, spa)
     e_gpu = atlas[:, :3].sum(dim=0, dtype=torch.float64).cpu().numpy() / spa
     if tile_size == 200:                        # the strided per-texel sample of the fixture
@@ -743,14 +758,13 @@ def staircase_scene(fmgi):
     return walls, np.zeros(0, dtype=fmgi.RECT_DTYPE), np.array([light], dtype=fmgi.RECT_DTYPE), base
 
 
-@pytest.mark.parametrize("tier", ["soup", "grid"])
+@pytest.mark.parametrize("tier", ["soup", "grid", "rooms"])
 def test_more_z_planes_than_the_plane_table(fmgi, oracle, tier):
     import refbind
 
     walls, windows, lights, num_texels = staircase_scene(fmgi)
     sc = refbind.Scene(walls, windows, lights, num_texels)
-    s = fmgi.DeviceScene(sc.walls, sc.windows, sc.lights, sc.num_texels,
-                         tier=fmgi.TIER_SOUP if tier == "soup" else fmgi.TIER_GRID)
+    s = fmgi.DeviceScene(sc.walls, sc.windows, sc.lights, sc.num_texels, tier=TIERS[tier])
     o, d = random_rays(sc, 200_000, 9)
     gi, gt = s.closest_hit(o, d)
     ci, ct = oracle.closest_hit(sc.walls, o, d, oracle.ACCEL_LINEAR)
@@ -890,7 +904,7 @@ def test_ambient_occlusion_matches_reference(fmgi, scene):
     assert abs(got[:, 0].mean() / want.mean() - 1) < 2e-5
 
 
-@pytest.mark.parametrize("tier", ["soup", "grid"])
+@pytest.mark.parametrize("tier", ["soup", "grid", "rooms"])
 def test_ambient_occlusion_matches_oracle_on_small_room(fmgi, oracle, tier):
     import refbind
 
@@ -898,8 +912,7 @@ def test_ambient_occlusion_matches_oracle_on_small_room(fmgi, oracle, tier):
     sc = refbind.Scene(walls, windows, lights, num_texels)
     want = oracle.ambient_occlusion(sc, fmgi.geosphere(4), oracle.ACCEL_LINEAR)
     tex = fmgi.aligned_texels(num_texels)
-    fmgi.ambient_occlusion(fmgi.make_geometry(sc.walls, sc.windows, sc.lights, tex),
-                           tier=fmgi.TIER_SOUP if tier == "soup" else fmgi.TIER_GRID)
+    fmgi.ambient_occlusion(fmgi.make_geometry(sc.walls, sc.windows, sc.lights, tex), tier=TIERS[tier])
     mask = sc.base_texel_mask()
     rel = np.abs(tex[mask, 0] - want[mask, 0]) / np.maximum(want[mask, 0], 1e-3)
     assert np.mean(rel < 1e-5) > 0.99 and rel.max() < 0.08
@@ -956,6 +969,35 @@ def test_random_soups_closest_hit_and_paths(fmgi, oracle, seed, tier):
     got = s.paths(0, 6, seed, 0, 20000)
     ref = oracle.trace_paths(sc, 0, 6, seed, 0, 20000)
     assert np.all(got == ref, axis=1).mean() > 0.99
+    s.close()
+
+
+@pytest.mark.parametrize("seed", [1, 2, 3])
+@pytest.mark.parametrize("tier", ["grid", "rooms"])
+def test_random_axis_parallel_soups(fmgi, oracle, seed, tier):
+    """160 axis-parallel rectangles of all six orientations floating at random in a box - overlapping, crossing,
+    seen from behind (back-face culling lets rays through): nothing like a flat, the hard case for the room tier's
+    box decomposition, whose leaves must still put every rectangle on a face."""
+    import refbind
+
+    walls, windows, lights, num_texels = random_scene(fmgi, seed, n_axis=160, n_general=0)
+    sc = refbind.Scene(walls, windows, lights, num_texels)
+    s = fmgi.DeviceScene(sc.walls, sc.windows, sc.lights, sc.num_texels, tier=TIERS[tier])
+    o, d = random_rays(sc, 200_000, seed)
+    gi, gt = s.closest_hit(o, d)
+    ci, ct = oracle.closest_hit(sc.walls, o, d, oracle.ACCEL_LINEAR)
+    at_edge, elsewhere = split_mismatches(sc.walls, o, d, gi, gt, ci, ct)
+    assert elsewhere == 0 and at_edge <= 8, (at_edge, elsewhere)
+    both = (gi >= 0) & (gi == ci)
+    assert both.mean() > 0.15
+    assert np.max(np.abs(gt[both] - ct[both]) / np.maximum(ct[both], 1e-3)) < 1e-4
+    got = s.paths(0, 6, seed, 0, 20000)
+    ref = oracle.trace_paths(sc, 0, 6, seed, 0, 20000)
+    assert np.all(got == ref, axis=1).mean() > 0.99
+    spa = 100000
+    atlas, st = gpu_bake(s, spa, max_depth=6, seed=seed)
+    want, so = oracle.bake(sc, spa, 6, oracle.ACCEL_LINEAR, oracle.RNG_PHILOX, seed)
+    assert st["photons"] == so["photons"] and abs(st["deposits"] - so["deposits"]) <= 1e-3 * so["deposits"] + 2
     s.close()
 
 

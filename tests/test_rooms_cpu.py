@@ -1,0 +1,62 @@
+"""CPU checks of the room tier's box decomposition (csrc/rooms_build.cpp): a host replay of the device traversal against a
+brute-force scan with the reference's intersects() semantics (rectangle.c:67-95) on random rays.
+tests/cpu/rooms_check.cpp does the work; no GPU, no CUDA library involved."""
+import re
+import subprocess
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+ROOT = Path(__file__).resolve().parent.parent
+CSRC = ROOT / "flatmatch-global-illumination_b200" / "csrc"
+
+
+@pytest.fixture(scope="session")
+def rooms_checker(tmp_path_factory):
+    exe = tmp_path_factory.mktemp("rooms") / "rooms_check"
+    subprocess.run(["g++", "-O2", "-std=c++17", "-ffp-contract=off", "-I", str(ROOT / "include"),
+                    str(ROOT / "tests" / "cpu" / "rooms_check.cpp"), str(CSRC / "rooms_build.cpp"), "-o", str(exe)], check=True)
+    return exe
+
+
+def run_check(checker, tmp_path, walls, windows, lights, rays, expect=0):
+    path = tmp_path / "scene.bin"
+    with open(path, "wb") as f:
+        np.array([len(walls), len(windows), len(lights)], dtype="<i4").tofile(f)
+        for t in (walls, windows, lights):
+            np.ascontiguousarray(t).tofile(f)
+    r = subprocess.run([str(checker), str(path), str(rays)], capture_output=True, text=True)
+    assert r.returncode == expect, r.stdout[-3000:] + r.stderr[-1000:]
+    return r.stdout
+
+
+@pytest.mark.parametrize("fixture,rays,max_steps", [("scene", 100000, 2.2), ("synth800", 100000, 1.6), ("synth4000", 20000, 1.6)])
+def test_rooms_of_the_fixture_layouts(rooms_checker, tmp_path, request, fixture, rays, max_steps):
+    sc = request.getfixturevalue(fixture)
+    out = run_check(rooms_checker, tmp_path, sc.walls, sc.windows, sc.lights, rays)
+    steps = float(re.search(r"steps/ray ([0-9.]+)", out).group(1))
+    assert steps < max_steps, out           # a ray in a room leaves it through ONE face: one or two boxes per ray
+
+
+def test_rooms_with_many_z_planes(rooms_checker, tmp_path, fmgi):
+    from test_gpu_parity import staircase_scene
+
+    walls, windows, lights, _ = staircase_scene(fmgi)
+    run_check(rooms_checker, tmp_path, walls, windows, lights, 100000)
+
+
+@pytest.mark.parametrize("seed", [1, 2, 3])
+def test_rooms_of_random_axis_parallel_soups(rooms_checker, tmp_path, fmgi, seed):
+    from test_gpu_parity import random_scene
+
+    walls, windows, lights, _ = random_scene(fmgi, seed, n_axis=160, n_general=0)
+    run_check(rooms_checker, tmp_path, walls, windows, lights, 100000)
+
+
+def test_rooms_refuse_arbitrarily_oriented_colliders(rooms_checker, tmp_path, fmgi):
+    from test_gpu_parity import random_scene
+
+    walls, windows, lights, _ = random_scene(fmgi, 1)
+    out = run_check(rooms_checker, tmp_path, walls, windows, lights, 100, expect=3)
+    assert "refused" in out

@@ -1,0 +1,4 @@
+set -u
+mkdir -p gpurun_out
+ncu --set full --import-source on --clock-control none -k regex:k_trace -s 2 -c 1 -o gpurun_out/prof_rooms_example -f python bench.py --no-cpu --no-app --no-secondary --steps 1 --warmup 1 --e2e-steps 0 > gpurun_out/rooms_ncu1.log 2>&1
+ls -la gpurun_out/prof_rooms*
