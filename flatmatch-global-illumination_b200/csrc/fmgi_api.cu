@@ -147,10 +147,11 @@ struct fmgi_scene {
     ShadeRect *d_shade = nullptr;
     EmitterRec *d_emitters = nullptr;
     GridRec *d_grid_table = nullptr;            // grid tier / plane tables
-    RoomLeaf *d_room_leaves = nullptr;          // room tier
-    RoomEntry *d_room_entries = nullptr;
+    RoomBox *d_room_boxes = nullptr;            // room tier
+    RoomFaceNode *d_room_face_nodes = nullptr;
+    RoomBounds *d_room_bounds = nullptr;
     RoomNode *d_room_nodes = nullptr;
-    int32_t *d_room_start_range = nullptr, *d_room_start_leaves = nullptr;
+    int32_t *d_room_start_range = nullptr, *d_room_start_boxes = nullptr;
     unsigned long long *d_jobs = nullptr;       // per accumulation pass: chunk_begin[E+1], photon_first[E], photon_count[E]
     size_t job_tables = 0;                      // passes the job-table buffers have room for
     float4 *d_scratch = nullptr;                // per-pass fp32 atlas when a bake needs several passes
@@ -208,14 +209,15 @@ TraceParams base_params(const fmgi_scene *s)
     p.photon_count = s->d_jobs + (2 * p.num_emitters + 1);
     p.work_counter = s->d_counters + 4;
     p.counters = s->d_counters;
-    p.room_leaves = reinterpret_cast<const float4 *>(s->d_room_leaves);
-    p.room_entries = reinterpret_cast<const float4 *>(s->d_room_entries);
+    p.room_boxes = reinterpret_cast<const float4 *>(s->d_room_boxes);
+    p.room_face_nodes = reinterpret_cast<const float4 *>(s->d_room_face_nodes);
+    p.room_bounds = reinterpret_cast<const float4 *>(s->d_room_bounds);
     p.room_nodes = reinterpret_cast<const float4 *>(s->d_room_nodes);
     p.room_start_range = s->d_room_start_range;
-    p.room_start_leaves = s->d_room_start_leaves;
+    p.room_start_boxes = s->d_room_start_boxes;
     for (int k = 0; k < 3; k++) { p.room_lo[k] = s->build->rooms.root_lo[k]; p.room_hi[k] = s->build->rooms.root_hi[k]; }
-    p.room_num_leaves = (unsigned)s->build->rooms.leaves.size();
-    p.room_num_entries = (unsigned)s->build->rooms.entries.size();
+    p.room_num_boxes = (unsigned)s->build->rooms.boxes.size();
+    p.room_num_face_nodes = (unsigned)s->build->rooms.face_nodes.size();
     p.room_num_nodes = (unsigned)s->build->rooms.nodes.size();
     p.grid_records = (unsigned)s->grid_records;
     p.num_walls = (unsigned)s->host.num_walls;
@@ -276,6 +278,13 @@ cudaError_t with_trace_kernel(int tier, int deposit, bool probe, int min_blocks,
     }
     if (tier == kTierRooms) {
         if (probe) return fn(k_trace<kTierRooms, FMGI_DEPOSIT_VEC4, true, 3>);
+        if (deposit == FMGI_DEPOSIT_VEC4) {         // boxes per iteration of the photon loop (experiments)
+            static const int steps = getenv("FMGI_ROOM_STEPS") ? atoi(getenv("FMGI_ROOM_STEPS")) : 2;
+            if (steps == 1) return fn(k_trace<kTierRooms, FMGI_DEPOSIT_VEC4, false, 4, false, 1>);
+            if (steps == 3) return fn(k_trace<kTierRooms, FMGI_DEPOSIT_VEC4, false, 4, false, 3>);
+            if (steps == 4) return fn(k_trace<kTierRooms, FMGI_DEPOSIT_VEC4, false, 4, false, 4>);
+            if (steps >= 64) return fn(k_trace<kTierRooms, FMGI_DEPOSIT_VEC4, false, 4, false, kRoomMaxSteps>);
+        }
         FMGI_PICK_DEPOSIT(kTierRooms, 4)
     }
     if (tier == FMGI_TIER_GRID) {
@@ -440,11 +449,12 @@ int scene_from_build(fmgi_scene **out, std::shared_ptr<HostBuild> b, const fmgi_
     s->smem_bytes = b->smem_bytes; s->tests_per_ray = b->tests_per_ray;
     DeviceGuard guard(o.device);
     if (s->kernel_tier == kTierRooms) {
-        FMGI_CUDA(upload(&s->d_room_leaves, b->rooms.leaves));
-        FMGI_CUDA(upload(&s->d_room_entries, b->rooms.entries));
+        FMGI_CUDA(upload(&s->d_room_boxes, b->rooms.boxes));
+        FMGI_CUDA(upload(&s->d_room_face_nodes, b->rooms.face_nodes));
+        FMGI_CUDA(upload(&s->d_room_bounds, b->rooms.bounds));
         FMGI_CUDA(upload(&s->d_room_nodes, b->rooms.nodes));
         FMGI_CUDA(upload(&s->d_room_start_range, b->rooms.start_range));
-        FMGI_CUDA(upload(&s->d_room_start_leaves, b->rooms.start_leaves));
+        FMGI_CUDA(upload(&s->d_room_start_boxes, b->rooms.start_boxes));
     } else if (s->kernel_tier != FMGI_TIER_SOUP) {
         if (b->device_grid) {
             const double tg0 = now_ms();
@@ -564,8 +574,8 @@ void fmgi_scene_destroy(fmgi_scene *s)
     MemPool &pool = MemPool::get();
     pool.free(s->d_axis); pool.free(s->d_general); pool.free(s->d_shade); pool.free(s->d_emitters);
     pool.free(s->d_grid_table);
-    pool.free(s->d_room_leaves); pool.free(s->d_room_entries); pool.free(s->d_room_nodes);
-    pool.free(s->d_room_start_range); pool.free(s->d_room_start_leaves);
+    pool.free(s->d_room_boxes); pool.free(s->d_room_face_nodes); pool.free(s->d_room_bounds); pool.free(s->d_room_nodes);
+    pool.free(s->d_room_start_range); pool.free(s->d_room_start_boxes);
     pool.free(s->d_jobs); pool.free(s->d_counters); pool.free(s->d_scratch);
     pool.free(s->d_tile_walls); pool.free(s->h_tile_walls);
     pool.free(s->d_png_walls); pool.free(s->h_png_walls);

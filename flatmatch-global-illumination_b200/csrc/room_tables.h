@@ -2,15 +2,23 @@
 //
 // Every collider parseLayout.c emits is an axis-parallel rectangle, and a flat is mostly empty boxes: rooms,
 // door and window niches, the inside of walls.  A kd-tree splits the scene's bounding box at collider planes
-// until NO collider lies inside a leaf box: all of them sit on leaf faces.  A ray then never tests a collider
-// "on spec": it leaves its box through one of the three faces it travels towards, and the face's entry list says
-// what is there - a collider that faces into the box (hit: the closest one by construction), or a neighbouring
-// box (portal: continue there), or nothing (the ray leaves the scene).  A ray in a room does ONE step (its own
-// room's walls), a ray through a doorway three; no grid walk through empty cells, no per-cell candidate tests, no
-// separate pass over the horizontal planes (floors, ceilings, sills and lintels are faces like any other).
-// Back-face culling (rectangle.c:70-72) is structural: a face lists only the colliders whose normal points into
-// its box.  Ties (rectangle edges shared by two colliders) go to the lowest wall index, as the reference's strict
-// `<` does (photonmap.cl:199): the colliders of a face come first and in index order.
+// until NO collider lies inside a leaf box, and leaves that share a whole collider-free face are merged back into
+// bigger boxes: all colliders sit on box faces.  A ray then never tests a collider "on spec": it leaves its box
+// through one of the three faces it travels towards, and the face says what is at the exit point - a collider that
+// faces into the box (hit: the closest one by construction), a neighbouring box (portal: continue there), or
+// nothing (the ray leaves the scene).  A ray in a room does ONE step (its own room's walls), a ray through a doorway
+// three; no grid walk through empty cells, no per-cell candidate tests, no separate pass over the horizontal planes
+// (floors, ceilings, sills and lintels are faces like any other).
+//
+// What is on a face is a partition of the face into rectangles (colliders, portals, nothing), stored as a small 2-D
+// kd-tree over the face's two in-plane coordinates: a face with one thing on it - a floor, a ceiling, a plain wall -
+// is a terminal code in the box record itself and costs no lookup at all; a wall with a door is two or three
+// compare-and-descend steps.  No containment tests: an exit point that rounding puts an ulp outside the face still
+// descends to the nearest part.
+// Back-face culling (rectangle.c:70-72) is structural: a face shows only the colliders whose normal points into
+// its box.  Where coplanar colliders overlap, the part belongs to the lowest wall index, as the reference's strict
+// `<` decides (photonmap.cl:199); a point exactly on the edge between two parts belongs to the part on the higher
+// side of the split.
 #pragma once
 #include <stdint.h>
 #include <vector>
@@ -19,27 +27,48 @@
 
 namespace fmgi {
 
-// One leaf box.  Face f = 2 * axis + (1 if the ray leaves towards +axis): its entries are
-// E[face_begin[f] .. face_begin[f + 1]).
-struct RoomLeaf {
-    float lo[3], hi[3];
-    int32_t pad0[2];
-    int32_t face_begin[7];
-    int32_t pad1;
+// What a face (or a part of it) holds: kind in the top two bits, index below.
+enum : uint32_t {
+    kRoomCodeNode = 0u << 30,        // index of a RoomFaceNode: descend
+    kRoomCodeWall = 1u << 30,        // wall index: a hit
+    kRoomCodeBox = 2u << 30,         // box index: the ray goes on there
+    kRoomCodeMiss = 3u << 30,        // nothing: the ray leaves the scene
+    kRoomCodeKind = 3u << 30,
+    kRoomCodeIndex = ~(3u << 30),
 };
-static_assert(sizeof(RoomLeaf) == 64, "RoomLeaf is four float4");
 
-// One rectangle on a leaf face, in the face's two in-plane axes (ascending axis order).
-struct RoomEntry {
-    float u_lo, u_hi, v_lo, v_hi;
-    int32_t target;          // >= 0: wall index (a hit); < 0: ~(index of the leaf behind the face) (a portal)
-    float c;                 // the face's plane coordinate
+// One box, as eight 32-byte records: record o serves the rays of octant o = (d.x > 0) | (d.y > 0) << 1 |
+// (d.z > 0) << 2 and holds the three faces such a ray can leave through - their plane coordinates and codes - so
+// ONE 256-bit load, at an address that depends on the box and the ray's octant only, fetches all a step needs.
+struct RoomOctant {
+    float far[3];
+    uint32_t code[3];
+    uint32_t pad[2];
+};
+struct RoomBox {
+    RoomOctant oct[8];
+};
+static_assert(sizeof(RoomBox) == 256, "RoomBox is sixteen float4");
+
+// One node of a face's 2-D kd-tree: the coordinate (axis 0: the lower in-plane axis, 1: the higher) against `split`;
+// below -> lo, at or above -> hi (codes).
+struct RoomFaceNode {
+    float split;
+    uint32_t lo, hi;
+    uint32_t axis;
+};
+static_assert(sizeof(RoomFaceNode) == 16, "RoomFaceNode is one float4");
+
+// Bounds of a box (where does a new photon start; host replay).
+struct RoomBounds {
+    float lo[3], hi_x;
+    float hi_y, hi_z;
     int32_t pad[2];
 };
-static_assert(sizeof(RoomEntry) == 32, "RoomEntry is two float4");
+static_assert(sizeof(RoomBounds) == 32, "RoomBounds is two float4");
 
-// The kd-tree the leaves come from, kept for point location (a new photon's first leaf, probe rays): inner node:
-// split plane `v` of `axis`, children left (below) / right (above); leaf: axis = -1, left = leaf index.
+// The kd-tree the boxes come from, kept for point location (a new photon's first box, probe rays): inner node:
+// split plane `v` of `axis`, children left (below) / right (above); leaf: axis = -1, left = box index.
 struct RoomNode {
     float v;
     int32_t axis, left, right;
@@ -47,28 +76,32 @@ struct RoomNode {
 static_assert(sizeof(RoomNode) == 16, "RoomNode is one float4");
 
 struct RoomScene {
-    std::vector<RoomLeaf> leaves;
-    std::vector<RoomEntry> entries;
+    std::vector<RoomBox> boxes;
+    std::vector<RoomBounds> bounds;            // per box
+    std::vector<RoomFaceNode> face_nodes;
     std::vector<RoomNode> nodes;               // nodes[0] = root
-    // where an emitter's photons start: the leaves that touch the emitter rectangle (windows, then lights):
-    // start_leaves[start_range[2e] .. start_range[2e + 1]) - one or two boxes, checked by containment; the tree
-    // descent is the fallback
+    // where an emitter's photons start: the boxes that touch the emitter rectangle (windows, then lights), largest
+    // share first: start_boxes[start_range[2e] .. start_range[2e + 1]); a single candidate needs no test, several
+    // are checked by containment, the tree descent is the fallback
     std::vector<int32_t> start_range;
-    std::vector<int32_t> start_leaves;
+    std::vector<int32_t> start_boxes;
     float root_lo[3] = {0, 0, 0}, root_hi[3] = {0, 0, 0};
     int max_depth = 0;
+    size_t kd_leaves = 0;                      // boxes before merging
+    size_t face_parts = 0, wall_parts = 0;     // terminal codes over all faces; those that are colliders
     double build_ms = 0;
 };
 
 // Builds the decomposition.  Returns "" on success, else why the scene cannot use the room tier (an arbitrarily
-// oriented collider, too many leaves): the caller then stays on the grid tier.
+// oriented collider, too many boxes): the caller then stays on the grid tier.
 const char *build_rooms(RoomScene &out, const fmgi_rect *walls, int num_walls, const fmgi_rect *windows, int num_windows,
                         const fmgi_rect *lights, int num_lights);
 
-// Host replay of the device traversal (tests/cpu, tools): wall index or -1, ray parameter, steps and entries tested.
-int rooms_closest_hit(const RoomScene &rs, int leaf, const float o[3], const float d[3], float &t_out, int &leaf_out,
+// Host replay of the device traversal (tests/cpu, tools): wall index or -1, ray parameter, boxes crossed and face
+// tree nodes visited.
+int rooms_closest_hit(const RoomScene &rs, int box, const float o[3], const float d[3], float &t_out, int &box_out,
                       long &steps, long &tests);
-// Leaf a ray that starts at p and travels along d is in (-1: outside the root box): tree descent, a point exactly
+// Box a ray that starts at p and travels along d is in (-1: outside the root box): tree descent, a point exactly
 // on a split plane belongs to the side the ray travels towards.
 int rooms_locate(const RoomScene &rs, const float p[3], const float d[3]);
 

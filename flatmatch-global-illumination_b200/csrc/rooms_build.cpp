@@ -4,16 +4,19 @@
 //   1. every collider becomes an axis-parallel rectangle record (normal axis, side, plane coordinate, extents);
 //      a scene with an arbitrarily oriented collider is refused (the grid tier handles it);
 //   2. kd-tree over the padded bounding box: a node whose open box still contains a piece of some collider is
-//      split at the collider plane that covers the largest share of the node's cross-section (room-separating
-//      walls, floor and ceiling first; sills and lintels last, when the node is already the niche they sit in);
-//   3. per leaf and face: the colliders on that face whose normal points into the box, in wall-index order, then the
-//      leaves behind the face (found by a tree query of the face rectangle);
-//   4. per emitter: nothing - photons locate their first leaf by a tree descent (RoomNode) on the device.
+//      split at a collider plane - big nodes at the plane nearest their middle, small ones at the plane that
+//      covers the largest share of the node's cross-section - until nothing lies inside a leaf;
+//   3. leaves are merged back: two boxes that share a whole face with no collider on it become one box (a split
+//      plane runs through the whole node, also through the rooms its wall does not touch), to a fixed point;
+//   4. per box and face: the colliders on that face whose normal points into the box and the boxes behind the face,
+//      as a partition of the face stored as a 2-D kd-tree of RoomFaceNode (a face with one thing on it is a code);
+//   5. per emitter: the boxes its rectangle touches.
 #include <algorithm>
 #include <chrono>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
-#include <map>
+#include <unordered_map>
 
 #include "room_tables.h"
 
@@ -45,10 +48,10 @@ int to_axis_rect(const fmgi_rect &r, int id, ARect &out)
     if (!(wl > 0) || !(hl > 0) || !(nl > 0)) return 1;
     const int ai = single_axis3(r.width), aj = single_axis3(r.height), ak = single_axis3(r.n);
     if (ai < 0 || aj < 0 || ak < 0 || ai == aj || ak == ai || ak == aj) return 2;
-    out.axis = ak; out.neg = r.n[ak] > 0 ? 0 : 1; out.id = id; out.c = r.pos[ak];
+    out.axis = ak; out.neg = r.n[ak] > 0 ? 0 : 1; out.id = id; out.c = r.pos[ak] + 0.0f;
     for (int k = 0; k < 3; k++) {
         const float a = r.pos[k], b = r.pos[k] + r.width[k] + r.height[k];
-        out.lo[k] = fminf(a, b); out.hi[k] = fmaxf(a, b);
+        out.lo[k] = fminf(a, b) + 0.0f; out.hi[k] = fmaxf(a, b) + 0.0f;          // + 0: no negative zeros
     }
     out.lo[ak] = out.hi[ak] = out.c;
     return 0;
@@ -76,9 +79,25 @@ bool touches(const Box &b, const ARect &r)
 
 struct Node { int axis; float v; int left, right, leaf; };
 
-}  // namespace
-
-namespace {
+struct Key3 {
+    uint32_t k[3];
+    bool operator==(const Key3 &o) const { return k[0] == o.k[0] && k[1] == o.k[1] && k[2] == o.k[2]; }
+};
+struct Key3Hash {
+    size_t operator()(const Key3 &x) const
+    {
+        uint64_t h = x.k[0] * 0x9E3779B97F4A7C15ull;
+        h = (h ^ (h >> 29)) + x.k[1] * 0xBF58476D1CE4E5B9ull;
+        h = (h ^ (h >> 31)) + x.k[2] * 0x94D049BB133111EBull;
+        return (size_t)(h ^ (h >> 32));
+    }
+};
+Key3 key_of(const float p[3])
+{
+    Key3 k;
+    for (int i = 0; i < 3; i++) { const float f = p[i] + 0.0f; memcpy(&k.k[i], &f, 4); }
+    return k;
+}
 
 // leaves whose boxes lie just behind plane coordinate c (on side `beyond`: +1 higher, -1 lower) of axis a and overlap
 // the open rectangle [qlo, qhi] of the other two axes with positive area
@@ -98,6 +117,85 @@ void query_face(const std::vector<Node> &nodes, int n, int a, float c, int beyon
     }
 }
 
+// ---- a face's partition as a 2-D kd-tree ----------------------------------------------------------------------
+
+struct FaceItem {
+    float lo[2], hi[2];          // in-plane extents (not clipped to the face)
+    uint32_t code;               // kRoomCodeWall | wall index, or kRoomCodeBox | box index
+};
+
+struct Region { float lo[2], hi[2]; };
+
+bool overlaps(const FaceItem &it, const Region &r)
+{
+    return fmaxf(it.lo[0], r.lo[0]) < fminf(it.hi[0], r.hi[0]) && fmaxf(it.lo[1], r.lo[1]) < fminf(it.hi[1], r.hi[1]);
+}
+bool covers(const FaceItem &it, const Region &r)
+{
+    return it.lo[0] <= r.lo[0] && it.hi[0] >= r.hi[0] && it.lo[1] <= r.lo[1] && it.hi[1] >= r.hi[1];
+}
+
+struct FaceTreeBuilder {
+    RoomScene &out;
+    explicit FaceTreeBuilder(RoomScene &o) : out(o) {}
+
+    // `items`: colliders in wall-index order first, then portals; all overlap `r` with positive area.
+    uint32_t build(const Region &r, const std::vector<FaceItem> &items, int depth)
+    {
+        if (items.empty()) { out.face_parts++; return kRoomCodeMiss; }
+        // the part belongs to the first item (lowest wall index; a collider hides the box behind it) if that covers it
+        const FaceItem &first = items[0];
+        const bool first_is_wall = (first.code & kRoomCodeKind) == kRoomCodeWall;
+        if (covers(first, r) && (first_is_wall || items.size() == 1)) {
+            out.face_parts++;
+            out.wall_parts += first_is_wall;
+            return first.code;
+        }
+        // candidate split lines: item edges strictly inside the region
+        int best_axis = -1;
+        float best_v = 0;
+        double best_cost = 1e300;
+        const double ext[2] = {(double)r.hi[0] - r.lo[0], (double)r.hi[1] - r.lo[1]};
+        auto consider = [&](int ax, float v) {
+            if (!(v > r.lo[ax] && v < r.hi[ax])) return;
+            double cost;
+            if (items.size() > 48) {
+                // long lists (the boxes around the building): the edge nearest the middle of the longer side
+                cost = fabs((double)v - 0.5 * ((double)r.lo[ax] + r.hi[ax])) / ext[ax] + (ext[ax] >= ext[1 - ax] ? 0.0 : 1.0);
+            } else {
+                // expected number of further decisions ~ share of the region x (items on that side - 1)
+                int nl = 0, nr = 0;
+                for (const FaceItem &it : items) {
+                    nl += fmaxf(it.lo[ax], r.lo[ax]) < fminf(it.hi[ax], v);
+                    nr += fmaxf(it.lo[ax], v) < fminf(it.hi[ax], r.hi[ax]);
+                }
+                const double fl = ((double)v - r.lo[ax]) / ext[ax];
+                cost = fl * (nl - 1) + (1.0 - fl) * (nr - 1) + 1e-3 * fabs(fl - 0.5);
+            }
+            if (cost < best_cost) { best_cost = cost; best_axis = ax; best_v = v; }
+        };
+        for (const FaceItem &it : items)
+            for (int ax = 0; ax < 2; ax++) { consider(ax, it.lo[ax]); consider(ax, it.hi[ax]); }
+        if (best_axis < 0 || depth > 64) {          // nothing cuts the region, yet nothing covers it: keep the first
+            out.face_parts++;
+            out.wall_parts += first_is_wall;
+            return first.code;
+        }
+        Region rl = r, rh = r;
+        rl.hi[best_axis] = best_v; rh.lo[best_axis] = best_v;
+        std::vector<FaceItem> il, ih;
+        for (const FaceItem &it : items) {
+            if (overlaps(it, rl)) il.push_back(it);
+            if (overlaps(it, rh)) ih.push_back(it);
+        }
+        const uint32_t self = (uint32_t)out.face_nodes.size();
+        out.face_nodes.push_back(RoomFaceNode{best_v, 0u, 0u, (uint32_t)best_axis});
+        const uint32_t lo = build(rl, il, depth + 1), hi = build(rh, ih, depth + 1);
+        out.face_nodes[self].lo = lo; out.face_nodes[self].hi = hi;
+        return kRoomCodeNode | self;
+    }
+};
+
 }  // namespace
 
 const char *build_rooms(RoomScene &out, const fmgi_rect *walls, int num_walls, const fmgi_rect *windows, int num_windows,
@@ -105,6 +203,8 @@ const char *build_rooms(RoomScene &out, const fmgi_rect *walls, int num_walls, c
 {
     const auto t0 = std::chrono::steady_clock::now();
     out = RoomScene();
+    bool do_merge = true;
+    if (const char *v = getenv("FMGI_ROOMS_MERGE")) do_merge = atoi(v) != 0;
     std::vector<ARect> rects;
     rects.reserve((size_t)num_walls);
     for (int i = 0; i < num_walls; i++) {
@@ -113,6 +213,7 @@ const char *build_rooms(RoomScene &out, const fmgi_rect *walls, int num_walls, c
         if (rc == 2) return "an arbitrarily oriented collider";
         if (rc == 0) rects.push_back(r);
     }
+    if ((size_t)num_walls > kRoomCodeIndex) return "more than 2^30 walls";
     // padded bounding box of everything a ray can start from or hit
     Box root;
     for (int k = 0; k < 3; k++) { root.lo[k] = INFINITY; root.hi[k] = -INFINITY; }
@@ -133,7 +234,8 @@ const char *build_rooms(RoomScene &out, const fmgi_rect *walls, int num_walls, c
     std::vector<Node> nodes;
     struct Work { int node; Box box; std::vector<int> ids; int depth; };
     std::vector<Work> stack;
-    std::vector<std::vector<int>> leaf_rects;
+    std::vector<Box> boxes;                     // kd leaves, later merged
+    std::vector<std::vector<int>> box_rects;    // colliders that touch the box
     {
         Work w;
         w.node = 0; w.box = root; w.depth = 0;
@@ -143,44 +245,64 @@ const char *build_rooms(RoomScene &out, const fmgi_rect *walls, int num_walls, c
         stack.push_back(std::move(w));
     }
     const size_t max_leaves = 8u << 20;
+    struct Plane { int axis; float c; double cover; };
+    std::vector<Plane> planes;
     while (!stack.empty()) {
         Work w = std::move(stack.back());
         stack.pop_back();
         out.max_depth = std::max(out.max_depth, w.depth);
-        // score the collider planes that still cut this box
-        std::map<std::pair<int, float>, double> cover;
-        for (int id : w.ids) {
-            const ARect &r = rects[id];
-            if (!interior(w.box, r)) continue;
-            double area = 1.0;
-            for (int k = 0; k < 3; k++)
-                if (k != r.axis) area *= (double)fminf(r.hi[k], w.box.hi[k]) - (double)fmaxf(r.lo[k], w.box.lo[k]);
-            cover[{r.axis, r.c}] += area;
+        int best_axis = -1;
+        float best_c = 0;
+        if (w.ids.size() > 96) {
+            // big node: of the collider planes that cut it, the one nearest the middle of its longest side that has any
+            int order[3] = {0, 1, 2};
+            std::sort(order, order + 3, [&](int a, int b) { return w.box.hi[a] - w.box.lo[a] > w.box.hi[b] - w.box.lo[b]; });
+            for (int oi = 0; oi < 3 && best_axis < 0; oi++) {
+                const int a = order[oi];
+                const float mid = 0.5f * (w.box.lo[a] + w.box.hi[a]);
+                float best_d = INFINITY;
+                for (int id : w.ids) {
+                    const ARect &r = rects[id];
+                    if (r.axis != a || !(fabsf(r.c - mid) < best_d) || !interior(w.box, r)) continue;
+                    best_d = fabsf(r.c - mid); best_axis = a; best_c = r.c;
+                }
+            }
+        } else {
+            // small node: score the collider planes that still cut it by the share of the cross-section they cover
+            planes.clear();
+            for (int id : w.ids) {
+                const ARect &r = rects[id];
+                if (!interior(w.box, r)) continue;
+                double area = 1.0;
+                for (int k = 0; k < 3; k++)
+                    if (k != r.axis) area *= (double)fminf(r.hi[k], w.box.hi[k]) - (double)fmaxf(r.lo[k], w.box.lo[k]);
+                bool found = false;
+                for (Plane &pl : planes)
+                    if (pl.axis == r.axis && pl.c == r.c) { pl.cover += area; found = true; break; }
+                if (!found) planes.push_back(Plane{r.axis, r.c, area});
+            }
+            double best_score = -1;
+            for (const Plane &pl : planes) {
+                const int a = pl.axis;
+                double cross = 1.0;
+                for (int k = 0; k < 3; k++)
+                    if (k != a) cross *= (double)w.box.hi[k] - (double)w.box.lo[k];
+                // coverage first; among equals the plane nearest the middle of the box
+                const double mid = 1.0 - fabs(((double)pl.c - w.box.lo[a]) / ((double)w.box.hi[a] - w.box.lo[a]) - 0.5);
+                const double score = pl.cover / cross + 1e-6 * mid;
+                if (score > best_score || (score == best_score && (a < best_axis || (a == best_axis && pl.c < best_c)))) {
+                    best_score = score; best_axis = a; best_c = pl.c;
+                }
+            }
         }
-        if (cover.empty()) {
-            const int leaf = (int)out.leaves.size();
-            if ((size_t)leaf >= max_leaves) return "more than 8M leaf boxes";
-            RoomLeaf L;
-            memset(&L, 0, sizeof L);
-            for (int k = 0; k < 3; k++) { L.lo[k] = w.box.lo[k]; L.hi[k] = w.box.hi[k]; }
-            out.leaves.push_back(L);
-            leaf_rects.push_back(std::move(w.ids));
+        if (best_axis < 0) {
+            const int leaf = (int)boxes.size();
+            if ((size_t)leaf >= max_leaves) return "more than 8M boxes";
+            boxes.push_back(w.box);
+            box_rects.push_back(std::move(w.ids));
             nodes[w.node].axis = -1;
             nodes[w.node].leaf = leaf;
             continue;
-        }
-        int best_axis = -1;
-        float best_c = 0;
-        double best_score = -1;
-        for (const auto &kv : cover) {
-            const int a = kv.first.first;
-            double cross = 1.0;
-            for (int k = 0; k < 3; k++)
-                if (k != a) cross *= (double)w.box.hi[k] - (double)w.box.lo[k];
-            // coverage first; among equals the plane nearest the middle of the box
-            const double mid = 1.0 - fabs(((double)kv.first.second - w.box.lo[a]) / ((double)w.box.hi[a] - w.box.lo[a]) - 0.5);
-            const double score = kv.second / cross + 1e-6 * mid;
-            if (score > best_score) { best_score = score; best_axis = a; best_c = kv.first.second; }
         }
         Work lw, rw;
         lw.box = w.box; rw.box = w.box;
@@ -197,46 +319,126 @@ const char *build_rooms(RoomScene &out, const fmgi_rect *walls, int num_walls, c
         stack.push_back(std::move(lw));
         stack.push_back(std::move(rw));
     }
+    out.kd_leaves = boxes.size();
 
-    // ---- face lists: colliders facing into the box (index order), then the leaves behind the face ------------------
+    // ---- merge boxes across collider-free shared faces ---------------------------------------------------------------
+    const size_t nb0 = boxes.size();
+    std::vector<int> merged_into(nb0);
+    for (size_t i = 0; i < nb0; i++) merged_into[i] = (int)i;
+    if (do_merge) {
+        std::unordered_map<Key3, int, Key3Hash> by_corner;
+        by_corner.reserve(nb0 * 2);
+        for (size_t i = 0; i < nb0; i++) by_corner[key_of(boxes[i].lo)] = (int)i;
+        std::vector<char> alive(nb0, 1);
+        bool changed = true;
+        const int axis_order[3] = {2, 0, 1};
+        while (changed) {
+            changed = false;
+            for (int ao = 0; ao < 3; ao++) {
+                const int a = axis_order[ao], u = a == 0 ? 1 : 0, v = a == 2 ? 1 : 2;
+                for (size_t i = 0; i < nb0; i++) {
+                    if (!alive[i]) continue;
+                    for (;;) {
+                        Box &A = boxes[i];
+                        float corner[3] = {A.lo[0], A.lo[1], A.lo[2]};
+                        corner[a] = A.hi[a];
+                        const auto it = by_corner.find(key_of(corner));
+                        if (it == by_corner.end()) break;
+                        const int j = it->second;
+                        if (j == (int)i || !alive[j]) break;
+                        const Box &B = boxes[j];
+                        if (B.hi[u] != A.hi[u] || B.hi[v] != A.hi[v]) break;
+                        // a collider (facing either way) on the shared face keeps the boxes apart
+                        bool wall = false;
+                        for (int id : box_rects[i]) {
+                            const ARect &r = rects[id];
+                            if (r.axis == a && r.c == A.hi[a] && fmaxf(r.lo[u], A.lo[u]) < fminf(r.hi[u], A.hi[u]) &&
+                                fmaxf(r.lo[v], A.lo[v]) < fminf(r.hi[v], A.hi[v])) { wall = true; break; }
+                        }
+                        if (wall) break;
+                        A.hi[a] = B.hi[a];
+                        box_rects[i].insert(box_rects[i].end(), box_rects[j].begin(), box_rects[j].end());
+                        std::vector<int>().swap(box_rects[j]);
+                        alive[j] = 0;
+                        merged_into[j] = (int)i;
+                        by_corner.erase(it);
+                        changed = true;
+                    }
+                }
+            }
+        }
+    }
+    // final box ids
+    std::vector<int> final_id(nb0, -1);
+    int num_boxes = 0;
+    for (size_t i = 0; i < nb0; i++)
+        if (merged_into[i] == (int)i) final_id[i] = num_boxes++;
+    auto resolve = [&](int leaf) {
+        int r = leaf;
+        while (merged_into[r] != r) r = merged_into[r];
+        for (int q = leaf; merged_into[q] != q;) { const int nq = merged_into[q]; merged_into[q] = r; q = nq; }
+        return r;
+    };
+    if ((size_t)num_boxes > kRoomCodeIndex) return "more than 2^30 boxes";
+    out.boxes.resize((size_t)num_boxes);
+    out.bounds.resize((size_t)num_boxes);
+
+    // ---- faces ------------------------------------------------------------------------------------------------------------
+    FaceTreeBuilder ftb(out);
     std::vector<int> behind;
-    for (size_t li = 0; li < out.leaves.size(); li++) {
-        RoomLeaf &L = out.leaves[li];
-        std::sort(leaf_rects[li].begin(), leaf_rects[li].end(), [&](int a, int b) { return rects[a].id < rects[b].id; });
+    std::vector<FaceItem> items;
+    for (size_t i = 0; i < nb0; i++) {
+        if (final_id[i] < 0) continue;
+        const Box &A = boxes[i];
+        std::vector<int> &ids = box_rects[i];
+        std::sort(ids.begin(), ids.end(), [&](int a, int b) { return rects[a].id < rects[b].id; });
+        ids.erase(std::unique(ids.begin(), ids.end()), ids.end());
+        RoomBounds &bd = out.bounds[(size_t)final_id[i]];
+        memset(&bd, 0, sizeof bd);
+        bd.lo[0] = A.lo[0]; bd.lo[1] = A.lo[1]; bd.lo[2] = A.lo[2]; bd.hi_x = A.hi[0]; bd.hi_y = A.hi[1]; bd.hi_z = A.hi[2];
+        uint32_t code[6];
         for (int f = 0; f < 6; f++) {
             const int a = f >> 1, side = f & 1;
-            const float c = side ? L.hi[a] : L.lo[a];
+            const float c = side ? A.hi[a] : A.lo[a];
             const int u = a == 0 ? 1 : 0, v = a == 2 ? 1 : 2;
-            L.face_begin[f] = (int32_t)out.entries.size();
-            for (int id : leaf_rects[li]) {
+            items.clear();
+            for (int id : ids) {
                 const ARect &r = rects[id];
                 // leaving towards +axis (side 1) faces normals -axis, and the other way round (rectangle.c:70-72)
                 if (r.axis != a || r.c != c || r.neg != side) continue;
-                if (!(fmaxf(r.lo[u], L.lo[u]) < fminf(r.hi[u], L.hi[u])) || !(fmaxf(r.lo[v], L.lo[v]) < fminf(r.hi[v], L.hi[v])))
+                if (!(fmaxf(r.lo[u], A.lo[u]) < fminf(r.hi[u], A.hi[u])) || !(fmaxf(r.lo[v], A.lo[v]) < fminf(r.hi[v], A.hi[v])))
                     continue;
-                RoomEntry e;
-                memset(&e, 0, sizeof e);
-                e.u_lo = r.lo[u]; e.u_hi = r.hi[u]; e.v_lo = r.lo[v]; e.v_hi = r.hi[v];
-                e.target = r.id; e.c = c;
-                out.entries.push_back(e);
+                items.push_back(FaceItem{{r.lo[u], r.lo[v]}, {r.hi[u], r.hi[v]}, kRoomCodeWall | (uint32_t)r.id});
             }
             behind.clear();
             const bool at_root = side ? c >= root.hi[a] : c <= root.lo[a];
-            if (!at_root) query_face(nodes, 0, a, c, side ? +1 : -1, L.lo, L.hi, behind);
+            if (!at_root) query_face(nodes, 0, a, c, side ? +1 : -1, A.lo, A.hi, behind);
+            for (int &nb : behind) nb = resolve(nb);
+            std::sort(behind.begin(), behind.end());
+            behind.erase(std::unique(behind.begin(), behind.end()), behind.end());
             for (int nb : behind) {
-                const RoomLeaf &B = out.leaves[nb];
-                RoomEntry e;
-                memset(&e, 0, sizeof e);
-                e.u_lo = B.lo[u]; e.u_hi = B.hi[u]; e.v_lo = B.lo[v]; e.v_hi = B.hi[v];
-                e.target = ~nb; e.c = c;
-                out.entries.push_back(e);
+                const Box &B = boxes[nb];
+                items.push_back(FaceItem{{B.lo[u], B.lo[v]}, {B.hi[u], B.hi[v]}, kRoomCodeBox | (uint32_t)final_id[nb]});
             }
+            const Region face = {{A.lo[u], A.lo[v]}, {A.hi[u], A.hi[v]}};
+            code[f] = ftb.build(face, items, 0);
         }
-        L.face_begin[6] = (int32_t)out.entries.size();
+        RoomBox &rb = out.boxes[(size_t)final_id[i]];
+        memset(&rb, 0, sizeof rb);
+        for (int o = 0; o < 8; o++)
+            for (int k = 0; k < 3; k++) {
+                const int side = (o >> k) & 1;
+                rb.oct[o].far[k] = side ? A.hi[k] : A.lo[k];
+                rb.oct[o].code[k] = code[2 * k + side];
+            }
     }
-    // per emitter: the leaves its rectangle touches (closed overlap with the rectangle grown by the start offset)
+    if (out.face_nodes.size() > kRoomCodeIndex) return "more than 2^30 face nodes";
+    if (out.face_nodes.empty()) out.face_nodes.push_back(RoomFaceNode{0.0f, kRoomCodeMiss, kRoomCodeMiss, 0u});   // never empty
+
+    // ---- per emitter: the boxes its rectangle touches (closed overlap with the rectangle grown by the start offset) --------
     {
         std::vector<int> stack_n;
+        std::vector<std::pair<double, int>> cand;
         for (int e = 0; e < num_windows + num_lights; e++) {
             const fmgi_rect &r = e < num_windows ? windows[e] : lights[e - num_windows];
             float lo[3], hi[3];
@@ -244,24 +446,37 @@ const char *build_rooms(RoomScene &out, const fmgi_rect *walls, int num_walls, c
                 const float a = r.pos[k], b2 = r.pos[k] + r.width[k] + r.height[k];
                 lo[k] = fminf(a, b2) - 3e-5f; hi[k] = fmaxf(a, b2) + 3e-5f;
             }
-            out.start_range.push_back((int32_t)out.start_leaves.size());
+            out.start_range.push_back((int32_t)out.start_boxes.size());
+            cand.clear();
             stack_n.assign(1, 0);
             while (!stack_n.empty()) {
                 const Node nd = nodes[stack_n.back()];
                 stack_n.pop_back();
-                if (nd.axis < 0) { out.start_leaves.push_back(nd.leaf); continue; }
+                if (nd.axis < 0) {
+                    const int b = resolve(nd.leaf);
+                    double vol = 1.0;
+                    for (int k = 0; k < 3; k++) vol *= (double)fminf(hi[k], boxes[b].hi[k]) - (double)fmaxf(lo[k], boxes[b].lo[k]);
+                    bool seen = false;
+                    for (auto &c : cand) seen |= c.second == final_id[b];
+                    if (!seen) cand.push_back({-vol, final_id[b]});
+                    continue;
+                }
                 if (lo[nd.axis] <= nd.v) stack_n.push_back(nd.left);
                 if (hi[nd.axis] >= nd.v) stack_n.push_back(nd.right);
             }
-            out.start_range.push_back((int32_t)out.start_leaves.size());
+            std::sort(cand.begin(), cand.end());
+            for (auto &c : cand) out.start_boxes.push_back(c.second);
+            out.start_range.push_back((int32_t)out.start_boxes.size());
         }
+        if (out.start_boxes.empty()) out.start_boxes.push_back(0);
+        if (out.start_range.empty()) { out.start_range.push_back(0); out.start_range.push_back(0); }
     }
     // the tree itself, for point location
     out.nodes.resize(nodes.size());
     for (size_t i = 0; i < nodes.size(); i++) {
         RoomNode &n = out.nodes[i];
         n.v = nodes[i].v; n.axis = nodes[i].axis;
-        n.left = nodes[i].axis < 0 ? nodes[i].leaf : nodes[i].left;
+        n.left = nodes[i].axis < 0 ? final_id[resolve(nodes[i].leaf)] : nodes[i].left;
         n.right = nodes[i].right;
     }
     for (int k = 0; k < 3; k++) { out.root_lo[k] = root.lo[k]; out.root_hi[k] = root.hi[k]; }
@@ -269,7 +484,7 @@ const char *build_rooms(RoomScene &out, const fmgi_rect *walls, int num_walls, c
     return "";
 }
 
-// Leaf a ray that starts at p and travels along d is in: tree descent; a point exactly on a split plane belongs to
+// Box a ray that starts at p and travels along d is in: tree descent; a point exactly on a split plane belongs to
 // the side the ray travels towards.
 int rooms_locate(const RoomScene &rs, const float p[3], const float d[3])
 {
@@ -285,40 +500,41 @@ int rooms_locate(const RoomScene &rs, const float p[3], const float d[3])
     return rs.nodes[n].left;
 }
 
-// Host replay of the device traversal.
-int rooms_closest_hit(const RoomScene &rs, int leaf, const float o[3], const float d[3], float &t_out, int &leaf_out,
+// Host replay of the device traversal (rooms_walk in trace_kernels.cuh), same float operations.
+int rooms_closest_hit(const RoomScene &rs, int box, const float o[3], const float d[3], float &t_out, int &box_out,
                       long &steps, long &tests)
 {
-    const float inf = INFINITY;
-    t_out = inf;
-    leaf_out = leaf;
-    for (int guard = 0; guard < 1 << 16 && leaf >= 0; guard++) {
-        const RoomLeaf &L = rs.leaves[leaf];
+    t_out = INFINITY;
+    box_out = box;
+    const int oct = (d[0] > 0 ? 1 : 0) | (d[1] > 0 ? 2 : 0) | (d[2] > 0 ? 4 : 0);
+    float inv[3];
+    for (int k = 0; k < 3; k++) inv[k] = d[k] == 0 ? -1e30f : 1.0f / d[k];
+    for (int guard = 0; guard < 1 << 16 && box >= 0; guard++) {
+        const RoomOctant &R = rs.boxes[(size_t)box].oct[oct];
         steps++;
         float tk[3];
-        for (int k = 0; k < 3; k++) tk[k] = d[k] == 0 ? inf : ((d[k] > 0 ? L.hi[k] : L.lo[k]) - o[k]) / d[k];
+        for (int k = 0; k < 3; k++) tk[k] = (R.far[k] - o[k]) * inv[k];
         int a = 0;
-        if (tk[1] < tk[a]) a = 1;
-        if (tk[2] < tk[a]) a = 2;
-        const float t = tk[a];
-        if (!(t < inf)) return -1;
+        if (tk[1] < tk[0]) a = 1;
+        if (tk[2] < fminf(tk[0], tk[1])) a = 2;
+        const float t = fminf(fminf(tk[0], tk[1]), tk[2]);
         const int u = a == 0 ? 1 : 0, v = a == 2 ? 1 : 2;
-        const float pu = o[u] + t * d[u], pv = o[v] + t * d[v];
-        const int f = 2 * a + (d[a] > 0 ? 1 : 0);
-        int next = -1;
-        bool found = false;
-        for (int q = L.face_begin[f]; q < L.face_begin[f + 1]; q++) {
-            const RoomEntry &e = rs.entries[q];
+        const float pu = fmaf(t, d[u], o[u]), pv = fmaf(t, d[v], o[v]);
+        uint32_t code = R.code[a];
+        while ((code & kRoomCodeKind) == kRoomCodeNode) {
+            const RoomFaceNode &n = rs.face_nodes[code];
             tests++;
-            if (pu >= e.u_lo && pu <= e.u_hi && pv >= e.v_lo && pv <= e.v_hi) {
-                if (e.target >= 0) { t_out = t; leaf_out = leaf; return e.target; }
-                next = ~e.target;
-                found = true;
-                break;
-            }
+            code = (n.axis ? pv : pu) >= n.split ? n.hi : n.lo;
         }
-        if (!found) return -1;
-        leaf = next;
+        const uint32_t kind = code & kRoomCodeKind, index = code & kRoomCodeIndex;
+        if (kind == kRoomCodeWall) {
+            if (!(t >= 0)) return -1;                 // the plane lies behind the origin: not a hit (rectangle.c:76)
+            t_out = (R.far[a] - o[a]) / d[a];
+            box_out = box;
+            return (int)index;
+        }
+        if (kind == kRoomCodeMiss) return -1;
+        box = (int)index;
     }
     return -1;
 }

@@ -64,7 +64,11 @@ __device__ __forceinline__ SoupTables stage_soup(const TraceParams &p, float4 *s
 // horizontal rectangles looked up through the grid's plane tables) or FMGI_TIER_GRID (floor-plan grid in L2).
 // kCount: also count the rectangle tests the grid lookups execute (fmgi_options.count_tests; two more
 // instructions in the walk loop, so not the default).
-template <int kTier, int kDeposit, bool kProbe, int kMinBlocks, bool kCount = false>
+// kRoomSteps (room tier): boxes a lane's ray crosses per iteration of the photon loop.  The room tier does not walk a
+// ray to its hit before the warp goes on: a lane whose ray is still between boxes after kRoomSteps keeps walking in
+// the next iteration while the lanes that hit something shade, deposit and draw their next ray - the warp never
+// waits for its longest walk.
+template <int kTier, int kDeposit, bool kProbe, int kMinBlocks, bool kCount = false, int kRoomSteps = 2>
 __global__ void __launch_bounds__(kTraceThreads, kMinBlocks) k_trace(const TraceParams p)
 {
     extern __shared__ float4 smem[];
@@ -79,6 +83,9 @@ __global__ void __launch_bounds__(kTraceThreads, kMinBlocks) k_trace(const Trace
     float px = 0, py = 0, pz = 0, dx = 0, dy = 0, dz = 1;
     float cr = 0, cg = 0, cb = 0, roulette = 0;
     int depth = 0, emitter = 0, hit_id = 0, leaf = 0;            // leaf: the photon's box (room tier)
+    bool walking = false;                                        // room tier: the lane's ray is between boxes
+    float ix = 0, iy = 0, iz = 0;                                // room tier: rooms_inv of the direction
+    int boxes = 0;                                               // room tier: boxes the current ray has crossed
     unsigned long long photon = 0;
     // the warp's chunk (warp uniform): photon indices w_base + [w_pos, w_cnt) of emitter w_emitter
     unsigned long long w_base = 0;
@@ -134,7 +141,7 @@ __global__ void __launch_bounds__(kTraceThreads, kMinBlocks) k_trace(const Trace
 
         bool dep = false;
         int idx = 0;
-        if (alive) {
+        if (alive && !(kTier == kTierRooms && walking)) {
             // ---- P. one Philox2x32 block per event: emission direction (event 0) or the bounce just done ----
             const uint32_t idw = philox_event_word((uint32_t)(photon >> 32), (uint32_t)emitter, 0u);
             const Philox2 w = philox2x32_10((uint32_t)photon, idw | ((uint32_t)depth << 28), p.philox_keys);
@@ -171,19 +178,30 @@ __global__ void __launch_bounds__(kTraceThreads, kMinBlocks) k_trace(const Trace
                 pz = __fadd_rn(__fadd_rn(pz, __fmul_rn(e1.z, sx)), __fmul_rn(e2.z, sy));
             }
 
+            if (kTier == kTierRooms) {
+                if (is_new) leaf = rooms_start(p, emitter, px, py, pz, dx, dy, dz);
+                ix = rooms_inv(dx); iy = rooms_inv(dy); iz = rooms_inv(dz);
+                boxes = 0;
+            }
+            n_rays++;
+        }
+        if (alive) {
             // ---- C. closest hit (photonmap.c:198 / photonmap.cl:194-206) ---------------------------
             float t;
             if (kTier == FMGI_TIER_SOUP) hit_id = closest_hit_soup(soup, px, py, pz, dx, dy, dz, t);
             else if (kTier == kTierSoupPlanes) hit_id = closest_hit_soup_planes<kCount>(soup, p, px, py, pz, dx, dy, dz, t, n_tests);
             else if (kTier == kTierRooms) {
-                if (is_new) leaf = rooms_start(p, emitter, px, py, pz, dx, dy, dz);
-                hit_id = closest_hit_rooms<kCount>(p, leaf, px, py, pz, dx, dy, dz, t, &n_tests);
+                hit_id = rooms_walk<kCount, kRoomSteps>(p, leaf, px, py, pz, dx, dy, dz, ix, iy, iz, t, n_tests);
+                boxes += kRoomSteps;
+                if (hit_id == kRoomWalking && boxes >= kRoomMaxSteps) hit_id = -1;
+                walking = hit_id == kRoomWalking;
             }
             else hit_id = closest_hit_grid<kCount>(p, px, py, pz, dx, dy, dz, t, n_tests);
-            n_rays++;
 
             // ---- D. bounce: texel, roulette, attenuation (photonmap.c:200-247) ------------------------
-            if (hit_id < 0 || !FMGI_CHECK(p, (unsigned)hit_id < p.num_walls, 8)) {
+            if (kTier == kTierRooms && walking) {
+                // between boxes: nothing to shade yet
+            } else if (hit_id < 0 || !FMGI_CHECK(p, (unsigned)hit_id < p.num_walls, 8)) {
                 alive = false;                                   // photonmap.c:200-201: photon leaves the flat
             } else {
                 px = __fadd_rn(px, __fmul_rn(dx, t));            // photonmap.c:208

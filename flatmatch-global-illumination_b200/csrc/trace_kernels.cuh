@@ -41,6 +41,7 @@ constexpr unsigned kFullMask = 0xffffffffu;
 constexpr int kTierSoupPlanes = 3;
 // room tier (room_tables.h): FMGI_TIER_ROOMS
 constexpr int kTierRooms = FMGI_TIER_ROOMS;
+constexpr int kRoomBoxVec = 16;             // float4 per RoomBox (room_tables.h)
 
 struct TraceParams {
     // closest-hit tables (global memory; staged into shared memory by the soup kernel)
@@ -75,15 +76,17 @@ struct TraceParams {
     uint32_t philox_keys[10];       // seed + r * W: the Philox2x32 round keys of this bake (philox.cuh)
     int grid_has_misc;              // the walk lists hold misc records (scene_tables.h)
     int one;                        // 1, opaque to the compiler: x * one + y keeps integer updates on the FMA pipe
-    // room tier (room_tables.h): leaf boxes (4 float4 each), face entries (2 float4 each), kd-tree nodes (1 float4 each)
-    const float4 *room_leaves;
-    const float4 *room_entries;
+    // room tier (room_tables.h): boxes (16 float4 each: 8 octant records), face-tree nodes, box bounds (2 float4 each),
+    // kd-tree nodes for point location (1 float4 each)
+    const float4 *room_boxes;
+    const float4 *room_face_nodes;
+    const float4 *room_bounds;
     const float4 *room_nodes;
-    const int *room_start_range;    // per emitter: [2e], [2e + 1]: its candidate first leaves in room_start_leaves
-    const int *room_start_leaves;
+    const int *room_start_range;    // per emitter: [2e], [2e + 1]: its candidate first boxes in room_start_boxes
+    const int *room_start_boxes;
     float room_lo[3], room_hi[3];   // the root box
     // table sizes: read only by the bounds-checked build (FMGI_CHECKED, lib/libfmgi_cuda_checked.so)
-    unsigned grid_records, num_walls, num_texels, room_num_leaves, room_num_entries, room_num_nodes;
+    unsigned grid_records, num_walls, num_texels, room_num_boxes, room_num_face_nodes, room_num_nodes;
 };
 
 // ---- bounds-checked build ----------------------------------------------------------------------------------------
@@ -672,7 +675,7 @@ __device__ __forceinline__ int closest_hit_soup_planes(const SoupTables &s, cons
 
 // ---- closest hit through the box decomposition (room tier, room_tables.h) -----------------------------------------
 
-// Leaf a ray that starts at (x, y, z) and travels along d is in: kd-tree descent; a point exactly on a split plane
+// Box a ray that starts at (x, y, z) and travels along d is in: kd-tree descent; a point exactly on a split plane
 // belongs to the side the ray travels towards.  The point is clamped into the root box first.
 __device__ __forceinline__ int rooms_locate(const TraceParams &p, float x, float y, float z, float dx, float dy, float dz)
 {
@@ -693,78 +696,94 @@ __device__ __forceinline__ int rooms_locate(const TraceParams &p, float x, float
     return 0;
 }
 
-// First box of a photon emitted by `emitter`: one of the (one or two) boxes the emitter rectangle touches - the one
-// that contains the start point - else the tree descent.
+// First box of a photon emitted by `emitter`: the box the emitter rectangle lies in; where it touches several, the
+// one that contains the start point (largest share first), else the tree descent.
 __device__ __forceinline__ int rooms_start(const TraceParams &p, int emitter, float x, float y, float z, float dx, float dy,
                                            float dz)
 {
     const int b = __ldg(p.room_start_range + 2 * emitter), e = __ldg(p.room_start_range + 2 * emitter + 1);
+    if (e - b == 1) return __ldg(p.room_start_boxes + b);
     for (int q = b; q < e; q++) {
-        const int leaf = __ldg(p.room_start_leaves + q);
-        float4 b0, b1;
-        ldg256(p.room_leaves + 4 * leaf, b0, b1);
-        if (x >= b0.x && x <= b0.w && y >= b0.y && y <= b1.x && z >= b0.z && z <= b1.y) return leaf;
+        const int box = __ldg(p.room_start_boxes + q);
+        float4 b0, b1;                                   // {lo.x, lo.y, lo.z, hi.x}, {hi.y, hi.z, -, -}
+        ldg256(p.room_bounds + 2 * box, b0, b1);
+        if (x >= b0.x && x <= b0.w && y >= b0.y && y <= b1.x && z >= b0.z && z <= b1.y) return box;
     }
     return rooms_locate(p, x, y, z, dx, dy, dz);
 }
 
-// The ray leaves its box through the nearest of the three faces it travels towards; the face's entries - first the
-// colliders that face into the box, in wall-index order, then the boxes behind the face - say what is at the exit
-// point: a hit (the closest one: nothing lies inside a box), the next box, or nothing (the ray leaves the scene).
-// `leaf` is the box the ray starts in and, on return, the box the hit was found in: a bounce starts there.
-// A collider whose plane lies BEHIND the origin (negative ray parameter: an origin that rounding put a few ulps
-// beyond a wall) is not a hit (rectangle.c:76 rejects t < 0): the ray goes on into the box behind it.
+// 1 / d for the slab tests of the walk.  A ray parallel to an axis never reaches that axis' faces: d = 0 takes a
+// huge NEGATIVE finite value - the slab test then reads the box's lower bound (d > 0 is false), lower bound minus
+// origin is <= 0, and the product is a huge positive ray parameter (or 0 for an origin exactly on that face, which
+// hands the ray to the neighbour it touches).
+__device__ __forceinline__ float rooms_inv(float d) { return d == 0.0f ? -1e30f : rcp_fast(d); }
+
+constexpr int kRoomWalking = -2;          // rooms_walk: the ray is in box `box`, still on its way
+constexpr int kRoomMaxSteps = 4096;       // boxes per ray before the photon is given up (never reached by a sane table)
+constexpr unsigned kRoomKindShift = 30;   // room_tables.h: kRoomCode*
+
+// The ray leaves its box through the nearest of the three faces it travels towards; the face's code - after a
+// descent through the face's 2-D kd-tree where several things share the face - says what is at the exit point: a
+// collider that faces into the box (a hit - the closest one: nothing lies inside a box), the next box, or nothing
+// (the ray leaves the scene).  At most kSteps boxes per call: returns the wall index, -1 (miss), or kRoomWalking
+// with `box` = the box the ray is in now, so that the caller can interleave the walks of a warp's lanes with their
+// shading instead of waiting for the longest walk (k_trace).  On a hit `box` is the box the hit was found in: the
+// bounce starts there.  (ix, iy, iz) = rooms_inv of the direction.
+// A collider whose plane lies BEHIND the origin (negative ray parameter: an origin that rounding put an ulp
+// beyond a wall, in a corner) is not a hit (rectangle.c:76 rejects t < 0); the photon is given up.
+template <bool kCount, int kSteps>
+__device__ __forceinline__ int rooms_walk(const TraceParams &p, int &box, float ox, float oy, float oz, float dx, float dy,
+                                          float dz, float ix, float iy, float iz, float &t_out, unsigned &tests)
+{
+    // the ray's octant picks the 32-byte record of each box: far planes and face codes of the three faces ahead
+    const float4 *base = p.room_boxes + ((dx > 0.0f ? 2 : 0) + (dy > 0.0f ? 4 : 0) + (dz > 0.0f ? 8 : 0));
+    int cur = box;
+#pragma unroll 1
+    for (int s = 0; s < kSteps; s++) {
+        if (!FMGI_CHECK(p, (unsigned)cur < p.room_num_boxes, 21)) return -1;
+        float4 r0, r1;                                   // {far.x, far.y, far.z, code.x}, {code.y, code.z, -, -}
+        ldg256(base + kRoomBoxVec * cur, r0, r1);
+        const float tx = (r0.x - ox) * ix, ty = (r0.y - oy) * iy, tz = (r0.z - oz) * iz;
+        // nearest face; the two in-plane coordinates of the exit point, in ascending axis order
+        const float txy = fminf(tx, ty);
+        const bool ax_y = ty < tx, ax_z = tz < txy;
+        const float t = fminf(txy, tz);
+        const float hx = fmaf(t, dx, ox), hy = fmaf(t, dy, oy), hz = fmaf(t, dz, oz);
+        const float pu = (ax_y || ax_z) ? hx : hy, pv = ax_z ? hy : hz;
+        unsigned code = __float_as_uint(ax_z ? r1.y : (ax_y ? r1.x : r0.w));
+        while ((code >> kRoomKindShift) == 0u) {         // several things on this face: descend its 2-D kd-tree
+            if (!FMGI_CHECK(p, code < p.room_num_face_nodes, 22)) return -1;
+            const float4 n = __ldg(p.room_face_nodes + code);       // {split, lo, hi, axis}
+            if (kCount) tests++;
+            code = __float_as_uint(((__float_as_uint(n.w) != 0u ? pv : pu) >= n.x) ? n.z : n.y);
+        }
+        const unsigned kind = code >> kRoomKindShift, index = code & ((1u << kRoomKindShift) - 1u);
+        if (kind == 2u) { cur = (int)index; continue; }
+        if (kind == 1u && t >= 0.0f) {
+            // the distance with the reference's formula for an axis-parallel normal, IEEE division
+            const float ca = ax_z ? r0.z : (ax_y ? r0.y : r0.x);
+            const float oa = ax_z ? oz : (ax_y ? oy : ox), da = ax_z ? dz : (ax_y ? dy : dx);
+            t_out = __fdiv_rn(__fsub_rn(ca, oa), da);
+            box = cur;
+            return (int)index;
+        }
+        return -1;                                       // nothing there: the ray leaves the scene
+    }
+    box = cur;
+    return kRoomWalking;
+}
+
+// The whole walk of one ray (probes, ambient occlusion).
 template <bool kCount = false>
 __device__ __forceinline__ int closest_hit_rooms(const TraceParams &p, int &leaf, float ox, float oy, float oz, float dx,
                                                  float dy, float dz, float &t_out, unsigned *tests = nullptr)
 {
-    const float inf = __int_as_float(0x7f800000);
-    const float ix = rcp_fast(dx), iy = rcp_fast(dy), iz = rcp_fast(dz);
-    const bool xp = dx > 0.0f, yp = dy > 0.0f, zp = dz > 0.0f;
-    t_out = inf;
-    int cur = leaf;
-#pragma unroll 1
-    for (int guard = 0; guard < 4096; guard++) {
-        if (!FMGI_CHECK(p, (unsigned)cur < p.room_num_leaves, 21)) return -1;
-        const float4 *L = p.room_leaves + 4 * cur;
-        float4 b0, b1;                                   // {lo.x, lo.y, lo.z, hi.x}, {hi.y, hi.z, -, -}
-        ldg256(L, b0, b1);
-        float tx = ((xp ? b0.w : b0.x) - ox) * ix, ty = ((yp ? b1.x : b0.y) - oy) * iy, tz = ((zp ? b1.y : b0.z) - oz) * iz;
-        tx = dx == 0.0f ? inf : tx; ty = dy == 0.0f ? inf : ty; tz = dz == 0.0f ? inf : tz;
-        // nearest face; the two in-plane coordinates of the exit point, in ascending axis order
-        const bool ax_y = ty < tx, ax_z = tz < fminf(tx, ty);
-        const float t = fminf(fminf(tx, ty), tz);
-        const int a = ax_z ? 2 : (ax_y ? 1 : 0);
-        const float hx = fmaf(t, dx, ox), hy = fmaf(t, dy, oy), hz = fmaf(t, dz, oz);
-        const float pu = a == 0 ? hy : hx, pv = a == 2 ? hy : hz;
-        const int f = 2 * a + ((a == 0 ? xp : (a == 1 ? yp : zp)) ? 1 : 0);
-        const int *fb = reinterpret_cast<const int *>(L + 2) + f;
-        int q = __ldg(fb);
-        const int qe = __ldg(fb + 1);
-        int next = -1;
-        for (; q < qe; q++) {
-            if (!FMGI_CHECK(p, (unsigned)q < p.room_num_entries, 22)) break;
-            float4 e0, e1;                               // {u_lo, u_hi, v_lo, v_hi}, {target, c, -, -}
-            ldg256(p.room_entries + 2 * q, e0, e1);
-            if (kCount) (*tests)++;
-            if (pu >= e0.x && pu <= e0.y && pv >= e0.z && pv <= e0.w) {
-                const int target = __float_as_int(e1.x);
-                if (target >= 0) {
-                    if (t < 0.0f) continue;              // the plane lies behind the origin
-                    // the distance with the reference's formula for an axis-parallel normal, IEEE division
-                    const float oa = a == 0 ? ox : (a == 1 ? oy : oz), da = a == 0 ? dx : (a == 1 ? dy : dz);
-                    t_out = __fdiv_rn(__fsub_rn(e1.y, oa), da);
-                    leaf = cur;
-                    return target;
-                }
-                next = ~target;
-                break;
-            }
-        }
-        if (next < 0) return -1;                         // nothing behind this part of the face: the ray leaves the scene
-        cur = next;
-    }
-    return -1;
+    unsigned n = 0;
+    t_out = __int_as_float(0x7f800000);
+    const int r = rooms_walk<kCount, kRoomMaxSteps>(p, leaf, ox, oy, oz, dx, dy, dz, rooms_inv(dx), rooms_inv(dy), rooms_inv(dz),
+                                                    t_out, n);
+    if (kCount && tests) *tests += n;
+    return r == kRoomWalking ? -1 : r;
 }
 
 // ---- texel index: rectangle.c:205-230, same operations in the same order, no contraction ----------

@@ -26,6 +26,11 @@ MARKERS = {
         (r"int finish\(", "finish"),
         (r"int closest_hit_grid\(", "closest-hit call"),
         (r"int closest_hit_soup_planes\(", "soup + planes"),
+        (r"int rooms_locate\(", "rooms locate"),
+        (r"int rooms_start\(", "rooms start"),
+        (r"float rooms_inv\(", "rooms walk"),
+        (r"ldg256\(E, e0, e1\)", "rooms entry chain"),
+        (r"^// The whole walk of one ray", "rooms whole walk"),
         (r"int tile_index\(", "tile index"),
         (r"void sample_hemisphere\(", "sampler"),
         (r"void deposit\(", "deposit"),

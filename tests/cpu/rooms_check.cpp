@@ -60,10 +60,8 @@ int main(int argc, char **argv)
     RoomScene rs;
     const char *why = build_rooms(rs, walls.data(), cnt[0], windows.data(), cnt[1], lights.data(), cnt[2]);
     if (why[0]) { printf("refused: %s\n", why); return 3; }
-    size_t wall_entries = 0;
-    for (const RoomEntry &e : rs.entries) wall_entries += e.target >= 0;
-    printf("rooms: %zu leaves, %zu entries (%zu colliders, %zu portals), depth %d, build %.1f ms\n", rs.leaves.size(),
-           rs.entries.size(), wall_entries, rs.entries.size() - wall_entries, rs.max_depth, rs.build_ms);
+    printf("rooms: %zu boxes (%zu kd leaves), %zu face parts (%zu colliders), %zu face nodes, depth %d, build %.1f ms\n",
+           rs.boxes.size(), rs.kd_leaves, rs.face_parts, rs.wall_parts, rs.face_nodes.size(), rs.max_depth, rs.build_ms);
 
     // rays as the path produces them: half start inside the bounding box, half on a wall (offset 1e-5 along the ray)
     float lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
@@ -74,7 +72,7 @@ int main(int argc, char **argv)
                 lo[k] = fminf(lo[k], x); hi[k] = fmaxf(hi[k], x);
             }
     long steps = 0, tests = 0, mism = 0, mism_edge = 0, hits = 0, max_steps = 0;
-    std::vector<long> hist(32, 0);
+    std::vector<long> hist(32, 0), ehist(32, 0);
     for (int i = 0; i < num_rays; i++) {
         float o[3], d[3];
         double n2 = 0;
@@ -100,12 +98,13 @@ int main(int argc, char **argv)
         }
         float t;
         int leaf_out;
-        long s0 = steps;
+        long s0 = steps, e0 = tests;
         const int leaf = rooms_locate(rs, o, d);
         const int got = leaf < 0 ? -1 : rooms_closest_hit(rs, leaf, o, d, t, leaf_out, steps, tests);
         const long st = steps - s0;
         max_steps = std::max(max_steps, st);
         hist[std::min<long>(st, 31)]++;
+        ehist[std::min<long>(tests - e0, 31)]++;
         hits += got >= 0;
         if (got != want) {
             mism++;
@@ -116,10 +115,67 @@ int main(int argc, char **argv)
             mism_edge++;
         }
     }
-    printf("rays %d: hits %.3f, steps/ray %.3f (max %ld), entry tests/ray %.3f, index mismatches %ld, distance mismatches %ld\n",
+    printf("rays %d: hits %.3f, steps/ray %.3f (max %ld), face nodes/ray %.3f, index mismatches %ld, distance mismatches %ld\n",
            num_rays, (double)hits / num_rays, (double)steps / num_rays, max_steps, (double)tests / num_rays, mism, mism_edge);
     printf("steps histogram:");
     for (int i = 0; i < 16; i++) printf(" %d:%.3f", i, (double)hist[i] / num_rays);
+    // the rays a bake traces: photons from the emitters (by area), diffuse bounces, up to 4 deposits
+    {
+        std::vector<fmgi_rect> em(windows);
+        em.insert(em.end(), lights.begin(), lights.end());
+        std::vector<double> cum;
+        double tot = 0;
+        for (const fmgi_rect &r : em) {
+            const double w = sqrt((double)r.width[0] * r.width[0] + r.width[1] * r.width[1] + r.width[2] * r.width[2]);
+            const double h = sqrt((double)r.height[0] * r.height[0] + r.height[1] * r.height[1] + r.height[2] * r.height[2]);
+            tot += w * h;
+            cum.push_back(tot);
+        }
+        long psteps = 0, pnodes = 0, prays = 0;
+        std::vector<long> ph(32, 0), pn(32, 0);
+        for (int i = 0; i < num_rays / 2 && !em.empty(); i++) {
+            const double x = urand() * tot;
+            const size_t e = std::lower_bound(cum.begin(), cum.end(), x) - cum.begin();
+            const fmgi_rect *src = &em[std::min(e, em.size() - 1)];
+            float o[3], d[3], nrm[3] = {src->n[0], src->n[1], src->n[2]};
+            const float a = (float)urand(), b = (float)urand();
+            for (int k = 0; k < 3; k++) o[k] = src->pos[k] + a * src->width[k] + b * src->height[k];
+            int box = -2;
+            for (int depth = 0; depth < 4; depth++) {
+                double n2;
+                do {
+                    n2 = 0;
+                    for (int k = 0; k < 3; k++) { d[k] = (float)(urand() * 2 - 1); n2 += (double)d[k] * d[k]; }
+                } while (n2 < 1e-4 || n2 > 1);
+                float dn = 0;
+                for (int k = 0; k < 3; k++) { d[k] = (float)(d[k] / sqrt(n2)); dn += d[k] * nrm[k]; }
+                if (dn < 0) for (int k = 0; k < 3; k++) d[k] -= 2 * dn * nrm[k];
+                for (int k = 0; k < 3; k++) o[k] += d[k] * 1e-5f;
+                if (box == -2) box = rooms_locate(rs, o, d);
+                if (box < 0) break;
+                long s0 = steps, n0 = tests;
+                float t;
+                int box_out;
+                const int got = rooms_closest_hit(rs, box, o, d, t, box_out, steps, tests);
+                prays++;
+                psteps += steps - s0; pnodes += tests - n0;
+                ph[std::min<long>(steps - s0, 31)]++; pn[std::min<long>(tests - n0, 31)]++;
+                steps = s0; tests = n0;
+                if (got < 0) break;
+                for (int k = 0; k < 3; k++) { o[k] += d[k] * t; nrm[k] = walls[got].n[k]; }
+                box = box_out;
+            }
+        }
+        if (prays) {
+            printf("\nphoton rays %ld: steps/ray %.3f, face nodes/ray %.3f\nphoton steps histogram:", prays, (double)psteps / prays,
+                   (double)pnodes / prays);
+            for (int i = 0; i < 12; i++) printf(" %d:%.3f", i, (double)ph[i] / prays);
+            printf("\nphoton face nodes histogram:");
+            for (int i = 0; i < 12; i++) printf(" %d:%.3f", i, (double)pn[i] / prays);
+        }
+    }
+    printf("\nface nodes histogram:");
+    for (int i = 0; i < 16; i++) printf(" %d:%.3f", i, (double)ehist[i] / num_rays);
     printf("\n");
     return mism > num_rays / 20000 + 2 || mism_edge ? 1 : 0;
 }
