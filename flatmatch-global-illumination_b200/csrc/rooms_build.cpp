@@ -12,10 +12,13 @@
 //      as a partition of the face stored as a 2-D kd-tree of RoomFaceNode (a face with one thing on it is a code);
 //   5. per emitter: the boxes its rectangle touches.
 #include <algorithm>
+#include <atomic>
 #include <chrono>
 #include <cmath>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <thread>
 #include <unordered_map>
 
 #include "room_tables.h"
@@ -136,8 +139,9 @@ bool covers(const FaceItem &it, const Region &r)
 }
 
 struct FaceTreeBuilder {
-    RoomScene &out;
-    explicit FaceTreeBuilder(RoomScene &o) : out(o) {}
+    struct Out { std::vector<RoomFaceNode> face_nodes; size_t face_parts = 0, wall_parts = 0; };
+    Out out;                     // node codes are local to `out.face_nodes`; the caller offsets them when it concatenates
+    std::vector<float> cand[2];
 
     // `items`: colliders in wall-index order first, then portals; all overlap `r` with positive area.
     uint32_t build(const Region &r, const std::vector<FaceItem> &items, int depth)
@@ -159,7 +163,7 @@ struct FaceTreeBuilder {
         auto consider = [&](int ax, float v) {
             if (!(v > r.lo[ax] && v < r.hi[ax])) return;
             double cost;
-            if (items.size() > 48) {
+            if (items.size() > 24) {
                 // long lists (the boxes around the building): the edge nearest the middle of the longer side
                 cost = fabs((double)v - 0.5 * ((double)r.lo[ax] + r.hi[ax])) / ext[ax] + (ext[ax] >= ext[1 - ax] ? 0.0 : 1.0);
             } else {
@@ -174,8 +178,14 @@ struct FaceTreeBuilder {
             }
             if (cost < best_cost) { best_cost = cost; best_axis = ax; best_v = v; }
         };
-        for (const FaceItem &it : items)
-            for (int ax = 0; ax < 2; ax++) { consider(ax, it.lo[ax]); consider(ax, it.hi[ax]); }
+        for (int ax = 0; ax < 2; ax++) {
+            std::vector<float> &c = cand[ax];
+            c.clear();
+            for (const FaceItem &it : items) { c.push_back(it.lo[ax]); c.push_back(it.hi[ax]); }
+            std::sort(c.begin(), c.end());
+            c.erase(std::unique(c.begin(), c.end()), c.end());
+            for (float v : c) consider(ax, v);
+        }
         if (best_axis < 0 || depth > 64) {          // nothing cuts the region, yet nothing covers it: keep the first
             out.face_parts++;
             out.wall_parts += first_is_wall;
@@ -195,6 +205,134 @@ struct FaceTreeBuilder {
         return kRoomCodeNode | self;
     }
 };
+
+
+// ---- kd-tree over the colliders ------------------------------------------------------------------------------------
+
+struct KdWork { int node; Box box; std::vector<int> ids; int depth; };
+struct KdSubtree {
+    int root_node = 0, max_depth = 0;
+    std::vector<Node> nodes;                    // nodes[0] = the subtree's root; children are local indices
+    std::vector<Box> boxes;
+    std::vector<std::vector<int>> box_rects;
+};
+
+// The plane a node is split at; false: no collider lies inside the node's box (a leaf).
+bool kd_choose_split(const std::vector<ARect> &rects, const KdWork &w, int &best_axis, float &best_c)
+{
+    best_axis = -1;
+    best_c = 0;
+    if (w.ids.size() > 96) {
+        // big node: of the collider planes that cut it, the one nearest the middle of its longest side that has any
+        int order[3] = {0, 1, 2};
+        std::sort(order, order + 3, [&](int a, int b) { return w.box.hi[a] - w.box.lo[a] > w.box.hi[b] - w.box.lo[b]; });
+        for (int oi = 0; oi < 3 && best_axis < 0; oi++) {
+            const int a = order[oi];
+            const float mid = 0.5f * (w.box.lo[a] + w.box.hi[a]);
+            float best_d = INFINITY;
+            for (int id : w.ids) {
+                const ARect &r = rects[id];
+                if (r.axis != a || !(fabsf(r.c - mid) < best_d) || !interior(w.box, r)) continue;
+                best_d = fabsf(r.c - mid); best_axis = a; best_c = r.c;
+            }
+        }
+        return best_axis >= 0;
+    }
+    // small node: score the collider planes that still cut it by the share of the cross-section they cover
+    struct Plane { int axis; float c; double cover; };
+    Plane planes[128];
+    int np = 0;
+    for (int id : w.ids) {
+        const ARect &r = rects[id];
+        if (!interior(w.box, r)) continue;
+        double area = 1.0;
+        for (int k = 0; k < 3; k++)
+            if (k != r.axis) area *= (double)fminf(r.hi[k], w.box.hi[k]) - (double)fmaxf(r.lo[k], w.box.lo[k]);
+        bool found = false;
+        for (int q = 0; q < np; q++)
+            if (planes[q].axis == r.axis && planes[q].c == r.c) { planes[q].cover += area; found = true; break; }
+        if (!found) planes[np++] = Plane{r.axis, r.c, area};
+    }
+    double best_score = -1;
+    for (int q = 0; q < np; q++) {
+        const Plane &pl = planes[q];
+        const int a = pl.axis;
+        double cross = 1.0;
+        for (int k = 0; k < 3; k++)
+            if (k != a) cross *= (double)w.box.hi[k] - (double)w.box.lo[k];
+        // coverage first; among equals the plane nearest the middle of the box
+        const double mid = 1.0 - fabs(((double)pl.c - w.box.lo[a]) / ((double)w.box.hi[a] - w.box.lo[a]) - 0.5);
+        const double score = pl.cover / cross + 1e-6 * mid;
+        if (score > best_score || (score == best_score && (a < best_axis || (a == best_axis && pl.c < best_c)))) {
+            best_score = score; best_axis = a; best_c = pl.c;
+        }
+    }
+    return best_axis >= 0;
+}
+
+void kd_split(const std::vector<ARect> &rects, const KdWork &w, int axis, float c, KdWork &lw, KdWork &rw)
+{
+    lw.box = w.box; rw.box = w.box;
+    lw.box.hi[axis] = c; rw.box.lo[axis] = c;
+    lw.depth = rw.depth = w.depth + 1;
+    lw.ids.reserve(w.ids.size()); rw.ids.reserve(w.ids.size());
+    for (int id : w.ids) {
+        if (touches(lw.box, rects[id])) lw.ids.push_back(id);
+        if (touches(rw.box, rects[id])) rw.ids.push_back(id);
+    }
+}
+
+void kd_build_subtree(const std::vector<ARect> &rects, KdWork root, KdSubtree &out)
+{
+    out.root_node = root.node;
+    root.node = 0;
+    out.nodes.push_back(Node{-1, 0.0f, -1, -1, -1});
+    std::vector<KdWork> stack;
+    stack.push_back(std::move(root));
+    while (!stack.empty()) {
+        KdWork w = std::move(stack.back());
+        stack.pop_back();
+        out.max_depth = std::max(out.max_depth, w.depth);
+        int axis;
+        float c;
+        if (!kd_choose_split(rects, w, axis, c)) {
+            out.nodes[w.node].axis = -1;
+            out.nodes[w.node].leaf = (int)out.boxes.size();
+            out.boxes.push_back(w.box);
+            out.box_rects.push_back(std::move(w.ids));
+            continue;
+        }
+        KdWork lw, rw;
+        kd_split(rects, w, axis, c, lw, rw);
+        lw.node = (int)out.nodes.size(); out.nodes.push_back(Node{-1, 0.0f, -1, -1, -1});
+        rw.node = (int)out.nodes.size(); out.nodes.push_back(Node{-1, 0.0f, -1, -1, -1});
+        out.nodes[w.node].axis = axis; out.nodes[w.node].v = c;
+        out.nodes[w.node].left = lw.node; out.nodes[w.node].right = rw.node;
+        stack.push_back(std::move(lw));
+        stack.push_back(std::move(rw));
+    }
+}
+
+// fn(i) for i in [0, n) on a pool of threads (a handful of items: on the calling thread)
+template <typename Fn>
+void run_parallel(size_t n, Fn fn)
+{
+    unsigned threads = std::thread::hardware_concurrency();
+    if (const char *v = getenv("FMGI_BUILD_THREADS")) threads = (unsigned)atoi(v);
+    threads = std::min<unsigned>(std::max(threads, 1u), 16u);
+    if (n < 4 || threads == 1) {
+        for (size_t i = 0; i < n; i++) fn(i);
+        return;
+    }
+    std::atomic<size_t> next{0};
+    auto worker = [&]() {
+        for (size_t i = next.fetch_add(1); i < n; i = next.fetch_add(1)) fn(i);
+    };
+    std::vector<std::thread> pool;
+    for (unsigned t = 1; t < threads; t++) pool.emplace_back(worker);
+    worker();
+    for (std::thread &t : pool) t.join();
+}
 
 }  // namespace
 
@@ -231,95 +369,64 @@ const char *build_rooms(RoomScene &out, const fmgi_rect *walls, int num_walls, c
     for (int k = 0; k < 3; k++) { root.lo[k] -= 1.0f; root.hi[k] += 1.0f; }
 
     // ---- kd-tree ------------------------------------------------------------------------------------------
+    // The top of the tree is split here until there are a few dozen subtrees; those are independent and built by a
+    // pool of threads into their own arrays, concatenated in subtree order (the result does not depend on the
+    // number of threads).
     std::vector<Node> nodes;
-    struct Work { int node; Box box; std::vector<int> ids; int depth; };
-    std::vector<Work> stack;
     std::vector<Box> boxes;                     // kd leaves, later merged
     std::vector<std::vector<int>> box_rects;    // colliders that touch the box
-    {
-        Work w;
-        w.node = 0; w.box = root; w.depth = 0;
-        w.ids.resize(rects.size());
-        for (size_t i = 0; i < rects.size(); i++) w.ids[i] = (int)i;
-        nodes.push_back(Node{-1, 0.0f, -1, -1, -1});
-        stack.push_back(std::move(w));
-    }
     const size_t max_leaves = 8u << 20;
-    struct Plane { int axis; float c; double cover; };
-    std::vector<Plane> planes;
-    while (!stack.empty()) {
-        Work w = std::move(stack.back());
-        stack.pop_back();
-        out.max_depth = std::max(out.max_depth, w.depth);
-        int best_axis = -1;
-        float best_c = 0;
-        if (w.ids.size() > 96) {
-            // big node: of the collider planes that cut it, the one nearest the middle of its longest side that has any
-            int order[3] = {0, 1, 2};
-            std::sort(order, order + 3, [&](int a, int b) { return w.box.hi[a] - w.box.lo[a] > w.box.hi[b] - w.box.lo[b]; });
-            for (int oi = 0; oi < 3 && best_axis < 0; oi++) {
-                const int a = order[oi];
-                const float mid = 0.5f * (w.box.lo[a] + w.box.hi[a]);
-                float best_d = INFINITY;
-                for (int id : w.ids) {
-                    const ARect &r = rects[id];
-                    if (r.axis != a || !(fabsf(r.c - mid) < best_d) || !interior(w.box, r)) continue;
-                    best_d = fabsf(r.c - mid); best_axis = a; best_c = r.c;
-                }
-            }
-        } else {
-            // small node: score the collider planes that still cut it by the share of the cross-section they cover
-            planes.clear();
-            for (int id : w.ids) {
-                const ARect &r = rects[id];
-                if (!interior(w.box, r)) continue;
-                double area = 1.0;
-                for (int k = 0; k < 3; k++)
-                    if (k != r.axis) area *= (double)fminf(r.hi[k], w.box.hi[k]) - (double)fmaxf(r.lo[k], w.box.lo[k]);
-                bool found = false;
-                for (Plane &pl : planes)
-                    if (pl.axis == r.axis && pl.c == r.c) { pl.cover += area; found = true; break; }
-                if (!found) planes.push_back(Plane{r.axis, r.c, area});
-            }
-            double best_score = -1;
-            for (const Plane &pl : planes) {
-                const int a = pl.axis;
-                double cross = 1.0;
-                for (int k = 0; k < 3; k++)
-                    if (k != a) cross *= (double)w.box.hi[k] - (double)w.box.lo[k];
-                // coverage first; among equals the plane nearest the middle of the box
-                const double mid = 1.0 - fabs(((double)pl.c - w.box.lo[a]) / ((double)w.box.hi[a] - w.box.lo[a]) - 0.5);
-                const double score = pl.cover / cross + 1e-6 * mid;
-                if (score > best_score || (score == best_score && (a < best_axis || (a == best_axis && pl.c < best_c)))) {
-                    best_score = score; best_axis = a; best_c = pl.c;
-                }
-            }
+    {
+        std::vector<KdWork> top;
+        {
+            KdWork w;
+            w.node = 0; w.box = root; w.depth = 0;
+            w.ids.resize(rects.size());
+            for (size_t i = 0; i < rects.size(); i++) w.ids[i] = (int)i;
+            nodes.push_back(Node{-1, 0.0f, -1, -1, -1});
+            top.push_back(std::move(w));
         }
-        if (best_axis < 0) {
-            const int leaf = (int)boxes.size();
-            if ((size_t)leaf >= max_leaves) return "more than 8M boxes";
-            boxes.push_back(w.box);
-            box_rects.push_back(std::move(w.ids));
-            nodes[w.node].axis = -1;
-            nodes[w.node].leaf = leaf;
-            continue;
+        const size_t want = rects.size() >= 4096 ? 64 : 1;
+        while (top.size() < want) {
+            size_t big = 0;
+            for (size_t i = 1; i < top.size(); i++)
+                if (top[i].ids.size() > top[big].ids.size()) big = i;
+            if (top[big].ids.size() <= 256) break;
+            KdWork w = std::move(top[big]);
+            int axis;
+            float c;
+            if (!kd_choose_split(rects, w, axis, c)) { top[big] = std::move(w); break; }
+            KdWork lw, rw;
+            kd_split(rects, w, axis, c, lw, rw);
+            lw.node = (int)nodes.size(); nodes.push_back(Node{-1, 0.0f, -1, -1, -1});
+            rw.node = (int)nodes.size(); nodes.push_back(Node{-1, 0.0f, -1, -1, -1});
+            nodes[w.node].axis = axis; nodes[w.node].v = c;
+            nodes[w.node].left = lw.node; nodes[w.node].right = rw.node;
+            top[big] = std::move(lw);
+            top.push_back(std::move(rw));
         }
-        Work lw, rw;
-        lw.box = w.box; rw.box = w.box;
-        lw.box.hi[best_axis] = best_c; rw.box.lo[best_axis] = best_c;
-        lw.depth = rw.depth = w.depth + 1;
-        for (int id : w.ids) {
-            if (touches(lw.box, rects[id])) lw.ids.push_back(id);
-            if (touches(rw.box, rects[id])) rw.ids.push_back(id);
+        std::vector<KdSubtree> subs(top.size());
+        run_parallel(top.size(), [&](size_t i) { kd_build_subtree(rects, std::move(top[i]), subs[i]); });
+        for (size_t i = 0; i < subs.size(); i++) {
+            KdSubtree &st = subs[i];
+            const int node_off = (int)nodes.size() - 1, leaf_off = (int)boxes.size();      // local node k > 0 -> node_off + k
+            out.max_depth = std::max(out.max_depth, st.max_depth);
+            auto fix = [&](Node n) {
+                if (n.axis < 0) n.leaf += leaf_off;
+                else { n.left += node_off; n.right += node_off; }
+                return n;
+            };
+            nodes[st.root_node] = fix(st.nodes[0]);
+            for (size_t k = 1; k < st.nodes.size(); k++) nodes.push_back(fix(st.nodes[k]));
+            for (size_t k = 0; k < st.boxes.size(); k++) {
+                boxes.push_back(st.boxes[k]);
+                box_rects.push_back(std::move(st.box_rects[k]));
+            }
+            if (boxes.size() >= max_leaves) return "more than 8M boxes";
         }
-        lw.node = (int)nodes.size(); nodes.push_back(Node{-1, 0.0f, -1, -1, -1});
-        rw.node = (int)nodes.size(); nodes.push_back(Node{-1, 0.0f, -1, -1, -1});
-        nodes[w.node].axis = best_axis; nodes[w.node].v = best_c;
-        nodes[w.node].left = lw.node; nodes[w.node].right = rw.node;
-        stack.push_back(std::move(lw));
-        stack.push_back(std::move(rw));
     }
     out.kd_leaves = boxes.size();
+    const auto t_kd = std::chrono::steady_clock::now();
 
     // ---- merge boxes across collider-free shared faces ---------------------------------------------------------------
     const size_t nb0 = boxes.size();
@@ -368,6 +475,7 @@ const char *build_rooms(RoomScene &out, const fmgi_rect *walls, int num_walls, c
             }
         }
     }
+    const auto t_merge = std::chrono::steady_clock::now();
     // final box ids
     std::vector<int> final_id(nb0, -1);
     int num_boxes = 0;
@@ -383,58 +491,85 @@ const char *build_rooms(RoomScene &out, const fmgi_rect *walls, int num_walls, c
     out.boxes.resize((size_t)num_boxes);
     out.bounds.resize((size_t)num_boxes);
 
-    // ---- faces ------------------------------------------------------------------------------------------------------------
-    FaceTreeBuilder ftb(out);
-    std::vector<int> behind;
-    std::vector<FaceItem> items;
-    for (size_t i = 0; i < nb0; i++) {
-        if (final_id[i] < 0) continue;
-        const Box &A = boxes[i];
-        std::vector<int> &ids = box_rects[i];
-        std::sort(ids.begin(), ids.end(), [&](int a, int b) { return rects[a].id < rects[b].id; });
-        ids.erase(std::unique(ids.begin(), ids.end()), ids.end());
-        RoomBounds &bd = out.bounds[(size_t)final_id[i]];
-        memset(&bd, 0, sizeof bd);
-        bd.lo[0] = A.lo[0]; bd.lo[1] = A.lo[1]; bd.lo[2] = A.lo[2]; bd.hi_x = A.hi[0]; bd.hi_y = A.hi[1]; bd.hi_z = A.hi[2];
-        uint32_t code[6];
-        for (int f = 0; f < 6; f++) {
-            const int a = f >> 1, side = f & 1;
-            const float c = side ? A.hi[a] : A.lo[a];
-            const int u = a == 0 ? 1 : 0, v = a == 2 ? 1 : 2;
-            items.clear();
-            for (int id : ids) {
-                const ARect &r = rects[id];
-                // leaving towards +axis (side 1) faces normals -axis, and the other way round (rectangle.c:70-72)
-                if (r.axis != a || r.c != c || r.neg != side) continue;
-                if (!(fmaxf(r.lo[u], A.lo[u]) < fminf(r.hi[u], A.hi[u])) || !(fmaxf(r.lo[v], A.lo[v]) < fminf(r.hi[v], A.hi[v])))
-                    continue;
-                items.push_back(FaceItem{{r.lo[u], r.lo[v]}, {r.hi[u], r.hi[v]}, kRoomCodeWall | (uint32_t)r.id});
+    // ---- faces (independent per box: chunks of boxes on the thread pool, face nodes concatenated in chunk order) ----------
+    std::vector<int> root_of(nb0);
+    for (size_t i = 0; i < nb0; i++) root_of[i] = resolve((int)i);
+    std::vector<int> live;
+    live.reserve((size_t)num_boxes);
+    for (size_t i = 0; i < nb0; i++)
+        if (final_id[i] >= 0) live.push_back((int)i);
+    const size_t chunk = 64, num_chunks = (live.size() + chunk - 1) / chunk;
+    std::vector<FaceTreeBuilder::Out> chunk_out(num_chunks);
+    run_parallel(num_chunks, [&](size_t ch) {
+        FaceTreeBuilder ftb;
+        std::vector<int> behind;
+        std::vector<FaceItem> items;
+        for (size_t li = ch * chunk; li < std::min(live.size(), (ch + 1) * chunk); li++) {
+            const int i = live[li];
+            const Box &A = boxes[i];
+            std::vector<int> &ids = box_rects[i];
+            std::sort(ids.begin(), ids.end(), [&](int a, int b) { return rects[a].id < rects[b].id; });
+            ids.erase(std::unique(ids.begin(), ids.end()), ids.end());
+            RoomBounds &bd = out.bounds[(size_t)final_id[i]];
+            memset(&bd, 0, sizeof bd);
+            bd.lo[0] = A.lo[0]; bd.lo[1] = A.lo[1]; bd.lo[2] = A.lo[2]; bd.hi_x = A.hi[0]; bd.hi_y = A.hi[1]; bd.hi_z = A.hi[2];
+            uint32_t code[6];
+            for (int f = 0; f < 6; f++) {
+                const int a = f >> 1, side = f & 1;
+                const float c = side ? A.hi[a] : A.lo[a];
+                const int u = a == 0 ? 1 : 0, v = a == 2 ? 1 : 2;
+                items.clear();
+                for (int id : ids) {
+                    const ARect &r = rects[id];
+                    // leaving towards +axis (side 1) faces normals -axis, and the other way round (rectangle.c:70-72)
+                    if (r.axis != a || r.c != c || r.neg != side) continue;
+                    if (!(fmaxf(r.lo[u], A.lo[u]) < fminf(r.hi[u], A.hi[u])) || !(fmaxf(r.lo[v], A.lo[v]) < fminf(r.hi[v], A.hi[v])))
+                        continue;
+                    items.push_back(FaceItem{{r.lo[u], r.lo[v]}, {r.hi[u], r.hi[v]}, kRoomCodeWall | (uint32_t)r.id});
+                }
+                behind.clear();
+                const bool at_root = side ? c >= root.hi[a] : c <= root.lo[a];
+                if (!at_root) query_face(nodes, 0, a, c, side ? +1 : -1, A.lo, A.hi, behind);
+                for (int &nb : behind) nb = root_of[nb];
+                std::sort(behind.begin(), behind.end());
+                behind.erase(std::unique(behind.begin(), behind.end()), behind.end());
+                for (int nb : behind) {
+                    const Box &B = boxes[nb];
+                    items.push_back(FaceItem{{B.lo[u], B.lo[v]}, {B.hi[u], B.hi[v]}, kRoomCodeBox | (uint32_t)final_id[nb]});
+                }
+                const Region face = {{A.lo[u], A.lo[v]}, {A.hi[u], A.hi[v]}};
+                code[f] = ftb.build(face, items, 0);
             }
-            behind.clear();
-            const bool at_root = side ? c >= root.hi[a] : c <= root.lo[a];
-            if (!at_root) query_face(nodes, 0, a, c, side ? +1 : -1, A.lo, A.hi, behind);
-            for (int &nb : behind) nb = resolve(nb);
-            std::sort(behind.begin(), behind.end());
-            behind.erase(std::unique(behind.begin(), behind.end()), behind.end());
-            for (int nb : behind) {
-                const Box &B = boxes[nb];
-                items.push_back(FaceItem{{B.lo[u], B.lo[v]}, {B.hi[u], B.hi[v]}, kRoomCodeBox | (uint32_t)final_id[nb]});
-            }
-            const Region face = {{A.lo[u], A.lo[v]}, {A.hi[u], A.hi[v]}};
-            code[f] = ftb.build(face, items, 0);
+            RoomBox &rb = out.boxes[(size_t)final_id[i]];
+            memset(&rb, 0, sizeof rb);
+            for (int o = 0; o < 8; o++)
+                for (int k = 0; k < 3; k++) {
+                    const int side = (o >> k) & 1;
+                    rb.oct[o].far[k] = side ? A.hi[k] : A.lo[k];
+                    rb.oct[o].code[k] = code[2 * k + side];
+                }
         }
-        RoomBox &rb = out.boxes[(size_t)final_id[i]];
-        memset(&rb, 0, sizeof rb);
-        for (int o = 0; o < 8; o++)
-            for (int k = 0; k < 3; k++) {
-                const int side = (o >> k) & 1;
-                rb.oct[o].far[k] = side ? A.hi[k] : A.lo[k];
-                rb.oct[o].code[k] = code[2 * k + side];
-            }
+        chunk_out[ch] = std::move(ftb.out);
+    });
+    for (size_t ch = 0; ch < num_chunks; ch++) {
+        const uint32_t off = (uint32_t)out.face_nodes.size();
+        auto fix = [off](uint32_t code) { return (code & kRoomCodeKind) == kRoomCodeNode ? code + off : code; };
+        for (RoomFaceNode n : chunk_out[ch].face_nodes) {
+            n.lo = fix(n.lo); n.hi = fix(n.hi);
+            out.face_nodes.push_back(n);
+        }
+        for (size_t li = ch * chunk; li < std::min(live.size(), (ch + 1) * chunk); li++) {
+            RoomBox &rb = out.boxes[(size_t)final_id[live[li]]];
+            for (int o = 0; o < 8; o++)
+                for (int k = 0; k < 3; k++) rb.oct[o].code[k] = fix(rb.oct[o].code[k]);
+        }
+        out.face_parts += chunk_out[ch].face_parts;
+        out.wall_parts += chunk_out[ch].wall_parts;
     }
     if (out.face_nodes.size() > kRoomCodeIndex) return "more than 2^30 face nodes";
     if (out.face_nodes.empty()) out.face_nodes.push_back(RoomFaceNode{0.0f, kRoomCodeMiss, kRoomCodeMiss, 0u});   // never empty
 
+    const auto t_faces = std::chrono::steady_clock::now();
     // ---- per emitter: the boxes its rectangle touches (closed overlap with the rectangle grown by the start offset) --------
     {
         std::vector<int> stack_n;
@@ -481,6 +616,11 @@ const char *build_rooms(RoomScene &out, const fmgi_rect *walls, int num_walls, c
     }
     for (int k = 0; k < 3; k++) { out.root_lo[k] = root.lo[k]; out.root_hi[k] = root.hi[k]; }
     out.build_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    if (getenv("FMGI_ROOMS_TIMING")) {
+        auto ms = [](auto a, auto b) { return std::chrono::duration<double, std::milli>(b - a).count(); };
+        fprintf(stderr, "[rooms] kd %.2f ms, merge %.2f ms, faces %.2f ms, emitters + tree %.2f ms\n", ms(t0, t_kd), ms(t_kd, t_merge),
+                ms(t_merge, t_faces), ms(t_faces, std::chrono::steady_clock::now()));
+    }
     return "";
 }
 
