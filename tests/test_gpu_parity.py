@@ -258,7 +258,8 @@ def test_rectangle_test_counter_is_opt_in_and_changes_nothing(dev_scene, dev_sce
     assert 2.0 < sc["rect_tests"] / sc["rays"] < 10.0
     assert np.allclose(plain, counted, rtol=1e-5, atol=1e-2)
     auto, sa = gpu_bake(dev_scene, spa, max_depth=5, seed=21)          # AUTO picks the room tier for this flat
-    assert sa["tier"] == 4 and sa["rays"] == sp["rays"]
+    # same photons; the handful of rays through rectangle edges may end differently in the two structures
+    assert sa["tier"] == 4 and sa["photons"] == sp["photons"] and abs(sa["rays"] - sp["rays"]) <= 1e-5 * sp["rays"]
 
 
 def test_deposit_peak_probe(fmgi, scene):
