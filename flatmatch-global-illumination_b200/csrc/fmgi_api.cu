@@ -263,7 +263,7 @@ unsigned long long fill_jobs(const fmgi_scene *s, int spa, const fmgi_options &o
 
 // Picks the instantiation for (tier, deposit, probe, resident CTAs per SM) and applies `fn` to it.
 template <typename Fn>
-cudaError_t with_trace_kernel(int tier, int deposit, bool probe, int min_blocks, bool count, Fn fn)
+cudaError_t with_trace_kernel(int tier, int deposit, bool probe, int min_blocks, bool count, Fn fn, int room_steps = 2)
 {
     if (count && !probe) {      // counting variant: one instantiation per tier
         if (tier == kTierRooms) return fn(k_trace<kTierRooms, FMGI_DEPOSIT_VEC4, false, 4, true>);
@@ -278,8 +278,12 @@ cudaError_t with_trace_kernel(int tier, int deposit, bool probe, int min_blocks,
     }
     if (tier == kTierRooms) {
         if (probe) return fn(k_trace<kTierRooms, FMGI_DEPOSIT_VEC4, true, 3>);
-        if (deposit == FMGI_DEPOSIT_VEC4) {         // boxes per iteration of the photon loop (experiments)
-            static const int steps = getenv("FMGI_ROOM_STEPS") ? atoi(getenv("FMGI_ROOM_STEPS")) : 2;
+        if (deposit == FMGI_DEPOSIT_VEC4) {
+            // boxes per iteration of the photon loop: 3 while the box table is L1-resident (example.png: 6.16 vs 6.27 ms),
+            // 2 for big scenes, where every further box is an L2 round trip the lanes that are ready to shade wait for
+            // (synth4000: 76.4 vs 78.7 ms); FMGI_ROOM_STEPS = 1..4 or 64 (whole walk) overrides
+            static const int forced = getenv("FMGI_ROOM_STEPS") ? atoi(getenv("FMGI_ROOM_STEPS")) : 0;
+            const int steps = forced ? forced : room_steps;
             if (steps == 1) return fn(k_trace<kTierRooms, FMGI_DEPOSIT_VEC4, false, 4, false, 1>);
             if (steps == 3) return fn(k_trace<kTierRooms, FMGI_DEPOSIT_VEC4, false, 4, false, 3>);
             if (steps == 4) return fn(k_trace<kTierRooms, FMGI_DEPOSIT_VEC4, false, 4, false, 4>);
@@ -325,7 +329,7 @@ cudaError_t launch_trace(fmgi_scene *s, const TraceParams &p, int deposit, bool 
         kernel<<<blocks, kTraceThreads, s->smem_bytes, st>>>(p);
         s->launches++;
         return cudaGetLastError();
-    });
+    }, s->build->rooms.boxes.size() <= 1024 ? 3 : 2);
 }
 
 

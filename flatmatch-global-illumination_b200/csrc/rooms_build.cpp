@@ -589,6 +589,14 @@ const char *build_rooms(RoomScene &out, const fmgi_rect *walls, int num_walls, c
                 stack_n.pop_back();
                 if (nd.axis < 0) {
                     const int b = resolve(nd.leaf);
+                    // photons start on the normal's side of the rectangle: a box that ends at its plane on the other
+                    // side holds none of them
+                    bool behind_emitter = false;
+                    for (int k = 0; k < 3; k++) {
+                        if (r.n[k] > 0 && r.width[k] == 0 && r.height[k] == 0 && boxes[b].hi[k] <= r.pos[k]) behind_emitter = true;
+                        if (r.n[k] < 0 && r.width[k] == 0 && r.height[k] == 0 && boxes[b].lo[k] >= r.pos[k]) behind_emitter = true;
+                    }
+                    if (behind_emitter) continue;
                     double vol = 1.0;
                     for (int k = 0; k < 3; k++) vol *= (double)fminf(hi[k], boxes[b].hi[k]) - (double)fmaxf(lo[k], boxes[b].lo[k]);
                     bool seen = false;

@@ -737,40 +737,41 @@ __device__ __forceinline__ int rooms_walk(const TraceParams &p, int &box, float 
 {
     // the ray's octant picks the 32-byte record of each box: far planes and face codes of the three faces ahead
     const float4 *base = p.room_boxes + ((dx > 0.0f ? 2 : 0) + (dy > 0.0f ? 4 : 0) + (dz > 0.0f ? 8 : 0));
-    int cur = box;
+    int cur = box, s = 0;
+    unsigned code;
+    float t, ca, oa, da;                                 // exit face of the last box: ray parameter, plane, origin / direction along its axis
 #pragma unroll 1
-    for (int s = 0; s < kSteps; s++) {
-        if (!FMGI_CHECK(p, (unsigned)cur < p.room_num_boxes, 21)) return -1;
+    for (;;) {
+        if (!FMGI_CHECK(p, (unsigned)cur < p.room_num_boxes, 21)) { code = 3u << kRoomKindShift; break; }
         float4 r0, r1;                                   // {far.x, far.y, far.z, code.x}, {code.y, code.z, -, -}
         ldg256(base + kRoomBoxVec * cur, r0, r1);
         const float tx = (r0.x - ox) * ix, ty = (r0.y - oy) * iy, tz = (r0.z - oz) * iz;
         // nearest face; the two in-plane coordinates of the exit point, in ascending axis order
         const float txy = fminf(tx, ty);
         const bool ax_y = ty < tx, ax_z = tz < txy;
-        const float t = fminf(txy, tz);
+        t = fminf(txy, tz);
         const float hx = fmaf(t, dx, ox), hy = fmaf(t, dy, oy), hz = fmaf(t, dz, oz);
         const float pu = (ax_y || ax_z) ? hx : hy, pv = ax_z ? hy : hz;
-        unsigned code = __float_as_uint(ax_z ? r1.y : (ax_y ? r1.x : r0.w));
+        code = __float_as_uint(ax_z ? r1.y : (ax_y ? r1.x : r0.w));
+        ca = ax_z ? r0.z : (ax_y ? r0.y : r0.x);
+        oa = ax_z ? oz : (ax_y ? oy : ox);
+        da = ax_z ? dz : (ax_y ? dy : dx);
         while ((code >> kRoomKindShift) == 0u) {         // several things on this face: descend its 2-D kd-tree
-            if (!FMGI_CHECK(p, code < p.room_num_face_nodes, 22)) return -1;
+            if (!FMGI_CHECK(p, code < p.room_num_face_nodes, 22)) { code = 3u << kRoomKindShift; break; }
             const float4 n = __ldg(p.room_face_nodes + code);       // {split, lo, hi, axis}
             if (kCount) tests++;
             code = __float_as_uint(((__float_as_uint(n.w) != 0u ? pv : pu) >= n.x) ? n.z : n.y);
         }
-        const unsigned kind = code >> kRoomKindShift, index = code & ((1u << kRoomKindShift) - 1u);
-        if (kind == 2u) { cur = (int)index; continue; }
-        if (kind == 1u && t >= 0.0f) {
-            // the distance with the reference's formula for an axis-parallel normal, IEEE division
-            const float ca = ax_z ? r0.z : (ax_y ? r0.y : r0.x);
-            const float oa = ax_z ? oz : (ax_y ? oy : ox), da = ax_z ? dz : (ax_y ? dy : dx);
-            t_out = __fdiv_rn(__fsub_rn(ca, oa), da);
-            box = cur;
-            return (int)index;
-        }
-        return -1;                                       // nothing there: the ray leaves the scene
+        if ((code >> kRoomKindShift) != 2u) break;       // a collider or nothing: the walk ends here
+        cur = (int)(code & ((1u << kRoomKindShift) - 1u));
+        if (++s == kSteps) { box = cur; return kRoomWalking; }
     }
+    // all lanes whose walk ended, together: a hit needs the collider in front of the origin
     box = cur;
-    return kRoomWalking;
+    if ((code >> kRoomKindShift) != 1u || !(t >= 0.0f)) return -1;      // nothing there: the ray leaves the scene
+    // the distance with the reference's formula for an axis-parallel normal, IEEE division
+    t_out = __fdiv_rn(__fsub_rn(ca, oa), da);
+    return (int)(code & ((1u << kRoomKindShift) - 1u));
 }
 
 // The whole walk of one ray (probes, ambient occlusion).

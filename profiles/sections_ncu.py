@@ -29,7 +29,8 @@ MARKERS = {
         (r"int rooms_locate\(", "rooms locate"),
         (r"int rooms_start\(", "rooms start"),
         (r"float rooms_inv\(", "rooms walk"),
-        (r"ldg256\(E, e0, e1\)", "rooms entry chain"),
+        (r"while \(\(code >> kRoomKindShift\)", "rooms face tree"),
+        (r"all lanes whose walk ended, together", "rooms step outcome"),
         (r"^// The whole walk of one ray", "rooms whole walk"),
         (r"int tile_index\(", "tile index"),
         (r"void sample_hemisphere\(", "sampler"),
