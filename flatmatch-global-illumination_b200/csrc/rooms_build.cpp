@@ -19,7 +19,6 @@
 #include <cstdlib>
 #include <cstring>
 #include <thread>
-#include <unordered_map>
 
 #include "room_tables.h"
 
@@ -433,9 +432,23 @@ const char *build_rooms(RoomScene &out, const fmgi_rect *walls, int num_walls, c
     std::vector<int> merged_into(nb0);
     for (size_t i = 0; i < nb0; i++) merged_into[i] = (int)i;
     if (do_merge) {
-        std::unordered_map<Key3, int, Key3Hash> by_corner;
-        by_corner.reserve(nb0 * 2);
-        for (size_t i = 0; i < nb0; i++) by_corner[key_of(boxes[i].lo)] = (int)i;
+        // box by lower corner: open addressing, never erased (a merged-away box is marked dead instead)
+        size_t cap = 16;
+        while (cap < nb0 * 2) cap *= 2;
+        std::vector<Key3> slot_key(cap);
+        std::vector<int> slot_box(cap, -1);
+        auto find_box = [&](const Key3 &k) {
+            for (size_t h = Key3Hash()(k) & (cap - 1);; h = (h + 1) & (cap - 1)) {
+                if (slot_box[h] < 0) return -1;
+                if (slot_key[h] == k) return slot_box[h];
+            }
+        };
+        for (size_t i = 0; i < nb0; i++) {
+            const Key3 k = key_of(boxes[i].lo);
+            size_t h = Key3Hash()(k) & (cap - 1);
+            while (slot_box[h] >= 0) h = (h + 1) & (cap - 1);
+            slot_key[h] = k; slot_box[h] = (int)i;
+        }
         std::vector<char> alive(nb0, 1);
         bool changed = true;
         const int axis_order[3] = {2, 0, 1};
@@ -449,10 +462,8 @@ const char *build_rooms(RoomScene &out, const fmgi_rect *walls, int num_walls, c
                         Box &A = boxes[i];
                         float corner[3] = {A.lo[0], A.lo[1], A.lo[2]};
                         corner[a] = A.hi[a];
-                        const auto it = by_corner.find(key_of(corner));
-                        if (it == by_corner.end()) break;
-                        const int j = it->second;
-                        if (j == (int)i || !alive[j]) break;
+                        const int j = find_box(key_of(corner));
+                        if (j < 0 || j == (int)i || !alive[j]) break;
                         const Box &B = boxes[j];
                         if (B.hi[u] != A.hi[u] || B.hi[v] != A.hi[v]) break;
                         // a collider (facing either way) on the shared face keeps the boxes apart
@@ -468,7 +479,6 @@ const char *build_rooms(RoomScene &out, const fmgi_rect *walls, int num_walls, c
                         std::vector<int>().swap(box_rects[j]);
                         alive[j] = 0;
                         merged_into[j] = (int)i;
-                        by_corner.erase(it);
                         changed = true;
                     }
                 }

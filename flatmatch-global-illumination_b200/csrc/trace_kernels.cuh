@@ -745,6 +745,7 @@ __device__ __forceinline__ int rooms_walk(const TraceParams &p, int &box, float 
         if (!FMGI_CHECK(p, (unsigned)cur < p.room_num_boxes, 21)) { code = 3u << kRoomKindShift; break; }
         float4 r0, r1;                                   // {far.x, far.y, far.z, code.x}, {code.y, code.z, -, -}
         ldg256(base + kRoomBoxVec * cur, r0, r1);
+        if (kCount) tests++;                             // counted: boxes crossed + face-tree nodes visited
         const float tx = (r0.x - ox) * ix, ty = (r0.y - oy) * iy, tz = (r0.z - oz) * iz;
         // nearest face; the two in-plane coordinates of the exit point, in ascending axis order
         const float txy = fminf(tx, ty);

@@ -96,7 +96,8 @@ typedef struct fmgi_stats {
     uint64_t rays;            /* closest-hit queries */
     uint64_t deposits;        /* texel deposits = photon-bounces (the BASELINE metric's unit) */
     uint64_t mirror_bounces;
-    uint64_t rect_tests;      /* rectangle tests executed (all lanes); grid lookups only with count_tests */
+    uint64_t rect_tests;      /* rectangle tests executed (all lanes); grid lookups only with count_tests; room tier
+                                 (count_tests): boxes crossed + face-tree nodes visited */
     uint64_t kernel_launches; /* our kernels launched */
     double   trace_ms;        /* device time of the trace kernels (CUDA events), max over GPUs */
     double   h2d_ms, d2h_ms;  /* atlas upload (runs under the trace) / read-back, CUDA events, max over GPUs */
@@ -109,7 +110,8 @@ typedef struct fmgi_stats {
     /* host-buffer entry points only (fmgi_bake, fmgi_bake_tiles), host clock, max over GPUs */
     double   init_ms;         /* cudaSetDevice + stream/event creation: the CUDA context on the first call of a process */
     double   prepare_ms;      /* rectangle tables (scene_prep.cpp) */
-    double   grid_build_ms;   /* floor-plan grid: host classification + per-cell assembly (host, or device for >= 2048 colliders) */
+    double   grid_build_ms;   /* floor-plan grid: host classification + per-cell assembly (host, or device for >= 2048 colliders);
+                                 room tier: the box decomposition (rooms_build.cpp, host thread pool) */
     double   upload_ms;       /* table upload + kernel attribute queries per GPU */
     int32_t  pool_rays;       /* 0: k_trace ran; K > 0: the pooled kernel (trace_pool.cuh) with K rays per lane */
     int32_t  bounds_violations; /* -1: regular build; >= 0: lib/libfmgi_cuda_checked.so (-DFMGI_CHECKED) - data-dependent
