@@ -281,7 +281,9 @@ void kd_split(const std::vector<ARect> &rects, const KdWork &w, int axis, float 
     }
 }
 
-void kd_build_subtree(const std::vector<ARect> &rects, KdWork root, KdSubtree &out)
+// `leaves`: kd leaves of all subtrees so far; past `max_leaves` the build is given up (not a floor plan: rectangles
+// floating in space cut each other into a number of boxes that grows much faster than their own number).
+void kd_build_subtree(const std::vector<ARect> &rects, KdWork root, KdSubtree &out, std::atomic<size_t> &leaves, size_t max_leaves)
 {
     out.root_node = root.node;
     root.node = 0;
@@ -295,6 +297,7 @@ void kd_build_subtree(const std::vector<ARect> &rects, KdWork root, KdSubtree &o
         int axis;
         float c;
         if (!kd_choose_split(rects, w, axis, c)) {
+            if (leaves.fetch_add(1) >= max_leaves) return;
             out.nodes[w.node].axis = -1;
             out.nodes[w.node].leaf = (int)out.boxes.size();
             out.boxes.push_back(w.box);
@@ -374,7 +377,8 @@ const char *build_rooms(RoomScene &out, const fmgi_rect *walls, int num_walls, c
     std::vector<Node> nodes;
     std::vector<Box> boxes;                     // kd leaves, later merged
     std::vector<std::vector<int>> box_rects;    // colliders that touch the box
-    const size_t max_leaves = 8u << 20;
+    const size_t max_leaves = std::min<size_t>(8u << 20, 16 * rects.size() + 1024);
+    std::atomic<size_t> leaves{0};
     {
         std::vector<KdWork> top;
         {
@@ -405,7 +409,8 @@ const char *build_rooms(RoomScene &out, const fmgi_rect *walls, int num_walls, c
             top.push_back(std::move(rw));
         }
         std::vector<KdSubtree> subs(top.size());
-        run_parallel(top.size(), [&](size_t i) { kd_build_subtree(rects, std::move(top[i]), subs[i]); });
+        run_parallel(top.size(), [&](size_t i) { kd_build_subtree(rects, std::move(top[i]), subs[i], leaves, max_leaves); });
+        if (leaves.load() > max_leaves) return "too many boxes for its number of colliders (not a floor plan)";
         for (size_t i = 0; i < subs.size(); i++) {
             KdSubtree &st = subs[i];
             const int node_off = (int)nodes.size() - 1, leaf_off = (int)boxes.size();      // local node k > 0 -> node_off + k
@@ -421,7 +426,6 @@ const char *build_rooms(RoomScene &out, const fmgi_rect *walls, int num_walls, c
                 boxes.push_back(st.boxes[k]);
                 box_rects.push_back(std::move(st.box_rects[k]));
             }
-            if (boxes.size() >= max_leaves) return "more than 8M boxes";
         }
     }
     out.kd_leaves = boxes.size();

@@ -16,7 +16,7 @@ CSRC = ROOT / "flatmatch-global-illumination_b200" / "csrc"
 def rooms_checker(tmp_path_factory):
     exe = tmp_path_factory.mktemp("rooms") / "rooms_check"
     subprocess.run(["g++", "-O2", "-std=c++17", "-ffp-contract=off", "-I", str(ROOT / "include"),
-                    str(ROOT / "tests" / "cpu" / "rooms_check.cpp"), str(CSRC / "rooms_build.cpp"), "-o", str(exe)], check=True)
+                    str(ROOT / "tests" / "cpu" / "rooms_check.cpp"), str(CSRC / "rooms_build.cpp"), "-o", str(exe), "-lpthread"], check=True)
     return exe
 
 
@@ -60,3 +60,13 @@ def test_rooms_refuse_arbitrarily_oriented_colliders(rooms_checker, tmp_path, fm
     walls, windows, lights, _ = random_scene(fmgi, 1)
     out = run_check(rooms_checker, tmp_path, walls, windows, lights, 100, expect=3)
     assert "refused" in out
+
+
+def test_rooms_refuse_big_random_soups(rooms_checker, tmp_path, fmgi):
+    """1000 rectangles floating in space cut each other into 20 boxes per rectangle (a flat: one box per two): the
+    builder gives up early and AUTO stays on the grid."""
+    from test_gpu_parity import random_scene
+
+    walls, windows, lights, _ = random_scene(fmgi, 1, n_axis=1000, n_general=0)
+    out = run_check(rooms_checker, tmp_path, walls, windows, lights, 100, expect=3)
+    assert "too many boxes" in out
