@@ -50,12 +50,12 @@ struct RoomBox {
 };
 static_assert(sizeof(RoomBox) == 256, "RoomBox is sixteen float4");
 
-// One node of a face's 2-D kd-tree: the coordinate (axis 0: the lower in-plane axis, 1: the higher) against `split`;
-// below -> lo, at or above -> hi (codes).
+// One node of a face's 2-D kd-tree: the exit point (u: the lower in-plane axis, v: the higher) goes to `hi` when
+// u >= split_u AND v >= split_v, else to `lo` (codes).  A split along one axis leaves the other at -inf - the device
+// compares both without asking which one the node is about.
 struct RoomFaceNode {
-    float split;
+    float split_u, split_v;
     uint32_t lo, hi;
-    uint32_t axis;
 };
 static_assert(sizeof(RoomFaceNode) == 16, "RoomFaceNode is one float4");
 

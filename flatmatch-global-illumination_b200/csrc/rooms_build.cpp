@@ -137,17 +137,35 @@ bool covers(const FaceItem &it, const Region &r)
     return it.lo[0] <= r.lo[0] && it.hi[0] >= r.hi[0] && it.lo[1] <= r.lo[1] && it.hi[1] >= r.hi[1];
 }
 
+bool g_face_cost_depth = true;          // FMGI_ROOMS_FACE_COST=expected: the pre-SIMT cost (experiments)
+
 struct FaceTreeBuilder {
     struct Out { std::vector<RoomFaceNode> face_nodes; size_t face_parts = 0, wall_parts = 0; };
     Out out;                     // node codes are local to `out.face_nodes`; the caller offsets them when it concatenates
     std::vector<float> cand[2];
 
-    // `items`: colliders in wall-index order first, then portals; all overlap `r` with positive area.
-    uint32_t build(const Region &r, const std::vector<FaceItem> &items, int depth)
+    // The items of a node are pool[begin, end): colliders in wall-index order first, then portals; all overlap `r` with
+    // positive area.  The children's lists are appended to the pool and dropped again when the node is done - no
+    // allocation per node.
+    std::vector<FaceItem> pool;
+    uint32_t build(const Region &r, const std::vector<FaceItem> &items_in)
     {
-        if (items.empty()) { out.face_parts++; return kRoomCodeMiss; }
+        pool.assign(items_in.begin(), items_in.end());
+        return build(r, 0, pool.size(), 0);
+    }
+    struct ItemRange {
+        const FaceItem *b, *e;
+        const FaceItem *begin() const { return b; }
+        const FaceItem *end() const { return e; }
+        size_t size() const { return (size_t)(e - b); }
+        const FaceItem &operator[](size_t i) const { return b[i]; }
+    };
+    uint32_t build(const Region &r, size_t begin, size_t end, int depth)
+    {
+        if (begin == end) { out.face_parts++; return kRoomCodeMiss; }
+        const ItemRange items{pool.data() + begin, pool.data() + end};
         // the part belongs to the first item (lowest wall index; a collider hides the box behind it) if that covers it
-        const FaceItem &first = items[0];
+        const FaceItem first = items[0];
         const bool first_is_wall = (first.code & kRoomCodeKind) == kRoomCodeWall;
         if (covers(first, r) && (first_is_wall || items.size() == 1)) {
             out.face_parts++;
@@ -166,24 +184,35 @@ struct FaceTreeBuilder {
                 // long lists (the boxes around the building): the edge nearest the middle of the longer side
                 cost = fabs((double)v - 0.5 * ((double)r.lo[ax] + r.hi[ax])) / ext[ax] + (ext[ax] >= ext[1 - ax] ? 0.0 : 1.0);
             } else {
-                // expected number of further decisions ~ share of the region x (items on that side - 1)
+                // a warp waits for the deepest descent among its lanes: the levels still needed below the fuller side
+                // first, then the expected number of further decisions (share of the region x (items on that side - 1))
                 int nl = 0, nr = 0;
                 for (const FaceItem &it : items) {
                     nl += fmaxf(it.lo[ax], r.lo[ax]) < fminf(it.hi[ax], v);
                     nr += fmaxf(it.lo[ax], v) < fminf(it.hi[ax], r.hi[ax]);
                 }
                 const double fl = ((double)v - r.lo[ax]) / ext[ax];
-                cost = fl * (nl - 1) + (1.0 - fl) * (nr - 1) + 1e-3 * fabs(fl - 0.5);
+                int levels = 0;
+                while ((1 << levels) < std::max(nl, nr)) levels++;
+                cost = (g_face_cost_depth ? (double)levels : 0.0) + 0.1 * (fl * (nl - 1) + (1.0 - fl) * (nr - 1)) + 1e-4 * fabs(fl - 0.5);
             }
-            if (cost < best_cost) { best_cost = cost; best_axis = ax; best_v = v; }
+            if (cost < best_cost || (cost == best_cost && (ax < best_axis || (ax == best_axis && v < best_v)))) {
+                best_cost = cost; best_axis = ax; best_v = v;
+            }
         };
-        for (int ax = 0; ax < 2; ax++) {
-            std::vector<float> &c = cand[ax];
-            c.clear();
-            for (const FaceItem &it : items) { c.push_back(it.lo[ax]); c.push_back(it.hi[ax]); }
-            std::sort(c.begin(), c.end());
-            c.erase(std::unique(c.begin(), c.end()), c.end());
-            for (float v : c) consider(ax, v);
+        if (items.size() > 24) {
+            // long lists: no need to look at a value twice, the cost is a function of the value alone
+            for (const FaceItem &it : items)
+                for (int ax = 0; ax < 2; ax++) { consider(ax, it.lo[ax]); consider(ax, it.hi[ax]); }
+        } else {
+            for (int ax = 0; ax < 2; ax++) {
+                std::vector<float> &c = cand[ax];
+                c.clear();
+                for (const FaceItem &it : items) { c.push_back(it.lo[ax]); c.push_back(it.hi[ax]); }
+                std::sort(c.begin(), c.end());
+                c.erase(std::unique(c.begin(), c.end()), c.end());
+                for (float v : c) consider(ax, v);
+            }
         }
         if (best_axis < 0 || depth > 64) {          // nothing cuts the region, yet nothing covers it: keep the first
             out.face_parts++;
@@ -192,14 +221,19 @@ struct FaceTreeBuilder {
         }
         Region rl = r, rh = r;
         rl.hi[best_axis] = best_v; rh.lo[best_axis] = best_v;
-        std::vector<FaceItem> il, ih;
-        for (const FaceItem &it : items) {
-            if (overlaps(it, rl)) il.push_back(it);
-            if (overlaps(it, rh)) ih.push_back(it);
-        }
+        // `items` points into the pool, which grows here: go by index from now on
+        const size_t mark = pool.size();
+        pool.reserve(mark + 2 * (end - begin));
+        for (size_t q = begin; q < end; q++)
+            if (overlaps(pool[q], rl)) pool.push_back(pool[q]);
+        const size_t mid = pool.size();
+        for (size_t q = begin; q < end; q++)
+            if (overlaps(pool[q], rh)) pool.push_back(pool[q]);
+        const size_t stop = pool.size();
         const uint32_t self = (uint32_t)out.face_nodes.size();
-        out.face_nodes.push_back(RoomFaceNode{best_v, 0u, 0u, (uint32_t)best_axis});
-        const uint32_t lo = build(rl, il, depth + 1), hi = build(rh, ih, depth + 1);
+        out.face_nodes.push_back(RoomFaceNode{best_axis == 0 ? best_v : -INFINITY, best_axis == 1 ? best_v : -INFINITY, 0u, 0u});
+        const uint32_t lo = build(rl, mark, mid, depth + 1), hi = build(rh, mid, stop, depth + 1);
+        pool.resize(mark);
         out.face_nodes[self].lo = lo; out.face_nodes[self].hi = hi;
         return kRoomCodeNode | self;
     }
@@ -315,14 +349,15 @@ void kd_build_subtree(const std::vector<ARect> &rects, KdWork root, KdSubtree &o
     }
 }
 
-// fn(i) for i in [0, n) on a pool of threads (a handful of items: on the calling thread)
+// fn(i) for i in [0, n) on a pool of threads
 template <typename Fn>
 void run_parallel(size_t n, Fn fn)
 {
     unsigned threads = std::thread::hardware_concurrency();
     if (const char *v = getenv("FMGI_BUILD_THREADS")) threads = (unsigned)atoi(v);
     threads = std::min<unsigned>(std::max(threads, 1u), 16u);
-    if (n < 4 || threads == 1) {
+    threads = (unsigned)std::min<size_t>(threads, n);
+    if (threads <= 1) {
         for (size_t i = 0; i < n; i++) fn(i);
         return;
     }
@@ -345,6 +380,7 @@ const char *build_rooms(RoomScene &out, const fmgi_rect *walls, int num_walls, c
     out = RoomScene();
     bool do_merge = true;
     if (const char *v = getenv("FMGI_ROOMS_MERGE")) do_merge = atoi(v) != 0;
+    if (const char *v = getenv("FMGI_ROOMS_FACE_COST")) g_face_cost_depth = v[0] != 'e';
     std::vector<ARect> rects;
     rects.reserve((size_t)num_walls);
     for (int i = 0; i < num_walls; i++) {
@@ -389,25 +425,31 @@ const char *build_rooms(RoomScene &out, const fmgi_rect *walls, int num_walls, c
             nodes.push_back(Node{-1, 0.0f, -1, -1, -1});
             top.push_back(std::move(w));
         }
+        // level by level, the nodes of a level in parallel, until there are enough subtrees (or the nodes are small)
         const size_t want = rects.size() >= 4096 ? 64 : 1;
-        while (top.size() < want) {
-            size_t big = 0;
-            for (size_t i = 1; i < top.size(); i++)
-                if (top[i].ids.size() > top[big].ids.size()) big = i;
-            if (top[big].ids.size() <= 256) break;
-            KdWork w = std::move(top[big]);
-            int axis;
-            float c;
-            if (!kd_choose_split(rects, w, axis, c)) { top[big] = std::move(w); break; }
-            KdWork lw, rw;
-            kd_split(rects, w, axis, c, lw, rw);
-            lw.node = (int)nodes.size(); nodes.push_back(Node{-1, 0.0f, -1, -1, -1});
-            rw.node = (int)nodes.size(); nodes.push_back(Node{-1, 0.0f, -1, -1, -1});
-            nodes[w.node].axis = axis; nodes[w.node].v = c;
-            nodes[w.node].left = lw.node; nodes[w.node].right = rw.node;
-            top[big] = std::move(lw);
-            top.push_back(std::move(rw));
+        std::vector<KdWork> small;
+        struct Split { bool ok; int axis; float c; KdWork lw, rw; };
+        while (!top.empty() && top.size() + small.size() < want) {
+            std::vector<Split> sp(top.size());
+            run_parallel(top.size(), [&](size_t i) {
+                Split &x = sp[i];
+                x.ok = top[i].ids.size() > 256 && kd_choose_split(rects, top[i], x.axis, x.c);
+                if (x.ok) kd_split(rects, top[i], x.axis, x.c, x.lw, x.rw);
+            });
+            std::vector<KdWork> next;
+            for (size_t i = 0; i < top.size(); i++) {
+                Split &x = sp[i];
+                if (!x.ok) { small.push_back(std::move(top[i])); continue; }
+                x.lw.node = (int)nodes.size(); nodes.push_back(Node{-1, 0.0f, -1, -1, -1});
+                x.rw.node = (int)nodes.size(); nodes.push_back(Node{-1, 0.0f, -1, -1, -1});
+                Node &n = nodes[top[i].node];
+                n.axis = x.axis; n.v = x.c; n.left = x.lw.node; n.right = x.rw.node;
+                next.push_back(std::move(x.lw));
+                next.push_back(std::move(x.rw));
+            }
+            top = std::move(next);
         }
+        for (KdWork &w : small) top.push_back(std::move(w));
         std::vector<KdSubtree> subs(top.size());
         run_parallel(top.size(), [&](size_t i) { kd_build_subtree(rects, std::move(top[i]), subs[i], leaves, max_leaves); });
         if (leaves.load() > max_leaves) return "too many boxes for its number of colliders (not a floor plan)";
@@ -512,7 +554,10 @@ const char *build_rooms(RoomScene &out, const fmgi_rect *walls, int num_walls, c
     live.reserve((size_t)num_boxes);
     for (size_t i = 0; i < nb0; i++)
         if (final_id[i] >= 0) live.push_back((int)i);
-    const size_t chunk = 64, num_chunks = (live.size() + chunk - 1) / chunk;
+    // the boxes around the building touch thousands of colliders and neighbours: they go first, so that no thread is
+    // left alone with one at the end
+    std::stable_sort(live.begin(), live.end(), [&](int a, int b) { return box_rects[a].size() > box_rects[b].size(); });
+    const size_t chunk = 4, num_chunks = (live.size() + chunk - 1) / chunk;
     std::vector<FaceTreeBuilder::Out> chunk_out(num_chunks);
     run_parallel(num_chunks, [&](size_t ch) {
         FaceTreeBuilder ftb;
@@ -552,7 +597,7 @@ const char *build_rooms(RoomScene &out, const fmgi_rect *walls, int num_walls, c
                     items.push_back(FaceItem{{B.lo[u], B.lo[v]}, {B.hi[u], B.hi[v]}, kRoomCodeBox | (uint32_t)final_id[nb]});
                 }
                 const Region face = {{A.lo[u], A.lo[v]}, {A.hi[u], A.hi[v]}};
-                code[f] = ftb.build(face, items, 0);
+                code[f] = ftb.build(face, items);
             }
             RoomBox &rb = out.boxes[(size_t)final_id[i]];
             memset(&rb, 0, sizeof rb);
@@ -581,7 +626,7 @@ const char *build_rooms(RoomScene &out, const fmgi_rect *walls, int num_walls, c
         out.wall_parts += chunk_out[ch].wall_parts;
     }
     if (out.face_nodes.size() > kRoomCodeIndex) return "more than 2^30 face nodes";
-    if (out.face_nodes.empty()) out.face_nodes.push_back(RoomFaceNode{0.0f, kRoomCodeMiss, kRoomCodeMiss, 0u});   // never empty
+    if (out.face_nodes.empty()) out.face_nodes.push_back(RoomFaceNode{0.0f, 0.0f, kRoomCodeMiss, kRoomCodeMiss});   // never empty
 
     const auto t_faces = std::chrono::steady_clock::now();
     // ---- per emitter: the boxes its rectangle touches (closed overlap with the rectangle grown by the start offset) --------
@@ -686,7 +731,7 @@ int rooms_closest_hit(const RoomScene &rs, int box, const float o[3], const floa
         while ((code & kRoomCodeKind) == kRoomCodeNode) {
             const RoomFaceNode &n = rs.face_nodes[code];
             tests++;
-            code = (n.axis ? pv : pu) >= n.split ? n.hi : n.lo;
+            code = (pu >= n.split_u && pv >= n.split_v) ? n.hi : n.lo;
         }
         const uint32_t kind = code & kRoomCodeKind, index = code & kRoomCodeIndex;
         if (kind == kRoomCodeWall) {

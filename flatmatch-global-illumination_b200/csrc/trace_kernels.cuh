@@ -737,14 +737,16 @@ __device__ __forceinline__ int rooms_walk(const TraceParams &p, int &box, float 
 {
     // the ray's octant picks the 32-byte record of each box: far planes and face codes of the three faces ahead
     const float4 *base = p.room_boxes + ((dx > 0.0f ? 2 : 0) + (dy > 0.0f ? 4 : 0) + (dz > 0.0f ? 8 : 0));
-    int cur = box, s = 0;
+    const float4 *face_nodes = p.room_face_nodes;
+    unsigned cur = (unsigned)box;
+    int s = 0;
     unsigned code;
     float t, ca, oa, da;                                 // exit face of the last box: ray parameter, plane, origin / direction along its axis
 #pragma unroll 1
     for (;;) {
-        if (!FMGI_CHECK(p, (unsigned)cur < p.room_num_boxes, 21)) { code = 3u << kRoomKindShift; break; }
+        if (!FMGI_CHECK(p, cur < p.room_num_boxes, 21)) { code = 3u << kRoomKindShift; break; }
         float4 r0, r1;                                   // {far.x, far.y, far.z, code.x}, {code.y, code.z, -, -}
-        ldg256(base + kRoomBoxVec * cur, r0, r1);
+        ldg256(base + (size_t)kRoomBoxVec * cur, r0, r1);
         if (kCount) tests++;                             // counted: boxes crossed + face-tree nodes visited
         const float tx = (r0.x - ox) * ix, ty = (r0.y - oy) * iy, tz = (r0.z - oz) * iz;
         // nearest face; the two in-plane coordinates of the exit point, in ascending axis order
@@ -759,16 +761,16 @@ __device__ __forceinline__ int rooms_walk(const TraceParams &p, int &box, float 
         da = ax_z ? dz : (ax_y ? dy : dx);
         while ((code >> kRoomKindShift) == 0u) {         // several things on this face: descend its 2-D kd-tree
             if (!FMGI_CHECK(p, code < p.room_num_face_nodes, 22)) { code = 3u << kRoomKindShift; break; }
-            const float4 n = __ldg(p.room_face_nodes + code);       // {split, lo, hi, axis}
+            const float4 n = __ldg(face_nodes + code);   // {split u, split v, lo, hi}: hi when both coordinates are at or above
             if (kCount) tests++;
-            code = __float_as_uint(((__float_as_uint(n.w) != 0u ? pv : pu) >= n.x) ? n.z : n.y);
+            code = __float_as_uint((pu >= n.x && pv >= n.y) ? n.w : n.z);
         }
         if ((code >> kRoomKindShift) != 2u) break;       // a collider or nothing: the walk ends here
-        cur = (int)(code & ((1u << kRoomKindShift) - 1u));
-        if (++s == kSteps) { box = cur; return kRoomWalking; }
+        cur = code & ((1u << kRoomKindShift) - 1u);
+        if (++s == kSteps) { box = (int)cur; return kRoomWalking; }
     }
     // all lanes whose walk ended, together: a hit needs the collider in front of the origin
-    box = cur;
+    box = (int)cur;
     if ((code >> kRoomKindShift) != 1u || !(t >= 0.0f)) return -1;      // nothing there: the ray leaves the scene
     // the distance with the reference's formula for an axis-parallel normal, IEEE division
     t_out = __fdiv_rn(__fsub_rn(ca, oa), da);
