@@ -870,7 +870,7 @@ int bake_impl(struct Geometry *geo_, int spa, const fmgi_options *opt, fmgi_stat
         fmgi_stats st = {};
         int rc = FMGI_OK;
         std::string err;
-        double init_ms = 0, create_ms = 0, sync_ms = 0, alloc_ms = 0;
+        double init_ms = 0, create_ms = 0, sync_ms = 0, alloc_ms = 0, h2d_call_ms = 0, trace_call_ms = 0;
         float h2d_ms = 0, fold_ms = 0, d2h_ms = 0;
     };
     std::vector<PerGpu> gpus(G);
@@ -916,11 +916,18 @@ int bake_impl(struct Geometry *geo_, int spa, const fmgi_options *opt, fmgi_stat
         const double ts0 = now_ms();
         rc = fmgi_scene_trace(me.scene, me.atlas, spa, &og, dv.trace);
         if (rc) return bail(rc);
+        me.trace_call_ms = now_ms() - ts0;
         cudaSetDevice(me.device);
-        // the caller's atlas (CL_MEM_COPY_HOST_PTR, global_illumination_cl.c:295) rides on the copy stream
-        e = cudaEventRecord(dv.ev[0], dv.copy);
+        // the caller's atlas (CL_MEM_COPY_HOST_PTR, global_illumination_cl.c:295) rides on the copy stream - but not
+        // before the trace kernel has started: the trace stream's own small upload (the job tables) sits behind the
+        // atlas clear, and an atlas upload that reaches the copy engine first holds it up for its whole length
+        // (measured on the 1.83 GB atlas: kernel start 33 ms late)
+        e = cudaStreamWaitEvent(dv.copy, me.scene->ev_start, 0);
+        if (e == cudaSuccess) e = cudaEventRecord(dv.ev[0], dv.copy);
+        const double th0 = now_ms();
         if (e == cudaSuccess && slice)
             e = cudaMemcpyAsync(me.init, geo->texels + 4 * me.lo, slice * sizeof(float4), cudaMemcpyHostToDevice, dv.copy);
+        me.h2d_call_ms = now_ms() - th0;
         if (e == cudaSuccess) e = cudaEventRecord(dv.ev[1], dv.copy);
         if (e != cudaSuccess) return bail(fail(FMGI_ERR_CUDA, std::string("atlas upload: ") + cudaGetErrorString(e)));
         rc = fmgi_scene_sync(me.scene, &me.st);
@@ -1068,10 +1075,10 @@ int bake_impl(struct Geometry *geo_, int spa, const fmgi_options *opt, fmgi_stat
     if (getenv("FMGI_DEBUG_TIMING"))
         fprintf(stderr, "[fmgi] bake: total %.3f ms (host tables %.3f [grid %.3f], context/streams %.3f, table upload %.3f, "
                         "atlas h2d %.3f (overlapped), trace+sync host %.3f [device %.3f], fold %.3f + d2h %.3f [host %.3f], "
-                        "tiles %.3f, atlas alloc %.3f, cache trim %.3f, driver init %.3f, context %.3f)\n",
+                        "tiles %.3f, atlas alloc %.3f, cache trim %.3f, driver init %.3f, context %.3f; trace enqueue %.3f, h2d enqueue %.3f)\n",
                 now_ms() - t_begin, build_ms, build->grid_ms, gpus[0].init_ms, gpus[0].create_ms, gpus[0].h2d_ms,
                 gpus[0].sync_ms, gpus[0].st.trace_ms, gpus[0].fold_ms, gpus[0].d2h_ms, fold_host_ms, tiles_ms,
-                gpus[0].alloc_ms, trim_ms, driver_ms, context_ms);
+                gpus[0].alloc_ms, trim_ms, driver_ms, context_ms, gpus[0].trace_call_ms, gpus[0].h2d_call_ms);
     return rc;
 }
 

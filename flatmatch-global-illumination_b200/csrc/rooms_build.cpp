@@ -351,9 +351,9 @@ void kd_build_subtree(const std::vector<ARect> &rects, KdWork root, KdSubtree &o
 
 // fn(i) for i in [0, n) on a pool of threads
 template <typename Fn>
-void run_parallel(size_t n, Fn fn)
+void run_parallel(size_t n, Fn fn, bool worth_threads = true)
 {
-    unsigned threads = std::thread::hardware_concurrency();
+    unsigned threads = worth_threads ? std::thread::hardware_concurrency() : 1u;
     if (const char *v = getenv("FMGI_BUILD_THREADS")) threads = (unsigned)atoi(v);
     threads = std::min<unsigned>(std::max(threads, 1u), 16u);
     threads = (unsigned)std::min<size_t>(threads, n);
@@ -559,6 +559,7 @@ const char *build_rooms(RoomScene &out, const fmgi_rect *walls, int num_walls, c
     std::stable_sort(live.begin(), live.end(), [&](int a, int b) { return box_rects[a].size() > box_rects[b].size(); });
     const size_t chunk = 4, num_chunks = (live.size() + chunk - 1) / chunk;
     std::vector<FaceTreeBuilder::Out> chunk_out(num_chunks);
+    // (a flat of a few hundred rectangles is built in half a millisecond: starting threads would cost more)
     run_parallel(num_chunks, [&](size_t ch) {
         FaceTreeBuilder ftb;
         std::vector<int> behind;
@@ -609,7 +610,7 @@ const char *build_rooms(RoomScene &out, const fmgi_rect *walls, int num_walls, c
                 }
         }
         chunk_out[ch] = std::move(ftb.out);
-    });
+    }, rects.size() >= 2048);
     for (size_t ch = 0; ch < num_chunks; ch++) {
         const uint32_t off = (uint32_t)out.face_nodes.size();
         auto fix = [off](uint32_t code) { return (code & kRoomCodeKind) == kRoomCodeNode ? code + off : code; };
