@@ -374,6 +374,10 @@ __global__ void __launch_bounds__(kTraceThreads) k_ambient_occlusion(const Trace
         const float cz = __fadd_rn(__fadd_rn(q0.z, __fmul_rn(wz, fx)), __fmul_rn(hz, fy));
         (void)q1; (void)q2; (void)th;
         float dist_sum = 0.0f, fac_sum = 0.0f;
+        // room tier: all rays of a texel start in the box in front of its wall - one tree descent per texel
+        int box0 = 0;
+        if (kTier == kTierRooms)
+            box0 = rooms_locate(p, fmaf(fn.x, 1E-5f, cx), fmaf(fn.y, 1E-5f, cy), fmaf(fn.z, 1E-5f, cz), fn.x, fn.y, fn.z);
         for (int k = 0; k < num_dirs; k++) {
             const float4 d = __ldg(dirs + k);
             // photonmap.c:41-45: in.x * b0 + in.y * b1 + in.z * b2, (b0, b1, b2) = (U, V, n)
@@ -383,7 +387,8 @@ __global__ void __launch_bounds__(kTraceThreads) k_ambient_occlusion(const Trace
             const float ox = __fadd_rn(cx, __fmul_rn(dx, 1E-5f)), oy = __fadd_rn(cy, __fmul_rn(dy, 1E-5f)),
                         oz = __fadd_rn(cz, __fmul_rn(dz, 1E-5f));                         // photonmap.c:457
             float t;
-            const int id = kTier == kTierRooms ? closest_hit_rooms_from_anywhere(p, ox, oy, oz, dx, dy, dz, t)
+            int box = box0;
+            const int id = kTier == kTierRooms ? closest_hit_rooms(p, box, ox, oy, oz, dx, dy, dz, t)
                          : kTier == FMGI_TIER_SOUP ? closest_hit_soup(soup, ox, oy, oz, dx, dy, dz, t)
                          : kTier == kTierSoupPlanes ? closest_hit_soup_planes<false>(soup, p, ox, oy, oz, dx, dy, dz, t, tests)
                                                     : closest_hit_grid<false>(p, ox, oy, oz, dx, dy, dz, t, tests);

@@ -771,7 +771,8 @@ __device__ __forceinline__ int rooms_walk(const TraceParams &p, int &box, float 
     }
     // all lanes whose walk ended, together: a hit needs the collider in front of the origin
     box = (int)cur;
-    if ((code >> kRoomKindShift) != 1u || !(t >= 0.0f)) return -1;      // nothing there: the ray leaves the scene
+    // (a ray parallel to the collider it starts on is culled like a back face, rectangle.c:70-72: n.d = 0)
+    if ((code >> kRoomKindShift) != 1u || !(t >= 0.0f) || da == 0.0f) return -1;      // nothing there: the ray leaves the scene
     // the distance with the reference's formula for an axis-parallel normal, IEEE division
     t_out = __fdiv_rn(__fsub_rn(ca, oa), da);
     return (int)(code & ((1u << kRoomKindShift) - 1u));
