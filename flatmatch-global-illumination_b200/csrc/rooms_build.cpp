@@ -44,10 +44,9 @@ int single_axis3(const float v[4])
 // 0: ok, 1: degenerate (zero area: can never be hit), 2: not axis parallel
 int to_axis_rect(const fmgi_rect &r, int id, ARect &out)
 {
-    const float wl = sqrtf(r.width[0] * r.width[0] + r.width[1] * r.width[1] + r.width[2] * r.width[2]);
-    const float hl = sqrtf(r.height[0] * r.height[0] + r.height[1] * r.height[1] + r.height[2] * r.height[2]);
-    const float nl = sqrtf(r.n[0] * r.n[0] + r.n[1] * r.n[1] + r.n[2] * r.n[2]);
-    if (!(wl > 0) || !(hl > 0) || !(nl > 0)) return 1;
+    const auto zero3 = [](const float v[4]) { return v[0] == 0 && v[1] == 0 && v[2] == 0; };
+    const auto nan3 = [](const float v[4]) { return v[0] != v[0] || v[1] != v[1] || v[2] != v[2]; };
+    if (zero3(r.width) || zero3(r.height) || zero3(r.n) || nan3(r.width) || nan3(r.height) || nan3(r.n)) return 1;
     const int ai = single_axis3(r.width), aj = single_axis3(r.height), ak = single_axis3(r.n);
     if (ai < 0 || aj < 0 || ak < 0 || ai == aj || ak == ai || ak == aj) return 2;
     out.axis = ak; out.neg = r.n[ak] > 0 ? 0 : 1; out.id = id; out.c = r.pos[ak] + 0.0f;
@@ -64,16 +63,6 @@ bool interior(const Box &b, const ARect &r)
 {
     const int a = r.axis;
     if (!(r.c > b.lo[a] && r.c < b.hi[a])) return false;
-    for (int k = 0; k < 3; k++)
-        if (k != a && !(fmaxf(r.lo[k], b.lo[k]) < fminf(r.hi[k], b.hi[k]))) return false;
-    return true;
-}
-
-// r has a piece of positive area inside or on the boundary of the box
-bool touches(const Box &b, const ARect &r)
-{
-    const int a = r.axis;
-    if (!(r.c >= b.lo[a] && r.c <= b.hi[a])) return false;
     for (int k = 0; k < 3; k++)
         if (k != a && !(fmaxf(r.lo[k], b.lo[k]) < fminf(r.hi[k], b.hi[k]))) return false;
     return true;
@@ -309,9 +298,16 @@ void kd_split(const std::vector<ARect> &rects, const KdWork &w, int axis, float 
     lw.box.hi[axis] = c; rw.box.lo[axis] = c;
     lw.depth = rw.depth = w.depth + 1;
     lw.ids.reserve(w.ids.size()); rw.ids.reserve(w.ids.size());
+    // every rectangle of the node touches the node's box: only the split axis decides which children it touches
+    // (touches(): its plane within the closed range, or its extent overlapping the open one)
+    const float blo = w.box.lo[axis], bhi = w.box.hi[axis];
     for (int id : w.ids) {
-        if (touches(lw.box, rects[id])) lw.ids.push_back(id);
-        if (touches(rw.box, rects[id])) rw.ids.push_back(id);
+        const ARect &r = rects[id];
+        bool left, right;
+        if (r.axis == axis) { left = r.c <= c; right = r.c >= c; }
+        else { left = fmaxf(r.lo[axis], blo) < fminf(r.hi[axis], c); right = fmaxf(r.lo[axis], c) < fminf(r.hi[axis], bhi); }
+        if (left) lw.ids.push_back(id);
+        if (right) rw.ids.push_back(id);
     }
 }
 
@@ -377,6 +373,14 @@ const char *build_rooms(RoomScene &out, const fmgi_rect *walls, int num_walls, c
                         const fmgi_rect *lights, int num_lights)
 {
     const auto t0 = std::chrono::steady_clock::now();
+    const bool timing = getenv("FMGI_ROOMS_TIMING") != nullptr;
+    auto lap_t = t0;
+    auto lap = [&](const char *what) {
+        if (!timing) return;
+        const auto now = std::chrono::steady_clock::now();
+        fprintf(stderr, "[rooms]   %-28s %.2f ms\n", what, std::chrono::duration<double, std::milli>(now - lap_t).count());
+        lap_t = now;
+    };
     out = RoomScene();
     bool do_merge = true;
     if (const char *v = getenv("FMGI_ROOMS_MERGE")) do_merge = atoi(v) != 0;
@@ -400,12 +404,14 @@ const char *build_rooms(RoomScene &out, const fmgi_rect *walls, int num_walls, c
                 root.lo[k] = fminf(root.lo[k], x); root.hi[k] = fmaxf(root.hi[k], x);
             }
     };
-    for (int i = 0; i < num_walls; i++) grow(walls[i]);
+    for (const ARect &r : rects)                 // (a degenerate wall cannot be hit and does not count)
+        for (int k = 0; k < 3; k++) { root.lo[k] = fminf(root.lo[k], r.lo[k]); root.hi[k] = fmaxf(root.hi[k], r.hi[k]); }
     for (int i = 0; i < num_windows; i++) grow(windows[i]);
     for (int i = 0; i < num_lights; i++) grow(lights[i]);
     if (!(root.hi[0] >= root.lo[0])) for (int k = 0; k < 3; k++) { root.lo[k] = 0; root.hi[k] = 1; }
     for (int k = 0; k < 3; k++) { root.lo[k] -= 1.0f; root.hi[k] += 1.0f; }
 
+    lap("rectangles + root box");
     // ---- kd-tree ------------------------------------------------------------------------------------------
     // The top of the tree is split here until there are a few dozen subtrees; those are independent and built by a
     // pool of threads into their own arrays, concatenated in subtree order (the result does not depend on the
@@ -450,9 +456,16 @@ const char *build_rooms(RoomScene &out, const fmgi_rect *walls, int num_walls, c
             top = std::move(next);
         }
         for (KdWork &w : small) top.push_back(std::move(w));
+        lap("kd top levels");
         std::vector<KdSubtree> subs(top.size());
         run_parallel(top.size(), [&](size_t i) { kd_build_subtree(rects, std::move(top[i]), subs[i], leaves, max_leaves); });
         if (leaves.load() > max_leaves) return "too many boxes for its number of colliders (not a floor plan)";
+        lap("kd subtrees (parallel)");
+        size_t more_nodes = 0, more_boxes = 0;
+        for (const KdSubtree &st : subs) { more_nodes += st.nodes.size(); more_boxes += st.boxes.size(); }
+        nodes.reserve(nodes.size() + more_nodes);
+        boxes.reserve(more_boxes);
+        box_rects.reserve(more_boxes);
         for (size_t i = 0; i < subs.size(); i++) {
             KdSubtree &st = subs[i];
             const int node_off = (int)nodes.size() - 1, leaf_off = (int)boxes.size();      // local node k > 0 -> node_off + k
@@ -471,6 +484,7 @@ const char *build_rooms(RoomScene &out, const fmgi_rect *walls, int num_walls, c
         }
     }
     out.kd_leaves = boxes.size();
+    lap("kd concatenate");
     const auto t_kd = std::chrono::steady_clock::now();
 
     // ---- merge boxes across collider-free shared faces ---------------------------------------------------------------
@@ -496,6 +510,12 @@ const char *build_rooms(RoomScene &out, const fmgi_rect *walls, int num_walls, c
             slot_key[h] = k; slot_box[h] = (int)i;
         }
         std::vector<char> alive(nb0, 1);
+        // Per box and axis: the box found at the far corner (-3: not looked up yet, -1: none - for good, since lower
+        // corners never move and dead boxes stay dead) and the shape versions of the pair when it was last examined;
+        // later rounds skip the pairs that have not changed.
+        std::vector<int> nbr[3];
+        std::vector<uint32_t> seen_i[3], seen_j[3], version(nb0, 1);
+        for (int a = 0; a < 3; a++) { nbr[a].assign(nb0, -3); seen_i[a].assign(nb0, 0); seen_j[a].assign(nb0, 0); }
         bool changed = true;
         const int axis_order[3] = {2, 0, 1};
         while (changed) {
@@ -506,10 +526,18 @@ const char *build_rooms(RoomScene &out, const fmgi_rect *walls, int num_walls, c
                     if (!alive[i]) continue;
                     for (;;) {
                         Box &A = boxes[i];
-                        float corner[3] = {A.lo[0], A.lo[1], A.lo[2]};
-                        corner[a] = A.hi[a];
-                        const int j = find_box(key_of(corner));
-                        if (j < 0 || j == (int)i || !alive[j]) break;
+                        int j = nbr[a][i];
+                        if (j == -1) break;
+                        if (j >= 0 && seen_i[a][i] == version[i] && seen_j[a][i] == version[j]) break;
+                        if (j < 0) {
+                            float corner[3] = {A.lo[0], A.lo[1], A.lo[2]};
+                            corner[a] = A.hi[a];
+                            j = find_box(key_of(corner));
+                            if (j == (int)i) j = -1;
+                            nbr[a][i] = j;
+                        }
+                        if (j < 0 || !alive[j]) { nbr[a][i] = -1; break; }
+                        seen_i[a][i] = version[i]; seen_j[a][i] = version[j];
                         const Box &B = boxes[j];
                         if (B.hi[u] != A.hi[u] || B.hi[v] != A.hi[v]) break;
                         // a collider (facing either way) on the shared face keeps the boxes apart
@@ -525,12 +553,15 @@ const char *build_rooms(RoomScene &out, const fmgi_rect *walls, int num_walls, c
                         std::vector<int>().swap(box_rects[j]);
                         alive[j] = 0;
                         merged_into[j] = (int)i;
+                        version[i]++;
+                        nbr[a][i] = -3;                 // the far corner along this axis moved
                         changed = true;
                     }
                 }
             }
         }
     }
+    lap("merge");
     const auto t_merge = std::chrono::steady_clock::now();
     // final box ids
     std::vector<int> final_id(nb0, -1);
@@ -557,6 +588,7 @@ const char *build_rooms(RoomScene &out, const fmgi_rect *walls, int num_walls, c
     // the boxes around the building touch thousands of colliders and neighbours: they go first, so that no thread is
     // left alone with one at the end
     std::stable_sort(live.begin(), live.end(), [&](int a, int b) { return box_rects[a].size() > box_rects[b].size(); });
+    lap("faces: order boxes");
     const size_t chunk = 4, num_chunks = (live.size() + chunk - 1) / chunk;
     std::vector<FaceTreeBuilder::Out> chunk_out(num_chunks);
     // (a flat of a few hundred rectangles is built in half a millisecond: starting threads would cost more)
@@ -611,24 +643,35 @@ const char *build_rooms(RoomScene &out, const fmgi_rect *walls, int num_walls, c
         }
         chunk_out[ch] = std::move(ftb.out);
     }, rects.size() >= 2048);
+    lap("faces (parallel)");
+    std::vector<size_t> chunk_off(num_chunks + 1, 0);
     for (size_t ch = 0; ch < num_chunks; ch++) {
-        const uint32_t off = (uint32_t)out.face_nodes.size();
-        auto fix = [off](uint32_t code) { return (code & kRoomCodeKind) == kRoomCodeNode ? code + off : code; };
-        for (RoomFaceNode n : chunk_out[ch].face_nodes) {
-            n.lo = fix(n.lo); n.hi = fix(n.hi);
-            out.face_nodes.push_back(n);
-        }
-        for (size_t li = ch * chunk; li < std::min(live.size(), (ch + 1) * chunk); li++) {
-            RoomBox &rb = out.boxes[(size_t)final_id[live[li]]];
-            for (int o = 0; o < 8; o++)
-                for (int k = 0; k < 3; k++) rb.oct[o].code[k] = fix(rb.oct[o].code[k]);
-        }
+        chunk_off[ch + 1] = chunk_off[ch] + chunk_out[ch].face_nodes.size();
         out.face_parts += chunk_out[ch].face_parts;
         out.wall_parts += chunk_out[ch].wall_parts;
     }
+    out.face_nodes.resize(chunk_off[num_chunks]);
+    const size_t groups = (num_chunks + 255) / 256;
+    run_parallel(groups, [&](size_t gi) {
+        for (size_t ch = gi * 256; ch < std::min(num_chunks, (gi + 1) * 256); ch++) {
+            const uint32_t off = (uint32_t)chunk_off[ch];
+            auto fix = [off](uint32_t code) { return (code & kRoomCodeKind) == kRoomCodeNode ? code + off : code; };
+            RoomFaceNode *dst = out.face_nodes.data() + off;
+            for (RoomFaceNode n : chunk_out[ch].face_nodes) {
+                n.lo = fix(n.lo); n.hi = fix(n.hi);
+                *dst++ = n;
+            }
+            for (size_t li = ch * chunk; li < std::min(live.size(), (ch + 1) * chunk); li++) {
+                RoomBox &rb = out.boxes[(size_t)final_id[live[li]]];
+                for (int o = 0; o < 8; o++)
+                    for (int k = 0; k < 3; k++) rb.oct[o].code[k] = fix(rb.oct[o].code[k]);
+            }
+        }
+    }, rects.size() >= 2048);
     if (out.face_nodes.size() > kRoomCodeIndex) return "more than 2^30 face nodes";
     if (out.face_nodes.empty()) out.face_nodes.push_back(RoomFaceNode{0.0f, 0.0f, kRoomCodeMiss, kRoomCodeMiss});   // never empty
 
+    lap("faces concatenate");
     const auto t_faces = std::chrono::steady_clock::now();
     // ---- per emitter: the boxes its rectangle touches (closed overlap with the rectangle grown by the start offset) --------
     {
