@@ -151,7 +151,7 @@ struct fmgi_scene {
     RoomFaceNode *d_room_face_nodes = nullptr;
     RoomBounds *d_room_bounds = nullptr;
     RoomNode *d_room_nodes = nullptr;
-    int32_t *d_room_start_range = nullptr, *d_room_start_boxes = nullptr;
+    RoomStart *d_room_starts = nullptr;
     unsigned long long *d_jobs = nullptr;       // per accumulation pass: chunk_begin[E+1], photon_first[E], photon_count[E]
     size_t job_tables = 0;                      // passes the job-table buffers have room for
     float4 *d_scratch = nullptr;                // per-pass fp32 atlas when a bake needs several passes
@@ -213,8 +213,7 @@ TraceParams base_params(const fmgi_scene *s)
     p.room_face_nodes = reinterpret_cast<const float4 *>(s->d_room_face_nodes);
     p.room_bounds = reinterpret_cast<const float4 *>(s->d_room_bounds);
     p.room_nodes = reinterpret_cast<const float4 *>(s->d_room_nodes);
-    p.room_start_range = s->d_room_start_range;
-    p.room_start_boxes = s->d_room_start_boxes;
+    p.room_starts = reinterpret_cast<const int2 *>(s->d_room_starts);
     for (int k = 0; k < 3; k++) { p.room_lo[k] = s->build->rooms.root_lo[k]; p.room_hi[k] = s->build->rooms.root_hi[k]; }
     p.room_num_boxes = (unsigned)s->build->rooms.boxes.size();
     p.room_num_face_nodes = (unsigned)s->build->rooms.face_nodes.size();
@@ -457,8 +456,7 @@ int scene_from_build(fmgi_scene **out, std::shared_ptr<HostBuild> b, const fmgi_
         FMGI_CUDA(upload(&s->d_room_face_nodes, b->rooms.face_nodes));
         FMGI_CUDA(upload(&s->d_room_bounds, b->rooms.bounds));
         FMGI_CUDA(upload(&s->d_room_nodes, b->rooms.nodes));
-        FMGI_CUDA(upload(&s->d_room_start_range, b->rooms.start_range));
-        FMGI_CUDA(upload(&s->d_room_start_boxes, b->rooms.start_boxes));
+        FMGI_CUDA(upload(&s->d_room_starts, b->rooms.starts));
     } else if (s->kernel_tier != FMGI_TIER_SOUP) {
         if (b->device_grid) {
             const double tg0 = now_ms();
@@ -579,7 +577,7 @@ void fmgi_scene_destroy(fmgi_scene *s)
     pool.free(s->d_axis); pool.free(s->d_general); pool.free(s->d_shade); pool.free(s->d_emitters);
     pool.free(s->d_grid_table);
     pool.free(s->d_room_boxes); pool.free(s->d_room_face_nodes); pool.free(s->d_room_bounds); pool.free(s->d_room_nodes);
-    pool.free(s->d_room_start_range); pool.free(s->d_room_start_boxes);
+    pool.free(s->d_room_starts);
     pool.free(s->d_jobs); pool.free(s->d_counters); pool.free(s->d_scratch);
     pool.free(s->d_tile_walls); pool.free(s->h_tile_walls);
     pool.free(s->d_png_walls); pool.free(s->h_png_walls);

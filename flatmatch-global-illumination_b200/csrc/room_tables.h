@@ -67,6 +67,15 @@ struct RoomBounds {
 };
 static_assert(sizeof(RoomBounds) == 32, "RoomBounds is two float4");
 
+// Where an emitter's photons start: the boxes in front of the emitter rectangle partition it like the things on a box
+// face partition the face - `code` is a box, or the root of a 2-D kd-tree of RoomFaceNode over the rectangle's two
+// in-plane coordinates (normal along `axis`), or "nothing" (an emitter that is not axis parallel, or lies outside the
+// boxes: the photon's first box is then found by descending the kd-tree below).
+struct RoomStart {
+    uint32_t code;
+    int32_t axis;
+};
+
 // The kd-tree the boxes come from, kept for point location (a new photon's first box, probe rays): inner node:
 // split plane `v` of `axis`, children left (below) / right (above); leaf: axis = -1, left = box index.
 struct RoomNode {
@@ -80,11 +89,7 @@ struct RoomScene {
     std::vector<RoomBounds> bounds;            // per box
     std::vector<RoomFaceNode> face_nodes;
     std::vector<RoomNode> nodes;               // nodes[0] = root
-    // where an emitter's photons start: the boxes that touch the emitter rectangle (windows, then lights), largest
-    // share first: start_boxes[start_range[2e] .. start_range[2e + 1]); a single candidate needs no test, several
-    // are checked by containment, the tree descent is the fallback
-    std::vector<int32_t> start_range;
-    std::vector<int32_t> start_boxes;
+    std::vector<RoomStart> starts;             // per emitter (windows, then lights)
     float root_lo[3] = {0, 0, 0}, root_hi[3] = {0, 0, 0};
     int max_depth = 0;
     size_t kd_leaves = 0;                      // boxes before merging
@@ -104,5 +109,7 @@ int rooms_closest_hit(const RoomScene &rs, int box, const float o[3], const floa
 // Box a ray that starts at p and travels along d is in (-1: outside the root box): tree descent, a point exactly
 // on a split plane belongs to the side the ray travels towards.
 int rooms_locate(const RoomScene &rs, const float p[3], const float d[3]);
+// First box of a photon of `emitter` that starts at p (device: rooms_start): the emitter's partition, else the descent.
+int rooms_start_box(const RoomScene &rs, int emitter, const float p[3], const float d[3]);
 
 }  // namespace fmgi

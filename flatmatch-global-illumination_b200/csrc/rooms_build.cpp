@@ -673,50 +673,61 @@ const char *build_rooms(RoomScene &out, const fmgi_rect *walls, int num_walls, c
 
     lap("faces concatenate");
     const auto t_faces = std::chrono::steady_clock::now();
-    // ---- per emitter: the boxes its rectangle touches (closed overlap with the rectangle grown by the start offset) --------
+    // ---- per emitter: the boxes in front of its rectangle, as a partition of the rectangle (the same 2-D kd-trees as the
+    // faces; an emitter in front of ONE box - a ceiling light, a window in its niche - is that box's code) -----------------
     {
         std::vector<int> stack_n;
-        std::vector<std::pair<double, int>> cand;
+        std::vector<int> seen;
+        std::vector<FaceItem> items;
+        FaceTreeBuilder ftb;
+        out.starts.assign((size_t)(num_windows + num_lights), RoomStart{kRoomCodeMiss, -1});
         for (int e = 0; e < num_windows + num_lights; e++) {
-            const fmgi_rect &r = e < num_windows ? windows[e] : lights[e - num_windows];
-            float lo[3], hi[3];
-            for (int k = 0; k < 3; k++) {
-                const float a = r.pos[k], b2 = r.pos[k] + r.width[k] + r.height[k];
-                lo[k] = fminf(a, b2) - 3e-5f; hi[k] = fmaxf(a, b2) + 3e-5f;
-            }
-            out.start_range.push_back((int32_t)out.start_boxes.size());
-            cand.clear();
+            ARect er;
+            if (to_axis_rect(e < num_windows ? windows[e] : lights[e - num_windows], e, er) != 0) continue;   // tree descent
+            const int a = er.axis, u = a == 0 ? 1 : 0, v = a == 2 ? 1 : 2;
+            items.clear();
+            seen.clear();
             stack_n.assign(1, 0);
             while (!stack_n.empty()) {
                 const Node nd = nodes[stack_n.back()];
                 stack_n.pop_back();
                 if (nd.axis < 0) {
-                    const int b = resolve(nd.leaf);
-                    // photons start on the normal's side of the rectangle: a box that ends at its plane on the other
-                    // side holds none of them
-                    bool behind_emitter = false;
-                    for (int k = 0; k < 3; k++) {
-                        if (r.n[k] > 0 && r.width[k] == 0 && r.height[k] == 0 && boxes[b].hi[k] <= r.pos[k]) behind_emitter = true;
-                        if (r.n[k] < 0 && r.width[k] == 0 && r.height[k] == 0 && boxes[b].lo[k] >= r.pos[k]) behind_emitter = true;
-                    }
-                    if (behind_emitter) continue;
-                    double vol = 1.0;
-                    for (int k = 0; k < 3; k++) vol *= (double)fminf(hi[k], boxes[b].hi[k]) - (double)fmaxf(lo[k], boxes[b].lo[k]);
-                    bool seen = false;
-                    for (auto &c : cand) seen |= c.second == final_id[b];
-                    if (!seen) cand.push_back({-vol, final_id[b]});
+                    const int b = root_of[nd.leaf];
+                    const Box &B = boxes[b];
+                    // photons start at most 1e-5 off the plane, on the normal's side (er.neg: normal along -axis)
+                    if (er.neg ? !(B.lo[a] < er.c && er.c <= B.hi[a]) : !(B.lo[a] <= er.c && er.c < B.hi[a])) continue;
+                    if (!(fmaxf(B.lo[u], er.lo[u]) < fminf(B.hi[u], er.hi[u])) || !(fmaxf(B.lo[v], er.lo[v]) < fminf(B.hi[v], er.hi[v])))
+                        continue;
+                    if (std::find(seen.begin(), seen.end(), b) != seen.end()) continue;
+                    seen.push_back(b);
+                    items.push_back(FaceItem{{B.lo[u], B.lo[v]}, {B.hi[u], B.hi[v]}, kRoomCodeBox | (uint32_t)final_id[b]});
                     continue;
                 }
-                if (lo[nd.axis] <= nd.v) stack_n.push_back(nd.left);
-                if (hi[nd.axis] >= nd.v) stack_n.push_back(nd.right);
+                if (nd.axis == a) {
+                    if (er.c < nd.v || (er.c == nd.v && er.neg)) stack_n.push_back(nd.left);
+                    if (er.c > nd.v || (er.c == nd.v && !er.neg)) stack_n.push_back(nd.right);
+                } else {
+                    if (er.lo[nd.axis] < nd.v) stack_n.push_back(nd.left);
+                    if (er.hi[nd.axis] > nd.v) stack_n.push_back(nd.right);
+                }
             }
-            std::sort(cand.begin(), cand.end());
-            for (auto &c : cand) out.start_boxes.push_back(c.second);
-            out.start_range.push_back((int32_t)out.start_boxes.size());
+            const Region region = {{er.lo[u], er.lo[v]}, {er.hi[u], er.hi[v]}};
+            const size_t first_node = ftb.out.face_nodes.size();
+            uint32_t code = ftb.build(region, items);
+            // the emitters' nodes go behind the faces' nodes
+            const uint32_t off = (uint32_t)out.face_nodes.size() - (uint32_t)first_node;
+            auto fix = [off](uint32_t c) { return (c & kRoomCodeKind) == kRoomCodeNode ? c + off : c; };
+            for (size_t q = first_node; q < ftb.out.face_nodes.size(); q++) {
+                RoomFaceNode n = ftb.out.face_nodes[q];
+                n.lo = fix(n.lo); n.hi = fix(n.hi);
+                out.face_nodes.push_back(n);
+            }
+            ftb.out.face_nodes.resize(first_node);
+            out.starts[(size_t)e] = RoomStart{fix(code), a};
         }
-        if (out.start_boxes.empty()) out.start_boxes.push_back(0);
-        if (out.start_range.empty()) { out.start_range.push_back(0); out.start_range.push_back(0); }
+        if (out.starts.empty()) out.starts.push_back(RoomStart{kRoomCodeMiss, -1});
     }
+    if (out.face_nodes.size() > kRoomCodeIndex) return "more than 2^30 face nodes";
     // the tree itself, for point location
     out.nodes.resize(nodes.size());
     for (size_t i = 0; i < nodes.size(); i++) {
@@ -749,6 +760,19 @@ int rooms_locate(const RoomScene &rs, const float p[3], const float d[3])
         n = right ? nd.right : nd.left;
     }
     return rs.nodes[n].left;
+}
+
+int rooms_start_box(const RoomScene &rs, int emitter, const float p[3], const float d[3])
+{
+    const RoomStart &st = rs.starts[(size_t)emitter];
+    uint32_t code = st.code;
+    const float pu = st.axis == 0 ? p[1] : p[0], pv = st.axis == 2 ? p[1] : p[2];
+    while ((code & kRoomCodeKind) == kRoomCodeNode) {
+        const RoomFaceNode &n = rs.face_nodes[code];
+        code = (pu >= n.split_u && pv >= n.split_v) ? n.hi : n.lo;
+    }
+    if ((code & kRoomCodeKind) == kRoomCodeBox) return (int)(code & kRoomCodeIndex);
+    return rooms_locate(rs, p, d);
 }
 
 // Host replay of the device traversal (rooms_walk in trace_kernels.cuh), same float operations.

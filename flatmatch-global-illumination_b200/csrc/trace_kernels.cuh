@@ -82,8 +82,7 @@ struct TraceParams {
     const float4 *room_face_nodes;
     const float4 *room_bounds;
     const float4 *room_nodes;
-    const int *room_start_range;    // per emitter: [2e], [2e + 1]: its candidate first boxes in room_start_boxes
-    const int *room_start_boxes;
+    const int2 *room_starts;        // per emitter: {code, normal axis} (RoomStart)
     float room_lo[3], room_hi[3];   // the root box
     // table sizes: read only by the bounds-checked build (FMGI_CHECKED, lib/libfmgi_cuda_checked.so)
     unsigned grid_records, num_walls, num_texels, room_num_boxes, room_num_face_nodes, room_num_nodes;
@@ -675,6 +674,10 @@ __device__ __forceinline__ int closest_hit_soup_planes(const SoupTables &s, cons
 
 // ---- closest hit through the box decomposition (room tier, room_tables.h) -----------------------------------------
 
+constexpr int kRoomWalking = -2;          // rooms_walk: the ray is in box `box`, still on its way
+constexpr int kRoomMaxSteps = 4096;       // boxes per ray before the photon is given up (never reached by a sane table)
+constexpr unsigned kRoomKindShift = 30;   // room_tables.h: kRoomCode*
+
 // Box a ray that starts at (x, y, z) and travels along d is in: kd-tree descent; a point exactly on a split plane
 // belongs to the side the ray travels towards.  The point is clamped into the root box first.
 __device__ __forceinline__ int rooms_locate(const TraceParams &p, float x, float y, float z, float dx, float dy, float dz)
@@ -696,19 +699,21 @@ __device__ __forceinline__ int rooms_locate(const TraceParams &p, float x, float
     return 0;
 }
 
-// First box of a photon emitted by `emitter`: the box the emitter rectangle lies in; where it touches several, the
-// one that contains the start point (largest share first), else the tree descent.
+// First box of a photon emitted by `emitter`: the boxes in front of the emitter rectangle partition it - one box (a
+// ceiling light, a window in its niche: no lookup), or a descent through the rectangle's 2-D kd-tree with the start
+// point's two in-plane coordinates; an emitter the builder could not place falls back to the kd-tree of the boxes.
 __device__ __forceinline__ int rooms_start(const TraceParams &p, int emitter, float x, float y, float z, float dx, float dy,
                                            float dz)
 {
-    const int b = __ldg(p.room_start_range + 2 * emitter), e = __ldg(p.room_start_range + 2 * emitter + 1);
-    if (e - b == 1) return __ldg(p.room_start_boxes + b);
-    for (int q = b; q < e; q++) {
-        const int box = __ldg(p.room_start_boxes + q);
-        float4 b0, b1;                                   // {lo.x, lo.y, lo.z, hi.x}, {hi.y, hi.z, -, -}
-        ldg256(p.room_bounds + 2 * box, b0, b1);
-        if (x >= b0.x && x <= b0.w && y >= b0.y && y <= b1.x && z >= b0.z && z <= b1.y) return box;
+    const int2 st = __ldg(p.room_starts + emitter);
+    unsigned code = (unsigned)st.x;
+    const float pu = st.y == 0 ? y : x, pv = st.y == 2 ? y : z;
+    while ((code >> kRoomKindShift) == 0u) {
+        if (!FMGI_CHECK(p, code < p.room_num_face_nodes, 23)) return 0;
+        const float4 n = __ldg(p.room_face_nodes + code);
+        code = __float_as_uint((pu >= n.x && pv >= n.y) ? n.w : n.z);
     }
+    if ((code >> kRoomKindShift) == 2u) return (int)(code & ((1u << kRoomKindShift) - 1u));
     return rooms_locate(p, x, y, z, dx, dy, dz);
 }
 
@@ -718,9 +723,6 @@ __device__ __forceinline__ int rooms_start(const TraceParams &p, int emitter, fl
 // hands the ray to the neighbour it touches).
 __device__ __forceinline__ float rooms_inv(float d) { return d == 0.0f ? -1e30f : rcp_fast(d); }
 
-constexpr int kRoomWalking = -2;          // rooms_walk: the ray is in box `box`, still on its way
-constexpr int kRoomMaxSteps = 4096;       // boxes per ray before the photon is given up (never reached by a sane table)
-constexpr unsigned kRoomKindShift = 30;   // room_tables.h: kRoomCode*
 
 // The ray leaves its box through the nearest of the three faces it travels towards; the face's code - after a
 // descent through the face's 2-D kd-tree where several things share the face - says what is at the exit point: a

@@ -72,6 +72,7 @@ int main(int argc, char **argv)
                 lo[k] = fminf(lo[k], x); hi[k] = fmaxf(hi[k], x);
             }
     long steps = 0, tests = 0, mism = 0, mism_edge = 0, hits = 0, max_steps = 0;
+    bool bad_starts = false;
     std::vector<long> hist(32, 0), ehist(32, 0);
     for (int i = 0; i < num_rays; i++) {
         float o[3], d[3];
@@ -131,7 +132,7 @@ int main(int argc, char **argv)
             tot += w * h;
             cum.push_back(tot);
         }
-        long psteps = 0, pnodes = 0, prays = 0;
+        long psteps = 0, pnodes = 0, prays = 0, start_checks = 0, start_mismatch = 0;
         std::vector<long> ph(32, 0), pn(32, 0);
         for (int i = 0; i < num_rays / 2 && !em.empty(); i++) {
             const double x = urand() * tot;
@@ -151,7 +152,16 @@ int main(int argc, char **argv)
                 for (int k = 0; k < 3; k++) { d[k] = (float)(d[k] / sqrt(n2)); dn += d[k] * nrm[k]; }
                 if (dn < 0) for (int k = 0; k < 3; k++) d[k] -= 2 * dn * nrm[k];
                 for (int k = 0; k < 3; k++) o[k] += d[k] * 1e-5f;
-                if (box == -2) box = rooms_locate(rs, o, d);
+                if (box == -2) {
+                    box = rooms_locate(rs, o, d);
+                    // the emitter's partition must name the box the tree descent finds (device: rooms_start)
+                    const int emitter = (int)std::min(e, em.size() - 1);
+                    start_checks++;
+                    if (rooms_start_box(rs, emitter, o, d) != box) {
+                        // a start point within 1e-5 of a box edge may sit in the neighbour: count, tolerate a few
+                        start_mismatch++;
+                    }
+                }
                 if (box < 0) break;
                 long s0 = steps, n0 = tests;
                 float t;
@@ -166,6 +176,8 @@ int main(int argc, char **argv)
                 box = box_out;
             }
         }
+        printf("\nstart boxes: %ld photons, %ld not in the box the tree descent finds", start_checks, start_mismatch);
+        if (start_mismatch > start_checks / 2000 + 1) bad_starts = true;
         if (prays) {
             printf("\nphoton rays %ld: steps/ray %.3f, face nodes/ray %.3f\nphoton steps histogram:", prays, (double)psteps / prays,
                    (double)pnodes / prays);
@@ -177,5 +189,5 @@ int main(int argc, char **argv)
     printf("\nface nodes histogram:");
     for (int i = 0; i < 16; i++) printf(" %d:%.3f", i, (double)ehist[i] / num_rays);
     printf("\n");
-    return mism > num_rays / 20000 + 2 || mism_edge ? 1 : 0;
+    return mism > num_rays / 20000 + 2 || mism_edge || bad_starts ? 1 : 0;
 }
