@@ -447,7 +447,7 @@ def measure(h, workload, steps, warmup, e2e_steps, photons=0.0, total_photons=0.
                      "peak_source": f"{sms} SMs x 128 lanes x 2 x {pk.get('sm_max_mhz', 1965.0):.0f} MHz ({pk_kind})",
                      "flops_per_ray": flops_per_ray, "rect_tests_per_ray": tests_per_ray,
                      "note": "algorithmic FP32 work per SURVEY.md 8(d): 13*T+150 flops per ray; T = rectangle tests per ray "
-                             "(room tier: boxes crossed, a 14-flop slab test each, + face-tree nodes visited)"},
+                             "(room tier: boxes crossed, a 14-flop slab test each, + face grids looked up)"},
         "gpu_launches": launches,
     }
     if e2e:

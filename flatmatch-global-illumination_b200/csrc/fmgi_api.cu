@@ -148,7 +148,8 @@ struct fmgi_scene {
     EmitterRec *d_emitters = nullptr;
     GridRec *d_grid_table = nullptr;            // grid tier / plane tables
     RoomBox *d_room_boxes = nullptr;            // room tier
-    RoomFaceNode *d_room_face_nodes = nullptr;
+    RoomFaceGrid *d_room_face_grids = nullptr;
+    uint32_t *d_room_face_cells = nullptr;
     RoomBounds *d_room_bounds = nullptr;
     RoomNode *d_room_nodes = nullptr;
     RoomStart *d_room_starts = nullptr;
@@ -210,13 +211,15 @@ TraceParams base_params(const fmgi_scene *s)
     p.work_counter = s->d_counters + 4;
     p.counters = s->d_counters;
     p.room_boxes = reinterpret_cast<const float4 *>(s->d_room_boxes);
-    p.room_face_nodes = reinterpret_cast<const float4 *>(s->d_room_face_nodes);
+    p.room_face_grids = reinterpret_cast<const float4 *>(s->d_room_face_grids);
+    p.room_face_cells = s->d_room_face_cells;
     p.room_bounds = reinterpret_cast<const float4 *>(s->d_room_bounds);
     p.room_nodes = reinterpret_cast<const float4 *>(s->d_room_nodes);
     p.room_starts = reinterpret_cast<const int2 *>(s->d_room_starts);
     for (int k = 0; k < 3; k++) { p.room_lo[k] = s->build->rooms.root_lo[k]; p.room_hi[k] = s->build->rooms.root_hi[k]; }
     p.room_num_boxes = (unsigned)s->build->rooms.boxes.size();
-    p.room_num_face_nodes = (unsigned)s->build->rooms.face_nodes.size();
+    p.room_num_face_grids = (unsigned)s->build->rooms.face_grids.size();
+    p.room_num_face_cells = (unsigned)s->build->rooms.face_cells.size();
     p.room_num_nodes = (unsigned)s->build->rooms.nodes.size();
     p.grid_records = (unsigned)s->grid_records;
     p.num_walls = (unsigned)s->host.num_walls;
@@ -453,7 +456,8 @@ int scene_from_build(fmgi_scene **out, std::shared_ptr<HostBuild> b, const fmgi_
     DeviceGuard guard(o.device);
     if (s->kernel_tier == kTierRooms) {
         FMGI_CUDA(upload(&s->d_room_boxes, b->rooms.boxes));
-        FMGI_CUDA(upload(&s->d_room_face_nodes, b->rooms.face_nodes));
+        FMGI_CUDA(upload(&s->d_room_face_grids, b->rooms.face_grids));
+        FMGI_CUDA(upload(&s->d_room_face_cells, b->rooms.face_cells));
         FMGI_CUDA(upload(&s->d_room_bounds, b->rooms.bounds));
         FMGI_CUDA(upload(&s->d_room_nodes, b->rooms.nodes));
         FMGI_CUDA(upload(&s->d_room_starts, b->rooms.starts));
@@ -576,7 +580,7 @@ void fmgi_scene_destroy(fmgi_scene *s)
     MemPool &pool = MemPool::get();
     pool.free(s->d_axis); pool.free(s->d_general); pool.free(s->d_shade); pool.free(s->d_emitters);
     pool.free(s->d_grid_table);
-    pool.free(s->d_room_boxes); pool.free(s->d_room_face_nodes); pool.free(s->d_room_bounds); pool.free(s->d_room_nodes);
+    pool.free(s->d_room_boxes); pool.free(s->d_room_face_grids); pool.free(s->d_room_face_cells); pool.free(s->d_room_bounds); pool.free(s->d_room_nodes);
     pool.free(s->d_room_starts);
     pool.free(s->d_jobs); pool.free(s->d_counters); pool.free(s->d_scratch);
     pool.free(s->d_tile_walls); pool.free(s->h_tile_walls);

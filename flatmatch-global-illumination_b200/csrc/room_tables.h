@@ -18,7 +18,7 @@
 // Back-face culling (rectangle.c:70-72) is structural: a face shows only the colliders whose normal points into
 // its box.  Where coplanar colliders overlap, the part belongs to the lowest wall index, as the reference's strict
 // `<` decides (photonmap.cl:199); a point exactly on the edge between two parts belongs to the part on the higher
-// side of the split.
+// side of the edge.
 #pragma once
 #include <stdint.h>
 #include <vector>
@@ -29,7 +29,7 @@ namespace fmgi {
 
 // What a face (or a part of it) holds: kind in the top two bits, index below.
 enum : uint32_t {
-    kRoomCodeNode = 0u << 30,        // index of a RoomFaceNode: descend
+    kRoomCodeNode = 0u << 30,        // index of a RoomFaceGrid: look the exit point up
     kRoomCodeWall = 1u << 30,        // wall index: a hit
     kRoomCodeBox = 2u << 30,         // box index: the ray goes on there
     kRoomCodeMiss = 3u << 30,        // nothing: the ray leaves the scene
@@ -50,14 +50,18 @@ struct RoomBox {
 };
 static_assert(sizeof(RoomBox) == 256, "RoomBox is sixteen float4");
 
-// One node of a face's 2-D kd-tree: the exit point (u: the lower in-plane axis, v: the higher) goes to `hi` when
-// u >= split_u AND v >= split_v, else to `lo` (codes).  A split along one axis leaves the other at -inf - the device
-// compares both without asking which one the node is about.
-struct RoomFaceNode {
-    float split_u, split_v;
-    uint32_t lo, hi;
+// One lookup record of a face that holds several things: up to three ascending split values per in-plane coordinate
+// (u: the lower in-plane axis, v: the higher; unused splits are +inf) cut the face into up to 4 x 4 cells, and the cell
+// the exit point falls into - cell (iu, iv), iu = number of u splits the coordinate is at or above - holds the code of
+// what is there: cells[base + iu + stride * iv].  A wall with a door is ONE record (left | door | right) x (opening |
+// lintel); a cell that still holds several things (more than three edges along an axis) is the code of a further
+// record.  One 256-bit load, six compares, one 32-bit load - no loop over tree levels, whose trip count a warp's
+// deepest lane would dictate.
+struct RoomFaceGrid {
+    float su[3], sv[3];
+    uint32_t base, stride;
 };
-static_assert(sizeof(RoomFaceNode) == 16, "RoomFaceNode is one float4");
+static_assert(sizeof(RoomFaceGrid) == 32, "RoomFaceGrid is two float4");
 
 // Bounds of a box (where does a new photon start; host replay).
 struct RoomBounds {
@@ -68,8 +72,8 @@ struct RoomBounds {
 static_assert(sizeof(RoomBounds) == 32, "RoomBounds is two float4");
 
 // Where an emitter's photons start: the boxes in front of the emitter rectangle partition it like the things on a box
-// face partition the face - `code` is a box, or the root of a 2-D kd-tree of RoomFaceNode over the rectangle's two
-// in-plane coordinates (normal along `axis`), or "nothing" (an emitter that is not axis parallel, or lies outside the
+// face partition the face - `code` is a box, or a RoomFaceGrid over the rectangle's two in-plane coordinates (normal
+// along `axis`), or "nothing" (an emitter that is not axis parallel, or lies outside the
 // boxes: the photon's first box is then found by descending the kd-tree below).
 struct RoomStart {
     uint32_t code;
@@ -87,7 +91,8 @@ static_assert(sizeof(RoomNode) == 16, "RoomNode is one float4");
 struct RoomScene {
     std::vector<RoomBox> boxes;
     std::vector<RoomBounds> bounds;            // per box
-    std::vector<RoomFaceNode> face_nodes;
+    std::vector<RoomFaceGrid> face_grids;
+    std::vector<uint32_t> face_cells;          // the codes the grids index
     std::vector<RoomNode> nodes;               // nodes[0] = root
     std::vector<RoomStart> starts;             // per emitter (windows, then lights)
     float root_lo[3] = {0, 0, 0}, root_hi[3] = {0, 0, 0};
@@ -103,7 +108,7 @@ const char *build_rooms(RoomScene &out, const fmgi_rect *walls, int num_walls, c
                         const fmgi_rect *lights, int num_lights);
 
 // Host replay of the device traversal (tests/cpu, tools): wall index or -1, ray parameter, boxes crossed and face
-// tree nodes visited.
+// grids looked up.
 int rooms_closest_hit(const RoomScene &rs, int box, const float o[3], const float d[3], float &t_out, int &box_out,
                       long &steps, long &tests);
 // Box a ray that starts at p and travels along d is in (-1: outside the root box): tree descent, a point exactly

@@ -9,7 +9,7 @@
 //   3. leaves are merged back: two boxes that share a whole face with no collider on it become one box (a split
 //      plane runs through the whole node, also through the rooms its wall does not touch), to a fixed point;
 //   4. per box and face: the colliders on that face whose normal points into the box and the boxes behind the face,
-//      as a partition of the face stored as a 2-D kd-tree of RoomFaceNode (a face with one thing on it is a code);
+//      as a partition of the face stored as RoomFaceGrid records (a face with one thing on it is a code);
 //   5. per emitter: the boxes its rectangle touches.
 #include <algorithm>
 #include <atomic>
@@ -126,108 +126,82 @@ bool covers(const FaceItem &it, const Region &r)
     return it.lo[0] <= r.lo[0] && it.hi[0] >= r.hi[0] && it.lo[1] <= r.lo[1] && it.hi[1] >= r.hi[1];
 }
 
-bool g_face_cost_depth = true;          // FMGI_ROOMS_FACE_COST=expected: the pre-SIMT cost (experiments)
+// A face (or an emitter rectangle) as RoomFaceGrid records: the edges of the things on it cut it into cells.
+struct FaceGridBuilder {
+    struct Out {
+        std::vector<RoomFaceGrid> grids;
+        std::vector<uint32_t> cells;
+        size_t face_parts = 0, wall_parts = 0;
+    };
+    Out out;                     // grid codes / cell bases are local to `out`; the caller offsets them when it concatenates
 
-struct FaceTreeBuilder {
-    struct Out { std::vector<RoomFaceNode> face_nodes; size_t face_parts = 0, wall_parts = 0; };
-    Out out;                     // node codes are local to `out.face_nodes`; the caller offsets them when it concatenates
-    std::vector<float> cand[2];
-
-    // The items of a node are pool[begin, end): colliders in wall-index order first, then portals; all overlap `r` with
-    // positive area.  The children's lists are appended to the pool and dropped again when the node is done - no
-    // allocation per node.
+    // The items of a region are pool[begin, end): colliders in wall-index order first, then portals; all overlap the
+    // region with positive area.  The cells' lists are appended to the pool and dropped again when the cell is done -
+    // no allocation per cell.
     std::vector<FaceItem> pool;
+    std::vector<float> edges;
     uint32_t build(const Region &r, const std::vector<FaceItem> &items_in)
     {
         pool.assign(items_in.begin(), items_in.end());
         return build(r, 0, pool.size(), 0);
     }
-    struct ItemRange {
-        const FaceItem *b, *e;
-        const FaceItem *begin() const { return b; }
-        const FaceItem *end() const { return e; }
-        size_t size() const { return (size_t)(e - b); }
-        const FaceItem &operator[](size_t i) const { return b[i]; }
-    };
+
+    // up to three of the item edges strictly inside (lo, hi) along `ax`: all of them, or the quartiles
+    int pick_splits(size_t begin, size_t end, int ax, float lo, float hi, float split[3])
+    {
+        edges.clear();
+        for (size_t q = begin; q < end; q++) {
+            const float a = pool[q].lo[ax], b = pool[q].hi[ax];
+            if (a > lo && a < hi) edges.push_back(a);
+            if (b > lo && b < hi) edges.push_back(b);
+        }
+        std::sort(edges.begin(), edges.end());
+        edges.erase(std::unique(edges.begin(), edges.end()), edges.end());
+        const size_t n = edges.size();
+        if (n <= 3) {
+            for (size_t k = 0; k < n; k++) split[k] = edges[k];
+            return (int)n;
+        }
+        split[0] = edges[n / 4]; split[1] = edges[n / 2]; split[2] = edges[(3 * n) / 4];
+        return 3;
+    }
+
     uint32_t build(const Region &r, size_t begin, size_t end, int depth)
     {
         if (begin == end) { out.face_parts++; return kRoomCodeMiss; }
-        const ItemRange items{pool.data() + begin, pool.data() + end};
-        // the part belongs to the first item (lowest wall index; a collider hides the box behind it) if that covers it
-        const FaceItem first = items[0];
+        // the region belongs to the first item (lowest wall index; a collider hides the box behind it) if that covers it
+        const FaceItem first = pool[begin];
         const bool first_is_wall = (first.code & kRoomCodeKind) == kRoomCodeWall;
-        if (covers(first, r) && (first_is_wall || items.size() == 1)) {
+        if (covers(first, r) && (first_is_wall || end - begin == 1)) {
             out.face_parts++;
             out.wall_parts += first_is_wall;
             return first.code;
         }
-        // candidate split lines: item edges strictly inside the region
-        int best_axis = -1;
-        float best_v = 0;
-        double best_cost = 1e300;
-        const double ext[2] = {(double)r.hi[0] - r.lo[0], (double)r.hi[1] - r.lo[1]};
-        auto consider = [&](int ax, float v) {
-            if (!(v > r.lo[ax] && v < r.hi[ax])) return;
-            double cost;
-            if (items.size() > 24) {
-                // long lists (the boxes around the building): the edge nearest the middle of the longer side
-                cost = fabs((double)v - 0.5 * ((double)r.lo[ax] + r.hi[ax])) / ext[ax] + (ext[ax] >= ext[1 - ax] ? 0.0 : 1.0);
-            } else {
-                // a warp waits for the deepest descent among its lanes: the levels still needed below the fuller side
-                // first, then the expected number of further decisions (share of the region x (items on that side - 1))
-                int nl = 0, nr = 0;
-                for (const FaceItem &it : items) {
-                    nl += fmaxf(it.lo[ax], r.lo[ax]) < fminf(it.hi[ax], v);
-                    nr += fmaxf(it.lo[ax], v) < fminf(it.hi[ax], r.hi[ax]);
-                }
-                const double fl = ((double)v - r.lo[ax]) / ext[ax];
-                int levels = 0;
-                while ((1 << levels) < std::max(nl, nr)) levels++;
-                cost = (g_face_cost_depth ? (double)levels : 0.0) + 0.1 * (fl * (nl - 1) + (1.0 - fl) * (nr - 1)) + 1e-4 * fabs(fl - 0.5);
-            }
-            if (cost < best_cost || (cost == best_cost && (ax < best_axis || (ax == best_axis && v < best_v)))) {
-                best_cost = cost; best_axis = ax; best_v = v;
-            }
-        };
-        if (items.size() > 24) {
-            // long lists: no need to look at a value twice, the cost is a function of the value alone
-            for (const FaceItem &it : items)
-                for (int ax = 0; ax < 2; ax++) { consider(ax, it.lo[ax]); consider(ax, it.hi[ax]); }
-        } else {
-            for (int ax = 0; ax < 2; ax++) {
-                std::vector<float> &c = cand[ax];
-                c.clear();
-                for (const FaceItem &it : items) { c.push_back(it.lo[ax]); c.push_back(it.hi[ax]); }
-                std::sort(c.begin(), c.end());
-                c.erase(std::unique(c.begin(), c.end()), c.end());
-                for (float v : c) consider(ax, v);
-            }
-        }
-        if (best_axis < 0 || depth > 64) {          // nothing cuts the region, yet nothing covers it: keep the first
+        float su[3] = {INFINITY, INFINITY, INFINITY}, sv[3] = {INFINITY, INFINITY, INFINITY};
+        const int nu = pick_splits(begin, end, 0, r.lo[0], r.hi[0], su), nv = pick_splits(begin, end, 1, r.lo[1], r.hi[1], sv);
+        if ((nu == 0 && nv == 0) || depth > 64) {     // nothing cuts the region, yet nothing covers it: keep the first
             out.face_parts++;
             out.wall_parts += first_is_wall;
             return first.code;
         }
-        Region rl = r, rh = r;
-        rl.hi[best_axis] = best_v; rh.lo[best_axis] = best_v;
-        // `items` points into the pool, which grows here: go by index from now on
-        const size_t mark = pool.size();
-        pool.reserve(mark + 2 * (end - begin));
-        for (size_t q = begin; q < end; q++)
-            if (overlaps(pool[q], rl)) pool.push_back(pool[q]);
-        const size_t mid = pool.size();
-        for (size_t q = begin; q < end; q++)
-            if (overlaps(pool[q], rh)) pool.push_back(pool[q]);
-        const size_t stop = pool.size();
-        const uint32_t self = (uint32_t)out.face_nodes.size();
-        out.face_nodes.push_back(RoomFaceNode{best_axis == 0 ? best_v : -INFINITY, best_axis == 1 ? best_v : -INFINITY, 0u, 0u});
-        const uint32_t lo = build(rl, mark, mid, depth + 1), hi = build(rh, mid, stop, depth + 1);
-        pool.resize(mark);
-        out.face_nodes[self].lo = lo; out.face_nodes[self].hi = hi;
+        const uint32_t self = (uint32_t)out.grids.size(), base = (uint32_t)out.cells.size(), stride = (uint32_t)nu + 1;
+        out.grids.push_back(RoomFaceGrid{{su[0], su[1], su[2]}, {sv[0], sv[1], sv[2]}, base, stride});
+        out.cells.resize(out.cells.size() + (size_t)(nu + 1) * (nv + 1), kRoomCodeMiss);
+        for (int iv = 0; iv <= nv; iv++)
+            for (int iu = 0; iu <= nu; iu++) {
+                Region c;
+                c.lo[0] = iu == 0 ? r.lo[0] : su[iu - 1]; c.hi[0] = iu == nu ? r.hi[0] : su[iu];
+                c.lo[1] = iv == 0 ? r.lo[1] : sv[iv - 1]; c.hi[1] = iv == nv ? r.hi[1] : sv[iv];
+                const size_t mark = pool.size();
+                for (size_t q = begin; q < end; q++)
+                    if (overlaps(pool[q], c)) { const FaceItem it = pool[q]; pool.push_back(it); }
+                const uint32_t code = build(c, mark, pool.size(), depth + 1);
+                pool.resize(mark);
+                out.cells[base + (uint32_t)iu + stride * (uint32_t)iv] = code;
+            }
         return kRoomCodeNode | self;
     }
 };
-
 
 // ---- kd-tree over the colliders ------------------------------------------------------------------------------------
 
@@ -384,7 +358,6 @@ const char *build_rooms(RoomScene &out, const fmgi_rect *walls, int num_walls, c
     out = RoomScene();
     bool do_merge = true;
     if (const char *v = getenv("FMGI_ROOMS_MERGE")) do_merge = atoi(v) != 0;
-    if (const char *v = getenv("FMGI_ROOMS_FACE_COST")) g_face_cost_depth = v[0] != 'e';
     std::vector<ARect> rects;
     rects.reserve((size_t)num_walls);
     for (int i = 0; i < num_walls; i++) {
@@ -590,10 +563,10 @@ const char *build_rooms(RoomScene &out, const fmgi_rect *walls, int num_walls, c
     std::stable_sort(live.begin(), live.end(), [&](int a, int b) { return box_rects[a].size() > box_rects[b].size(); });
     lap("faces: order boxes");
     const size_t chunk = 4, num_chunks = (live.size() + chunk - 1) / chunk;
-    std::vector<FaceTreeBuilder::Out> chunk_out(num_chunks);
+    std::vector<FaceGridBuilder::Out> chunk_out(num_chunks);
     // (a flat of a few hundred rectangles is built in half a millisecond: starting threads would cost more)
     run_parallel(num_chunks, [&](size_t ch) {
-        FaceTreeBuilder ftb;
+        FaceGridBuilder ftb;
         std::vector<int> behind;
         std::vector<FaceItem> items;
         for (size_t li = ch * chunk; li < std::min(live.size(), (ch + 1) * chunk); li++) {
@@ -644,23 +617,24 @@ const char *build_rooms(RoomScene &out, const fmgi_rect *walls, int num_walls, c
         chunk_out[ch] = std::move(ftb.out);
     }, rects.size() >= 2048);
     lap("faces (parallel)");
-    std::vector<size_t> chunk_off(num_chunks + 1, 0);
+    std::vector<size_t> grid_off(num_chunks + 1, 0), cell_off(num_chunks + 1, 0);
     for (size_t ch = 0; ch < num_chunks; ch++) {
-        chunk_off[ch + 1] = chunk_off[ch] + chunk_out[ch].face_nodes.size();
+        grid_off[ch + 1] = grid_off[ch] + chunk_out[ch].grids.size();
+        cell_off[ch + 1] = cell_off[ch] + chunk_out[ch].cells.size();
         out.face_parts += chunk_out[ch].face_parts;
         out.wall_parts += chunk_out[ch].wall_parts;
     }
-    out.face_nodes.resize(chunk_off[num_chunks]);
+    out.face_grids.resize(grid_off[num_chunks]);
+    out.face_cells.resize(cell_off[num_chunks]);
     const size_t groups = (num_chunks + 255) / 256;
     run_parallel(groups, [&](size_t gi) {
         for (size_t ch = gi * 256; ch < std::min(num_chunks, (gi + 1) * 256); ch++) {
-            const uint32_t off = (uint32_t)chunk_off[ch];
-            auto fix = [off](uint32_t code) { return (code & kRoomCodeKind) == kRoomCodeNode ? code + off : code; };
-            RoomFaceNode *dst = out.face_nodes.data() + off;
-            for (RoomFaceNode n : chunk_out[ch].face_nodes) {
-                n.lo = fix(n.lo); n.hi = fix(n.hi);
-                *dst++ = n;
-            }
+            const uint32_t goff = (uint32_t)grid_off[ch], coff = (uint32_t)cell_off[ch];
+            auto fix = [goff](uint32_t code) { return (code & kRoomCodeKind) == kRoomCodeNode ? code + goff : code; };
+            RoomFaceGrid *gd = out.face_grids.data() + goff;
+            for (RoomFaceGrid g : chunk_out[ch].grids) { g.base += coff; *gd++ = g; }
+            uint32_t *cd = out.face_cells.data() + coff;
+            for (uint32_t c : chunk_out[ch].cells) *cd++ = fix(c);
             for (size_t li = ch * chunk; li < std::min(live.size(), (ch + 1) * chunk); li++) {
                 RoomBox &rb = out.boxes[(size_t)final_id[live[li]]];
                 for (int o = 0; o < 8; o++)
@@ -668,9 +642,6 @@ const char *build_rooms(RoomScene &out, const fmgi_rect *walls, int num_walls, c
             }
         }
     }, rects.size() >= 2048);
-    if (out.face_nodes.size() > kRoomCodeIndex) return "more than 2^30 face nodes";
-    if (out.face_nodes.empty()) out.face_nodes.push_back(RoomFaceNode{0.0f, 0.0f, kRoomCodeMiss, kRoomCodeMiss});   // never empty
-
     lap("faces concatenate");
     const auto t_faces = std::chrono::steady_clock::now();
     // ---- per emitter: the boxes in front of its rectangle, as a partition of the rectangle (the same 2-D kd-trees as the
@@ -679,7 +650,7 @@ const char *build_rooms(RoomScene &out, const fmgi_rect *walls, int num_walls, c
         std::vector<int> stack_n;
         std::vector<int> seen;
         std::vector<FaceItem> items;
-        FaceTreeBuilder ftb;
+        FaceGridBuilder ftb;
         out.starts.assign((size_t)(num_windows + num_lights), RoomStart{kRoomCodeMiss, -1});
         for (int e = 0; e < num_windows + num_lights; e++) {
             ARect er;
@@ -712,22 +683,20 @@ const char *build_rooms(RoomScene &out, const fmgi_rect *walls, int num_walls, c
                 }
             }
             const Region region = {{er.lo[u], er.lo[v]}, {er.hi[u], er.hi[v]}};
-            const size_t first_node = ftb.out.face_nodes.size();
-            uint32_t code = ftb.build(region, items);
-            // the emitters' nodes go behind the faces' nodes
-            const uint32_t off = (uint32_t)out.face_nodes.size() - (uint32_t)first_node;
-            auto fix = [off](uint32_t c) { return (c & kRoomCodeKind) == kRoomCodeNode ? c + off : c; };
-            for (size_t q = first_node; q < ftb.out.face_nodes.size(); q++) {
-                RoomFaceNode n = ftb.out.face_nodes[q];
-                n.lo = fix(n.lo); n.hi = fix(n.hi);
-                out.face_nodes.push_back(n);
-            }
-            ftb.out.face_nodes.resize(first_node);
+            ftb.out = FaceGridBuilder::Out();
+            const uint32_t code = ftb.build(region, items);
+            // the emitters' records go behind the faces' records
+            const uint32_t goff = (uint32_t)out.face_grids.size(), coff = (uint32_t)out.face_cells.size();
+            auto fix = [goff](uint32_t c) { return (c & kRoomCodeKind) == kRoomCodeNode ? c + goff : c; };
+            for (RoomFaceGrid g : ftb.out.grids) { g.base += coff; out.face_grids.push_back(g); }
+            for (uint32_t c : ftb.out.cells) out.face_cells.push_back(fix(c));
             out.starts[(size_t)e] = RoomStart{fix(code), a};
         }
         if (out.starts.empty()) out.starts.push_back(RoomStart{kRoomCodeMiss, -1});
     }
-    if (out.face_nodes.size() > kRoomCodeIndex) return "more than 2^30 face nodes";
+    if (out.face_grids.size() > kRoomCodeIndex) return "more than 2^30 face records";
+    if (out.face_grids.empty()) out.face_grids.push_back(RoomFaceGrid{{INFINITY, INFINITY, INFINITY}, {INFINITY, INFINITY, INFINITY}, 0u, 1u});
+    if (out.face_cells.empty()) out.face_cells.push_back(kRoomCodeMiss);          // the device tables are never empty
     // the tree itself, for point location
     out.nodes.resize(nodes.size());
     for (size_t i = 0; i < nodes.size(); i++) {
@@ -762,15 +731,21 @@ int rooms_locate(const RoomScene &rs, const float p[3], const float d[3])
     return rs.nodes[n].left;
 }
 
+// the cell of grid record `g` the point (pu, pv) falls into (device: the same six compares)
+static uint32_t rooms_grid_lookup(const RoomScene &rs, uint32_t g, float pu, float pv)
+{
+    const RoomFaceGrid &G = rs.face_grids[g];
+    const uint32_t iu = (pu >= G.su[0]) + (pu >= G.su[1]) + (pu >= G.su[2]);
+    const uint32_t iv = (pv >= G.sv[0]) + (pv >= G.sv[1]) + (pv >= G.sv[2]);
+    return rs.face_cells[G.base + iu + G.stride * iv];
+}
+
 int rooms_start_box(const RoomScene &rs, int emitter, const float p[3], const float d[3])
 {
     const RoomStart &st = rs.starts[(size_t)emitter];
     uint32_t code = st.code;
     const float pu = st.axis == 0 ? p[1] : p[0], pv = st.axis == 2 ? p[1] : p[2];
-    while ((code & kRoomCodeKind) == kRoomCodeNode) {
-        const RoomFaceNode &n = rs.face_nodes[code];
-        code = (pu >= n.split_u && pv >= n.split_v) ? n.hi : n.lo;
-    }
+    while ((code & kRoomCodeKind) == kRoomCodeNode) code = rooms_grid_lookup(rs, code, pu, pv);
     if ((code & kRoomCodeKind) == kRoomCodeBox) return (int)(code & kRoomCodeIndex);
     return rooms_locate(rs, p, d);
 }
@@ -797,9 +772,8 @@ int rooms_closest_hit(const RoomScene &rs, int box, const float o[3], const floa
         const float pu = fmaf(t, d[u], o[u]), pv = fmaf(t, d[v], o[v]);
         uint32_t code = R.code[a];
         while ((code & kRoomCodeKind) == kRoomCodeNode) {
-            const RoomFaceNode &n = rs.face_nodes[code];
             tests++;
-            code = (pu >= n.split_u && pv >= n.split_v) ? n.hi : n.lo;
+            code = rooms_grid_lookup(rs, code, pu, pv);
         }
         const uint32_t kind = code & kRoomCodeKind, index = code & kRoomCodeIndex;
         if (kind == kRoomCodeWall) {

@@ -76,16 +76,17 @@ struct TraceParams {
     uint32_t philox_keys[10];       // seed + r * W: the Philox2x32 round keys of this bake (philox.cuh)
     int grid_has_misc;              // the walk lists hold misc records (scene_tables.h)
     int one;                        // 1, opaque to the compiler: x * one + y keeps integer updates on the FMA pipe
-    // room tier (room_tables.h): boxes (16 float4 each: 8 octant records), face-tree nodes, box bounds (2 float4 each),
+    // room tier (room_tables.h): boxes (16 float4 each: 8 octant records), face grids and box bounds (2 float4 each),
     // kd-tree nodes for point location (1 float4 each)
     const float4 *room_boxes;
-    const float4 *room_face_nodes;
+    const float4 *room_face_grids;  // RoomFaceGrid records (2 float4 each)
+    const unsigned *room_face_cells; // the codes they index
     const float4 *room_bounds;
     const float4 *room_nodes;
     const int2 *room_starts;        // per emitter: {code, normal axis} (RoomStart)
     float room_lo[3], room_hi[3];   // the root box
     // table sizes: read only by the bounds-checked build (FMGI_CHECKED, lib/libfmgi_cuda_checked.so)
-    unsigned grid_records, num_walls, num_texels, room_num_boxes, room_num_face_nodes, room_num_nodes;
+    unsigned grid_records, num_walls, num_texels, room_num_boxes, room_num_face_grids, room_num_face_cells, room_num_nodes;
 };
 
 // ---- bounds-checked build ----------------------------------------------------------------------------------------
@@ -699,20 +700,41 @@ __device__ __forceinline__ int rooms_locate(const TraceParams &p, float x, float
     return 0;
 }
 
+// What is at (pu, pv) on a face (or an emitter rectangle) that holds several things: the cell of grid record `g` the
+// point falls into.  {su0, su1, su2, sv0}, {sv1, sv2, base, stride}; unused splits are +inf.
+__device__ __forceinline__ unsigned rooms_grid_lookup(const TraceParams &p, const float4 *__restrict__ grids,
+                                                      const unsigned *__restrict__ cells, unsigned g, float pu, float pv)
+{
+    if (!FMGI_CHECK(p, g < p.room_num_face_grids, 22)) return 3u << 30;
+    float4 g0, g1;
+    ldg256(grids + 2 * (size_t)g, g0, g1);
+    // cell = base + (u splits the coordinate is at or above) + stride * (v splits ...): six compares, each followed by
+    // a predicated add (from C the compiler builds 0 / 1 values and sums them: 28 instead of 18 instructions a lookup)
+    unsigned cell = __float_as_uint(g1.z);
+    asm("{\n\t.reg .pred p;\n\t"
+        "setp.ge.f32 p, %1, %3;\n\t@p add.u32 %0, %0, 1;\n\t"
+        "setp.ge.f32 p, %1, %4;\n\t@p add.u32 %0, %0, 1;\n\t"
+        "setp.ge.f32 p, %1, %5;\n\t@p add.u32 %0, %0, 1;\n\t"
+        "setp.ge.f32 p, %2, %6;\n\t@p add.u32 %0, %0, %9;\n\t"
+        "setp.ge.f32 p, %2, %7;\n\t@p add.u32 %0, %0, %9;\n\t"
+        "setp.ge.f32 p, %2, %8;\n\t@p add.u32 %0, %0, %9;\n\t"
+        "}"
+        : "+r"(cell)
+        : "f"(pu), "f"(pv), "f"(g0.x), "f"(g0.y), "f"(g0.z), "f"(g0.w), "f"(g1.x), "f"(g1.y), "r"(__float_as_uint(g1.w)));
+    if (!FMGI_CHECK(p, cell < p.room_num_face_cells, 24)) return 3u << 30;
+    return __ldg(cells + cell);
+}
+
 // First box of a photon emitted by `emitter`: the boxes in front of the emitter rectangle partition it - one box (a
-// ceiling light, a window in its niche: no lookup), or a descent through the rectangle's 2-D kd-tree with the start
-// point's two in-plane coordinates; an emitter the builder could not place falls back to the kd-tree of the boxes.
+// ceiling light, a window in its niche: no lookup), or a grid lookup with the start point's two in-plane
+// coordinates; an emitter the builder could not place falls back to the kd-tree of the boxes.
 __device__ __forceinline__ int rooms_start(const TraceParams &p, int emitter, float x, float y, float z, float dx, float dy,
                                            float dz)
 {
     const int2 st = __ldg(p.room_starts + emitter);
     unsigned code = (unsigned)st.x;
     const float pu = st.y == 0 ? y : x, pv = st.y == 2 ? y : z;
-    while ((code >> kRoomKindShift) == 0u) {
-        if (!FMGI_CHECK(p, code < p.room_num_face_nodes, 23)) return 0;
-        const float4 n = __ldg(p.room_face_nodes + code);
-        code = __float_as_uint((pu >= n.x && pv >= n.y) ? n.w : n.z);
-    }
+    while ((code >> kRoomKindShift) == 0u) code = rooms_grid_lookup(p, p.room_face_grids, p.room_face_cells, code, pu, pv);
     if ((code >> kRoomKindShift) == 2u) return (int)(code & ((1u << kRoomKindShift) - 1u));
     return rooms_locate(p, x, y, z, dx, dy, dz);
 }
@@ -725,7 +747,7 @@ __device__ __forceinline__ float rooms_inv(float d) { return d == 0.0f ? -1e30f 
 
 
 // The ray leaves its box through the nearest of the three faces it travels towards; the face's code - after a
-// descent through the face's 2-D kd-tree where several things share the face - says what is at the exit point: a
+// lookup in the face's grid record where several things share the face - says what is at the exit point: a
 // collider that faces into the box (a hit - the closest one: nothing lies inside a box), the next box, or nothing
 // (the ray leaves the scene).  At most kSteps boxes per call: returns the wall index, -1 (miss), or kRoomWalking
 // with `box` = the box the ray is in now, so that the caller can interleave the walks of a warp's lanes with their
@@ -739,7 +761,8 @@ __device__ __forceinline__ int rooms_walk(const TraceParams &p, int &box, float 
 {
     // the ray's octant picks the 32-byte record of each box: far planes and face codes of the three faces ahead
     const float4 *base = p.room_boxes + ((dx > 0.0f ? 2 : 0) + (dy > 0.0f ? 4 : 0) + (dz > 0.0f ? 8 : 0));
-    const float4 *face_nodes = p.room_face_nodes;
+    const float4 *face_grids = p.room_face_grids;
+    const unsigned *face_cells = p.room_face_cells;
     unsigned cur = (unsigned)box;
     int s = 0;
     unsigned code;
@@ -749,7 +772,7 @@ __device__ __forceinline__ int rooms_walk(const TraceParams &p, int &box, float 
         if (!FMGI_CHECK(p, cur < p.room_num_boxes, 21)) { code = 3u << kRoomKindShift; break; }
         float4 r0, r1;                                   // {far.x, far.y, far.z, code.x}, {code.y, code.z, -, -}
         ldg256(base + (size_t)kRoomBoxVec * cur, r0, r1);
-        if (kCount) tests++;                             // counted: boxes crossed + face-tree nodes visited
+        if (kCount) tests++;                             // counted: boxes crossed + face grids looked up
         const float tx = (r0.x - ox) * ix, ty = (r0.y - oy) * iy, tz = (r0.z - oz) * iz;
         // nearest face; the two in-plane coordinates of the exit point, in ascending axis order
         const float txy = fminf(tx, ty);
@@ -761,11 +784,9 @@ __device__ __forceinline__ int rooms_walk(const TraceParams &p, int &box, float 
         ca = ax_z ? r0.z : (ax_y ? r0.y : r0.x);
         oa = ax_z ? oz : (ax_y ? oy : ox);
         da = ax_z ? dz : (ax_y ? dy : dx);
-        while ((code >> kRoomKindShift) == 0u) {         // several things on this face: descend its 2-D kd-tree
-            if (!FMGI_CHECK(p, code < p.room_num_face_nodes, 22)) { code = 3u << kRoomKindShift; break; }
-            const float4 n = __ldg(face_nodes + code);   // {split u, split v, lo, hi}: hi when both coordinates are at or above
+        while ((code >> kRoomKindShift) == 0u) {         // several things on this face: look the exit point up
             if (kCount) tests++;
-            code = __float_as_uint((pu >= n.x && pv >= n.y) ? n.w : n.z);
+            code = rooms_grid_lookup(p, face_grids, face_cells, code, pu, pv);
         }
         if ((code >> kRoomKindShift) != 2u) break;       // a collider or nothing: the walk ends here
         cur = code & ((1u << kRoomKindShift) - 1u);

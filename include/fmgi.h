@@ -97,7 +97,7 @@ typedef struct fmgi_stats {
     uint64_t deposits;        /* texel deposits = photon-bounces (the BASELINE metric's unit) */
     uint64_t mirror_bounces;
     uint64_t rect_tests;      /* rectangle tests executed (all lanes); grid lookups only with count_tests; room tier
-                                 (count_tests): boxes crossed + face-tree nodes visited */
+                                 (count_tests): boxes crossed + face grids looked up */
     uint64_t kernel_launches; /* our kernels launched */
     double   trace_ms;        /* device time of the trace kernels (CUDA events), max over GPUs */
     double   h2d_ms, d2h_ms;  /* atlas upload (runs under the trace) / read-back, CUDA events, max over GPUs */

@@ -29,7 +29,8 @@ MARKERS = {
         (r"int rooms_locate\(", "rooms locate"),
         (r"int rooms_start\(", "rooms start"),
         (r"float rooms_inv\(", "rooms walk"),
-        (r"while \(\(code >> kRoomKindShift\)", "rooms face tree"),
+        (r"unsigned rooms_grid_lookup\(", "rooms face grid"),
+        (r"while \(\(code >> kRoomKindShift\) == 0u\) \{", "rooms face grid"),
         (r"all lanes whose walk ended, together", "rooms step outcome"),
         (r"^// The whole walk of one ray", "rooms whole walk"),
         (r"int tile_index\(", "tile index"),

@@ -60,8 +60,8 @@ int main(int argc, char **argv)
     RoomScene rs;
     const char *why = build_rooms(rs, walls.data(), cnt[0], windows.data(), cnt[1], lights.data(), cnt[2]);
     if (why[0]) { printf("refused: %s\n", why); return 3; }
-    printf("rooms: %zu boxes (%zu kd leaves), %zu face parts (%zu colliders), %zu face nodes, depth %d, build %.1f ms\n",
-           rs.boxes.size(), rs.kd_leaves, rs.face_parts, rs.wall_parts, rs.face_nodes.size(), rs.max_depth, rs.build_ms);
+    printf("rooms: %zu boxes (%zu kd leaves), %zu face parts (%zu colliders), %zu face grids with %zu cells, depth %d, build %.1f ms\n",
+           rs.boxes.size(), rs.kd_leaves, rs.face_parts, rs.wall_parts, rs.face_grids.size(), rs.face_cells.size(), rs.max_depth, rs.build_ms);
 
     // rays as the path produces them: half start inside the bounding box, half on a wall (offset 1e-5 along the ray)
     float lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
@@ -116,7 +116,7 @@ int main(int argc, char **argv)
             mism_edge++;
         }
     }
-    printf("rays %d: hits %.3f, steps/ray %.3f (max %ld), face nodes/ray %.3f, index mismatches %ld, distance mismatches %ld\n",
+    printf("rays %d: hits %.3f, steps/ray %.3f (max %ld), face lookups/ray %.3f, index mismatches %ld, distance mismatches %ld\n",
            num_rays, (double)hits / num_rays, (double)steps / num_rays, max_steps, (double)tests / num_rays, mism, mism_edge);
     printf("steps histogram:");
     for (int i = 0; i < 16; i++) printf(" %d:%.3f", i, (double)hist[i] / num_rays);
@@ -179,14 +179,14 @@ int main(int argc, char **argv)
         printf("\nstart boxes: %ld photons, %ld not in the box the tree descent finds", start_checks, start_mismatch);
         if (start_mismatch > start_checks / 2000 + 1) bad_starts = true;
         if (prays) {
-            printf("\nphoton rays %ld: steps/ray %.3f, face nodes/ray %.3f\nphoton steps histogram:", prays, (double)psteps / prays,
+            printf("\nphoton rays %ld: steps/ray %.3f, face lookups/ray %.3f\nphoton steps histogram:", prays, (double)psteps / prays,
                    (double)pnodes / prays);
             for (int i = 0; i < 12; i++) printf(" %d:%.3f", i, (double)ph[i] / prays);
-            printf("\nphoton face nodes histogram:");
+            printf("\nphoton face lookups histogram:");
             for (int i = 0; i < 12; i++) printf(" %d:%.3f", i, (double)pn[i] / prays);
         }
     }
-    printf("\nface nodes histogram:");
+    printf("\nface lookups histogram:");
     for (int i = 0; i < 16; i++) printf(" %d:%.3f", i, (double)ehist[i] / num_rays);
     printf("\n");
     return mism > num_rays / 20000 + 2 || mism_edge || bad_starts ? 1 : 0;

@@ -110,7 +110,7 @@ def test_tier_fixtures_run_the_kernels_they_name(dev_scene, dev_scene_soup, dev_
     assert gpu_bake(dev_scene_rooms, spa)[1]["tier"] == 4
     assert gpu_bake(dev_scene, spa)[1]["tier"] == 4           # AUTO: 172 axis-parallel colliders > 64 -> room tier
     t_rooms = gpu_bake(dev_scene_rooms, spa, count_tests=1)[1]
-    assert 1.0 < t_rooms["rect_tests"] / t_rooms["rays"] < 8.0     # boxes crossed + face-tree nodes visited per ray
+    assert 1.0 < t_rooms["rect_tests"] / t_rooms["rays"] < 8.0     # boxes crossed + face grids looked up per ray
     # rectangle tests per ray tell the kernels apart: plain soup scans every pair block of the ray's sign
     # (94 tests), soup + planes only the x / y lists plus the counted plane lookups, the grid a handful
     t_plain = gpu_bake(dev_scene_soup_plain, spa, count_tests=1)[1]
