@@ -777,7 +777,10 @@ int rooms_closest_hit(const RoomScene &rs, int box, const float o[3], const floa
         }
         const uint32_t kind = code & kRoomCodeKind, index = code & kRoomCodeIndex;
         if (kind == kRoomCodeWall) {
-            if (!(t >= 0)) return -1;                 // the plane lies behind the origin: not a hit (rectangle.c:76)
+            if (!(t >= 0)) {                          // the plane lies behind the origin: not a hit (rectangle.c:76) -
+                box = rooms_locate(rs, o, d);         // the origin is in another box: go on from there
+                continue;
+            }
             t_out = (R.far[a] - o[a]) / d[a];
             box_out = box;
             return (int)index;

@@ -725,6 +725,28 @@ __device__ __forceinline__ unsigned rooms_grid_lookup(const TraceParams &p, cons
     return __ldg(cells + cell);
 }
 
+// The same descent out of line, for the one ray in 1e5 whose walk finds its origin outside the box it was taken to be
+// in (rooms_walk): kept out of the walk's instruction stream.
+__device__ __noinline__ int rooms_relocate(const float4 *__restrict__ nodes, float lox, float loy, float loz, float hix, float hiy,
+                                           float hiz, float x, float y, float z, float dx, float dy, float dz)
+{
+    x = fminf(fmaxf(x, lox), hix);
+    y = fminf(fmaxf(y, loy), hiy);
+    z = fminf(fmaxf(z, loz), hiz);
+    int n = 0;
+#pragma unroll 1
+    for (int guard = 0; guard < 256; guard++) {
+        const float4 nd = __ldg(nodes + n);
+        const int axis = __float_as_int(nd.y);
+        if (axis < 0) return __float_as_int(nd.z);
+        const float c = axis == 0 ? x : (axis == 1 ? y : z);
+        const float dc = axis == 0 ? dx : (axis == 1 ? dy : dz);
+        const bool right = c > nd.x || (c == nd.x && dc > 0.0f);
+        n = right ? __float_as_int(nd.w) : __float_as_int(nd.z);
+    }
+    return 0;
+}
+
 // First box of a photon emitted by `emitter`: the boxes in front of the emitter rectangle partition it - one box (a
 // ceiling light, a window in its niche: no lookup), or a grid lookup with the start point's two in-plane
 // coordinates; an emitter the builder could not place falls back to the kd-tree of the boxes.
@@ -753,8 +775,8 @@ __device__ __forceinline__ float rooms_inv(float d) { return d == 0.0f ? -1e30f 
 // with `box` = the box the ray is in now, so that the caller can interleave the walks of a warp's lanes with their
 // shading instead of waiting for the longest walk (k_trace).  On a hit `box` is the box the hit was found in: the
 // bounce starts there.  (ix, iy, iz) = rooms_inv of the direction.
-// A collider whose plane lies BEHIND the origin (negative ray parameter: an origin that rounding put an ulp
-// beyond a wall, in a corner) is not a hit (rectangle.c:76 rejects t < 0); the photon is given up.
+// A collider whose plane lies BEHIND the origin (negative ray parameter) is not a hit (rectangle.c:76 rejects t < 0):
+// the origin is not in the box the walk took it to be in, and the walk goes on from the box it is in (kd-tree descent).
 template <bool kCount, int kSteps>
 __device__ __forceinline__ int rooms_walk(const TraceParams &p, int &box, float ox, float oy, float oz, float dx, float dy,
                                           float dz, float ix, float iy, float iz, float &t_out, unsigned &tests)
@@ -794,8 +816,18 @@ __device__ __forceinline__ int rooms_walk(const TraceParams &p, int &box, float 
     }
     // all lanes whose walk ended, together: a hit needs the collider in front of the origin
     box = (int)cur;
+    if ((code >> kRoomKindShift) != 1u) return -1;       // nothing there: the ray leaves the scene
+    if (!(t >= 0.0f)) {
+        // The wall's plane lies BEHIND the origin: the origin is not in this box but behind that wall - the 1e-5 step
+        // along the ray put a photon beside its window's niche, or rounding put a bounce point an ulp beyond the wall
+        // of a corner.  The reference does not hit such a wall (rectangle.c:76) and lets the photon fly on inside the
+        // wall's material; so do we: the walk goes on from the box the origin really is in (about one ray in 1e5).
+        box = rooms_relocate(p.room_nodes, p.room_lo[0], p.room_lo[1], p.room_lo[2], p.room_hi[0], p.room_hi[1], p.room_hi[2],
+                             ox, oy, oz, dx, dy, dz);
+        return kRoomWalking;
+    }
     // (a ray parallel to the collider it starts on is culled like a back face, rectangle.c:70-72: n.d = 0)
-    if ((code >> kRoomKindShift) != 1u || !(t >= 0.0f) || da == 0.0f) return -1;      // nothing there: the ray leaves the scene
+    if (da == 0.0f) return -1;
     // the distance with the reference's formula for an axis-parallel normal, IEEE division
     t_out = __fdiv_rn(__fsub_rn(ca, oa), da);
     return (int)(code & ((1u << kRoomKindShift) - 1u));
@@ -808,8 +840,11 @@ __device__ __forceinline__ int closest_hit_rooms(const TraceParams &p, int &leaf
 {
     unsigned n = 0;
     t_out = __int_as_float(0x7f800000);
-    const int r = rooms_walk<kCount, kRoomMaxSteps>(p, leaf, ox, oy, oz, dx, dy, dz, rooms_inv(dx), rooms_inv(dy), rooms_inv(dz),
-                                                    t_out, n);
+    const float ix = rooms_inv(dx), iy = rooms_inv(dy), iz = rooms_inv(dz);
+    int r = kRoomWalking;
+    // (a walk comes back "still walking" when it had to find the origin's box again; twice is already unheard of)
+    for (int again = 0; again < 4 && r == kRoomWalking; again++)
+        r = rooms_walk<kCount, kRoomMaxSteps>(p, leaf, ox, oy, oz, dx, dy, dz, ix, iy, iz, t_out, n);
     if (kCount && tests) *tests += n;
     return r == kRoomWalking ? -1 : r;
 }
