@@ -368,9 +368,26 @@ int build_host(std::shared_ptr<HostBuild> &out, const fmgi_rect *walls, int num_
     if (int rc = device_attrs(o.device, attr)) return rc;
 
     auto b = std::make_shared<HostBuild>();
+    int tier = o.tier;
+    if (const char *v = getenv("FMGI_TIER")) tier = atoi(v);
+    const bool want_rooms = tier == FMGI_TIER_ROOMS;
+    const bool auto_tier = tier != FMGI_TIER_SOUP && tier != FMGI_TIER_GRID && tier != FMGI_TIER_ROOMS;
+    // A big scene that will (try to) use the room tier: its box decomposition (rooms_build.cpp, 12 ms for 21.5k
+    // rectangles) does not depend on the rectangle tables (2 ms) - both at once.
+    const char *refused = nullptr;
+    std::thread rooms_thread;
+    if ((want_rooms || auto_tier) && num_walls >= 2048)
+        rooms_thread = std::thread([&]() {
+            const double tr0 = now_ms();
+            refused = build_rooms(b->rooms, walls, num_walls, windows, num_windows, lights, num_lights);
+            b->rooms_ms = now_ms() - tr0;
+        });
     const double t0 = now_ms();
     const char *why = prepare_scene(b->scene, walls, num_walls, windows, num_windows, lights, num_lights, num_texels);
-    if (why[0]) return fail(FMGI_ERR_ARG, why);
+    if (why[0]) {
+        if (rooms_thread.joinable()) rooms_thread.join();
+        return fail(FMGI_ERR_ARG, why);
+    }
     b->wall_area.resize(num_walls);
     b->wall_floor.resize(num_walls);
     b->wall_wh.reserve((size_t)6 * num_walls);
@@ -382,29 +399,31 @@ int build_host(std::shared_ptr<HostBuild> &out, const fmgi_rect *walls, int num_
         for (int c = 0; c < 3; c++) b->wall_wh.push_back(walls[i].height[c]);
     }
     b->prepare_ms = now_ms() - t0;
+    if (rooms_thread.joinable()) rooms_thread.join();
 
     // tier: brute force over the shared-memory soup for small scenes, floor-plan grid otherwise
     HostScene &hs = b->scene;
     const size_t soup_bytes = hs.axis.size() * sizeof(AxisPairBlock) + hs.general.size() * sizeof(GeneralRect);
     const int colliders = hs.num_axis_rects + (int)hs.general.size();
-    int tier = o.tier;
-    if (const char *v = getenv("FMGI_TIER")) tier = atoi(v);
     // AUTO: the brute-force soup only for a handful of colliders (one bare room); everything else walks the box
     // decomposition of the room tier when every collider is axis parallel (all parseLayout output is), else the
     // floor-plan grid (measured on the 172-rectangle example.png scene the grid is 20 % faster than the soup + plane
-    // tables, and the room tier 2x faster than the grid)
-    const bool want_rooms = tier == FMGI_TIER_ROOMS;
-    if (tier != FMGI_TIER_SOUP && tier != FMGI_TIER_GRID && tier != FMGI_TIER_ROOMS)
+    // tables, and the room tier 1.8x faster than the grid)
+    if (auto_tier)
         tier = (colliders <= 64 && soup_bytes <= (size_t)attr.smem_optin) ? FMGI_TIER_SOUP : FMGI_TIER_ROOMS;
     if (tier == FMGI_TIER_ROOMS) {
-        const double tr0 = now_ms();
-        const char *refused = build_rooms(b->rooms, walls, num_walls, windows, num_windows, lights, num_lights);
-        b->rooms_ms = now_ms() - tr0;
+        if (!refused) {
+            const double tr0 = now_ms();
+            refused = build_rooms(b->rooms, walls, num_walls, windows, num_windows, lights, num_lights);
+            b->rooms_ms = now_ms() - tr0;
+        }
         if (refused[0]) {
             if (want_rooms) return fail(FMGI_ERR_UNSUPPORTED, std::string("room tier: ") + refused);
             b->rooms = RoomScene();
             tier = FMGI_TIER_GRID;
         }
+    } else {
+        b->rooms = RoomScene();
     }
     b->tier = tier;
     b->kernel_tier = tier;

@@ -262,6 +262,21 @@ def test_rectangle_test_counter_is_opt_in_and_changes_nothing(dev_scene, dev_sce
     assert sa["tier"] == 4 and sa["photons"] == sp["photons"] and abs(sa["rays"] - sp["rays"]) <= 1e-5 * sp["rays"]
 
 
+def test_room_tier_deposits_the_grid_tiers_energy(dev_scene_rooms, dev_scene_grid, record):
+    """Same photons, same streams: the two closest-hit structures must find the same hits - the room tier neither loses
+    photons at corners or beside window niches (it relocates an origin that lies behind a wall, rooms_walk) nor
+    invents any.  Total energy to 2 ppm, ray counts to 1e-5 (rays through rectangle edges may end differently)."""
+    spa = 2_000_000                                   # 3e7 photons
+    a_r, s_r = gpu_bake(dev_scene_rooms, spa, max_depth=8, seed=77)
+    a_g, s_g = gpu_bake(dev_scene_grid, spa, max_depth=8, seed=77)
+    assert s_r["tier"] == 4 and s_g["tier"] == 2 and s_r["photons"] == s_g["photons"]
+    e_r, e_g = a_r[:, :3].sum(dtype=np.float64), a_g[:, :3].sum(dtype=np.float64)
+    record("energy_rooms_vs_grid_depth8", photons=int(s_r["photons"]), energy_rel_diff=float(e_r / e_g - 1),
+           rays_rel_diff=float(s_r["rays"] / s_g["rays"] - 1), deposits_rel_diff=float(s_r["deposits"] / s_g["deposits"] - 1))
+    assert abs(e_r / e_g - 1) < 2e-6
+    assert abs(s_r["rays"] / s_g["rays"] - 1) < 1e-5 and abs(s_r["deposits"] / s_g["deposits"] - 1) < 1e-5
+
+
 def test_deposit_peak_probe(fmgi, scene):
     """fmgi_probe_deposit_peak (the deposit roofline of SURVEY.md 8d-ii): the bare RED.E.ADD.F32x4 at uniform-random
     texels.  An L2-resident footprint sustains an order of magnitude more than the bake deposits (measured
