@@ -61,7 +61,8 @@ __device__ __forceinline__ SoupTables stage_soup(const TraceParams &p, float4 *s
 }
 
 // kTier: FMGI_TIER_SOUP (brute force over the shared-memory soup), kTierSoupPlanes (the same with the
-// horizontal rectangles looked up through the grid's plane tables) or FMGI_TIER_GRID (floor-plan grid in L2).
+// horizontal rectangles looked up through the grid's plane tables), FMGI_TIER_GRID (floor-plan grid in L2) or
+// kTierRooms (box decomposition, the default for axis-parallel scenes).
 // kCount: also count the rectangle tests the grid lookups execute (fmgi_options.count_tests; two more
 // instructions in the walk loop, so not the default).
 // kRoomSteps (room tier): boxes a lane's ray crosses per iteration of the photon loop.  The room tier does not walk a

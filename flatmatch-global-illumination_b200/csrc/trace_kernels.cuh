@@ -8,11 +8,16 @@
 //     dies (miss, or last allowed bounce) the warp's dead lanes are found with a ballot and
 //     refilled from the warp's chunk of the global photon index space, so the closest-hit loop
 //     always runs with full warps ("wavefront" compaction done in registers);
-//   * scenes above 64 colliders (example.png included) find the closest hit through a floor-plan
-//     grid (GridWalk): a 2-D DDA through per-cell, per-sign-combination wall lists whose loop is 34
-//     instructions of straight-line predicated PTX - test the pending record, step, fetch with ONE
-//     256-bit load that also carries the continuation - then one head lookup per z plane crossed
-//     before the wall hit;
+//   * scenes above 64 colliders whose colliders are all axis parallel (example.png included: everything
+//     parseLayout.c emits) find the closest hit by walking a box decomposition of the flat in which every
+//     collider lies on a box face (rooms_walk, room_tables.h): a ray leaves its box through the nearest of the
+//     three faces ahead - one 256-bit load, 25 instructions - and the face's code says what is there: a wall (the
+//     hit), the next box, nothing, or a grid record for a face that holds several things; the photon loop
+//     interleaves these box steps with the shading of the lanes that already hit something;
+//   * scenes with arbitrarily oriented colliders use a floor-plan grid (GridWalk): a 2-D DDA through per-cell,
+//     per-sign-combination wall lists whose loop is 35 instructions of straight-line predicated PTX - test the
+//     pending record, step, fetch with ONE 256-bit load that also carries the continuation - then one head lookup
+//     per z plane crossed before the wall hit;
 //   * a bare room keeps the brute-force soup in shared memory: per-axis lists of axis-parallel
 //     records, warp-uniform trip count, broadcast loads; back-face culling (rectangle.c:70-72)
 //     halves the work instead of costing a test: the records of one normal axis are split by normal
