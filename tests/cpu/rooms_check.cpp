@@ -63,6 +63,22 @@ int main(int argc, char **argv)
     printf("rooms: %zu boxes (%zu kd leaves), %zu face parts (%zu colliders), %zu face grids with %zu cells, depth %d, build %.1f ms\n",
            rs.boxes.size(), rs.kd_leaves, rs.face_parts, rs.wall_parts, rs.face_grids.size(), rs.face_cells.size(), rs.max_depth, rs.build_ms);
 
+    // a checksum of every table the device reads: the build must not depend on the number of builder threads
+    {
+        uint64_t h = 1469598103934665603ull;
+        auto mix = [&](const void *data, size_t bytes) {
+            const unsigned char *b = static_cast<const unsigned char *>(data);
+            for (size_t i = 0; i < bytes; i++) { h ^= b[i]; h *= 1099511628211ull; }
+        };
+        mix(rs.boxes.data(), rs.boxes.size() * sizeof(RoomBox));
+        mix(rs.bounds.data(), rs.bounds.size() * sizeof(RoomBounds));
+        mix(rs.face_grids.data(), rs.face_grids.size() * sizeof(RoomFaceGrid));
+        mix(rs.face_cells.data(), rs.face_cells.size() * sizeof(uint32_t));
+        mix(rs.nodes.data(), rs.nodes.size() * sizeof(RoomNode));
+        mix(rs.starts.data(), rs.starts.size() * sizeof(RoomStart));
+        printf("tables checksum %016llx\n", (unsigned long long)h);
+    }
+
     // rays as the path produces them: half start inside the bounding box, half on a wall (offset 1e-5 along the ray)
     float lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
     for (const fmgi_rect &r : walls)
