@@ -84,3 +84,21 @@ def test_rooms_do_not_depend_on_the_number_of_builder_threads(rooms_checker, tmp
                         env={"FMGI_BUILD_THREADS": threads})
         sums.add(re.search(r"tables checksum ([0-9a-f]+)", out).group(1))
     assert len(sums) == 1, sums
+
+
+def test_warp_replay_tool_builds_and_prefers_interleaved_steps(tmp_path, scene):
+    """tools/rooms_warp_sim.cpp (the analysis behind profiles/r2_rooms_lanes.md) still compiles against the tables and
+    reproduces the shape of the measurement: one box step per iteration costs clearly more warp instructions per ray than
+    two or three, and walking every ray to its end is not better than three."""
+    exe = tmp_path / "rooms_warp_sim"
+    subprocess.run(["g++", "-O2", "-std=c++17", "-I", str(ROOT / "include"), str(ROOT / "tools" / "rooms_warp_sim.cpp"),
+                    str(CSRC / "rooms_build.cpp"), "-o", str(exe), "-lpthread"], check=True)
+    path = tmp_path / "scene.bin"
+    with open(path, "wb") as f:
+        np.array([len(scene.walls), len(scene.windows), len(scene.lights)], dtype="<i4").tofile(f)
+        for t in (scene.walls, scene.windows, scene.lights):
+            np.ascontiguousarray(t).tofile(f)
+    out = subprocess.run([str(exe), str(path), "3", "60", "120"], capture_output=True, text=True, check=True).stdout
+    rows = {int(m.group(1)): float(m.group(2)) for m in re.finditer(r"^(\d+)\s+([0-9.]+)\s+[0-9.]+\s+[0-9.]+\s*$", out, re.M)}
+    assert {1, 2, 3, 64} <= set(rows), out
+    assert rows[1] > 1.15 * rows[3] and rows[64] >= rows[3] and abs(rows[2] / rows[3] - 1) < 0.1, out
